@@ -1,0 +1,738 @@
+// cdbg.cu -- host side of libcdbg_b200.so: context, device memory, stage orchestration and the C ABI of include/cdbg.h.
+//
+// The library is the product path: every stage runs as CUDA kernels from kernels.cuh on one B200; there is no CPU
+// implementation behind these entry points.  Stage boundaries that are disk files in the reference
+// (.h5 partitions -> .glue.N -> .unitigs.fa -> .links.N) are device arrays here.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/cdbg.h"
+#include "kernels.cuh"
+
+namespace {
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool used = false;
+};
+
+enum Stage { ST_EMPTY = 0, ST_PUSHED, ST_COUNTED, ST_COMPACTED, ST_LINKED };
+
+enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3, T_K5, T_K6R, T_K6S, T_N };
+
+}  // namespace
+
+struct cdbg_ctx {
+    cdbg_params prm{};
+    int k = 0, m = 0;
+    uint32_t amin = 1, amax = 0x7FFFFFFFu;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    Stage stage = ST_EMPTY;
+    cdbg_stats st{};
+    Timer tm[T_N];
+    uint32_t launches = 0;
+
+    // device allocations made through dalloc (freed by reset)
+    std::vector<void *> allocs;
+
+    // reads
+    uint8_t *d_bytes = nullptr;
+    uint64_t n_bytes = 0, cap_bytes = 0;
+    bool bytes_borrowed = false;
+    uint8_t *d_synth = nullptr;   // owned by the context across resets (bench input)
+    uint64_t synth_cap = 0;
+
+    // stage 1 results
+    uint64_t *d_solid_kmers = nullptr;
+    uint32_t *d_solid_counts = nullptr;
+    uint64_t S = 0;
+
+    // stage 2/3 results
+    uint32_t *d_link = nullptr;
+    uint64_t *d_edges = nullptr;
+    uint64_t n_edges = 0, edge_cap = 0;
+    uint64_t *d_info = nullptr;
+    uint32_t *d_unitig_of_kmer = nullptr;
+    char *d_seq = nullptr;
+    uint64_t *d_seq_off = nullptr;
+    unsigned long long *d_kc = nullptr;
+    uint32_t *d_abund = nullptr;
+    uint64_t U = 0, total_nt = 0;
+
+    // stage 4
+    LinkRec *d_links = nullptr;
+
+    // small device scratch for counters (zeroed per use)
+    unsigned long long *d_ctr = nullptr;   // [64]
+    int *d_flag = nullptr;                 // [4]
+    unsigned long long *h_ctr = nullptr;   // pinned [64]
+
+    // host result buffers (pinned, grown on demand)
+    char *h_seq = nullptr; size_t h_seq_cap = 0;
+    uint64_t *h_seq_off = nullptr; size_t h_seq_off_cap = 0;
+    uint64_t *h_kc = nullptr; size_t h_kc_cap = 0;
+    uint32_t *h_abund = nullptr; size_t h_abund_cap = 0;
+    cdbg_link_t *h_links = nullptr; size_t h_links_cap = 0;
+
+    int fail(int code, const char *fmt, ...) {
+        char buf[1024];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        if (prm.flags & CDBG_FLAG_VERBOSE) fprintf(stderr, "[cdbg] error: %s\n", buf);
+        return code;
+    }
+};
+
+namespace {
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            return ctx->fail(e_ == cudaErrorMemoryAllocation ? CDBG_ERR_OOM : CDBG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, \
+                             __LINE__, #call, cudaGetErrorString(e_));                                             \
+    } while (0)
+
+#define LAUNCH(kern, grid, block, smem, ...)                                   \
+    do {                                                                       \
+        kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);           \
+        ctx->launches++;                                                       \
+        CK(cudaGetLastError());                                                \
+    } while (0)
+
+template <typename T>
+int dalloc(cdbg_ctx *ctx, T **p, size_t n_elems) {
+    void *q = nullptr;
+    size_t bytes = std::max<size_t>(n_elems * sizeof(T), 256);
+    CK(cudaMallocAsync(&q, bytes, ctx->stream));
+    ctx->allocs.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return CDBG_OK;
+}
+
+template <typename T>
+int dfree(cdbg_ctx *ctx, T *&p) {
+    if (!p) return CDBG_OK;
+    auto it = std::find(ctx->allocs.begin(), ctx->allocs.end(), (void *)p);
+    if (it != ctx->allocs.end()) { ctx->allocs.erase(it); CK(cudaFreeAsync(p, ctx->stream)); }
+    p = nullptr;
+    return CDBG_OK;
+}
+
+template <typename T>
+int hgrow(cdbg_ctx *ctx, T **p, size_t *cap, size_t n_elems) {
+    if (n_elems <= *cap && *p) return CDBG_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = std::max<size_t>(n_elems + n_elems / 8, 1024);
+    void *q = nullptr;
+    CK(cudaHostAlloc(&q, want * sizeof(T), cudaHostAllocDefault));
+    *p = reinterpret_cast<T *>(q); *cap = want;
+    return CDBG_OK;
+}
+
+int tstart(cdbg_ctx *ctx, int i) {
+    Timer &t = ctx->tm[i];
+    if (!t.a) { CK(cudaEventCreate(&t.a)); CK(cudaEventCreate(&t.b)); }
+    CK(cudaEventRecord(t.a, ctx->stream));
+    return CDBG_OK;
+}
+int tstop(cdbg_ctx *ctx, int i) {
+    Timer &t = ctx->tm[i];
+    CK(cudaEventRecord(t.b, ctx->stream));
+    t.used = true;
+    return CDBG_OK;
+}
+float tread(cdbg_ctx *ctx, int i) {
+    Timer &t = ctx->tm[i];
+    if (!t.used) return 0.f;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return ms;
+}
+
+inline int grid_for(cdbg_ctx *ctx, uint64_t n, int block, int per_sm) {
+    uint64_t need = (n + block - 1) / block;
+    uint64_t cap = (uint64_t)ctx->n_sm * per_sm;
+    return (int)std::max<uint64_t>(1, std::min(need, cap));
+}
+
+uint32_t next_pow2(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ULL << 31);
+}
+
+// zero the counter scratch
+int ctr_zero(cdbg_ctx *ctx) {
+    CK(cudaMemsetAsync(ctx->d_ctr, 0, 64 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_flag, 0, 4 * sizeof(int), ctx->stream));
+    return CDBG_OK;
+}
+int ctr_read(cdbg_ctx *ctx) {
+    CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_ctr + 64, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CDBG_OK;
+}
+
+// exclusive scan of a u32 array into u64, total to *h_total (synchronises)
+int exclusive_scan(cdbg_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_out, uint64_t *h_total) {
+    uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n_tiles == 0) { *h_total = 0; return CDBG_OK; }
+    uint64_t *d_sums = nullptr;
+    int rc = dalloc(ctx, &d_sums, n_tiles + 1);
+    if (rc) return rc;
+    LAUNCH(scan_tile_sums, (unsigned)n_tiles, SCAN_THREADS, 0, d_in, n, d_sums);
+    LAUNCH(scan_sums_inplace, 1, SCAN_THREADS, 0, d_sums, n_tiles, d_sums + n_tiles);
+    LAUNCH(scan_apply, (unsigned)n_tiles, SCAN_THREADS, 0, d_in, n, d_sums, d_out);
+    CK(cudaMemcpyAsync(ctx->h_ctr + 32, d_sums + n_tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *h_total = ctx->h_ctr[32];
+    return dfree(ctx, d_sums);
+}
+
+int free_results(cdbg_ctx *ctx) {
+    for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
+    ctx->allocs.clear();
+    if (!ctx->bytes_borrowed) { /* owned buffer was in allocs */ }
+    ctx->d_bytes = nullptr; ctx->n_bytes = 0; ctx->cap_bytes = 0; ctx->bytes_borrowed = false;
+    ctx->d_solid_kmers = nullptr; ctx->d_solid_counts = nullptr; ctx->S = 0;
+    ctx->d_link = nullptr; ctx->d_edges = nullptr; ctx->n_edges = 0; ctx->edge_cap = 0;
+    ctx->d_info = nullptr; ctx->d_unitig_of_kmer = nullptr; ctx->d_seq = nullptr; ctx->d_seq_off = nullptr;
+    ctx->d_kc = nullptr; ctx->d_abund = nullptr; ctx->U = 0; ctx->total_nt = 0; ctx->d_links = nullptr;
+    ctx->stage = ST_EMPTY;
+    memset(&ctx->st, 0, sizeof ctx->st);
+    for (auto &t : ctx->tm) t.used = false;
+    ctx->launches = 0;
+    return CDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage 1
+
+int stage_count(cdbg_ctx *ctx) {
+    const int k = ctx->k;
+    const uint64_t n = ctx->n_bytes;
+    int rc;
+    tstart(ctx, T_COUNT);
+
+    // ---- K1a: histogram over bins
+    uint64_t n_tiles = (n + K1_TILE - 1) / K1_TILE;
+    uint32_t P = (uint32_t)std::min<uint64_t>(K1_MAX_BINS, std::max<uint64_t>(1, (n * 4 / 5 + 2499999) / 2500000));
+    ctx->st.n_count_bins = P;
+    unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;
+    uint64_t *d_bin_off = nullptr;
+    if ((rc = dalloc(ctx, &d_bin_count, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_cursor, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_off, P + 1))) return rc;
+    CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
+
+    K1Params kp{};
+    kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.P = P;
+    kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
+
+    std::vector<uint64_t> h_cnt(P), h_off(P + 1);
+    uint64_t I = 0;
+    if (n_tiles) {
+        size_t sm0 = k1_smem_bytes(0, P), sm1 = k1_smem_bytes(1, P);
+        CK(cudaFuncSetAttribute(k1_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+        CK(cudaFuncSetAttribute(k1_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+        int g0 = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6);
+        tstart(ctx, T_K1H);
+        LAUNCH(k1_extract<0>, g0, K1_THREADS, sm0, kp);
+        tstop(ctx, T_K1H);
+        CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t max_bin = 0;
+    for (uint32_t b = 0; b < P; b++) { h_off[b] = I; I += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
+    h_off[P] = I;
+    ctx->st.n_instances = I;
+
+    uint64_t *d_kmers = nullptr;
+    if ((rc = dalloc(ctx, &d_kmers, I + 1))) return rc;
+    if (I) {
+        CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        kp.out_kmers = d_kmers;
+        int g1 = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2);
+        tstart(ctx, T_K1S);
+        LAUNCH(k1_extract<1>, g1, K1_THREADS, k1_smem_bytes(1, P), kp);
+        tstop(ctx, T_K1S);
+    }
+
+    // ---- K2: per-bin counting in one L2-resident table
+    uint32_t cap = std::max<uint32_t>(1024, next_pow2(2 * max_bin));
+    uint64_t *d_keys = nullptr; uint32_t *d_counts = nullptr;
+    if ((rc = dalloc(ctx, &d_keys, cap))) return rc;
+    if ((rc = dalloc(ctx, &d_counts, cap))) return rc;
+    CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
+
+    uint64_t solid_cap = std::max<uint64_t>(I <= (1ULL << 28) ? I : std::max<uint64_t>(I / 4, 1ULL << 28), 1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
+        if ((rc = ctr_zero(ctx))) return rc;
+        tstart(ctx, T_K2);
+        for (uint32_t b = 0; b < P; b++) {
+            uint64_t nb = h_cnt[b];
+            if (!nb) continue;
+            uint32_t cap_b = std::max<uint32_t>(1024, next_pow2(2 * nb));
+            LAUNCH(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers + h_off[b], nb, d_keys, d_counts, cap_b - 1, ctx->d_flag);
+            LAUNCH(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
+                   ctx->d_solid_counts, solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
+        }
+        tstop(ctx, T_K2);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow");
+        ctx->S = ctx->h_ctr[0];
+        ctx->st.n_distinct = ctx->h_ctr[1];
+        if (ctx->S <= solid_cap) break;
+        if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "solid buffer overflow");
+        dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
+        solid_cap = ctx->S;
+    }
+    ctx->st.n_solid = ctx->S;
+    if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu): shard over more GPUs", (unsigned long long)ctx->S);
+    dfree(ctx, d_kmers); dfree(ctx, d_keys); dfree(ctx, d_counts);
+    dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+    tstop(ctx, T_COUNT);
+    ctx->stage = ST_COUNTED;
+    return CDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stages 2+3
+
+int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remaining) {
+    // pointer jumping until no element moves (paths done) or the number of moving elements stops shrinking (cycles)
+    uint64_t prev = ~0ULL;
+    *remaining = 0;
+    for (int round = 0; round < 80; round += 4) {
+        int rc = ctr_zero(ctx);
+        if (rc) return rc;
+        for (int j = 0; j < 4; j++) LAUNCH(k6_jump, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, n2, ctx->d_ctr + j);
+        ctx->st.rank_rounds += 4;
+        if ((rc = ctr_read(ctx))) return rc;
+        for (int j = 0; j < 4; j++) {
+            uint64_t c = ctx->h_ctr[j];
+            if (c == 0) { *remaining = 0; return CDBG_OK; }
+            if (c == prev) { *remaining = c; return CDBG_OK; }
+            prev = c;
+        }
+    }
+    return ctx->fail(CDBG_ERR_INTERNAL, "list ranking did not converge");
+}
+
+int stage_compact(cdbg_ctx *ctx) {
+    const int k = ctx->k;
+    const uint64_t S = ctx->S, n2 = 2 * S;
+    int rc;
+    tstart(ctx, T_COMPACT);
+
+    // ---- K3: end records, partitioned by hash of the canonical (k-1)-mer
+    uint32_t P = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1, (n2 + 499999) / 500000));
+    ctx->st.n_join_bins = P;
+    ctx->st.n_junction_records = n2;
+    unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;
+    uint64_t *d_bin_off = nullptr, *d_rec_key = nullptr, *d_rec_val = nullptr;
+    if ((rc = dalloc(ctx, &d_bin_count, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_cursor, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_off, P + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_rec_key, n2 + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_rec_val, n2 + 1))) return rc;
+    CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
+    K3Params p3{};
+    p3.solid_kmers = ctx->d_solid_kmers; p3.n_solid = S; p3.k = k; p3.P = P;
+    p3.bin_count = d_bin_count; p3.bin_off = d_bin_off; p3.bin_cursor = d_bin_cursor; p3.rec_key = d_rec_key; p3.rec_val = d_rec_val;
+    std::vector<uint64_t> h_cnt(P, 0), h_off(P + 1, 0);
+    uint64_t max_bin = 0;
+    tstart(ctx, T_K3);
+    if (S) {
+        LAUNCH(k3_ends<0>, grid_for(ctx, S, 256, 8), 256, 0, p3);
+        CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        uint64_t acc = 0;
+        for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
+        h_off[P] = acc;
+        CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k3_ends<1>, grid_for(ctx, S, 256, 8), 256, 0, p3);
+    }
+    tstop(ctx, T_K3);
+
+    // ---- K5: per-bin join
+    if ((rc = dalloc(ctx, &ctx->d_link, n2 + 1))) return rc;
+    uint32_t cap = std::max<uint32_t>(1024, next_pow2(2 * max_bin));
+    JoinTable T{};
+    if ((rc = dalloc(ctx, &T.keys, cap))) return rc;
+    if ((rc = dalloc(ctx, &T.cnt, cap))) return rc;
+    if ((rc = dalloc(ctx, &T.ids, (size_t)cap * 8))) return rc;
+    CK(cudaMemsetAsync(T.keys, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(T.cnt, 0, (size_t)cap * 4, ctx->stream));
+    ctx->edge_cap = std::max<uint64_t>(S / 2, 1 << 16);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = dalloc(ctx, &ctx->d_edges, ctx->edge_cap + 2 * 0))) return rc;
+        CK(cudaMemsetAsync(ctx->d_link, 0xFF, (n2 + 1) * 4, ctx->stream));
+        if ((rc = ctr_zero(ctx))) return rc;
+        tstart(ctx, T_K5);
+        for (uint32_t b = 0; b < P; b++) {
+            uint64_t nb = h_cnt[b];
+            if (!nb) continue;
+            uint32_t cap_b = std::max<uint32_t>(1024, next_pow2(2 * nb));
+            T.cap_mask = cap_b - 1;
+            LAUNCH(k5_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_rec_key + h_off[b], d_rec_val + h_off[b], nb, T, ctx->d_flag);
+            LAUNCH(k5_resolve, grid_for(ctx, cap_b, 256, 8), 256, 0, T, cap_b, ctx->d_link, ctx->d_edges, ctx->edge_cap, ctx->d_ctr + 0,
+                   ctx->d_ctr + 1);
+        }
+        tstop(ctx, T_K5);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K5 hash table overflow");
+        ctx->n_edges = ctx->h_ctr[0];
+        ctx->st.n_compactions = ctx->h_ctr[1];
+        // leave room for the two edges of every cut cycle (at most S/2 cycles, in practice a handful)
+        if (ctx->n_edges + 2048 <= ctx->edge_cap) break;
+        if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow");
+        dfree(ctx, ctx->d_edges);
+        ctx->edge_cap = ctx->n_edges + std::max<uint64_t>(ctx->n_edges / 8, 1 << 16);
+    }
+    dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
+    dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+
+    // ---- K6: list ranking
+    uint64_t *d_pair = nullptr;
+    if ((rc = dalloc(ctx, &d_pair, n2 + 1))) return rc;
+    tstart(ctx, T_K6R);
+    if (S) {
+        LAUNCH(k6_init, grid_for(ctx, n2, 256, 8), 256, 0, ctx->d_link, d_pair, n2);
+        uint64_t remaining = 0;
+        if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+        for (int guard = 0; remaining && guard < 4; guard++) {
+            // cycles: label with the minimum k-mer index, cut there, re-rank
+            uint8_t *d_cyc = nullptr; uint64_t *d_lab = nullptr;
+            if ((rc = dalloc(ctx, &d_cyc, n2 + 1))) return rc;
+            if ((rc = dalloc(ctx, &d_lab, n2 + 1))) return rc;
+            LAUNCH(k6_cycle_mark, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, ctx->d_link, n2, d_cyc, d_lab);
+            int rounds = 2;
+            for (uint64_t r = 1; r < remaining; r <<= 1) rounds++;
+            for (int r = 0; r < rounds; r++) LAUNCH(k6_cycle_min, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2);
+            if ((rc = ctr_zero(ctx))) return rc;
+            CK(cudaMemcpyAsync(ctx->d_ctr + 0, &ctx->n_edges, 8, cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH(k6_cycle_cut, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2, ctx->d_link, ctx->d_edges, ctx->edge_cap, ctx->d_ctr + 0,
+                   ctx->d_ctr + 1);
+            LAUNCH(k6_reinit_flagged, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, ctx->d_link, d_pair, n2);
+            if ((rc = ctr_read(ctx))) return rc;
+            if (ctx->h_ctr[0] > ctx->edge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow while cutting cycles");
+            ctx->n_edges = ctx->h_ctr[0];
+            ctx->st.n_cycles += ctx->h_ctr[1];
+            dfree(ctx, d_cyc); dfree(ctx, d_lab);
+            if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+        }
+        if (remaining) return ctx->fail(CDBG_ERR_INTERNAL, "cycles remain after cutting");
+    }
+    tstop(ctx, T_K6R);
+
+    // ---- unitig numbering + spelling
+    tstart(ctx, T_K6S);
+    uint32_t *d_head_flag = nullptr, *d_head_nt = nullptr;
+    uint64_t *d_uid_scan = nullptr, *d_nt_scan = nullptr;
+    if ((rc = dalloc(ctx, &ctx->d_info, S + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_head_flag, S + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_head_nt, S + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_uid_scan, S + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_nt_scan, S + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_unitig_of_kmer, S + 1))) return rc;
+    uint64_t U = 0, total_nt = 0;
+    if (S) {
+        LAUNCH(k6_finalize, grid_for(ctx, S, 256, 8), 256, 0, d_pair, S, k, ctx->d_info, d_head_flag, d_head_nt);
+        if ((rc = exclusive_scan(ctx, d_head_flag, S, d_uid_scan, &U))) return rc;
+        if ((rc = exclusive_scan(ctx, d_head_nt, S, d_nt_scan, &total_nt))) return rc;
+    }
+    ctx->U = U; ctx->total_nt = total_nt;
+    dfree(ctx, d_pair);
+    if ((rc = dalloc(ctx, &ctx->d_seq, total_nt + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_seq_off, U + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_kc, U + 1))) return rc;
+    CK(cudaMemsetAsync(ctx->d_kc, 0, (U + 1) * 8, ctx->stream));
+    if (ctx->prm.flags & CDBG_FLAG_ALL_ABUNDANCE_COUNTS) { if ((rc = dalloc(ctx, &ctx->d_abund, S + 1))) return rc; }
+    if (S) {
+        SpellParams sp{};
+        sp.solid_kmers = ctx->d_solid_kmers; sp.solid_counts = ctx->d_solid_counts; sp.S = S; sp.k = k;
+        sp.info = ctx->d_info; sp.uid_scan = d_uid_scan; sp.nt_scan = d_nt_scan;
+        sp.seq = ctx->d_seq; sp.seq_off = ctx->d_seq_off; sp.kc = ctx->d_kc; sp.abund = ctx->d_abund;
+        sp.unitig_of_kmer = ctx->d_unitig_of_kmer;
+        LAUNCH(k8_spell, grid_for(ctx, S, 256, 8), 256, 0, sp);
+    }
+    CK(cudaMemcpyAsync(ctx->d_seq_off + U, &ctx->total_nt, 8, cudaMemcpyHostToDevice, ctx->stream));
+    dfree(ctx, d_head_flag); dfree(ctx, d_head_nt); dfree(ctx, d_uid_scan); dfree(ctx, d_nt_scan);
+    tstop(ctx, T_K6S);
+    ctx->st.n_unitigs = U; ctx->st.total_nt = total_nt;
+    tstop(ctx, T_COMPACT);
+    ctx->stage = ST_COMPACTED;
+    return CDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage 4
+
+int stage_link(cdbg_ctx *ctx) {
+    int rc;
+    tstart(ctx, T_LINK);
+    if ((rc = dalloc(ctx, &ctx->d_links, ctx->n_edges + 1))) return rc;
+    if (ctx->n_edges)
+        LAUNCH(k9_translate, grid_for(ctx, ctx->n_edges, 256, 8), 256, 0, ctx->d_edges, ctx->n_edges, ctx->d_info, ctx->d_unitig_of_kmer,
+               ctx->d_links);
+    tstop(ctx, T_LINK);
+    ctx->st.n_links = ctx->n_edges;
+    ctx->stage = ST_LINKED;
+    return CDBG_OK;
+}
+
+void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
+    cudaStreamSynchronize(ctx->stream);
+    cdbg_stats &s = ctx->st;
+    s.n_bytes = ctx->n_bytes;
+    s.kernel_launches = ctx->launches;
+    s.ms_push = tread(ctx, T_PUSH); s.ms_count = tread(ctx, T_COUNT); s.ms_compact = tread(ctx, T_COMPACT);
+    s.ms_link = tread(ctx, T_LINK); s.ms_fetch = tread(ctx, T_FETCH);
+    s.ms_k1_hist = tread(ctx, T_K1H); s.ms_k1_scatter = tread(ctx, T_K1S); s.ms_k2 = tread(ctx, T_K2);
+    s.ms_k3 = tread(ctx, T_K3); s.ms_k5 = tread(ctx, T_K5); s.ms_k6_rank = tread(ctx, T_K6R); s.ms_k6_spell = tread(ctx, T_K6S);
+    if (out) *out = s;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+
+extern "C" {
+
+const char *cdbg_version(void) { return "cdbg_b200 0.1 (sm_100a, k<=31)"; }
+
+int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
+    if (!out || !params) return CDBG_ERR_PARAM;
+    *out = nullptr;
+    cdbg_ctx *ctx = new cdbg_ctx();
+    ctx->prm = *params;
+    auto bail = [&](int code) { *out = ctx; return code; };   // caller can still read cdbg_last_error, then destroy
+    // span dispatch of the reference (Integer.hpp:77-85): this build instantiates one 64-bit word, k < 32
+    if (params->kmer_size < 4 || params->kmer_size > 31)
+        return bail(ctx->fail(CDBG_ERR_PARAM, "unhandled kmer size %d (this build supports 4 <= k <= 31)", params->kmer_size));
+    if (params->abundance_min < 0) return bail(ctx->fail(CDBG_ERR_PARAM, "abundance-min must be >= 0"));
+    if (params->world_size > 1) return bail(ctx->fail(CDBG_ERR_PARAM, "world_size > 1 needs the sharded entry points (cdbg_shard_*)"));
+    ctx->k = params->kmer_size;
+    ctx->m = params->minimizer_size > 0 ? params->minimizer_size : 10;
+    if (ctx->m > ctx->k - 1) ctx->m = ctx->k - 1;   // ConfigurationAlgorithm.cpp:251
+    ctx->amin = (uint32_t)std::max(params->abundance_min, 1);
+    ctx->amax = params->abundance_max > 0 ? (uint32_t)params->abundance_max : 0x7FFFFFFFu;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return bail(ctx->fail(CDBG_ERR_CUDA, "no CUDA device available (%s): this library has no CPU fallback",
+                              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+    }
+    if (params->device < 0 || params->device >= ndev) return bail(ctx->fail(CDBG_ERR_PARAM, "bad device ordinal %d", params->device));
+    *out = ctx;
+    CK(cudaSetDevice(params->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, params->device));
+    ctx->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, params->device));
+    uint64_t thresh = ~0ULL;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CK(cudaMalloc(&ctx->d_ctr, 64 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->d_flag, 4 * sizeof(int)));
+    CK(cudaHostAlloc(&ctx->h_ctr, 80 * sizeof(unsigned long long), cudaHostAllocDefault));
+    return CDBG_OK;
+}
+
+void cdbg_destroy(cdbg_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->stream) {
+        cudaSetDevice(ctx->prm.device);
+        free_results(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->d_synth) cudaFree(ctx->d_synth);
+        if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+        if (ctx->d_flag) cudaFree(ctx->d_flag);
+        if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+        if (ctx->h_seq) cudaFreeHost(ctx->h_seq);
+        if (ctx->h_seq_off) cudaFreeHost(ctx->h_seq_off);
+        if (ctx->h_kc) cudaFreeHost(ctx->h_kc);
+        if (ctx->h_abund) cudaFreeHost(ctx->h_abund);
+        if (ctx->h_links) cudaFreeHost(ctx->h_links);
+        for (auto &t : ctx->tm) { if (t.a) cudaEventDestroy(t.a); if (t.b) cudaEventDestroy(t.b); }
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char *cdbg_last_error(const cdbg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cdbg_reset(cdbg_ctx *ctx) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    CK(cudaSetDevice(ctx->prm.device));
+    return free_results(ctx);
+}
+
+int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int location) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if (!bytes && n_bytes) return ctx->fail(CDBG_ERR_PARAM, "null reads pointer");
+    if (ctx->stage > ST_PUSHED) return ctx->fail(CDBG_ERR_STATE, "push_reads after count: call cdbg_reset first");
+    CK(cudaSetDevice(ctx->prm.device));
+    int rc;
+    tstart(ctx, T_PUSH);
+    if (location == CDBG_MEM_DEVICE && ctx->stage == ST_EMPTY && (reinterpret_cast<uintptr_t>(bytes) & 15) == 0) {
+        ctx->d_bytes = const_cast<uint8_t *>(bytes);   // used in place
+        ctx->n_bytes = n_bytes; ctx->bytes_borrowed = true;
+    } else {
+        // append (a break byte separates pushes)
+        uint64_t need = ctx->n_bytes + n_bytes + 1;
+        if (ctx->bytes_borrowed || need > ctx->cap_bytes) {
+            uint64_t cap = std::max<uint64_t>(need, ctx->cap_bytes * 2);
+            uint8_t *nb = nullptr;
+            if ((rc = dalloc(ctx, &nb, cap + 64))) return rc;
+            if (ctx->n_bytes) CK(cudaMemcpyAsync(nb, ctx->d_bytes, ctx->n_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (!ctx->bytes_borrowed) dfree(ctx, ctx->d_bytes);
+            ctx->d_bytes = nb; ctx->cap_bytes = cap; ctx->bytes_borrowed = false;
+        }
+        CK(cudaMemcpyAsync(ctx->d_bytes + ctx->n_bytes, bytes, n_bytes,
+                           location == CDBG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_bytes + ctx->n_bytes + n_bytes, '\n', 1, ctx->stream));
+        ctx->n_bytes += n_bytes + 1;
+    }
+    tstop(ctx, T_PUSH);
+    ctx->stage = ST_PUSHED;
+    return CDBG_OK;
+}
+
+int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if (ctx->stage != ST_PUSHED) return ctx->fail(CDBG_ERR_STATE, "cdbg_count needs pushed reads");
+    CK(cudaSetDevice(ctx->prm.device));
+    int rc = stage_count(ctx);
+    if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
+    return rc;
+}
+
+int cdbg_compact(cdbg_ctx *ctx, cdbg_stats *stats) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if (ctx->stage != ST_COUNTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_compact needs cdbg_count first");
+    CK(cudaSetDevice(ctx->prm.device));
+    int rc = stage_compact(ctx);
+    if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
+    return rc;
+}
+
+int cdbg_link(cdbg_ctx *ctx, cdbg_stats *stats) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if (ctx->stage != ST_COMPACTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_link needs cdbg_compact first");
+    CK(cudaSetDevice(ctx->prm.device));
+    int rc = stage_link(ctx);
+    if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
+    return rc;
+}
+
+int cdbg_get_stats(cdbg_ctx *ctx, cdbg_stats *stats) {
+    if (!ctx || !stats) return CDBG_ERR_PARAM;
+    fill_stats(ctx, stats);
+    return CDBG_OK;
+}
+
+int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
+    if (!ctx || !ctx->stream || !view) return CDBG_ERR_PARAM;
+    if (ctx->stage < ST_COMPACTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_get_unitigs needs cdbg_compact first");
+    CK(cudaSetDevice(ctx->prm.device));
+    int rc;
+    const uint64_t U = ctx->U, nt = ctx->total_nt, S = ctx->S;
+    const uint64_t nl = ctx->stage >= ST_LINKED ? ctx->n_edges : 0;
+    if ((rc = hgrow(ctx, &ctx->h_seq, &ctx->h_seq_cap, nt + 1))) return rc;
+    if ((rc = hgrow(ctx, &ctx->h_seq_off, &ctx->h_seq_off_cap, U + 1))) return rc;
+    if ((rc = hgrow(ctx, &ctx->h_kc, &ctx->h_kc_cap, U + 1))) return rc;
+    if ((rc = hgrow(ctx, &ctx->h_links, &ctx->h_links_cap, nl + 1))) return rc;
+    const bool ab = ctx->d_abund != nullptr;
+    if (ab) { if ((rc = hgrow(ctx, &ctx->h_abund, &ctx->h_abund_cap, S + 1))) return rc; }
+    tstart(ctx, T_FETCH);
+    if (nt) CK(cudaMemcpyAsync(ctx->h_seq, ctx->d_seq, nt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_seq_off, ctx->d_seq_off, (U + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (U) CK(cudaMemcpyAsync(ctx->h_kc, ctx->d_kc, U * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nl) CK(cudaMemcpyAsync(ctx->h_links, ctx->d_links, nl * sizeof(LinkRec), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ab && S) CK(cudaMemcpyAsync(ctx->h_abund, ctx->d_abund, S * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    tstop(ctx, T_FETCH);
+    CK(cudaStreamSynchronize(ctx->stream));
+    // group links by unitig, BEGIN ('-') links first: the order LinkTigs.cpp writes them in
+    std::sort(ctx->h_links, ctx->h_links + nl, [](const cdbg_link_t &a, const cdbg_link_t &b) {
+        if (a.from != b.from) return a.from < b.from;
+        if (a.from_sign != b.from_sign) return a.from_sign > b.from_sign;   // '-' (45) before '+' (43)
+        if (a.to != b.to) return a.to < b.to;
+        return a.to_sign < b.to_sign;
+    });
+    view->kmer_size = ctx->k;
+    view->n_unitigs = U; view->total_nt = nt;
+    view->seq = ctx->h_seq; view->seq_off = ctx->h_seq_off; view->kc = ctx->h_kc;
+    view->abund = ab ? ctx->h_abund : nullptr;
+    view->n_links = nl; view->links = ctx->h_links;
+    return CDBG_OK;
+}
+
+int cdbg_build(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int location, cdbg_unitig_view *view, cdbg_stats *stats) {
+    int rc;
+    if ((rc = cdbg_reset(ctx))) return rc;
+    if ((rc = cdbg_push_reads(ctx, bytes, n_bytes, location))) return rc;
+    if ((rc = cdbg_count(ctx, nullptr))) return rc;
+    if ((rc = cdbg_compact(ctx, nullptr))) return rc;
+    if ((rc = cdbg_link(ctx, nullptr))) return rc;
+    if (view) { if ((rc = cdbg_get_unitigs(ctx, view))) return rc; }
+    if (stats) fill_stats(ctx, stats);
+    return CDBG_OK;
+}
+
+int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n) {
+    if (!ctx || !ctx->stream || !n) return CDBG_ERR_PARAM;
+    if (ctx->stage < ST_COUNTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_get_solid_kmers needs cdbg_count first");
+    CK(cudaSetDevice(ctx->prm.device));
+    *n = ctx->S;
+    uint64_t c = std::min<uint64_t>(cap, ctx->S);
+    if (c && kmers) CK(cudaMemcpyAsync(kmers, ctx->d_solid_kmers, c * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (c && counts) CK(cudaMemcpyAsync(counts, ctx->d_solid_counts, c * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CDBG_OK;
+}
+
+int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t n_reads, uint32_t err_ppm, uint64_t seed,
+                     uint8_t **d_bytes, uint64_t *n_bytes) {
+    if (!ctx || !ctx->stream || !d_bytes || !n_bytes) return CDBG_ERR_PARAM;
+    if (read_len == 0 || genome_len < read_len) return ctx->fail(CDBG_ERR_PARAM, "bad synthetic read geometry");
+    CK(cudaSetDevice(ctx->prm.device));
+    uint64_t total = n_reads * ((uint64_t)read_len + 1);
+    if (total + 64 > ctx->synth_cap) {
+        if (ctx->d_synth) CK(cudaFree(ctx->d_synth));
+        ctx->d_synth = nullptr; ctx->synth_cap = 0;
+        CK(cudaMalloc(&ctx->d_synth, total + 64));
+        ctx->synth_cap = total + 64;
+    }
+    if (total) LAUNCH(synth_reads_kernel, grid_for(ctx, total, 256, 16), 256, 0, ctx->d_synth, genome_len, read_len, n_reads, err_ppm, seed);
+    CK(cudaStreamSynchronize(ctx->stream));
+    *d_bytes = ctx->d_synth; *n_bytes = total;
+    return CDBG_OK;
+}
+
+int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    CK(cudaSetDevice(ctx->prm.device));
+    CK(cudaMemcpyAsync(dst, d_src, n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CDBG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,656 @@
+// kernels.cuh -- the hand-written sm_100a kernels of the reads -> unitigs path (k <= 31).
+//
+// Stage map (DESIGN.md gives the byte counts and rooflines):
+//   K1  k1_extract<HIST|SCATTER>  reads -> canonical k-mers, radix-partitioned by hash           (a1,a2,a5; Model.hpp:857-884)
+//   K2  k2_insert / k2_emit       per-bin counting in an L2-resident table + solidity filter     (a6,a7; PartitionsCommand.cpp:1600-1805)
+//   K3  k3_ends<HIST|SCATTER>     solid k-mer -> two (k-1)-mer end records, partitioned          (a8,a9,a10; bcalm_algo.cpp:182-223, ograph.cpp:384-434)
+//   K5  k5_insert / k5_resolve    per-bin join on the canonical (k-1)-mer: compaction links
+//                                 or unitig-level edges                                          (a11; ograph.cpp:228-318, LinkTigs.cpp:268-457)
+//   K6  k6_* / k8_*               list ranking over the links, cycle cutting, unitig numbering,
+//                                 spelling + abundance sums                                      (a12,a13,a15,a16; ograph.cpp:126-213, bglue_algo.cpp:262-479)
+//   K9  k9_translate              k-mer-end edges -> L: records                                  (a17; LinkTigs.cpp:365-369,428-432)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kmer.cuh"
+
+#define NOLINK 0xFFFFFFFFu
+#define EMPTY_KEY 0xFFFFFFFFFFFFFFFFULL
+
+// ------------------------------------------------------------------------------------------------ small helpers
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// warp-aggregated append: every active lane with pred gets a distinct slot from *cursor (one atomic per warp)
+__device__ __forceinline__ uint64_t warp_append(unsigned long long *cursor, bool pred) {
+    unsigned m = __ballot_sync(__activemask(), pred);
+    if (!pred) return 0;
+    int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane_id()) - 1));
+}
+
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
+
+// ------------------------------------------------------------------------------------------------ K1: extract
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_PER_THREAD = 32;                       // positions per thread
+constexpr int K1_TILE = K1_THREADS * K1_PER_THREAD;     // 8192 positions per tile
+constexpr int K1_MAX_BINS = 2048;
+
+// pack 4 ASCII bytes (little-endian word, first char = lowest byte) into 8 bits, first char most significant,
+// plus a 4-bit validity mask (bit 3 = first char)
+__device__ __forceinline__ void pack4(uint32_t w, uint32_t &codes, uint32_t &valid) {
+    uint32_t c = (w >> 1) & 0x03030303u;
+    codes = (c * 0x40100401u) >> 24;
+    uint32_t u = w & 0xDFDFDFDFu;                       // fold lower case
+    uint32_t v = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+    valid = ((v & 0x01010101u) * 0x08040201u) >> 24 & 0xFu;
+}
+
+// 32 bytes (two uint4) -> 64-bit packed codes (first base in bits 63:62) + 32-bit validity (first base in bit 31)
+__device__ __forceinline__ void pack32(const uint4 a, const uint4 b, uint64_t &pk, uint32_t &vm) {
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    pk = 0; vm = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t c, v;
+        pack4(w[i], c, v);
+        pk = (pk << 8) | c;
+        vm = (vm << 4) | v;
+    }
+}
+
+// 32 bytes at `off` (a multiple of 32; `bytes` is 16-byte aligned); positions >= n read as a break
+__device__ __forceinline__ void load_pack32(const uint8_t *bytes, uint64_t n, uint64_t off, uint64_t &pk, uint32_t &vm) {
+    uint4 a, b;
+    if (off + 32 <= n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(bytes + off);
+        a = __ldg(src); b = __ldg(src + 1);
+    } else {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint64_t q = off + 4 * i + j;
+                x |= (uint32_t)(q < n ? bytes[q] : (uint8_t)'\n') << (8 * j);
+            }
+            w[i] = x;
+        }
+        a = make_uint4(w[0], w[1], w[2], w[3]); b = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    pack32(a, b, pk, vm);
+}
+
+// bit (63-i) of the result is set iff bases i .. i+k-1 are all valid (V has base j at bit 63-j)
+__device__ __forceinline__ uint64_t kmer_valid_mask(uint64_t V, int k) {
+    uint64_t W1 = V, W2 = W1 & (W1 << 1), W4 = W2 & (W2 << 2), W8 = W4 & (W4 << 4), W16 = W8 & (W8 << 8);
+    uint64_t r = ~0ULL;
+    int off = 0;
+    if (k & 16) { r &= W16 << off; off += 16; }
+    if (k & 8)  { r &= W8 << off;  off += 8; }
+    if (k & 4)  { r &= W4 << off;  off += 4; }
+    if (k & 2)  { r &= W2 << off;  off += 2; }
+    if (k & 1)  { r &= W1 << off; }
+    return r;
+}
+
+struct K1Params {
+    const uint8_t *bytes;      // 16-byte aligned; reads past n_bytes are treated as breaks
+    uint64_t n_bytes;
+    uint64_t n_tiles;
+    int k;
+    uint32_t P;                // number of bins
+    unsigned long long *bin_count;   // [P]  (HIST: out)
+    const uint64_t *bin_off;         // [P]  (SCATTER: in, exclusive offsets)
+    unsigned long long *bin_cursor;  // [P]  (SCATTER: running cursors, zero-initialised)
+    uint64_t *out_kmers;             // (SCATTER) partitioned canonical k-mers
+};
+
+// MODE 0: histogram of bins.  MODE 1: scatter with a tile-local counting sort so that each bin's k-mers of one tile
+// leave the SM as one contiguous run.
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // 8-byte arrays first, then the 4-byte ones
+    uint64_t *s_pk = reinterpret_cast<uint64_t *>(smem_raw);                 // [THREADS + 2] packed bases, 32 per word
+    uint64_t *s_gbase = s_pk + K1_THREADS + 2;                               // [P]       MODE 1: global base of each bin's run
+    uint64_t *s_stage = s_gbase + (MODE == 1 ? p.P : 0);                     // [K1_TILE] MODE 1: tile sorted by bin
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_stage + (MODE == 1 ? K1_TILE : 0));  // [THREADS + 2] validity bits
+    uint32_t *s_cnt = s_vm + K1_THREADS + 2;                                 // [P]   tile counts (MODE 1) / CTA histogram (MODE 0)
+    uint32_t *s_off = s_cnt + p.P;                                           // [P+1] MODE 1: exclusive offsets
+    uint32_t *s_cur = s_off + p.P + 1;                                       // [P]   MODE 1: running cursors
+    __shared__ uint32_t s_warp[K1_THREADS / 32];
+
+    const int t = threadIdx.x;
+    const int k = p.k;
+    const uint64_t kmask = kmer_mask(k);
+
+    if (MODE == 0) {
+        for (uint32_t i = t; i < p.P; i += K1_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+    }
+
+    for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint64_t tile_start = tile * (uint64_t)K1_TILE;
+        // ---- phase A: ASCII -> 2-bit, coalesced 32 B per thread
+        {
+            uint64_t pk; uint32_t vm;
+            load_pack32(p.bytes, p.n_bytes, tile_start + (uint64_t)t * 32, pk, vm);
+            s_pk[t] = pk; s_vm[t] = vm;
+            if (t == 0) {  // halo: the next 32 bases
+                load_pack32(p.bytes, p.n_bytes, tile_start + K1_TILE, pk, vm);
+                s_pk[K1_THREADS] = pk; s_vm[K1_THREADS] = vm;
+            }
+        }
+        if (MODE == 1) {
+            for (uint32_t i = t; i < p.P; i += K1_THREADS) s_cnt[i] = 0;
+        }
+        __syncthreads();
+
+        // ---- phase B: rolling canonical k-mers of 32 consecutive positions
+        const uint64_t hi0 = s_pk[t], lo0 = s_pk[t + 1];
+        const uint64_t V = ((uint64_t)s_vm[t] << 32) | s_vm[t + 1];
+        const uint64_t KV = kmer_valid_mask(V, k);
+        const uint32_t valid32 = (uint32_t)(KV >> 32);   // bit (31-i): k-mer at position i valid
+
+        auto sweep = [&](auto &&emit) {
+            uint64_t hi = hi0, lo = lo0;
+            uint64_t fwd = hi >> (64 - 2 * k);
+            uint64_t rc = revcomp64(fwd, k);
+#pragma unroll 4
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                if ((valid32 >> (31 - i)) & 1) {
+                    uint64_t c = fwd < rc ? fwd : rc;
+                    emit(c);
+                }
+            }
+        };
+        (void)kmask;
+
+        if (MODE == 0) {
+            sweep([&](uint64_t c) { atomicAdd(&s_cnt[hash_to_bin(mix64(c), p.P)], 1u); });
+            __syncthreads();   // s_pk reuse in the next tile
+        } else {
+            sweep([&](uint64_t c) { atomicAdd(&s_cnt[hash_to_bin(mix64(c), p.P)], 1u); });
+            __syncthreads();
+            // exclusive scan of s_cnt (P <= 2048: 256 threads x up to 8 bins each) + global reservation per bin
+            {
+                const uint32_t per = (p.P + K1_THREADS - 1) / K1_THREADS;
+                uint32_t b0 = t * per, sum = 0;
+                for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) sum += s_cnt[b0 + j];
+                // block scan of `sum` via warp shuffles
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+                if (lane_id() == 31) s_warp[t >> 5] = incl;
+                __syncthreads();
+                if (t < 32) {
+                    uint32_t w = t < K1_THREADS / 32 ? s_warp[t] : 0, wi = w;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane_id() >= d) wi += n; }
+                    if (t < K1_THREADS / 32) s_warp[t] = wi - w;
+                }
+                __syncthreads();
+                uint32_t run = s_warp[t >> 5] + incl - sum;
+                for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) {
+                    uint32_t c = s_cnt[b0 + j];
+                    s_off[b0 + j] = run; s_cur[b0 + j] = run;
+                    if (c) s_gbase[b0 + j] = p.bin_off[b0 + j] + atomicAdd(&p.bin_cursor[b0 + j], (unsigned long long)c);
+                    run += c;
+                }
+                if (t == K1_THREADS - 1) s_off[p.P] = run;
+            }
+            __syncthreads();
+            sweep([&](uint64_t c) {
+                uint32_t pos = atomicAdd(&s_cur[hash_to_bin(mix64(c), p.P)], 1u);
+                s_stage[pos] = c;
+            });
+            __syncthreads();
+            const uint32_t total = s_off[p.P];
+            for (uint32_t j = t; j < total; j += K1_THREADS) {
+                uint64_t c = s_stage[j];
+                uint32_t b = hash_to_bin(mix64(c), p.P);
+                p.out_kmers[s_gbase[b] + (j - s_off[b])] = c;
+            }
+            __syncthreads();
+        }
+    }
+
+    if (MODE == 0) {
+        __syncthreads();
+        for (uint32_t i = t; i < p.P; i += K1_THREADS) {
+            uint32_t c = s_cnt[i];
+            if (c) atomicAdd(&p.bin_count[i], (unsigned long long)c);
+        }
+    }
+}
+
+static inline size_t k1_smem_bytes(int mode, uint32_t P) {
+    size_t s = (size_t)(K1_THREADS + 2) * 8 + (size_t)(K1_THREADS + 2) * 4 + (size_t)P * 4;
+    if (mode == 1) s += (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(P + 1) * 4 + (size_t)P * 4;
+    return s + 16;
+}
+
+// ------------------------------------------------------------------------------------------------ K2: count
+
+// One bin at a time: the table (keys + counts) is sized to the bin and stays resident in the 126 MB L2.
+__global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *keys, uint32_t *counts,
+                                                 uint32_t cap_mask, int *overflow) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = kmers[i];
+        uint32_t slot = (uint32_t)mix64(key) & cap_mask;
+        uint32_t probes = 0;
+        for (;;) {
+            uint64_t cur = ld_volatile_u64(&keys[slot]);
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (cur == EMPTY_KEY) cur = key;
+            }
+            if (cur == key) { atomicAdd(&counts[slot], 1u); break; }
+            slot = (slot + 1) & cap_mask;
+            if (++probes > cap_mask) { *overflow = 1; break; }
+        }
+    }
+}
+
+// scan the table: emit solid (k-mer, count), count distinct, and reset every touched slot for the next bin
+__global__ void __launch_bounds__(256) k2_emit(uint64_t *keys, uint32_t *counts, uint32_t cap, uint32_t amin, uint32_t amax,
+                                               uint64_t *solid_kmers, uint32_t *solid_counts, uint64_t solid_cap,
+                                               unsigned long long *n_solid, unsigned long long *n_distinct) {
+    unsigned long long distinct = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((cap + 31u) & ~31u); i += gridDim.x * blockDim.x) {
+        uint64_t key = i < cap ? keys[i] : EMPTY_KEY;
+        bool occ = key != EMPTY_KEY;
+        uint32_t c = 0;
+        if (occ) { c = counts[i]; keys[i] = EMPTY_KEY; counts[i] = 0; distinct++; }
+        bool solid = occ && c >= amin && c <= amax;
+        uint64_t pos = warp_append(n_solid, solid);
+        if (solid && pos < solid_cap) { solid_kmers[pos] = key; solid_counts[pos] = c; }
+    }
+    // block reduce distinct
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) distinct += __shfl_xor_sync(0xFFFFFFFFu, distinct, d);
+    if (lane_id() == 0 && distinct) atomicAdd(n_distinct, distinct);
+}
+
+// ------------------------------------------------------------------------------------------------ K3: junction end records
+
+// A solid canonical k-mer x has two ends.  Each end is keyed by the canonical form c of its (k-1)-mer and lies on one SIDE
+// of c: IN  (the k-mer, suitably oriented, ends with c)  or OUT (it begins with c).  ograph.cpp:384-434 calls these the
+// `right` and `left` arrays; a palindromic c is on both sides (never compacts).
+//   record value: bits 31..0 = end id (2*kmer_index + {0: left end, 1: right end}), bit 32 = side (0 IN, 1 OUT), bit 33 = palindrome
+#define REC_SIDE_OUT (1ULL << 32)
+#define REC_PALIN (1ULL << 33)
+
+__device__ __forceinline__ void kmer_end_record(uint64_t x, int k, int end, uint32_t idx, uint64_t &key, uint64_t &val) {
+    const int k1 = k - 1;
+    uint64_t e = end == 0 ? (x >> 2) : (x & kmer_mask(k1));
+    uint64_t r = revcomp64(e, k1);
+    key = e < r ? e : r;
+    bool canon_fwd = e <= r;
+    // left end:  (k-1)-mer read forward is the prefix -> the k-mer begins with c (OUT) when canonical, else rc(k-mer) ends with c (IN)
+    // right end: suffix -> the k-mer ends with c (IN) when canonical, else rc(k-mer) begins with c (OUT)
+    bool out = (end == 0) ? canon_fwd : !canon_fwd;
+    val = (uint64_t)(2u * idx + (uint32_t)end) | (out ? REC_SIDE_OUT : 0) | (e == r ? REC_PALIN : 0);
+}
+
+struct K3Params {
+    const uint64_t *solid_kmers;
+    uint64_t n_solid;
+    int k;
+    uint32_t P;
+    unsigned long long *bin_count;   // [P]
+    const uint64_t *bin_off;         // [P]
+    unsigned long long *bin_cursor;  // [P]
+    uint64_t *rec_key;               // [2S]
+    uint64_t *rec_val;               // [2S]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k3_ends(K3Params p) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_solid; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = p.solid_kmers[i];
+#pragma unroll
+        for (int end = 0; end < 2; end++) {
+            uint64_t key, val;
+            kmer_end_record(x, p.k, end, (uint32_t)i, key, val);
+            uint32_t b = hash_to_bin(mix64(key), p.P);
+            if (MODE == 0) atomicAdd(&p.bin_count[b], 1ULL);
+            else {
+                uint64_t pos = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], 1ULL);
+                p.rec_key[pos] = key; p.rec_val[pos] = val;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5: junction join
+
+// table entry: key, packed counters (IN count in bits 7..0, OUT count in bits 15..8, palindrome flag bit 31) and up to 4 end
+// ids per side.  A (k-1)-mer has at most 4 IN and 4 OUT ends (one per extension base).
+struct JoinTable {
+    uint64_t *keys;     // [cap]
+    uint32_t *cnt;      // [cap]
+    uint32_t *ids;      // [cap * 8]  (0..3 IN, 4..7 OUT)
+    uint32_t cap_mask;
+};
+
+__global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ rec_key, const uint64_t *__restrict__ rec_val, uint64_t n,
+                                                 JoinTable T, int *overflow) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = rec_key[i], val = rec_val[i];
+        uint32_t slot = (uint32_t)mix64(key) & T.cap_mask;
+        uint32_t probes = 0;
+        for (;;) {
+            uint64_t cur = ld_volatile_u64(&T.keys[slot]);
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS((unsigned long long *)&T.keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (cur == EMPTY_KEY) cur = key;
+            }
+            if (cur == key) {
+                const bool out = (val & REC_SIDE_OUT) != 0, pal = (val & REC_PALIN) != 0;
+                // palindromic ends all go to the IN list (the join treats them as "all pairs")
+                const bool use_out = out && !pal;
+                uint32_t old = atomicAdd(&T.cnt[slot], use_out ? 0x100u : 0x1u);
+                if (pal) atomicOr(&T.cnt[slot], 0x80000000u);
+                uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
+                if (pos < 4) T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val;
+                break;
+            }
+            slot = (slot + 1) & T.cap_mask;
+            if (++probes > T.cap_mask) { *overflow = 1; break; }
+        }
+    }
+}
+
+// Decide every junction of the bin (ograph.cpp:228-318): exactly one IN end and one OUT end belonging to two different
+// k-mers and a non-palindromic key -> compaction link; otherwise every (IN, OUT) pair (every ordered pair for a
+// palindrome) is an edge between unitig extremities (LinkTigs.cpp:365-369,428-432).  Slots are reset for the next bin.
+__global__ void __launch_bounds__(256) k5_resolve(JoinTable T, uint32_t cap, uint32_t *link, uint64_t *edges, uint64_t edge_cap,
+                                                  unsigned long long *n_edges, unsigned long long *n_compact) {
+    unsigned long long compact = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        if (T.keys[i] == EMPTY_KEY) continue;
+        uint32_t c = T.cnt[i];
+        T.keys[i] = EMPTY_KEY; T.cnt[i] = 0;
+        uint32_t nin = c & 0xFF, nout = (c >> 8) & 0xFF; bool pal = (c >> 31) != 0;
+        if (nin > 4) nin = 4; if (nout > 4) nout = 4;
+        uint32_t in[4], out[4];
+        const uint4 vin = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8]);
+        const uint4 vout = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8 + 4]);
+        in[0] = vin.x; in[1] = vin.y; in[2] = vin.z; in[3] = vin.w;
+        out[0] = vout.x; out[1] = vout.y; out[2] = vout.z; out[3] = vout.w;
+        if (!pal && nin == 1 && nout == 1 && (in[0] >> 1) != (out[0] >> 1)) {
+            link[in[0]] = out[0]; link[out[0]] = in[0];
+            compact++;
+            continue;
+        }
+        uint32_t ne = pal ? nin * nin : 2 * nin * nout;
+        if (ne == 0) continue;
+        unsigned long long base = atomicAdd(n_edges, (unsigned long long)ne);
+        if (base + ne > edge_cap) continue;   // counted; host retries with a larger buffer
+        if (pal) {
+            for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nin; b++) edges[base++] = ((uint64_t)in[a] << 32) | in[b];
+        } else {
+            for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nout; b++) {
+                edges[base++] = ((uint64_t)in[a] << 32) | out[b];
+                edges[base++] = ((uint64_t)out[b] << 32) | in[a];
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) compact += __shfl_xor_sync(0xFFFFFFFFu, compact, d);
+    if (lane_id() == 0 && compact) atomicAdd(n_compact, compact);
+}
+
+// ------------------------------------------------------------------------------------------------ K6: list ranking
+//
+// Directed element x (0 <= x < 2S) = "traverse k-mer x>>1 entering through end x&1 (0 = left, 1 = right)"; it leaves through
+// end x^1, so succ(x) = link[x^1].  pair[x] = (next << 32 | hops to next); a traversal's last element points to itself.
+// Updates are in place and asynchronous: each pair is read/written as one 64-bit word and the invariant
+// "hops = distance from x to next along the list" holds at all times, so any interleaving converges.
+
+__global__ void __launch_bounds__(256) k6_init(const uint32_t *__restrict__ link, uint64_t *pair, uint64_t n2) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t s = link[x ^ 1];
+        pair[x] = s == NOLINK ? ((uint64_t)x << 32) : (((uint64_t)s << 32) | 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsigned long long *n_updated) {
+    unsigned long long upd = 0;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t p = ld_volatile_u64(&pair[x]);
+        uint32_t n = (uint32_t)(p >> 32);
+        if (n == (uint32_t)x) continue;                       // tail
+        uint64_t q = ld_volatile_u64(&pair[n]);
+        uint32_t n2_ = (uint32_t)(q >> 32);
+        if (n2_ == n) continue;                               // already points at the tail
+        *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)((uint32_t)p + (uint32_t)q);
+        upd++;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) upd += __shfl_xor_sync(0xFFFFFFFFu, upd, d);
+    if (lane_id() == 0 && upd) atomicAdd(n_updated, upd);
+}
+
+// ---- cycles: elements that never reach a tail.  Find the smallest k-mer index on each cycle by pointer doubling with a
+// running minimum, cut the link at that k-mer's left end (the reference cuts wherever its scan order happens to close
+// the cycle: bglue_algo.cpp:400-416), record the two edges of the cut junction, and re-rank the affected elements.
+
+__device__ __forceinline__ bool k6_unfinished(const uint64_t *pair, uint64_t x) {
+    uint32_t n = (uint32_t)(pair[x] >> 32);
+    if (n == (uint32_t)x) return false;
+    return (uint32_t)(pair[n] >> 32) != n;
+}
+
+__global__ void __launch_bounds__(256) k6_cycle_mark(const uint64_t *pair, const uint32_t *link, uint64_t n2, uint8_t *flag,
+                                                     uint64_t *lab) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        bool u = k6_unfinished(pair, x);
+        flag[x] = u;
+        if (u) lab[x] = ((uint64_t)link[x ^ 1] << 32) | (uint32_t)(x >> 1);   // (succ, min k-mer index so far)
+    }
+}
+
+__global__ void __launch_bounds__(256) k6_cycle_min(const uint8_t *flag, uint64_t *lab, uint64_t n2) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flag[x]) continue;
+        uint64_t a = ld_volatile_u64(&lab[x]);
+        uint64_t b = ld_volatile_u64(&lab[(uint32_t)(a >> 32)]);
+        uint32_t m = min((uint32_t)a, (uint32_t)b);
+        *(volatile uint64_t *)&lab[x] = (b & 0xFFFFFFFF00000000ULL) | m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k6_cycle_cut(const uint8_t *flag, const uint64_t *lab, uint64_t n2, uint32_t *link,
+                                                    uint64_t *edges, uint64_t edge_cap, unsigned long long *n_edges,
+                                                    unsigned long long *n_cycles) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flag[x] || (x & 1)) continue;
+        if ((uint32_t)lab[x] != (uint32_t)(x >> 1)) continue;    // not the minimum k-mer of its cycle
+        uint32_t e = (uint32_t)x;            // left end of the minimum k-mer
+        uint32_t f = link[e];
+        link[e] = NOLINK; link[f] = NOLINK;
+        unsigned long long base = atomicAdd(n_edges, 2ULL);
+        if (base + 2 <= edge_cap) {
+            edges[base] = ((uint64_t)e << 32) | f;
+            edges[base + 1] = ((uint64_t)f << 32) | e;
+        }
+        atomicAdd(n_cycles, 1ULL);
+    }
+}
+
+__global__ void __launch_bounds__(256) k6_reinit_flagged(const uint8_t *flag, const uint32_t *link, uint64_t *pair, uint64_t n2) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flag[x]) continue;
+        uint32_t s = link[x ^ 1];
+        pair[x] = s == NOLINK ? ((uint64_t)x << 32) : (((uint64_t)s << 32) | 1u);
+    }
+}
+
+// ---- unitig numbering.  For k-mer v: T0 = terminus reached going forward, T1 = terminus reached going backward; the unitig
+// starts at B = min(T0, T1).  info[v] = (B << 32) | pos << 1 | reversed.  Heads (pos == 0) also publish the unitig length.
+__global__ void __launch_bounds__(256) k6_finalize(const uint64_t *__restrict__ pair, uint64_t S, int k, uint64_t *info, uint32_t *head_flag,
+                                                   uint32_t *head_nt) {
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < S; v += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t p0 = pair[2 * v], p1 = pair[2 * v + 1];
+        uint32_t T0 = (uint32_t)(p0 >> 32) ^ 1u, T1 = (uint32_t)(p1 >> 32) ^ 1u;
+        uint32_t d0 = (uint32_t)p0, d1 = (uint32_t)p1;
+        uint32_t B, pos, rev;
+        if (T1 < T0) { B = T1; pos = d1; rev = 0; } else { B = T0; pos = d0; rev = 1; }
+        info[v] = ((uint64_t)B << 32) | ((uint64_t)pos << 1) | rev;
+        bool head = pos == 0;
+        head_flag[v] = head;
+        head_nt[v] = head ? (d0 + d1 + 1 + (uint32_t)(k - 1)) : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ exclusive scan (u32 -> u64)
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t &total) {
+    __shared__ uint64_t s_w[SCAN_THREADS / 32];
+    uint64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint64_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint64_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) { uint64_t s = s_w[w]; if (w < (int)(threadIdx.x >> 5)) woff += s; tot += s; }
+    total = tot;
+    __syncthreads();
+    return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const uint32_t *__restrict__ in, uint64_t n, uint64_t *tile_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint64_t s = 0;
+    for (int j = 0; j < SCAN_ITEMS; j++) { uint64_t i = base + (uint64_t)j * SCAN_THREADS + threadIdx.x; if (i < n) s += in[i]; }
+    uint64_t tot; block_exclusive_scan_u64(s, tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_inplace(uint64_t *tile_sums, uint64_t n_tiles, uint64_t *total_out) {
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+        uint64_t i = base + threadIdx.x;
+        uint64_t v = i < n_tiles ? tile_sums[i] : 0, tot;
+        uint64_t ex = block_exclusive_scan_u64(v, tot);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *tile_sums, uint64_t *out) {
+    // thread-contiguous items for a simple in-register scan
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS]; uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) { v[j] = (base + j < n) ? in[base + j] : 0; s += v[j]; }
+    uint64_t tot; uint64_t ex = block_exclusive_scan_u64(s, tot) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) { if (base + j < n) out[base + j] = ex; ex += v[j]; }
+}
+
+// ------------------------------------------------------------------------------------------------ K6/K8: spell
+
+struct SpellParams {
+    const uint64_t *solid_kmers; const uint32_t *solid_counts; uint64_t S; int k;
+    const uint64_t *info;          // per k-mer
+    const uint64_t *uid_scan;      // exclusive scan of head flags  (index by head k-mer)
+    const uint64_t *nt_scan;       // exclusive scan of head_nt     (index by head k-mer)
+    char *seq;                     // [total_nt]
+    uint64_t *seq_off;             // [U+1]
+    unsigned long long *kc;        // [U]
+    uint32_t *abund;               // [S] or null
+    uint32_t *unitig_of_kmer;      // [S] (for K9)
+};
+
+__global__ void __launch_bounds__(256) k8_spell(SpellParams p) {
+    const char NT[4] = {'A', 'C', 'T', 'G'};
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < p.S; v += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t inf = p.info[v];
+        uint32_t B = (uint32_t)(inf >> 32), pos = (uint32_t)inf >> 1, rev = (uint32_t)inf & 1u;
+        uint32_t h = B >> 1;
+        uint64_t u = p.uid_scan[h], off = p.nt_scan[h];
+        uint64_t x = p.solid_kmers[v];
+        if (rev) x = revcomp64(x, p.k);
+        if (pos == 0) {
+            p.seq_off[u] = off;
+            for (int j = 0; j < p.k; j++) p.seq[off + j] = NT[(x >> (2 * (p.k - 1 - j))) & 3];
+        } else {
+            p.seq[off + (p.k - 1) + pos] = NT[x & 3];
+        }
+        uint32_t c = p.solid_counts[v];
+        atomicAdd(&p.kc[u], (unsigned long long)c);
+        if (p.abund) p.abund[off - u * (uint64_t)(p.k - 1) + pos] = c;
+        p.unitig_of_kmer[v] = (uint32_t)u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K9: links
+
+struct LinkRec { uint32_t from, to; uint8_t from_sign, to_sign, pad0, pad1; };
+
+// edge (e -> f) between k-mer ends that are unitig extremities:  L:<'-' if e is the BEGIN of its unitig else '+'>:<unitig(f)>:
+// <'+' if f is a BEGIN else '-'>   (LinkTigs.cpp:377,438: rc = (pos == UNITIG_END))
+__global__ void __launch_bounds__(256) k9_translate(const uint64_t *__restrict__ edges, uint64_t n, const uint64_t *__restrict__ info,
+                                                    const uint32_t *__restrict__ unitig_of_kmer, LinkRec *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t ed = edges[i];
+        uint32_t e = (uint32_t)(ed >> 32), f = (uint32_t)ed;
+        bool e_begin = (uint32_t)(info[e >> 1] >> 32) == e;
+        bool f_begin = (uint32_t)(info[f >> 1] >> 32) == f;
+        LinkRec r;
+        r.from = unitig_of_kmer[e >> 1]; r.to = unitig_of_kmer[f >> 1];
+        r.from_sign = e_begin ? '-' : '+'; r.to_sign = f_begin ? '+' : '-';
+        r.pad0 = r.pad1 = 0;
+        out[i] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ misc
+
+__global__ void fill_u64(uint64_t *p, uint64_t n, uint64_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// synthetic reads (bench): genome base g(i) = hash(seed, i) & 3 generated on the fly, so no genome array is needed
+__device__ __forceinline__ uint32_t synth_base(uint64_t seed, uint64_t i) { return (uint32_t)(mix64(seed ^ (i * 0x9E3779B97F4A7C15ULL)) >> 61) & 3u; }
+
+__global__ void __launch_bounds__(256) synth_reads_kernel(uint8_t *out, uint64_t genome_len, uint32_t read_len, uint64_t n_reads,
+                                                          uint32_t err_ppm, uint64_t seed) {
+    const char NT[4] = {'A', 'C', 'T', 'G'};
+    const uint64_t stride = (uint64_t)read_len + 1;
+    const uint64_t total = n_reads * stride;
+    for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = idx / stride; uint32_t j = (uint32_t)(idx - r * stride);
+        if (j == read_len) { out[idx] = '\n'; continue; }
+        uint64_t hr = mix64(seed * 0xD1342543DE82EF95ULL + r + 1);
+        uint64_t start = hr % (genome_len - read_len + 1);
+        bool rev = (hr >> 63) != 0;
+        uint64_t gpos = rev ? start + (read_len - 1 - j) : start + j;
+        uint32_t b = synth_base(seed, gpos);
+        if (rev) b ^= 2u;
+        uint64_t he = mix64((seed + 0x5851F42D4C957F2DULL) ^ (idx * 0xA24BAED4963EE407ULL));
+        if ((uint32_t)(he % 1000000ULL) < err_ppm) b = (b + 1 + (uint32_t)((he >> 40) % 3)) & 3u;
+        out[idx] = NT[b];
+    }
+}

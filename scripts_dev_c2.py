@@ -1,0 +1,16 @@
+# dev helper: C2-scale run on the GPU with stage timings (not part of the product)
+import sys, time, json
+sys.path.insert(0, '.')
+import numpy as np
+from bcalm_b200.api import Cdbg, MEM_DEVICE
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+G = int(5_000_000 * scale); L = 100; n_reads = int(G * 30 / L)
+c = Cdbg(k=31, abundance_min=2)
+ptr, n = c.synth_reads(G, L, n_reads, 10000, 42)
+for it in range(3):
+    t0 = time.perf_counter()
+    v, s = c.build_raw(ptr, n, MEM_DEVICE, fetch=True)
+    dt = time.perf_counter() - t0
+    st = c.stats()
+    print(f"iter {it}: wall {dt*1e3:.2f} ms  {n_reads*L/dt/1e9:.2f} Gbases/s")
+    print(json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in st.items()}))
