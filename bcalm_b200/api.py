@@ -49,7 +49,7 @@ class _Link(C.Structure):
 
 class UnitigView(C.Structure):
     _fields_ = [("kmer_size", C.c_int32), ("n_unitigs", C.c_uint64), ("total_nt", C.c_uint64), ("seq", C.c_void_p),
-                ("seq_off", C.c_void_p), ("kc", C.c_void_p), ("abund", C.c_void_p), ("n_links", C.c_uint64), ("links", C.c_void_p)]
+                ("seq_off", C.c_void_p), ("kc", C.c_void_p), ("abund", C.c_void_p), ("n_links", C.c_uint64), ("links", C.c_void_p), ("link_off", C.c_void_p)]
 
 
 LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to_sign", "u1"), ("pad", "u1", (2,))])
@@ -99,6 +99,7 @@ class Graph:
     abund: np.ndarray | None
     links: np.ndarray
     stats: dict = field(default_factory=dict)
+    link_off: np.ndarray | None = None
 
     @property
     def n_unitigs(self) -> int:
@@ -204,7 +205,7 @@ class Cdbg:
         S = int(v.total_nt - U * (self.k - 1)) if U else 0
         return Graph(k=self.k, seq=arr(v.seq, v.total_nt, np.uint8), seq_off=arr(v.seq_off, U + 1, np.uint64),
                      kc=arr(v.kc, U, np.uint64), abund=arr(v.abund, S, np.uint32) if v.abund else None,
-                     links=arr(v.links, v.n_links, LINK_DTYPE), stats=self.stats())
+                     links=arr(v.links, v.n_links, LINK_DTYPE), stats=self.stats(), link_off=arr(v.link_off, U + 1, np.uint64))
 
     def unitigs(self, copy: bool = True) -> Graph:
         v = UnitigView()

@@ -70,6 +70,7 @@ struct cdbg_ctx {
 
     // stage 4
     LinkRec *d_links = nullptr;
+    uint64_t *d_link_off = nullptr;   // [U+1] CSR offsets of d_links by `from`
 
     // small device scratch for counters (zeroed per use)
     unsigned long long *d_ctr = nullptr;   // [64]
@@ -82,6 +83,7 @@ struct cdbg_ctx {
     uint64_t *h_kc = nullptr; size_t h_kc_cap = 0;
     uint32_t *h_abund = nullptr; size_t h_abund_cap = 0;
     cdbg_link_t *h_links = nullptr; size_t h_links_cap = 0;
+    uint64_t *h_link_off = nullptr; size_t h_link_off_cap = 0;
 
     int fail(int code, const char *fmt, ...) {
         char buf[1024];
@@ -209,7 +211,7 @@ int free_results(cdbg_ctx *ctx) {
     ctx->d_solid_kmers = nullptr; ctx->d_solid_counts = nullptr; ctx->S = 0;
     ctx->d_link = nullptr; ctx->d_edges = nullptr; ctx->n_edges = 0; ctx->edge_cap = 0;
     ctx->d_info = nullptr; ctx->d_unitig_of_kmer = nullptr; ctx->d_seq = nullptr; ctx->d_seq_off = nullptr;
-    ctx->d_kc = nullptr; ctx->d_abund = nullptr; ctx->U = 0; ctx->total_nt = 0; ctx->d_links = nullptr;
+    ctx->d_kc = nullptr; ctx->d_abund = nullptr; ctx->U = 0; ctx->total_nt = 0; ctx->d_links = nullptr; ctx->d_link_off = nullptr;
     ctx->stage = ST_EMPTY;
     memset(&ctx->st, 0, sizeof ctx->st);
     for (auto &t : ctx->tm) t.used = false;
@@ -271,7 +273,8 @@ int stage_count(cdbg_ctx *ctx) {
     }
 
     // ---- K2: per-bin counting in one L2-resident table
-    uint32_t cap = std::max<uint32_t>(1024, next_pow2(2 * max_bin));
+    auto table_cap = [](uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); };
+    uint32_t cap = table_cap(max_bin);
     uint64_t *d_keys = nullptr; uint32_t *d_counts = nullptr;
     if ((rc = dalloc(ctx, &d_keys, cap))) return rc;
     if ((rc = dalloc(ctx, &d_counts, cap))) return rc;
@@ -287,8 +290,8 @@ int stage_count(cdbg_ctx *ctx) {
         for (uint32_t b = 0; b < P; b++) {
             uint64_t nb = h_cnt[b];
             if (!nb) continue;
-            uint32_t cap_b = std::max<uint32_t>(1024, next_pow2(2 * nb));
-            LAUNCH(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers + h_off[b], nb, d_keys, d_counts, cap_b - 1, ctx->d_flag);
+            uint32_t cap_b = table_cap(nb);
+            LAUNCH(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers + h_off[b], nb, d_keys, d_counts, cap_b, ctx->d_flag);
             LAUNCH(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
                    ctx->d_solid_counts, solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
         }
@@ -359,20 +362,23 @@ int stage_compact(cdbg_ctx *ctx) {
     uint64_t max_bin = 0;
     tstart(ctx, T_K3);
     if (S) {
-        LAUNCH(k3_ends<0>, grid_for(ctx, S, 256, 8), 256, 0, p3);
+        CK(cudaFuncSetAttribute(k3_ends<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem_bytes(1, P)));
+        const int g3 = (int)std::min<uint64_t>((S + K3_TILE - 1) / K3_TILE, (uint64_t)ctx->n_sm * 4);
+        LAUNCH(k3_ends<0>, g3, K3_THREADS, k3_smem_bytes(0, P), p3);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         uint64_t acc = 0;
         for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
         h_off[P] = acc;
         CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(k3_ends<1>, grid_for(ctx, S, 256, 8), 256, 0, p3);
+        LAUNCH(k3_ends<1>, g3, K3_THREADS, k3_smem_bytes(1, P), p3);
     }
     tstop(ctx, T_K3);
 
     // ---- K5: per-bin join
     if ((rc = dalloc(ctx, &ctx->d_link, n2 + 1))) return rc;
-    uint32_t cap = std::max<uint32_t>(1024, next_pow2(2 * max_bin));
+    auto table_cap = [](uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); };
+    uint32_t cap = table_cap(max_bin);
     JoinTable T{};
     if ((rc = dalloc(ctx, &T.keys, cap))) return rc;
     if ((rc = dalloc(ctx, &T.cnt, cap))) return rc;
@@ -388,8 +394,8 @@ int stage_compact(cdbg_ctx *ctx) {
         for (uint32_t b = 0; b < P; b++) {
             uint64_t nb = h_cnt[b];
             if (!nb) continue;
-            uint32_t cap_b = std::max<uint32_t>(1024, next_pow2(2 * nb));
-            T.cap_mask = cap_b - 1;
+            uint32_t cap_b = table_cap(nb);
+            T.cap = cap_b;
             LAUNCH(k5_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_rec_key + h_off[b], d_rec_val + h_off[b], nb, T, ctx->d_flag);
             LAUNCH(k5_resolve, grid_for(ctx, cap_b, 256, 8), 256, 0, T, cap_b, ctx->d_link, ctx->d_edges, ctx->edge_cap, ctx->d_ctr + 0,
                    ctx->d_ctr + 1);
@@ -485,13 +491,24 @@ int stage_compact(cdbg_ctx *ctx) {
 
 int stage_link(cdbg_ctx *ctx) {
     int rc;
+    const uint64_t n = ctx->n_edges, U = ctx->U;
     tstart(ctx, T_LINK);
-    if ((rc = dalloc(ctx, &ctx->d_links, ctx->n_edges + 1))) return rc;
-    if (ctx->n_edges)
-        LAUNCH(k9_translate, grid_for(ctx, ctx->n_edges, 256, 8), 256, 0, ctx->d_edges, ctx->n_edges, ctx->d_info, ctx->d_unitig_of_kmer,
-               ctx->d_links);
+    LinkRec *d_tmp = nullptr; uint32_t *d_per = nullptr, *d_cur = nullptr;
+    if ((rc = dalloc(ctx, &ctx->d_links, n + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_link_off, U + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_tmp, n + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_per, U + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_cur, U + 1))) return rc;
+    CK(cudaMemsetAsync(d_per, 0, (U + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_cur, 0, (U + 1) * 4, ctx->stream));
+    if (n) LAUNCH(k9_translate, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_edges, n, ctx->d_info, ctx->d_unitig_of_kmer, d_tmp, d_per);
+    uint64_t total = 0;
+    if ((rc = exclusive_scan(ctx, d_per, U + 1, ctx->d_link_off, &total))) return rc;   // entry U = n
+    if (total != n) return ctx->fail(CDBG_ERR_INTERNAL, "link grouping lost records (%llu != %llu)", (unsigned long long)total, (unsigned long long)n);
+    if (n) LAUNCH(k9_group, grid_for(ctx, n, 256, 8), 256, 0, d_tmp, n, ctx->d_link_off, d_cur, ctx->d_links);
+    dfree(ctx, d_tmp); dfree(ctx, d_per); dfree(ctx, d_cur);
     tstop(ctx, T_LINK);
-    ctx->st.n_links = ctx->n_edges;
+    ctx->st.n_links = n;
     ctx->stage = ST_LINKED;
     return CDBG_OK;
 }
@@ -571,6 +588,7 @@ void cdbg_destroy(cdbg_ctx *ctx) {
         if (ctx->h_kc) cudaFreeHost(ctx->h_kc);
         if (ctx->h_abund) cudaFreeHost(ctx->h_abund);
         if (ctx->h_links) cudaFreeHost(ctx->h_links);
+        if (ctx->h_link_off) cudaFreeHost(ctx->h_link_off);
         for (auto &t : ctx->tm) { if (t.a) cudaEventDestroy(t.a); if (t.b) cudaEventDestroy(t.b); }
         cudaStreamDestroy(ctx->stream);
     }
@@ -660,6 +678,7 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
     if ((rc = hgrow(ctx, &ctx->h_seq_off, &ctx->h_seq_off_cap, U + 1))) return rc;
     if ((rc = hgrow(ctx, &ctx->h_kc, &ctx->h_kc_cap, U + 1))) return rc;
     if ((rc = hgrow(ctx, &ctx->h_links, &ctx->h_links_cap, nl + 1))) return rc;
+    if ((rc = hgrow(ctx, &ctx->h_link_off, &ctx->h_link_off_cap, U + 2))) return rc;
     const bool ab = ctx->d_abund != nullptr;
     if (ab) { if ((rc = hgrow(ctx, &ctx->h_abund, &ctx->h_abund_cap, S + 1))) return rc; }
     tstart(ctx, T_FETCH);
@@ -667,21 +686,16 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
     CK(cudaMemcpyAsync(ctx->h_seq_off, ctx->d_seq_off, (U + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (U) CK(cudaMemcpyAsync(ctx->h_kc, ctx->d_kc, U * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (nl) CK(cudaMemcpyAsync(ctx->h_links, ctx->d_links, nl * sizeof(LinkRec), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->stage >= ST_LINKED) CK(cudaMemcpyAsync(ctx->h_link_off, ctx->d_link_off, (U + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    else memset(ctx->h_link_off, 0, (U + 1) * 8);
     if (ab && S) CK(cudaMemcpyAsync(ctx->h_abund, ctx->d_abund, S * 4, cudaMemcpyDeviceToHost, ctx->stream));
     tstop(ctx, T_FETCH);
     CK(cudaStreamSynchronize(ctx->stream));
-    // group links by unitig, BEGIN ('-') links first: the order LinkTigs.cpp writes them in
-    std::sort(ctx->h_links, ctx->h_links + nl, [](const cdbg_link_t &a, const cdbg_link_t &b) {
-        if (a.from != b.from) return a.from < b.from;
-        if (a.from_sign != b.from_sign) return a.from_sign > b.from_sign;   // '-' (45) before '+' (43)
-        if (a.to != b.to) return a.to < b.to;
-        return a.to_sign < b.to_sign;
-    });
     view->kmer_size = ctx->k;
     view->n_unitigs = U; view->total_nt = nt;
     view->seq = ctx->h_seq; view->seq_off = ctx->h_seq_off; view->kc = ctx->h_kc;
     view->abund = ab ? ctx->h_abund : nullptr;
-    view->n_links = nl; view->links = ctx->h_links;
+    view->n_links = nl; view->links = ctx->h_links; view->link_off = ctx->h_link_off;
     return CDBG_OK;
 }
 

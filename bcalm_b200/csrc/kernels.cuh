@@ -34,6 +34,23 @@ __device__ __forceinline__ uint64_t warp_append(unsigned long long *cursor, bool
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
 
+// Sum `v` over the block and add it to *dst with ONE atomic per block: a same-address global atomic costs ~4 ns, so
+// per-warp accumulation (thousands of warps per launch) would dominate these short kernels.  All threads must call.
+__device__ __forceinline__ void block_add(unsigned long long *dst, unsigned long long v) {
+    __shared__ unsigned long long s_part[32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if (lane_id() == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long w = threadIdx.x < (blockDim.x + 31) / 32 ? s_part[threadIdx.x] : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) w += __shfl_xor_sync(0xFFFFFFFFu, w, d);
+        if (threadIdx.x == 0 && w) atomicAdd(dst, w);
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------ K1: extract
 
 constexpr int K1_THREADS = 256;
@@ -244,12 +261,15 @@ static inline size_t k1_smem_bytes(int mode, uint32_t P) {
 
 // ------------------------------------------------------------------------------------------------ K2: count
 
-// One bin at a time: the table (keys + counts) is sized to the bin and stays resident in the 126 MB L2.
+// One bin at a time: the table (keys + counts) is sized to the bin (1.5 slots per instance, any capacity: slot = mulhi(hash, cap))
+// and stays resident in the 126 MB L2.
+__device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t cap) { return (uint32_t)(((mix64(key) & 0xFFFFFFFFULL) * cap) >> 32); }
+
 __global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *keys, uint32_t *counts,
-                                                 uint32_t cap_mask, int *overflow) {
+                                                 uint32_t cap, int *overflow) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = kmers[i];
-        uint32_t slot = (uint32_t)mix64(key) & cap_mask;
+        uint32_t slot = table_slot(key, cap);
         uint32_t probes = 0;
         for (;;) {
             uint64_t cur = ld_volatile_u64(&keys[slot]);
@@ -258,30 +278,53 @@ __global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ km
                 if (cur == EMPTY_KEY) cur = key;
             }
             if (cur == key) { atomicAdd(&counts[slot], 1u); break; }
-            slot = (slot + 1) & cap_mask;
-            if (++probes > cap_mask) { *overflow = 1; break; }
+            slot = slot + 1 == cap ? 0 : slot + 1;
+            if (++probes > cap) { *overflow = 1; break; }
         }
     }
 }
 
-// scan the table: emit solid (k-mer, count), count distinct, and reset every touched slot for the next bin
+// scan the table: emit solid (k-mer, count), count distinct, and reset every touched slot for the next bin.  Solid pairs are
+// staged in shared memory and flushed with one global reservation per ~1000 pairs.
+constexpr int K2_EMIT_BUF = 1024;
 __global__ void __launch_bounds__(256) k2_emit(uint64_t *keys, uint32_t *counts, uint32_t cap, uint32_t amin, uint32_t amax,
                                                uint64_t *solid_kmers, uint32_t *solid_counts, uint64_t solid_cap,
                                                unsigned long long *n_solid, unsigned long long *n_distinct) {
+    __shared__ uint64_t sb_k[K2_EMIT_BUF];
+    __shared__ uint32_t sb_c[K2_EMIT_BUF];
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint32_t chunk = ((cap + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
+    const uint32_t begin = min(cap, blockIdx.x * chunk), end = min(cap, begin + chunk);
     unsigned long long distinct = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ((cap + 31u) & ~31u); i += gridDim.x * blockDim.x) {
-        uint64_t key = i < cap ? keys[i] : EMPTY_KEY;
-        bool occ = key != EMPTY_KEY;
-        uint32_t c = 0;
-        if (occ) { c = counts[i]; keys[i] = EMPTY_KEY; counts[i] = 0; distinct++; }
-        bool solid = occ && c >= amin && c <= amax;
-        uint64_t pos = warp_append(n_solid, solid);
-        if (solid && pos < solid_cap) { solid_kmers[pos] = key; solid_counts[pos] = c; }
+    auto flush = [&]() {   // called by all threads
+        if (threadIdx.x == 0) s_base = s_n ? atomicAdd(n_solid, (unsigned long long)s_n) : 0ULL;
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < s_n; j += blockDim.x) {
+            uint64_t pos = s_base + j;
+            if (pos < solid_cap) { solid_kmers[pos] = sb_k[j]; solid_counts[pos] = sb_c[j]; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+    };
+    for (uint32_t base = begin; base < end; base += 256) {
+        uint32_t i = base + threadIdx.x;
+        if (i < end) {
+            uint64_t key = keys[i];
+            if (key != EMPTY_KEY) {
+                uint32_t c = counts[i];
+                keys[i] = EMPTY_KEY; counts[i] = 0; distinct++;
+                if (c >= amin && c <= amax) { uint32_t pos = atomicAdd(&s_n, 1u); sb_k[pos] = key; sb_c[pos] = c; }
+            }
+        }
+        __syncthreads();
+        if (s_n > K2_EMIT_BUF - 256) flush();
     }
-    // block reduce distinct
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) distinct += __shfl_xor_sync(0xFFFFFFFFu, distinct, d);
-    if (lane_id() == 0 && distinct) atomicAdd(n_distinct, distinct);
+    flush();
+    block_add(n_distinct, distinct);
 }
 
 // ------------------------------------------------------------------------------------------------ K3: junction end records
@@ -317,23 +360,64 @@ struct K3Params {
     uint64_t *rec_val;               // [2S]
 };
 
+constexpr int K3_THREADS = 256;
+constexpr int K3_PER_THREAD = 4;                          // k-mers per thread per tile
+constexpr int K3_TILE = K3_THREADS * K3_PER_THREAD;       // 1024 k-mers = 2048 records per tile
+
+// MODE 0: histogram (CTA-private in shared memory, flushed once).  MODE 1: scatter; each tile reserves one run per bin with a
+// single global atomic, so the hot cursors are hit once per (tile, bin) instead of once per record.
 template <int MODE>
-__global__ void __launch_bounds__(256) k3_ends(K3Params p) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_solid; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t x = p.solid_kmers[i];
+__global__ void __launch_bounds__(K3_THREADS) k3_ends(K3Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw);                  // [P] MODE 1
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? p.P : 0));   // [P]
+    const int t = threadIdx.x;
+    const uint64_t n_tiles = (p.n_solid + K3_TILE - 1) / K3_TILE;
+    for (uint32_t i = t; i < p.P; i += K3_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t key[2 * K3_PER_THREAD], val[2 * K3_PER_THREAD];
+        uint32_t bin[2 * K3_PER_THREAD], rank[2 * K3_PER_THREAD];
 #pragma unroll
-        for (int end = 0; end < 2; end++) {
-            uint64_t key, val;
-            kmer_end_record(x, p.k, end, (uint32_t)i, key, val);
-            uint32_t b = hash_to_bin(mix64(key), p.P);
-            if (MODE == 0) atomicAdd(&p.bin_count[b], 1ULL);
-            else {
-                uint64_t pos = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], 1ULL);
-                p.rec_key[pos] = key; p.rec_val[pos] = val;
+        for (int j = 0; j < K3_PER_THREAD; j++) {
+            uint64_t i = tile * K3_TILE + (uint64_t)j * K3_THREADS + t;
+            bool ok = i < p.n_solid;
+            uint64_t x = ok ? p.solid_kmers[i] : 0;
+#pragma unroll
+            for (int end = 0; end < 2; end++) {
+                const int r = 2 * j + end;
+                kmer_end_record(x, p.k, end, (uint32_t)i, key[r], val[r]);
+                bin[r] = ok ? hash_to_bin(mix64(key[r]), p.P) : 0xFFFFFFFFu;
+                rank[r] = ok ? atomicAdd(&s_cnt[bin[r]], 1u) : 0;
             }
+        }
+        if (MODE == 1) {
+            __syncthreads();
+            for (uint32_t b = t; b < p.P; b += K3_THREADS) {
+                uint32_t c = s_cnt[b];
+                if (c) s_base[b] = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], (unsigned long long)c);
+                s_cnt[b] = 0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 2 * K3_PER_THREAD; r++) {
+                if (bin[r] == 0xFFFFFFFFu) continue;
+                uint64_t pos = s_base[bin[r]] + rank[r];
+                p.rec_key[pos] = key[r]; p.rec_val[pos] = val[r];
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (uint32_t b = t; b < p.P; b += K3_THREADS) {
+            uint32_t c = s_cnt[b];
+            if (c) atomicAdd(&p.bin_count[b], (unsigned long long)c);
         }
     }
 }
+
+static inline size_t k3_smem_bytes(int mode, uint32_t P) { return (size_t)P * 4 + (mode == 1 ? (size_t)P * 8 : 0) + 16; }
 
 // ------------------------------------------------------------------------------------------------ K5: junction join
 
@@ -343,14 +427,14 @@ struct JoinTable {
     uint64_t *keys;     // [cap]
     uint32_t *cnt;      // [cap]
     uint32_t *ids;      // [cap * 8]  (0..3 IN, 4..7 OUT)
-    uint32_t cap_mask;
+    uint32_t cap;
 };
 
 __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ rec_key, const uint64_t *__restrict__ rec_val, uint64_t n,
                                                  JoinTable T, int *overflow) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = rec_key[i], val = rec_val[i];
-        uint32_t slot = (uint32_t)mix64(key) & T.cap_mask;
+        uint32_t slot = table_slot(key, T.cap);
         uint32_t probes = 0;
         for (;;) {
             uint64_t cur = ld_volatile_u64(&T.keys[slot]);
@@ -368,8 +452,8 @@ __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ re
                 if (pos < 4) T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val;
                 break;
             }
-            slot = (slot + 1) & T.cap_mask;
-            if (++probes > T.cap_mask) { *overflow = 1; break; }
+            slot = slot + 1 == T.cap ? 0 : slot + 1;
+            if (++probes > T.cap) { *overflow = 1; break; }
         }
     }
 }
@@ -409,9 +493,7 @@ __global__ void __launch_bounds__(256) k5_resolve(JoinTable T, uint32_t cap, uin
             }
         }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) compact += __shfl_xor_sync(0xFFFFFFFFu, compact, d);
-    if (lane_id() == 0 && compact) atomicAdd(n_compact, compact);
+    block_add(n_compact, compact);
 }
 
 // ------------------------------------------------------------------------------------------------ K6: list ranking
@@ -440,9 +522,7 @@ __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsi
         *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)((uint32_t)p + (uint32_t)q);
         upd++;
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) upd += __shfl_xor_sync(0xFFFFFFFFu, upd, d);
-    if (lane_id() == 0 && upd) atomicAdd(n_updated, upd);
+    block_add(n_updated, upd);
 }
 
 // ---- cycles: elements that never reach a tail.  Find the smallest k-mer index on each cycle by pointer doubling with a
@@ -612,7 +692,7 @@ struct LinkRec { uint32_t from, to; uint8_t from_sign, to_sign, pad0, pad1; };
 // edge (e -> f) between k-mer ends that are unitig extremities:  L:<'-' if e is the BEGIN of its unitig else '+'>:<unitig(f)>:
 // <'+' if f is a BEGIN else '-'>   (LinkTigs.cpp:377,438: rc = (pos == UNITIG_END))
 __global__ void __launch_bounds__(256) k9_translate(const uint64_t *__restrict__ edges, uint64_t n, const uint64_t *__restrict__ info,
-                                                    const uint32_t *__restrict__ unitig_of_kmer, LinkRec *out) {
+                                                    const uint32_t *__restrict__ unitig_of_kmer, LinkRec *out, uint32_t *per_unitig) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t ed = edges[i];
         uint32_t e = (uint32_t)(ed >> 32), f = (uint32_t)ed;
@@ -623,6 +703,16 @@ __global__ void __launch_bounds__(256) k9_translate(const uint64_t *__restrict__
         r.from_sign = e_begin ? '-' : '+'; r.to_sign = f_begin ? '+' : '-';
         r.pad0 = r.pad1 = 0;
         out[i] = r;
+        atomicAdd(&per_unitig[r.from], 1u);
+    }
+}
+
+// group the links by `from` unitig (CSR): link_off = exclusive scan of per_unitig, cursor zero-initialised
+__global__ void __launch_bounds__(256) k9_group(const LinkRec *__restrict__ in, uint64_t n, const uint64_t *__restrict__ link_off,
+                                                uint32_t *cursor, LinkRec *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        LinkRec r = in[i];
+        out[link_off[r.from] + atomicAdd(&cursor[r.from], 1u)] = r;
     }
 }
 

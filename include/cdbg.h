@@ -108,7 +108,8 @@ typedef struct {
     const uint32_t *abund;    /* per-k-mer abundances in unitig order, unitig u starts at seq_off[u] - u*(k-1);
                                  NULL unless CDBG_FLAG_ALL_ABUNDANCE_COUNTS */
     uint64_t n_links;
-    const cdbg_link_t *links; /* sorted by (from, from_sign '-' first) */
+    const cdbg_link_t *links; /* grouped by `from` (CSR); order inside a group is unspecified, as in the reference */
+    const uint64_t *link_off; /* [n_unitigs + 1]: links of unitig u = links[link_off[u] .. link_off[u+1]) */
 } cdbg_unitig_view;
 
 int cdbg_create(cdbg_ctx **out, const cdbg_params *params);
