@@ -284,47 +284,70 @@ __global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ km
     }
 }
 
-// scan the table: emit solid (k-mer, count), count distinct, and reset every touched slot for the next bin.  Solid pairs are
-// staged in shared memory and flushed with one global reservation per ~1000 pairs.
-constexpr int K2_EMIT_BUF = 1024;
-__global__ void __launch_bounds__(256) k2_emit(uint64_t *keys, uint32_t *counts, uint32_t cap, uint32_t amin, uint32_t amax,
-                                               uint64_t *solid_kmers, uint32_t *solid_counts, uint64_t solid_cap,
-                                               unsigned long long *n_solid, unsigned long long *n_distinct) {
-    __shared__ uint64_t sb_k[K2_EMIT_BUF];
-    __shared__ uint32_t sb_c[K2_EMIT_BUF];
-    __shared__ uint32_t s_n;
+// scan the table: emit solid (k-mer, count), count distinct, and reset every touched slot for the next bin.
+// Each warp owns a contiguous run of slots.  Pass 1 counts the solid entries of the run (loads batched K2_EMIT_ILP deep),
+// the block reserves its output range with ONE global atomic, pass 2 re-reads the run (now in L2), writes the solid pairs
+// at warp-private offsets computed with ballots, and resets the slots.  Two barriers per block, no per-entry atomics.
+constexpr int K2_EMIT_ILP = 4;
+constexpr int K2_EMIT_THREADS = 256;
+__global__ void __launch_bounds__(K2_EMIT_THREADS) k2_emit(uint64_t *keys, uint32_t *counts, uint32_t cap, uint32_t amin, uint32_t amax,
+                                                           uint64_t *solid_kmers, uint32_t *solid_counts, uint64_t solid_cap,
+                                                           unsigned long long *n_solid, unsigned long long *n_distinct) {
+    __shared__ uint32_t s_wsolid[K2_EMIT_THREADS / 32];
     __shared__ unsigned long long s_base;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    const uint32_t chunk = ((cap + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
-    const uint32_t begin = min(cap, blockIdx.x * chunk), end = min(cap, begin + chunk);
-    unsigned long long distinct = 0;
-    auto flush = [&]() {   // called by all threads
-        if (threadIdx.x == 0) s_base = s_n ? atomicAdd(n_solid, (unsigned long long)s_n) : 0ULL;
-        __syncthreads();
-        for (uint32_t j = threadIdx.x; j < s_n; j += blockDim.x) {
-            uint64_t pos = s_base + j;
-            if (pos < solid_cap) { solid_kmers[pos] = sb_k[j]; solid_counts[pos] = sb_c[j]; }
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t n_warps = gridDim.x * (K2_EMIT_THREADS / 32);
+    const uint32_t per_warp = ((cap + n_warps - 1) / n_warps + 31u) & ~31u;
+    const uint32_t gw = blockIdx.x * (K2_EMIT_THREADS / 32) + warp;
+    const uint32_t wb = (uint32_t)min((uint64_t)cap, (uint64_t)gw * per_warp), we = (uint32_t)min((uint64_t)cap, (uint64_t)wb + per_warp);
+
+    uint32_t my_solid = 0, my_distinct = 0;
+    for (uint32_t base = wb; base < we; base += 32 * K2_EMIT_ILP) {
+        uint64_t key[K2_EMIT_ILP]; uint32_t c[K2_EMIT_ILP];
+#pragma unroll
+        for (int j = 0; j < K2_EMIT_ILP; j++) { uint32_t i = base + j * 32 + lane; key[j] = i < we ? keys[i] : EMPTY_KEY; }
+#pragma unroll
+        for (int j = 0; j < K2_EMIT_ILP; j++) { uint32_t i = base + j * 32 + lane; c[j] = key[j] != EMPTY_KEY ? counts[i] : 0; }
+#pragma unroll
+        for (int j = 0; j < K2_EMIT_ILP; j++) {
+            my_distinct += key[j] != EMPTY_KEY;
+            my_solid += (key[j] != EMPTY_KEY) && c[j] >= amin && c[j] <= amax;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-    };
-    for (uint32_t base = begin; base < end; base += 256) {
-        uint32_t i = base + threadIdx.x;
-        if (i < end) {
-            uint64_t key = keys[i];
-            if (key != EMPTY_KEY) {
-                uint32_t c = counts[i];
-                keys[i] = EMPTY_KEY; counts[i] = 0; distinct++;
-                if (c >= amin && c <= amax) { uint32_t pos = atomicAdd(&s_n, 1u); sb_k[pos] = key; sb_c[pos] = c; }
-            }
-        }
-        __syncthreads();
-        if (s_n > K2_EMIT_BUF - 256) flush();
     }
-    flush();
-    block_add(n_distinct, distinct);
+    uint32_t wsolid = my_solid;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) wsolid += __shfl_xor_sync(0xFFFFFFFFu, wsolid, d);
+    if (lane == 0) s_wsolid[warp] = wsolid;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < K2_EMIT_THREADS / 32; w++) { uint32_t v = s_wsolid[w]; s_wsolid[w] = tot; tot += v; }
+        s_base = tot ? atomicAdd(n_solid, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    uint64_t out = s_base + s_wsolid[warp];
+
+    for (uint32_t base = wb; base < we; base += 32 * K2_EMIT_ILP) {
+        uint64_t key[K2_EMIT_ILP]; uint32_t c[K2_EMIT_ILP];
+#pragma unroll
+        for (int j = 0; j < K2_EMIT_ILP; j++) { uint32_t i = base + j * 32 + lane; key[j] = i < we ? keys[i] : EMPTY_KEY; }
+#pragma unroll
+        for (int j = 0; j < K2_EMIT_ILP; j++) { uint32_t i = base + j * 32 + lane; c[j] = key[j] != EMPTY_KEY ? counts[i] : 0; }
+#pragma unroll
+        for (int j = 0; j < K2_EMIT_ILP; j++) {
+            uint32_t i = base + j * 32 + lane;
+            bool occ = key[j] != EMPTY_KEY;
+            bool solid = occ && c[j] >= amin && c[j] <= amax;
+            unsigned m = __ballot_sync(0xFFFFFFFFu, solid);
+            if (solid) {
+                uint64_t pos = out + __popc(m & ((1u << lane) - 1));
+                if (pos < solid_cap) { solid_kmers[pos] = key[j]; solid_counts[pos] = c[j]; }
+            }
+            out += __popc(m);
+            if (occ) { keys[i] = EMPTY_KEY; counts[i] = 0; }
+        }
+    }
+    block_add(n_distinct, (unsigned long long)my_distinct);
 }
 
 // ------------------------------------------------------------------------------------------------ K3: junction end records
@@ -510,16 +533,19 @@ __global__ void __launch_bounds__(256) k6_init(const uint32_t *__restrict__ link
     }
 }
 
+#define K6_DONE 0x80000000u   // bit 31 of the hop count: "next is the tail", nothing left to do for this element
+
 __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsigned long long *n_updated) {
     unsigned long long upd = 0;
     for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t p = ld_volatile_u64(&pair[x]);
+        if ((uint32_t)p & K6_DONE) continue;
         uint32_t n = (uint32_t)(p >> 32);
-        if (n == (uint32_t)x) continue;                       // tail
+        if (n == (uint32_t)x) { *(volatile uint64_t *)&pair[x] = p | K6_DONE; continue; }      // tail
         uint64_t q = ld_volatile_u64(&pair[n]);
         uint32_t n2_ = (uint32_t)(q >> 32);
-        if (n2_ == n) continue;                               // already points at the tail
-        *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)((uint32_t)p + (uint32_t)q);
+        if (n2_ == n) { *(volatile uint64_t *)&pair[x] = p | K6_DONE; continue; }              // already points at the tail
+        *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p + (uint32_t)q) & ~K6_DONE);
         upd++;
     }
     block_add(n_updated, upd);
@@ -530,7 +556,9 @@ __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsi
 // the cycle: bglue_algo.cpp:400-416), record the two edges of the cut junction, and re-rank the affected elements.
 
 __device__ __forceinline__ bool k6_unfinished(const uint64_t *pair, uint64_t x) {
-    uint32_t n = (uint32_t)(pair[x] >> 32);
+    uint64_t p = pair[x];
+    if ((uint32_t)p & K6_DONE) return false;
+    uint32_t n = (uint32_t)(p >> 32);
     if (n == (uint32_t)x) return false;
     return (uint32_t)(pair[n] >> 32) != n;
 }
@@ -587,7 +615,7 @@ __global__ void __launch_bounds__(256) k6_finalize(const uint64_t *__restrict__ 
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < S; v += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t p0 = pair[2 * v], p1 = pair[2 * v + 1];
         uint32_t T0 = (uint32_t)(p0 >> 32) ^ 1u, T1 = (uint32_t)(p1 >> 32) ^ 1u;
-        uint32_t d0 = (uint32_t)p0, d1 = (uint32_t)p1;
+        uint32_t d0 = (uint32_t)p0 & ~K6_DONE, d1 = (uint32_t)p1 & ~K6_DONE;
         uint32_t B, pos, rev;
         if (T1 < T0) { B = T1; pos = d1; rev = 0; } else { B = T0; pos = d0; rev = 1; }
         info[v] = ((uint64_t)B << 32) | ((uint64_t)pos << 1) | rev;
