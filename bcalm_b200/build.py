@@ -29,9 +29,10 @@ def _stale(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def sources():
+def sources(cli: bool = False):
     inc = os.path.join(os.path.dirname(HERE), "include", "cdbg.h")
-    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [inc]
+    fs = [f for f in sorted(os.listdir(CSRC)) if (f == "bcalm_main.cpp") == cli]
+    return [os.path.join(CSRC, f) for f in fs] + [inc]
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
@@ -47,9 +48,8 @@ def build_cli(force: bool = False) -> str | None:
     main = os.path.join(CSRC, "bcalm_main.cpp")
     if not os.path.exists(main):
         return None
-    if force or _stale(CLI, sources()):
-        subprocess.check_call([_nvcc(), *NVCC_FLAGS, "-o", CLI, main, "-L" + HERE, "-lcdbg_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN",
-                               "-lz", "-lpthread"])
+    if force or _stale(CLI, sources(cli=True) + [LIB]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", CLI, main, "-L" + HERE, "-lcdbg_b200", "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"])
     return CLI
 
 

@@ -1,0 +1,324 @@
+// bcalm_main.cpp -- `bcalm`-compatible command line host on top of the C ABI (include/cdbg.h).
+//
+// Drop-in for the reference CLI on the reads -> unitigs path:
+//   bcalm -in <fasta|fastq[.gz]|comma list|file of files> -kmer-size <k> -abundance-min <a> [-out <prefix>] [-nb-cores n]
+//         [-all-abundance-counts] [-verbose v] [-minimizer-size m] [-abundance-max x]
+// writes <prefix>.unitigs.fa with prefix = -out, else the basename of -in cut at its last dot, in the current directory
+// (G/debruijn/impl/GraphUnitigs.cpp:888-904, G/system/impl/FileSystemCommon.cpp:115-137), in the reference's header grammar
+//   ><id> LN:i:<len> KC:i:<sum> km:f:<mean, 1 decimal> [L:<+|->:<id>:<+|->]*      (G/bcalm2/bglue_algo.cpp:197-213, LinkTigs.cpp)
+// `-version` / `-v` print a version banner (src/main.cpp:30-37); errors print "EXCEPTION: <msg>" and exit non-zero
+// (src/main.cpp:44-48).  GATB knobs that only steer the reference's disk/memory plumbing are accepted and ignored.
+// Extra (not in the reference): -out-gfa <file> also writes GFA1 like scripts/convertToGFA.py.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/cdbg.h"
+
+namespace {
+
+struct Options {
+    std::string in, out, out_gfa;
+    int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
+    bool all_abund = false;
+};
+
+[[noreturn]] void die(const std::string &msg) {
+    printf("EXCEPTION: %s\n", msg.c_str());
+    exit(EXIT_FAILURE);
+}
+
+// options of the reference parser that take one argument / no argument and are irrelevant here
+const char *IGNORED_1[] = {"-max-memory", "-max-disk", "-out-dir", "-out-tmp", "-out-compress", "-storage-type", "-histo2D", "-histo",
+                           "-minimizer-type", "-repartition-type", "-bloom", "-debloom", "-debloom-impl", "-branching-nodes",
+                           "-topology-stats", "-integer-precision", "-nb-glue-partitions", "-solidity-custom", "-solidity-kind",
+                           "-histo-max", "-solid-kmers-out", "-edge-km"};
+const char *IGNORED_0[] = {"-no-mphf", "-kff", "-config-only", "-redo-bcalm", "-skip-bcalm", "-redo-bglue", "-skip-bglue", "-redo-links",
+                           "-skip-links"};
+
+void usage() {
+    printf("[bcalm_1 options]\n"
+           "       -in                   (1 arg) :    reads file (fasta/fastq, .gz, comma separated list or file of files)\n"
+           "       -kmer-size            (1 arg) :    size of a kmer  [default '31']\n"
+           "       -abundance-min        (1 arg) :    min abundance threshold for solid kmers  [default '2']\n"
+           "       -abundance-max        (1 arg) :    max abundance threshold for solid kmers  [default '2147483647']\n"
+           "       -minimizer-size       (1 arg) :    size of a minimizer  [default '10']\n"
+           "       -out                  (1 arg) :    output prefix  [default: basename of -in]\n"
+           "       -out-gfa              (1 arg) :    also write GFA1 to this file\n"
+           "       -all-abundance-counts (0 arg) :    output all k-mer abundance counts instead of mean\n"
+           "       -nb-cores             (1 arg) :    number of cores (host parsing threads)  [default '0']\n"
+           "       -device               (1 arg) :    CUDA device ordinal  [default '0']\n"
+           "       -verbose              (1 arg) :    verbosity level  [default '1']\n"
+           "       -version              (0 arg) :    version\n"
+           "       -help                 (0 arg) :    help\n"
+           "   GATB storage/memory knobs (-max-memory -max-disk -out-dir -out-tmp -storage-type ...) are accepted and ignored.\n");
+}
+
+Options parse(int argc, char **argv) {
+    Options o;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto need = [&](const char *name) -> std::string {
+            if (i + 1 >= argc) die(std::string("option ") + name + " needs an argument");
+            return argv[++i];
+        };
+        if (a == "-in") o.in = need("-in");
+        else if (a == "-out") o.out = need("-out");
+        else if (a == "-out-gfa") o.out_gfa = need("-out-gfa");
+        else if (a == "-kmer-size") o.k = atoi(need("-kmer-size").c_str());
+        else if (a == "-abundance-min") o.amin = atoi(need("-abundance-min").c_str());
+        else if (a == "-abundance-max") { long long v = atoll(need("-abundance-max").c_str()); o.amax = v >= 2147483647LL ? 0 : (int)v; }
+        else if (a == "-minimizer-size") o.m = atoi(need("-minimizer-size").c_str());
+        else if (a == "-nb-cores") o.cores = atoi(need("-nb-cores").c_str());
+        else if (a == "-verbose") o.verbose = atoi(need("-verbose").c_str());
+        else if (a == "-device") o.device = atoi(need("-device").c_str());
+        else if (a == "-all-abundance-counts") o.all_abund = true;
+        else if (a == "-help" || a == "-h") { usage(); exit(EXIT_SUCCESS); }
+        else {
+            bool known = false;
+            for (const char *s : IGNORED_1) if (a == s) { need(s); known = true; break; }
+            if (!known) for (const char *s : IGNORED_0) if (a == s) { known = true; break; }
+            if (!known) { usage(); die("Unknown parameter '" + a + "'"); }
+        }
+    }
+    if (o.in.empty()) { usage(); die("Option '-in' is mandatory"); }
+    return o;
+}
+
+// FileSystemCommon::getBaseName: posix basename, then cut at the LAST dot
+std::string base_name(const std::string &path) {
+    size_t s = path.find_last_of('/');
+    std::string b = s == std::string::npos ? path : path.substr(s + 1);
+    size_t d = b.find_last_of('.');
+    if (d != std::string::npos) b = b.substr(0, d);
+    return b;
+}
+
+std::string dir_name(const std::string &path) {
+    size_t s = path.find_last_of('/');
+    return s == std::string::npos ? std::string(".") : path.substr(0, s);
+}
+
+bool read_whole(const std::string &path, std::vector<char> &buf) {
+    gzFile f = gzopen(path.c_str(), "rb");   // transparently reads plain files too
+    if (!f) return false;
+    gzbuffer(f, 1 << 20);
+    buf.clear();
+    size_t cap = 1 << 24;
+    buf.resize(cap);
+    size_t n = 0;
+    for (;;) {
+        if (n == buf.size()) buf.resize(buf.size() * 2);
+        int got = gzread(f, buf.data() + n, (unsigned)std::min<size_t>(buf.size() - n, 1u << 30));
+        if (got < 0) { gzclose(f); return false; }
+        if (got == 0) break;
+        n += (size_t)got;
+    }
+    gzclose(f);
+    buf.resize(n);
+    return true;
+}
+
+// Append the nucleotide stream of one FASTA/FASTQ buffer to `out`: sequence characters only, one '\n' after each record
+// (multi-line FASTA records are joined: BankFasta.cpp:390-560).
+void parse_sequences(const std::vector<char> &in, std::vector<uint8_t> &out, uint64_t &n_records) {
+    const char *p = in.data(), *e = p + in.size();
+    out.reserve(out.size() + in.size());
+    while (p < e) {
+        if (*p == '>') {                                  // FASTA record
+            const char *nl = (const char *)memchr(p, '\n', e - p);
+            p = nl ? nl + 1 : e;
+            while (p < e && *p != '>') {
+                const char *l = (const char *)memchr(p, '\n', e - p);
+                const char *le = l ? l : e;
+                size_t len = le - p;
+                if (len && p[len - 1] == '\r') len--;
+                out.insert(out.end(), (const uint8_t *)p, (const uint8_t *)p + len);
+                p = l ? l + 1 : e;
+            }
+            out.push_back('\n');
+            n_records++;
+        } else if (*p == '@') {                           // FASTQ record (4 lines; multi-line FASTQ is not produced by sequencers)
+            const char *l1 = (const char *)memchr(p, '\n', e - p);
+            if (!l1) break;
+            const char *s = l1 + 1;
+            const char *l2 = (const char *)memchr(s, '\n', e - s);
+            const char *se = l2 ? l2 : e;
+            size_t len = se - s;
+            if (len && s[len - 1] == '\r') len--;
+            out.insert(out.end(), (const uint8_t *)s, (const uint8_t *)s + len);
+            out.push_back('\n');
+            n_records++;
+            if (!l2) break;
+            const char *l3 = (const char *)memchr(l2 + 1, '\n', e - (l2 + 1));   // '+' line
+            if (!l3) break;
+            const char *l4 = (const char *)memchr(l3 + 1, '\n', e - (l3 + 1));   // quality line
+            p = l4 ? l4 + 1 : e;
+        } else {
+            const char *nl = (const char *)memchr(p, '\n', e - p);   // blank / stray line
+            p = nl ? nl + 1 : e;
+        }
+    }
+}
+
+void load_input(const std::string &spec, std::vector<uint8_t> &stream, uint64_t &n_records, int depth = 0) {
+    size_t start = 0;
+    while (start <= spec.size()) {
+        size_t c = spec.find(',', start);
+        std::string path = spec.substr(start, c == std::string::npos ? std::string::npos : c - start);
+        start = c == std::string::npos ? spec.size() + 1 : c + 1;
+        if (path.empty()) continue;
+        std::vector<char> buf;
+        if (!read_whole(path, buf)) die("Unable to open file '" + path + "'");
+        size_t i = 0;
+        while (i < buf.size() && (buf[i] == '\n' || buf[i] == '\r' || buf[i] == ' ')) i++;
+        if (i == buf.size()) continue;
+        if (buf[i] == '>' || buf[i] == '@') {
+            parse_sequences(buf, stream, n_records);
+        } else {
+            if (depth > 2) die("file of files nested too deeply: " + path);
+            // file of files: one path per line, relative to the list's directory (G/bank/impl/BankAlbum.cpp)
+            std::string text(buf.begin(), buf.end()), dir = dir_name(path);
+            size_t ls = 0;
+            while (ls < text.size()) {
+                size_t le = text.find('\n', ls);
+                std::string line = text.substr(ls, le == std::string::npos ? std::string::npos : le - ls);
+                ls = le == std::string::npos ? text.size() : le + 1;
+                while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+                if (line.empty()) continue;
+                std::string sub = line[0] == '/' ? line : dir + "/" + line;
+                load_input(sub, stream, n_records, depth + 1);
+            }
+        }
+    }
+}
+
+inline void put_u64(std::string &s, uint64_t v) {
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) s.push_back(tmp[--n]);
+}
+
+// km:f: -- float32 mean printed with one decimal (bglue_algo.cpp:131-145, :75-81)
+inline void put_km(std::string &s, uint64_t kc, uint64_t n_kmers, const uint32_t *ab) {
+    float sum = 0.f;
+    if (ab && kc >= (1ULL << 24)) for (uint64_t i = 0; i < n_kmers; i++) sum += (float)(int)ab[i];
+    else sum = (float)kc;
+    float mean = sum / (float)n_kmers;
+    char tmp[48];
+    int n = snprintf(tmp, sizeof tmp, "%.1f", (double)mean);
+    s.append(tmp, n);
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc > 1 && (strcmp(argv[1], "-version") == 0 || strcmp(argv[1], "-v") == 0)) {
+        printf("BCALM 2 (B200-native cdbg), version v2.2.3-compatible\nUsing %s\n", cdbg_version());
+        return EXIT_SUCCESS;
+    }
+    Options o = parse(argc, argv);
+    const double t0 = now_s();
+    if (o.verbose) printf("BCALM 2 (B200-native), k=%d abundance-min=%d input=%s\n", o.k, o.amin, o.in.c_str());
+
+    cdbg_params prm{};
+    prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device;
+    prm.flags = (o.all_abund ? CDBG_FLAG_ALL_ABUNDANCE_COUNTS : 0) | (o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0);
+    prm.rank = 0; prm.world_size = 1;
+    cdbg_ctx *ctx = nullptr;
+    int rc = cdbg_create(&ctx, &prm);
+    if (rc != CDBG_OK) {
+        std::string msg = ctx ? cdbg_last_error(ctx) : "cdbg_create failed";
+        if (ctx) cdbg_destroy(ctx);
+        die(msg);
+    }
+
+    std::vector<uint8_t> stream;
+    uint64_t n_records = 0;
+    load_input(o.in, stream, n_records);
+    const double t1 = now_s();
+
+    cdbg_unitig_view v{};
+    cdbg_stats st{};
+    rc = cdbg_build(ctx, stream.data(), stream.size(), CDBG_MEM_HOST, &v, &st);
+    if (rc != CDBG_OK) { std::string msg = cdbg_last_error(ctx); cdbg_destroy(ctx); die(msg); }
+    const double t2 = now_s();
+
+    const std::string prefix = o.out.empty() ? base_name(o.in) : o.out;
+    const std::string out_path = prefix + ".unitigs.fa";
+    const int k = o.k;
+    std::string text;
+    text.reserve(v.total_nt + v.n_unitigs * 64 + v.n_links * 16 + 64);
+    for (uint64_t u = 0; u < v.n_unitigs; u++) {
+        const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
+        const uint32_t *ab = v.abund ? v.abund + (b - u * (uint64_t)(k - 1)) : nullptr;
+        text.push_back('>'); put_u64(text, u);
+        text += " LN:i:"; put_u64(text, len);
+        if (o.all_abund && ab) {
+            text += " ab:Z:";
+            for (uint64_t i = 0; i < nk; i++) { put_u64(text, ab[i]); text.push_back(' '); }
+        } else {
+            text += " KC:i:"; put_u64(text, v.kc[u]);
+            text += " km:f:"; put_km(text, v.kc[u], nk, ab);
+            text.push_back(' ');
+        }
+        for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
+            const cdbg_link_t &l = v.links[i];
+            text += " L:"; text.push_back((char)l.from_sign); text.push_back(':'); put_u64(text, l.to);
+            text.push_back(':'); text.push_back((char)l.to_sign);
+        }
+        text.push_back('\n');
+        text.append(v.seq + b, len);
+        text.push_back('\n');
+    }
+    FILE *f = fopen(out_path.c_str(), "wb");
+    if (!f) { cdbg_destroy(ctx); die("Unable to open output file '" + out_path + "'"); }
+    fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+
+    if (!o.out_gfa.empty()) {   // GFA1, same records as scripts/convertToGFA.py:74,97-114
+        std::string g;
+        g.reserve(text.size() + v.n_links * 24);
+        g += "H\tVN:Z:1.0\tks:i:"; put_u64(g, (uint64_t)k); g.push_back('\n');
+        for (uint64_t u = 0; u < v.n_unitigs; u++) {
+            const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
+            g += "S\t"; put_u64(g, u); g.push_back('\t'); g.append(v.seq + b, len);
+            g += "\tLN:i:"; put_u64(g, len); g += "\tKC:i:"; put_u64(g, v.kc[u]); g += "\tkm:f:"; put_km(g, v.kc[u], nk, nullptr);
+            g.push_back('\n');
+        }
+        for (uint64_t u = 0; u < v.n_unitigs; u++)
+            for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
+                const cdbg_link_t &l = v.links[i];
+                g += "L\t"; put_u64(g, u); g.push_back('\t'); g.push_back((char)l.from_sign); g.push_back('\t'); put_u64(g, l.to);
+                g.push_back('\t'); g.push_back((char)l.to_sign); g.push_back('\t'); put_u64(g, (uint64_t)(k - 1)); g += "M\n";
+            }
+        FILE *gf = fopen(o.out_gfa.c_str(), "wb");
+        if (!gf) { cdbg_destroy(ctx); die("Unable to open output file '" + o.out_gfa + "'"); }
+        fwrite(g.data(), 1, g.size(), gf);
+        fclose(gf);
+    }
+    const double t3 = now_s();
+
+    if (o.verbose) {
+        printf("sequences: %llu   nucleotide stream: %llu bytes\n", (unsigned long long)n_records, (unsigned long long)stream.size());
+        printf("kmers: %llu instances, %llu distinct, %llu solid\n", (unsigned long long)st.n_instances, (unsigned long long)st.n_distinct,
+               (unsigned long long)st.n_solid);
+        printf("unitigs: %llu (%llu nt), links: %llu, compactions: %llu, cycles cut: %llu\n", (unsigned long long)st.n_unitigs,
+               (unsigned long long)st.total_nt, (unsigned long long)st.n_links, (unsigned long long)st.n_compactions, (unsigned long long)st.n_cycles);
+        printf("device ms: count %.3f (K1 %.3f+%.3f, K2 %.3f)  compact %.3f (K3 %.3f, K5 %.3f, rank %.3f, spell %.3f)  link %.3f  fetch %.3f\n",
+               st.ms_count, st.ms_k1_hist, st.ms_k1_scatter, st.ms_k2, st.ms_compact, st.ms_k3, st.ms_k5, st.ms_k6_rank, st.ms_k6_spell, st.ms_link,
+               st.ms_fetch);
+        printf("wall s: parse %.3f  gpu (H2D+stages+D2H) %.3f  write %.3f  total %.3f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+        printf("output: %s\n", out_path.c_str());
+    }
+    cdbg_destroy(ctx);
+    return EXIT_SUCCESS;
+}

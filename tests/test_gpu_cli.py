@@ -1,0 +1,99 @@
+"""GPU tests of the `bcalm`-compatible CLI: input grammars (FASTA multi-line, FASTQ, gz, comma list, file of files), output
+file naming and header grammar, compared with the reference's golden unitigs.fa under the parity relation."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+from bcalm_b200 import build, parity
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+CASES = {c["name"]: c for c in load_golden()}
+
+
+@pytest.fixture(scope="module")
+def cli():
+    build.build_lib()
+    return build.build_cli()
+
+
+def run_cli(cli, cwd, *args):
+    p = subprocess.run([cli, *args], cwd=cwd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+def write_fasta(path, reads, width=None):
+    with open(path, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f">read{i} ACGT comment\n")
+            if width:
+                for j in range(0, len(r), width):
+                    f.write(r[j:j + width] + "\n")
+            else:
+                f.write(r + "\n")
+
+
+@pytest.mark.parametrize("name", ["tiny_read_k21", "minitip_k21_a1", "circular_test1", "circular_test2_polyA", "pufferize_refs",
+                                  "lowcx_11_ACGT_k7_a2", "reads_3_k31_a2", "reads_1_k21_a2"])
+def test_cli_matches_reference_golden(cli, tmp_path, name):
+    c = CASES[name]
+    fa = tmp_path / "input.reads.fa"
+    write_fasta(fa, c["reads"], width=37)          # multi-line FASTA
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(c["k"]), "-abundance-min", str(c["abundance_min"]),
+            "-minimizer-size", str(c["minimizer_size"]), "-max-memory", "1000", "-nb-cores", "2")
+    out = tmp_path / "input.reads.unitigs.fa"      # basename cut at the LAST dot, in the CWD
+    assert out.exists()
+    d = parity.diff(parity.parse_unitigs_fa(out.read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d == "", d
+
+
+def test_cli_fastq_gz_list_and_out_prefix(cli, tmp_path):
+    c = CASES["reads_2_k31_a2"]
+    reads = c["reads"]
+    half = len(reads) // 2
+    fq = tmp_path / "a.fq"
+    with open(fq, "w") as f:
+        for i, r in enumerate(reads[:half]):
+            f.write(f"@r{i}\n{r}\n+\n{'I' * len(r)}\n")
+    gz = tmp_path / "b.fa.gz"
+    with gzip.open(gz, "wt") as f:
+        for i, r in enumerate(reads[half:]):
+            f.write(f">r{i}\n{r}\n")
+    # comma separated list
+    run_cli(cli, tmp_path, "-in", f"{fq},{gz}", "-kmer-size", "31", "-abundance-min", "2", "-out", str(tmp_path / "viaComma"), "-verbose", "0")
+    # file of files
+    lst = tmp_path / "files.lst"
+    lst.write_text("a.fq\nb.fa.gz\n")
+    run_cli(cli, tmp_path, "-in", str(lst), "-kmer-size", "31", "-abundance-min", "2", "-out", str(tmp_path / "viaList"))
+    ref = parity.parse_unitigs_fa(c["unitigs_fa"])
+    for name in ("viaComma.unitigs.fa", "viaList.unitigs.fa"):
+        d = parity.diff(parity.parse_unitigs_fa((tmp_path / name).read_text()), ref, 31)
+        assert d == "", d
+
+
+def test_cli_all_abundance_counts_and_gfa(cli, tmp_path):
+    from oracle import oracle as orc
+    c = CASES["reads_0_k15_a2"]
+    fa = tmp_path / "x.fa"
+    write_fasta(fa, c["reads"])
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", "15", "-abundance-min", "2", "-all-abundance-counts", "-out-gfa", str(tmp_path / "x.gfa"))
+    recs = parity.parse_unitigs_fa((tmp_path / "x.unitigs.fa").read_text())
+    o = parity.graph_to_records(orc.run(c["reads"], 15, 2), with_ab=True)
+    # ab:Z: lists: compare as multisets of (canonical sequence, abundance list in canonical orientation)
+    def canon(recs_):
+        out = []
+        for r in recs_:
+            s, ab = r["seq"], r["ab"]
+            rc = parity.revcomp_str(s)
+            assert ab is not None and len(ab) == len(s) - 15 + 1
+            out.append((s, tuple(ab)) if s <= rc else (rc, tuple(reversed(ab))))
+        return sorted(out)
+    assert canon(recs) == canon(o)
+    gfa = (tmp_path / "x.gfa").read_text().splitlines()
+    assert gfa[0] == "H\tVN:Z:1.0\tks:i:15"
+    assert sum(1 for l in gfa if l.startswith("S\t")) == len(recs)
+    assert sum(1 for l in gfa if l.startswith("L\t")) == sum(len(r["links"]) for r in recs)
+    assert all(l.endswith("\t14M") for l in gfa if l.startswith("L\t"))
