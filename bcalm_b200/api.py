@@ -49,14 +49,15 @@ class _Link(C.Structure):
 
 class UnitigView(C.Structure):
     _fields_ = [("kmer_size", C.c_int32), ("n_unitigs", C.c_uint64), ("total_nt", C.c_uint64), ("seq", C.c_void_p),
-                ("seq_off", C.c_void_p), ("kc", C.c_void_p), ("abund", C.c_void_p), ("n_links", C.c_uint64), ("links", C.c_void_p), ("link_off", C.c_void_p)]
+                ("seq_off", C.c_void_p), ("kc", C.c_void_p), ("abund", C.c_void_p), ("n_links", C.c_uint64), ("links", C.c_void_p), ("link_off", C.c_void_p),
+                ("first_unitig", C.c_uint64), ("n_unitigs_total", C.c_uint64)]
 
 
 LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to_sign", "u1"), ("pad", "u1", (2,))])
 
 EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_count", "cdbg_compact",
            "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_synth_reads",
-           "cdbg_copy_to_host", "cdbg_version"]
+           "cdbg_copy_to_host", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init"]
 
 _lib = None
 
@@ -85,6 +86,8 @@ def load_library():
     L.cdbg_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
     L.cdbg_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.cdbg_version.restype = C.c_char_p
+    L.cdbg_nccl_unique_id.argtypes = [C.c_void_p]
+    L.cdbg_shard_init.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -100,6 +103,8 @@ class Graph:
     links: np.ndarray
     stats: dict = field(default_factory=dict)
     link_off: np.ndarray | None = None
+    first_unitig: int = 0          # sharded mode: global id of local unitig 0 (links always carry global ids)
+    n_unitigs_total: int = 0
 
     @property
     def n_unitigs(self) -> int:
@@ -120,11 +125,12 @@ class Cdbg:
     """One context = one GPU.  Usage: g = Cdbg(k=31, abundance_min=2).build(reads)"""
 
     def __init__(self, k: int = 31, abundance_min: int = 2, abundance_max: int = 0, minimizer_size: int = 0, device: int = 0,
-                 all_abundance_counts: bool = False, verbose: bool = False):
+                 all_abundance_counts: bool = False, verbose: bool = False, rank: int = 0, world_size: int = 1):
         self.lib = load_library()
         self.k = k
         flags = (FLAG_ALL_ABUNDANCE_COUNTS if all_abundance_counts else 0) | (FLAG_VERBOSE if verbose else 0)
-        self.params = Params(k, abundance_min, abundance_max, minimizer_size, device, flags, 0, 1)
+        self.params = Params(k, abundance_min, abundance_max, minimizer_size, device, flags, rank, world_size)
+        self.rank, self.world_size = rank, world_size
         self.h = C.c_void_p()
         rc = self.lib.cdbg_create(C.byref(self.h), C.byref(self.params))
         if rc != 0:
@@ -154,6 +160,27 @@ class Cdbg:
     def _ck(self, rc):
         if rc != 0:
             raise CdbgError(rc, self.lib.cdbg_last_error(self.h).decode())
+
+    # ---- sharded mode (one Cdbg per GPU / process)
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = load_library().cdbg_nccl_unique_id(buf)
+        if rc != 0:
+            raise CdbgError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def shard_init(self, unique_id: bytes):
+        """Collective: every rank passes the 128-byte id obtained by rank 0 from nccl_unique_id()."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.cdbg_shard_init(self.h, buf))
+
+    def shard_init_torch(self):
+        """Bootstrap through an initialised torch.distributed process group (any backend)."""
+        import torch.distributed as dist
+        obj = [self.nccl_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        self.shard_init(obj[0])
 
     # ---- stage calls
     def reset(self):
@@ -205,7 +232,8 @@ class Cdbg:
         S = int(v.total_nt - U * (self.k - 1)) if U else 0
         return Graph(k=self.k, seq=arr(v.seq, v.total_nt, np.uint8), seq_off=arr(v.seq_off, U + 1, np.uint64),
                      kc=arr(v.kc, U, np.uint64), abund=arr(v.abund, S, np.uint32) if v.abund else None,
-                     links=arr(v.links, v.n_links, LINK_DTYPE), stats=self.stats(), link_off=arr(v.link_off, U + 1, np.uint64))
+                     links=arr(v.links, v.n_links, LINK_DTYPE), stats=self.stats(), link_off=arr(v.link_off, U + 1, np.uint64),
+                     first_unitig=int(v.first_unitig), n_unitigs_total=int(v.n_unitigs_total))
 
     def unitigs(self, copy: bool = True) -> Graph:
         v = UnitigView()
@@ -234,6 +262,26 @@ class Cdbg:
         out = np.empty(n_bytes, np.uint8)
         self._ck(self.lib.cdbg_copy_to_host(self.h, out.ctypes.data, C.c_void_p(dptr), n_bytes))
         return out
+
+
+def merge_shards(graphs) -> Graph:
+    """Concatenate the per-rank graphs of a sharded build (ordered by first_unitig) into one Graph with global ids."""
+    gs = sorted(graphs, key=lambda g: (g.first_unitig, g.n_unitigs))
+    k = gs[0].k
+    seq = np.concatenate([g.seq for g in gs]) if gs else np.zeros(0, np.uint8)
+    offs, base, expect = [np.zeros(1, np.uint64)], 0, 0
+    for g in gs:
+        assert g.first_unitig == expect, "shards do not tile the unitig id range"
+        offs.append(g.seq_off[1:].astype(np.uint64) + np.uint64(base))
+        base += len(g.seq)
+        expect += g.n_unitigs
+    links = np.concatenate([g.links for g in gs])
+    order = np.argsort(links["from"], kind="stable")
+    links = links[order]
+    link_off = np.zeros(expect + 1, np.uint64)
+    np.cumsum(np.bincount(links["from"], minlength=expect), out=link_off[1:])
+    return Graph(k=k, seq=seq, seq_off=np.concatenate(offs), kc=np.concatenate([g.kc for g in gs]), abund=None, links=links,
+                 stats={"shards": [g.stats for g in gs]}, link_off=link_off, first_unitig=0, n_unitigs_total=expect)
 
 
 def build_unitigs(reads, k: int = 31, abundance_min: int = 2, **kw) -> Graph:

@@ -37,7 +37,7 @@ def sources(cli: bool = False):
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     if force or _stale(LIB, sources()):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "cdbg.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "cdbg.cu"), "-ldl"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

@@ -15,6 +15,7 @@
 
 #include "../../include/cdbg.h"
 #include "kernels.cuh"
+#include "shard.cuh"
 
 namespace {
 
@@ -66,11 +67,22 @@ struct cdbg_ctx {
     uint64_t *d_seq_off = nullptr;
     unsigned long long *d_kc = nullptr;
     uint32_t *d_abund = nullptr;
+    uint32_t *d_term_begin = nullptr, *d_term_end = nullptr;   // sharded mode: k-mer ends at which each local piece begins / ends
     uint64_t U = 0, total_nt = 0;
 
     // stage 4
     LinkRec *d_links = nullptr;
     uint64_t *d_link_off = nullptr;   // [U+1] CSR offsets of d_links by `from`
+
+    // sharded mode (world > 1)
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    uint64_t *d_link64 = nullptr;            // [2S] partner gid of every local k-mer end
+    ulonglong2 *d_sedges = nullptr;          // unitig-level edges (from gid, to gid) this GPU is responsible for
+    uint64_t n_sedges = 0, sedge_cap = 0;
+    uint64_t *d_pinfo = nullptr;             // [G] replicated piece-level ranking result
+    uint32_t *d_unitig_of_piece = nullptr;   // [G]
+    uint64_t piece_base_me = 0, n_pieces = 0, U_total = 0, u_first = 0;
 
     // small device scratch for counters (zeroed per use)
     unsigned long long *d_ctr = nullptr;   // [64]
@@ -211,7 +223,9 @@ int free_results(cdbg_ctx *ctx) {
     ctx->d_solid_kmers = nullptr; ctx->d_solid_counts = nullptr; ctx->S = 0;
     ctx->d_link = nullptr; ctx->d_edges = nullptr; ctx->n_edges = 0; ctx->edge_cap = 0;
     ctx->d_info = nullptr; ctx->d_unitig_of_kmer = nullptr; ctx->d_seq = nullptr; ctx->d_seq_off = nullptr;
-    ctx->d_kc = nullptr; ctx->d_abund = nullptr; ctx->U = 0; ctx->total_nt = 0; ctx->d_links = nullptr; ctx->d_link_off = nullptr;
+    ctx->d_kc = nullptr; ctx->d_abund = nullptr; ctx->U = 0; ctx->total_nt = 0; ctx->d_links = nullptr; ctx->d_link_off = nullptr; ctx->d_term_begin = nullptr; ctx->d_term_end = nullptr;
+    ctx->d_link64 = nullptr; ctx->d_sedges = nullptr; ctx->n_sedges = 0; ctx->sedge_cap = 0; ctx->d_pinfo = nullptr; ctx->d_unitig_of_piece = nullptr;
+    ctx->piece_base_me = 0; ctx->n_pieces = 0; ctx->U_total = 0; ctx->u_first = 0;
     ctx->stage = ST_EMPTY;
     memset(&ctx->st, 0, sizeof ctx->st);
     for (auto &t : ctx->tm) t.used = false;
@@ -336,6 +350,92 @@ int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remainin
     return ctx->fail(CDBG_ERR_INTERNAL, "list ranking did not converge");
 }
 
+// List ranking over `n_nodes` nodes with two ends each (link[2*n_nodes], NOLINK = chain end).  weight == nullptr: every node
+// counts 1 (k-mers); otherwise hop counts are weighted (pieces of several k-mers).  Cycles are cut at their smallest node;
+// the two edges of each cut junction are appended to edges[] (packed end ids) and *n_edges advanced.
+int run_ranking(cdbg_ctx *ctx, uint32_t *d_link, uint64_t n_nodes, const uint32_t *d_weight, uint64_t *d_edges, uint64_t edge_cap,
+                uint64_t *n_edges, uint64_t **d_pair_out) {
+    int rc;
+    const uint64_t n2 = 2 * n_nodes;
+    uint64_t *d_pair = nullptr;
+    if ((rc = dalloc(ctx, &d_pair, n2 + 1))) return rc;
+    *d_pair_out = d_pair;
+    if (!n_nodes) return CDBG_OK;
+    if (d_weight) LAUNCH(k6w_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_weight, d_pair, n2);
+    else LAUNCH(k6_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_pair, n2);
+    uint64_t remaining = 0;
+    if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+    for (int guard = 0; remaining && guard < 4; guard++) {
+        uint8_t *d_cyc = nullptr; uint64_t *d_lab = nullptr;
+        if ((rc = dalloc(ctx, &d_cyc, n2 + 1))) return rc;
+        if ((rc = dalloc(ctx, &d_lab, n2 + 1))) return rc;
+        LAUNCH(k6_cycle_mark, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, d_link, n2, d_cyc, d_lab);
+        int rounds = 2;
+        for (uint64_t r = 1; r < remaining; r <<= 1) rounds++;
+        for (int r = 0; r < rounds; r++) LAUNCH(k6_cycle_min, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2);
+        if ((rc = ctr_zero(ctx))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_ctr + 0, n_edges, 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k6_cycle_cut, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2, d_link, d_edges, edge_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
+        if (d_weight) LAUNCH(k6w_reinit_flagged, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_link, d_weight, d_pair, n2);
+        else LAUNCH(k6_reinit_flagged, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_link, d_pair, n2);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (ctx->h_ctr[0] > edge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow while cutting cycles");
+        *n_edges = ctx->h_ctr[0];
+        ctx->st.n_cycles += ctx->h_ctr[1];
+        dfree(ctx, d_cyc); dfree(ctx, d_lab);
+        if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+    }
+    if (remaining) return ctx->fail(CDBG_ERR_INTERNAL, "cycles remain after cutting");
+    return CDBG_OK;
+}
+
+// Unit (unitig / piece) numbering from the ranked pairs: info per node, exclusive scans of head flags and head lengths.
+int number_units(cdbg_ctx *ctx, const uint64_t *d_pair, uint64_t n_nodes, const uint32_t *d_weight, uint64_t **d_info, uint64_t **d_uid_scan,
+                 uint64_t **d_nt_scan, uint64_t *U, uint64_t *total_nt) {
+    int rc;
+    uint32_t *d_head_flag = nullptr, *d_head_nt = nullptr;
+    if ((rc = dalloc(ctx, d_info, n_nodes + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_head_flag, n_nodes + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_head_nt, n_nodes + 1))) return rc;
+    if ((rc = dalloc(ctx, d_uid_scan, n_nodes + 1))) return rc;
+    if ((rc = dalloc(ctx, d_nt_scan, n_nodes + 1))) return rc;
+    *U = 0; *total_nt = 0;
+    if (n_nodes) {
+        if (d_weight) LAUNCH(k6w_finalize, grid_for(ctx, n_nodes, 256, 8), 256, 0, d_pair, d_weight, n_nodes, ctx->k, *d_info, d_head_flag, d_head_nt);
+        else LAUNCH(k6_finalize, grid_for(ctx, n_nodes, 256, 8), 256, 0, d_pair, n_nodes, ctx->k, *d_info, d_head_flag, d_head_nt);
+        if ((rc = exclusive_scan(ctx, d_head_flag, n_nodes, *d_uid_scan, U))) return rc;
+        if ((rc = exclusive_scan(ctx, d_head_nt, n_nodes, *d_nt_scan, total_nt))) return rc;
+    }
+    dfree(ctx, d_head_flag); dfree(ctx, d_head_nt);
+    return CDBG_OK;
+}
+
+// Spell the U units (unitigs, or per-GPU pieces in sharded mode) numbered by number_units into ctx->d_seq / d_seq_off / d_kc.
+int spell_units(cdbg_ctx *ctx, const uint64_t *d_uid_scan, const uint64_t *d_nt_scan, bool want_terms) {
+    int rc;
+    const uint64_t S = ctx->S, U = ctx->U, total_nt = ctx->total_nt;
+    if ((rc = dalloc(ctx, &ctx->d_seq, total_nt + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_seq_off, U + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_kc, U + 1))) return rc;
+    CK(cudaMemsetAsync(ctx->d_kc, 0, (U + 1) * 8, ctx->stream));
+    if (ctx->prm.flags & CDBG_FLAG_ALL_ABUNDANCE_COUNTS) { if ((rc = dalloc(ctx, &ctx->d_abund, S + 1))) return rc; }
+    if (want_terms) {
+        if ((rc = dalloc(ctx, &ctx->d_term_begin, U + 1))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_term_end, U + 1))) return rc;
+    }
+    if (S) {
+        SpellParams sp{};
+        sp.solid_kmers = ctx->d_solid_kmers; sp.solid_counts = ctx->d_solid_counts; sp.S = S; sp.k = ctx->k;
+        sp.info = ctx->d_info; sp.uid_scan = d_uid_scan; sp.nt_scan = d_nt_scan;
+        sp.seq = ctx->d_seq; sp.seq_off = ctx->d_seq_off; sp.kc = ctx->d_kc; sp.abund = ctx->d_abund;
+        sp.unitig_of_kmer = ctx->d_unitig_of_kmer;
+        sp.link = ctx->d_link; sp.term_begin = want_terms ? ctx->d_term_begin : nullptr; sp.term_end = want_terms ? ctx->d_term_end : nullptr;
+        LAUNCH(k8_spell, grid_for(ctx, S, 256, 8), 256, 0, sp);
+    }
+    CK(cudaMemcpyAsync(ctx->d_seq_off + U, &ctx->total_nt, 8, cudaMemcpyHostToDevice, ctx->stream));
+    return CDBG_OK;
+}
+
 int stage_compact(cdbg_ctx *ctx) {
     const int k = ctx->k;
     const uint64_t S = ctx->S, n2 = 2 * S;
@@ -414,72 +514,19 @@ int stage_compact(cdbg_ctx *ctx) {
     dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
     dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
 
-    // ---- K6: list ranking
-    uint64_t *d_pair = nullptr;
-    if ((rc = dalloc(ctx, &d_pair, n2 + 1))) return rc;
+    // ---- K6: list ranking + unitig numbering
+    uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;
     tstart(ctx, T_K6R);
-    if (S) {
-        LAUNCH(k6_init, grid_for(ctx, n2, 256, 8), 256, 0, ctx->d_link, d_pair, n2);
-        uint64_t remaining = 0;
-        if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
-        for (int guard = 0; remaining && guard < 4; guard++) {
-            // cycles: label with the minimum k-mer index, cut there, re-rank
-            uint8_t *d_cyc = nullptr; uint64_t *d_lab = nullptr;
-            if ((rc = dalloc(ctx, &d_cyc, n2 + 1))) return rc;
-            if ((rc = dalloc(ctx, &d_lab, n2 + 1))) return rc;
-            LAUNCH(k6_cycle_mark, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, ctx->d_link, n2, d_cyc, d_lab);
-            int rounds = 2;
-            for (uint64_t r = 1; r < remaining; r <<= 1) rounds++;
-            for (int r = 0; r < rounds; r++) LAUNCH(k6_cycle_min, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2);
-            if ((rc = ctr_zero(ctx))) return rc;
-            CK(cudaMemcpyAsync(ctx->d_ctr + 0, &ctx->n_edges, 8, cudaMemcpyHostToDevice, ctx->stream));
-            LAUNCH(k6_cycle_cut, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2, ctx->d_link, ctx->d_edges, ctx->edge_cap, ctx->d_ctr + 0,
-                   ctx->d_ctr + 1);
-            LAUNCH(k6_reinit_flagged, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, ctx->d_link, d_pair, n2);
-            if ((rc = ctr_read(ctx))) return rc;
-            if (ctx->h_ctr[0] > ctx->edge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow while cutting cycles");
-            ctx->n_edges = ctx->h_ctr[0];
-            ctx->st.n_cycles += ctx->h_ctr[1];
-            dfree(ctx, d_cyc); dfree(ctx, d_lab);
-            if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
-        }
-        if (remaining) return ctx->fail(CDBG_ERR_INTERNAL, "cycles remain after cutting");
-    }
+    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, ctx->d_edges, ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
     tstop(ctx, T_K6R);
-
-    // ---- unitig numbering + spelling
     tstart(ctx, T_K6S);
-    uint32_t *d_head_flag = nullptr, *d_head_nt = nullptr;
-    uint64_t *d_uid_scan = nullptr, *d_nt_scan = nullptr;
-    if ((rc = dalloc(ctx, &ctx->d_info, S + 1))) return rc;
-    if ((rc = dalloc(ctx, &d_head_flag, S + 1))) return rc;
-    if ((rc = dalloc(ctx, &d_head_nt, S + 1))) return rc;
-    if ((rc = dalloc(ctx, &d_uid_scan, S + 1))) return rc;
-    if ((rc = dalloc(ctx, &d_nt_scan, S + 1))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_unitig_of_kmer, S + 1))) return rc;
     uint64_t U = 0, total_nt = 0;
-    if (S) {
-        LAUNCH(k6_finalize, grid_for(ctx, S, 256, 8), 256, 0, d_pair, S, k, ctx->d_info, d_head_flag, d_head_nt);
-        if ((rc = exclusive_scan(ctx, d_head_flag, S, d_uid_scan, &U))) return rc;
-        if ((rc = exclusive_scan(ctx, d_head_nt, S, d_nt_scan, &total_nt))) return rc;
-    }
+    if ((rc = number_units(ctx, d_pair, S, nullptr, &ctx->d_info, &d_uid_scan, &d_nt_scan, &U, &total_nt))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_unitig_of_kmer, S + 1))) return rc;
     ctx->U = U; ctx->total_nt = total_nt;
     dfree(ctx, d_pair);
-    if ((rc = dalloc(ctx, &ctx->d_seq, total_nt + 1))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_seq_off, U + 1))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_kc, U + 1))) return rc;
-    CK(cudaMemsetAsync(ctx->d_kc, 0, (U + 1) * 8, ctx->stream));
-    if (ctx->prm.flags & CDBG_FLAG_ALL_ABUNDANCE_COUNTS) { if ((rc = dalloc(ctx, &ctx->d_abund, S + 1))) return rc; }
-    if (S) {
-        SpellParams sp{};
-        sp.solid_kmers = ctx->d_solid_kmers; sp.solid_counts = ctx->d_solid_counts; sp.S = S; sp.k = k;
-        sp.info = ctx->d_info; sp.uid_scan = d_uid_scan; sp.nt_scan = d_nt_scan;
-        sp.seq = ctx->d_seq; sp.seq_off = ctx->d_seq_off; sp.kc = ctx->d_kc; sp.abund = ctx->d_abund;
-        sp.unitig_of_kmer = ctx->d_unitig_of_kmer;
-        LAUNCH(k8_spell, grid_for(ctx, S, 256, 8), 256, 0, sp);
-    }
-    CK(cudaMemcpyAsync(ctx->d_seq_off + U, &ctx->total_nt, 8, cudaMemcpyHostToDevice, ctx->stream));
-    dfree(ctx, d_head_flag); dfree(ctx, d_head_nt); dfree(ctx, d_uid_scan); dfree(ctx, d_nt_scan);
+    if ((rc = spell_units(ctx, d_uid_scan, d_nt_scan, false))) return rc;
+    dfree(ctx, d_uid_scan); dfree(ctx, d_nt_scan);
     tstop(ctx, T_K6S);
     ctx->st.n_unitigs = U; ctx->st.total_nt = total_nt;
     tstop(ctx, T_COMPACT);
@@ -513,6 +560,8 @@ int stage_link(cdbg_ctx *ctx) {
     return CDBG_OK;
 }
 
+#include "shard_host.inl"
+
 void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
     cudaStreamSynchronize(ctx->stream);
     cdbg_stats &s = ctx->st;
@@ -543,7 +592,12 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     if (params->kmer_size < 4 || params->kmer_size > 31)
         return bail(ctx->fail(CDBG_ERR_PARAM, "unhandled kmer size %d (this build supports 4 <= k <= 31)", params->kmer_size));
     if (params->abundance_min < 0) return bail(ctx->fail(CDBG_ERR_PARAM, "abundance-min must be >= 0"));
-    if (params->world_size > 1) return bail(ctx->fail(CDBG_ERR_PARAM, "world_size > 1 needs the sharded entry points (cdbg_shard_*)"));
+    if (params->world_size > MAX_WORLD || params->world_size < 0 || (params->world_size > 1 && (params->rank < 0 || params->rank >= params->world_size)))
+        return bail(ctx->fail(CDBG_ERR_PARAM, "bad rank/world_size %d/%d (at most %d shards)", params->rank, params->world_size, MAX_WORLD));
+    if (params->world_size > 1 && (params->flags & CDBG_FLAG_ALL_ABUNDANCE_COUNTS))
+        return bail(ctx->fail(CDBG_ERR_PARAM, "-all-abundance-counts is not available in sharded mode yet"));
+    ctx->world = params->world_size > 1 ? params->world_size : 1;
+    ctx->rank = ctx->world > 1 ? params->rank : 0;
     ctx->k = params->kmer_size;
     ctx->m = params->minimizer_size > 0 ? params->minimizer_size : 10;
     if (ctx->m > ctx->k - 1) ctx->m = ctx->k - 1;   // ConfigurationAlgorithm.cpp:251
@@ -579,6 +633,7 @@ void cdbg_destroy(cdbg_ctx *ctx) {
         cudaSetDevice(ctx->prm.device);
         free_results(ctx);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->comm) ncclCommDestroy(ctx->comm);
         if (ctx->d_synth) cudaFree(ctx->d_synth);
         if (ctx->d_ctr) cudaFree(ctx->d_ctr);
         if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -637,8 +692,9 @@ int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int l
 int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if (ctx->stage != ST_PUSHED) return ctx->fail(CDBG_ERR_STATE, "cdbg_count needs pushed reads");
+    if (ctx->world > 1 && !ctx->comm) return ctx->fail(CDBG_ERR_STATE, "sharded context: call cdbg_shard_init first");
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = stage_count(ctx);
+    int rc = ctx->world > 1 ? shard_stage_count(ctx) : stage_count(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }
@@ -647,7 +703,7 @@ int cdbg_compact(cdbg_ctx *ctx, cdbg_stats *stats) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if (ctx->stage != ST_COUNTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_compact needs cdbg_count first");
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = stage_compact(ctx);
+    int rc = ctx->world > 1 ? shard_stage_compact(ctx) : stage_compact(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }
@@ -656,7 +712,7 @@ int cdbg_link(cdbg_ctx *ctx, cdbg_stats *stats) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if (ctx->stage != ST_COMPACTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_link needs cdbg_compact first");
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = stage_link(ctx);
+    int rc = ctx->world > 1 ? shard_stage_link(ctx) : stage_link(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }
@@ -696,6 +752,8 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
     view->seq = ctx->h_seq; view->seq_off = ctx->h_seq_off; view->kc = ctx->h_kc;
     view->abund = ab ? ctx->h_abund : nullptr;
     view->n_links = nl; view->links = ctx->h_links; view->link_off = ctx->h_link_off;
+    view->first_unitig = ctx->world > 1 ? ctx->u_first : 0;
+    view->n_unitigs_total = ctx->world > 1 ? ctx->U_total : U;
     return CDBG_OK;
 }
 
@@ -738,6 +796,28 @@ int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint
     if (total) LAUNCH(synth_reads_kernel, grid_for(ctx, total, 256, 16), 256, 0, ctx->d_synth, genome_len, read_len, n_reads, err_ppm, seed);
     CK(cudaStreamSynchronize(ctx->stream));
     *d_bytes = ctx->d_synth; *n_bytes = total;
+    return CDBG_OK;
+}
+
+int cdbg_nccl_unique_id(uint8_t *out128) {
+    if (!out128) return CDBG_ERR_PARAM;
+    if (!g_nccl.load()) return CDBG_ERR_NCCL;
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return CDBG_ERR_NCCL;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return CDBG_OK;
+}
+
+int cdbg_shard_init(cdbg_ctx *ctx, const uint8_t *id128) {
+    if (!ctx || !ctx->stream || !id128) return CDBG_ERR_PARAM;
+    if (ctx->world <= 1) return ctx->fail(CDBG_ERR_STATE, "cdbg_shard_init on a context created with world_size <= 1");
+    if (ctx->comm) return CDBG_OK;
+    if (!g_nccl.load()) return ctx->fail(CDBG_ERR_NCCL, "%s", g_nccl.error);
+    CK(cudaSetDevice(ctx->prm.device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NK(ncclCommInitRank(&ctx->comm, ctx->world, id, ctx->rank));
     return CDBG_OK;
 }
 

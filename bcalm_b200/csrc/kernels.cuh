@@ -520,20 +520,23 @@ __global__ void __launch_bounds__(256) k5_resolve(JoinTable T, uint32_t cap, uin
 }
 
 // ------------------------------------------------------------------------------------------------ K6: list ranking
+#define K6_DONE 0x80000000u                                   // bit 31 of the hop count: nothing left to do for this element
+#define K6_NIL 0xFFFFFFFFu                                    // next of a tail
+#define K6_TAIL (((uint64_t)K6_NIL << 32) | K6_DONE)          // a tail: next = NIL, 0 hops, done
 //
 // Directed element x (0 <= x < 2S) = "traverse k-mer x>>1 entering through end x&1 (0 = left, 1 = right)"; it leaves through
-// end x^1, so succ(x) = link[x^1].  pair[x] = (next << 32 | hops to next); a traversal's last element points to itself.
+// end x^1, so succ(x) = link[x^1].  pair[x] = (next << 32 | hops to next); a traversal's last element (the tail) has next = NIL.
+// (A self-pointer must NOT mean "tail": on a cycle whose length is a power of two, doubling lands an element on itself.)
 // Updates are in place and asynchronous: each pair is read/written as one 64-bit word and the invariant
 // "hops = distance from x to next along the list" holds at all times, so any interleaving converges.
 
 __global__ void __launch_bounds__(256) k6_init(const uint32_t *__restrict__ link, uint64_t *pair, uint64_t n2) {
     for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t s = link[x ^ 1];
-        pair[x] = s == NOLINK ? ((uint64_t)x << 32) : (((uint64_t)s << 32) | 1u);
+        pair[x] = s == NOLINK ? K6_TAIL : (((uint64_t)s << 32) | 1u);
     }
 }
 
-#define K6_DONE 0x80000000u   // bit 31 of the hop count: "next is the tail", nothing left to do for this element
 
 __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsigned long long *n_updated) {
     unsigned long long upd = 0;
@@ -541,10 +544,9 @@ __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsi
         uint64_t p = ld_volatile_u64(&pair[x]);
         if ((uint32_t)p & K6_DONE) continue;
         uint32_t n = (uint32_t)(p >> 32);
-        if (n == (uint32_t)x) { *(volatile uint64_t *)&pair[x] = p | K6_DONE; continue; }      // tail
         uint64_t q = ld_volatile_u64(&pair[n]);
         uint32_t n2_ = (uint32_t)(q >> 32);
-        if (n2_ == n) { *(volatile uint64_t *)&pair[x] = p | K6_DONE; continue; }              // already points at the tail
+        if (n2_ == K6_NIL) { *(volatile uint64_t *)&pair[x] = p | K6_DONE; continue; }        // next is the tail: finished
         *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p + (uint32_t)q) & ~K6_DONE);
         upd++;
     }
@@ -559,8 +561,7 @@ __device__ __forceinline__ bool k6_unfinished(const uint64_t *pair, uint64_t x) 
     uint64_t p = pair[x];
     if ((uint32_t)p & K6_DONE) return false;
     uint32_t n = (uint32_t)(p >> 32);
-    if (n == (uint32_t)x) return false;
-    return (uint32_t)(pair[n] >> 32) != n;
+    return (uint32_t)(pair[n] >> 32) != K6_NIL;
 }
 
 __global__ void __launch_bounds__(256) k6_cycle_mark(const uint64_t *pair, const uint32_t *link, uint64_t n2, uint8_t *flag,
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(256) k6_reinit_flagged(const uint8_t *flag, co
     for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
         if (!flag[x]) continue;
         uint32_t s = link[x ^ 1];
-        pair[x] = s == NOLINK ? ((uint64_t)x << 32) : (((uint64_t)s << 32) | 1u);
+        pair[x] = s == NOLINK ? K6_TAIL : (((uint64_t)s << 32) | 1u);
     }
 }
 
@@ -614,7 +615,8 @@ __global__ void __launch_bounds__(256) k6_finalize(const uint64_t *__restrict__ 
                                                    uint32_t *head_nt) {
     for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < S; v += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t p0 = pair[2 * v], p1 = pair[2 * v + 1];
-        uint32_t T0 = (uint32_t)(p0 >> 32) ^ 1u, T1 = (uint32_t)(p1 >> 32) ^ 1u;
+        uint32_t n0 = (uint32_t)(p0 >> 32), n1 = (uint32_t)(p1 >> 32);
+        uint32_t T0 = (n0 == K6_NIL ? (uint32_t)(2 * v) : n0) ^ 1u, T1 = (n1 == K6_NIL ? (uint32_t)(2 * v + 1) : n1) ^ 1u;
         uint32_t d0 = (uint32_t)p0 & ~K6_DONE, d1 = (uint32_t)p1 & ~K6_DONE;
         uint32_t B, pos, rev;
         if (T1 < T0) { B = T1; pos = d1; rev = 0; } else { B = T0; pos = d0; rev = 1; }
@@ -689,6 +691,9 @@ struct SpellParams {
     unsigned long long *kc;        // [U]
     uint32_t *abund;               // [S] or null
     uint32_t *unitig_of_kmer;      // [S] (for K9)
+    const uint32_t *link;          // [2S] local links (only read when the terminus arrays are requested)
+    uint32_t *term_begin;          // [U] or null: k-mer end at which each unit begins
+    uint32_t *term_end;            // [U] or null: k-mer end at which it ends
 };
 
 __global__ void __launch_bounds__(256) k8_spell(SpellParams p) {
@@ -700,6 +705,11 @@ __global__ void __launch_bounds__(256) k8_spell(SpellParams p) {
         uint64_t u = p.uid_scan[h], off = p.nt_scan[h];
         uint64_t x = p.solid_kmers[v];
         if (rev) x = revcomp64(x, p.k);
+        if (p.term_begin) {
+            if (pos == 0) p.term_begin[u] = B;
+            uint32_t exit_end = 2u * (uint32_t)v + (rev ? 0u : 1u);
+            if (p.link[exit_end] == NOLINK) p.term_end[u] = exit_end;
+        }
         if (pos == 0) {
             p.seq_off[u] = off;
             for (int j = 0; j < p.k; j++) p.seq[off + j] = NT[(x >> (2 * (p.k - 1 - j))) & 3];

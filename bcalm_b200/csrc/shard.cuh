@@ -1,0 +1,609 @@
+// shard.cuh -- kernels of the minimizer-sharded multi-GPU path.
+//
+// Ownership: a canonical k-mer lives on GPU  owner(minimizer_k(x));  a junction (canonical (k-1)-mer c) is decided on GPU
+// owner(minimizer_{k-1}(c)).  minimizer = the canonical m-mer of smallest mmer_rank (kmer.cuh; the reference's structure,
+// Model.hpp:1040-1064,1254-1287, with a hash order instead of the sampled frequency order -- SURVEY N1).  Consecutive k-mers
+// of a read share their minimizer with probability ~1-2/(k-m+2), so ~90% of the graph's adjacencies stay on one GPU: each
+// GPU compacts its shard into local unitigs ("pieces", stage 2) and the cross-GPU stitching ("glue", stage 3) only sees the
+// piece ends.  Global ids: gid = rank << 32 | local end id.
+#pragma once
+#include "nccl_dyn.h"
+#include "kernels.cuh"
+
+#define GID_RANK(g) ((uint32_t)(((g) >> 32) & 0xFFu))
+#define GID_LOCAL(g) ((uint32_t)(g))
+#define GID_MASK 0x000000FFFFFFFFFFULL
+#define NOGID 0xFFFFFFFFFFFFFFFFULL
+
+static CDBG_HD uint32_t owner_of_rank(uint32_t minrank, uint32_t world) {
+    uint32_t h = minrank ^ 0x68E31DA4u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return (uint32_t)(((uint64_t)h * world) >> 32);
+}
+
+// smallest canonical m-mer rank of the n-mer x (straightforward form: used per junction record, not per read position)
+static CDBG_HD uint32_t min_rank_of(uint64_t x, int n, int m) {
+    const uint64_t mm = kmer_mask(m);
+    uint32_t best = 0xFFFFFFFFu;
+    for (int j = 0; j + m <= n; j++) {
+        uint64_t mer = (x >> (2 * (n - m - j))) & mm;
+        uint32_t r = mmer_rank((uint32_t)canonical64(mer, m));
+        best = r < best ? r : best;
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 (sharded)
+
+constexpr int K1S_THREADS = 256;
+constexpr int K1S_TILE = 4096;                              // positions per tile, lane-consecutive (16 per thread)
+constexpr int K1S_WORDS = K1S_TILE / 32 + 2;                // packed words incl. 64 halo positions
+constexpr int K1S_RANKS = K1S_TILE + 32;                    // m-mer ranks incl. halo (window <= 32)
+
+struct K1SParams {
+    const uint8_t *bytes; uint64_t n_bytes; uint64_t n_tiles;
+    int k, m; uint32_t world, P_local;                      // P = world * P_local bins, destination-major
+    unsigned long long *bin_count; const uint64_t *bin_off; unsigned long long *bin_cursor;
+    uint64_t *out_kmers;
+};
+
+__device__ __forceinline__ uint64_t funnel_left(uint64_t hi, uint64_t lo, int bits) {   // (hi:lo) << bits, top 64 bits; bits in [0, 63]
+    return bits ? (hi << bits) | (lo >> (64 - bits)) : hi;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t P = p.world * p.P_local;
+    uint64_t *s_pk = reinterpret_cast<uint64_t *>(smem_raw);                   // [K1S_WORDS]
+    uint64_t *s_gbase = s_pk + K1S_WORDS;                                      // [P]        MODE 1
+    uint64_t *s_c = s_gbase + (MODE == 1 ? P : 0);                             // [K1S_TILE] MODE 1: stashed k-mers
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_c + (MODE == 1 ? K1S_TILE : 0));   // [K1S_WORDS]
+    uint32_t *s_R = s_vm + K1S_WORDS;                                          // [K1S_RANKS]
+    uint32_t *s_cnt = s_R + K1S_RANKS;                                         // [P]
+    uint32_t *s_cur = s_cnt + P;                                               // [P]        MODE 1
+    uint16_t *s_b = reinterpret_cast<uint16_t *>(s_cur + (MODE == 1 ? P : 0)); // [K1S_TILE] MODE 1: stashed bins
+    const int t = threadIdx.x, k = p.k, m = p.m, w = k - m + 1;
+
+    if (MODE == 0) { for (uint32_t i = t; i < P; i += K1S_THREADS) s_cnt[i] = 0; __syncthreads(); }
+
+    for (uint64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint64_t tile_start = tile * (uint64_t)K1S_TILE;
+        if (t < K1S_WORDS) { uint64_t pk; uint32_t vm; load_pack32(p.bytes, p.n_bytes, tile_start + (uint64_t)t * 32, pk, vm); s_pk[t] = pk; s_vm[t] = vm; }
+        if (MODE == 1) for (uint32_t i = t; i < P; i += K1S_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        // ranks of the canonical m-mers starting at every position of the tile (+ halo)
+        for (int q = t; q < K1S_RANKS; q += K1S_THREADS) {
+            int wi = q >> 5, o = q & 31;
+            uint64_t mf = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * m);
+            s_R[q] = mmer_rank((uint32_t)canonical64(mf, m));
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < K1S_TILE / K1S_THREADS; j++) {
+            const int q = t + j * K1S_THREADS;
+            const int wi = q >> 5, o = q & 31;
+            const uint64_t V = (((uint64_t)s_vm[wi] << 32) | s_vm[wi + 1]) << o;
+            const bool valid = ((~V) >> (64 - k)) == 0;
+            uint64_t c = EMPTY_KEY; uint32_t bin = 0;
+            if (valid) {
+                uint64_t fwd = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * k);
+                uint64_t rc = revcomp64(fwd, k);
+                c = fwd < rc ? fwd : rc;
+                uint32_t mr = 0xFFFFFFFFu;
+                for (int d = 0; d < w; d++) mr = min(mr, s_R[q + d]);
+                bin = owner_of_rank(mr, p.world) * p.P_local + hash_to_bin(mix64(c), p.P_local);
+                atomicAdd(&s_cnt[bin], 1u);
+            }
+            if (MODE == 1) { s_c[q] = c; s_b[q] = (uint16_t)bin; }
+        }
+        __syncthreads();
+        if (MODE == 1) {
+            for (uint32_t b = t; b < P; b += K1S_THREADS) {
+                uint32_t cn = s_cnt[b];
+                if (cn) s_gbase[b] = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], (unsigned long long)cn);
+                s_cur[b] = 0;
+            }
+            __syncthreads();
+            for (int j = 0; j < K1S_TILE / K1S_THREADS; j++) {
+                const int q = t + j * K1S_THREADS;
+                uint64_t c = s_c[q];
+                if (c == EMPTY_KEY) continue;
+                uint32_t b = s_b[q];
+                p.out_kmers[s_gbase[b] + atomicAdd(&s_cur[b], 1u)] = c;
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (uint32_t i = t; i < P; i += K1S_THREADS) { uint32_t cn = s_cnt[i]; if (cn) atomicAdd(&p.bin_count[i], (unsigned long long)cn); }
+    }
+}
+
+static inline size_t k1s_smem_bytes(int mode, uint32_t P) {
+    size_t s = (size_t)K1S_WORDS * 8 + (size_t)K1S_WORDS * 4 + (size_t)K1S_RANKS * 4 + (size_t)P * 4;
+    if (mode == 1) s += (size_t)P * 8 + (size_t)K1S_TILE * 8 + (size_t)P * 4 + (size_t)K1S_TILE * 2;
+    return s + 32;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-run views
+
+// A bin received from `world` sources is a set of runs inside the receive buffer.
+constexpr int MAX_WORLD = 16;
+struct Runs {
+    uint64_t off[MAX_WORLD];     // start of each run (elements)
+    uint64_t pre[MAX_WORLD + 1]; // exclusive prefix of run lengths
+    int n;
+};
+__device__ __forceinline__ uint64_t runs_index(const Runs &r, uint64_t i) {
+    int s = 0;
+#pragma unroll
+    for (int j = 1; j < MAX_WORLD; j++) if (j < r.n && i >= r.pre[j]) s = j;
+    return r.off[s] + (i - r.pre[s]);
+}
+
+__global__ void __launch_bounds__(256) k2s_insert(const uint64_t *__restrict__ kmers, Runs runs, uint64_t *keys, uint32_t *counts, uint32_t cap,
+                                                  int *overflow) {
+    const uint64_t n = runs.pre[runs.n];
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = kmers[runs_index(runs, i)];
+        uint32_t slot = table_slot(key, cap), probes = 0;
+        for (;;) {
+            uint64_t cur = ld_volatile_u64(&keys[slot]);
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (cur == EMPTY_KEY) cur = key;
+            }
+            if (cur == key) { atomicAdd(&counts[slot], 1u); break; }
+            slot = slot + 1 == cap ? 0 : slot + 1;
+            if (++probes > cap) { *overflow = 1; break; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3 (sharded)
+
+// record value: bits 39..0 = gid of the k-mer end, bit 62 = side OUT, bit 63 = palindrome
+#define SREC_SIDE_OUT (1ULL << 62)
+#define SREC_PALIN (1ULL << 63)
+
+struct K3SParams {
+    const uint64_t *solid_kmers; uint64_t n_solid; int k, m; uint32_t rank, world, P_local;
+    unsigned long long *bin_count; const uint64_t *bin_off; unsigned long long *bin_cursor;
+    uint64_t *rec_key, *rec_val;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(K3_THREADS) k3s_ends(K3SParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t P = p.world * p.P_local;
+    uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? P : 0));
+    const int t = threadIdx.x;
+    const uint64_t n_tiles = (p.n_solid + K3_TILE - 1) / K3_TILE;
+    for (uint32_t i = t; i < P; i += K3_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint64_t key[2 * K3_PER_THREAD], val[2 * K3_PER_THREAD];
+        uint32_t bin[2 * K3_PER_THREAD], rnk[2 * K3_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < K3_PER_THREAD; j++) {
+            uint64_t i = tile * K3_TILE + (uint64_t)j * K3_THREADS + t;
+            bool ok = i < p.n_solid;
+            uint64_t x = ok ? p.solid_kmers[i] : 0;
+#pragma unroll
+            for (int end = 0; end < 2; end++) {
+                const int r = 2 * j + end;
+                uint64_t v;
+                kmer_end_record(x, p.k, end, (uint32_t)i, key[r], v);
+                val[r] = ((uint64_t)p.rank << 32) | (uint32_t)v | ((v & REC_SIDE_OUT) ? SREC_SIDE_OUT : 0) | ((v & REC_PALIN) ? SREC_PALIN : 0);
+                bin[r] = 0xFFFFFFFFu; rnk[r] = 0;
+                if (ok) {
+                    int mm = p.m < p.k - 1 ? p.m : p.k - 1;
+                    bin[r] = owner_of_rank(min_rank_of(key[r], p.k - 1, mm), p.world) * p.P_local + hash_to_bin(mix64(key[r]), p.P_local);
+                    rnk[r] = atomicAdd(&s_cnt[bin[r]], 1u);
+                }
+            }
+        }
+        if (MODE == 1) {
+            __syncthreads();
+            for (uint32_t b = t; b < P; b += K3_THREADS) {
+                uint32_t c = s_cnt[b];
+                if (c) s_base[b] = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], (unsigned long long)c);
+                s_cnt[b] = 0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 2 * K3_PER_THREAD; r++) {
+                if (bin[r] == 0xFFFFFFFFu) continue;
+                uint64_t pos = s_base[bin[r]] + rnk[r];
+                p.rec_key[pos] = key[r]; p.rec_val[pos] = val[r];
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (uint32_t b = t; b < P; b += K3_THREADS) { uint32_t c = s_cnt[b]; if (c) atomicAdd(&p.bin_count[b], (unsigned long long)c); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5 (sharded)
+
+struct JoinTable64 { uint64_t *keys; uint32_t *cnt; uint64_t *ids; uint32_t cap; };   // ids[cap*8]: gids, 0..3 IN, 4..7 OUT
+
+__global__ void __launch_bounds__(256) k5s_insert(const uint64_t *__restrict__ rec_key, const uint64_t *__restrict__ rec_val, Runs runs,
+                                                  JoinTable64 T, int *overflow) {
+    const uint64_t n = runs.pre[runs.n];
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t src = runs_index(runs, i);
+        const uint64_t key = rec_key[src], val = rec_val[src];
+        uint32_t slot = table_slot(key, T.cap), probes = 0;
+        for (;;) {
+            uint64_t cur = ld_volatile_u64(&T.keys[slot]);
+            if (cur == EMPTY_KEY) {
+                cur = atomicCAS((unsigned long long *)&T.keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                if (cur == EMPTY_KEY) cur = key;
+            }
+            if (cur == key) {
+                const bool pal = (val & SREC_PALIN) != 0, use_out = (val & SREC_SIDE_OUT) != 0 && !pal;
+                uint32_t old = atomicAdd(&T.cnt[slot], use_out ? 0x100u : 0x1u);
+                if (pal) atomicOr(&T.cnt[slot], 0x80000000u);
+                uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
+                if (pos < 4) T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = val & GID_MASK;
+                break;
+            }
+            slot = slot + 1 == T.cap ? 0 : slot + 1;
+            if (++probes > T.cap) { *overflow = 1; break; }
+        }
+    }
+}
+
+// Same decision rule as k5_resolve, but the results are MESSAGES because the ends may live on other GPUs:
+//   link message (a, b): "end a is compacted with end b" (emitted twice, once per direction, routed to rank(a));
+//   edge (e, f): unitig-level edge between extremities.  Two-pass warp-chunk scan like k2_emit: count, reserve once per block, write.
+__global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, ulonglong2 *link_msgs, uint64_t link_cap, unsigned long long *n_link_msgs,
+                                                   ulonglong2 *edges, uint64_t edge_cap, unsigned long long *n_edges) {
+    __shared__ uint32_t s_wl[8], s_we[8];
+    __shared__ unsigned long long s_bl, s_be;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t n_warps = gridDim.x * 8;
+    const uint32_t per_warp = ((cap + n_warps - 1) / n_warps + 31u) & ~31u;
+    const uint32_t gw = blockIdx.x * 8 + warp;
+    const uint32_t wb = (uint32_t)min((uint64_t)cap, (uint64_t)gw * per_warp), we = (uint32_t)min((uint64_t)cap, (uint64_t)wb + per_warp);
+    auto classify = [&](uint32_t i, uint32_t &nin, uint32_t &nout, bool &pal, bool &compact) {
+        uint32_t c = T.cnt[i];
+        nin = min(c & 0xFFu, 4u); nout = min((c >> 8) & 0xFFu, 4u); pal = (c >> 31) != 0;
+        compact = !pal && nin == 1 && nout == 1 && (T.ids[(size_t)i * 8] >> 1) != (T.ids[(size_t)i * 8 + 4] >> 1);
+    };
+    uint32_t my_l = 0, my_e = 0;
+    for (uint32_t i = wb + lane; i < we; i += 32) {
+        if (T.keys[i] == EMPTY_KEY) continue;
+        uint32_t nin, nout; bool pal, compact;
+        classify(i, nin, nout, pal, compact);
+        if (compact) my_l += 2; else my_e += pal ? nin * nin : 2 * nin * nout;
+    }
+    uint32_t wl = my_l, wed = my_e;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { wl += __shfl_xor_sync(0xFFFFFFFFu, wl, d); wed += __shfl_xor_sync(0xFFFFFFFFu, wed, d); }
+    if (lane == 0) { s_wl[warp] = wl; s_we[warp] = wed; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tl = 0, te = 0;
+        for (int x = 0; x < 8; x++) { uint32_t a = s_wl[x]; s_wl[x] = tl; tl += a; uint32_t b = s_we[x]; s_we[x] = te; te += b; }
+        s_bl = tl ? atomicAdd(n_link_msgs, (unsigned long long)tl) : 0ULL;
+        s_be = te ? atomicAdd(n_edges, (unsigned long long)te) : 0ULL;
+    }
+    __syncthreads();
+    // lane-exclusive offsets inside the warp
+    uint32_t xl = my_l, xe = my_e;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xFFFFFFFFu, xl, d), b = __shfl_up_sync(0xFFFFFFFFu, xe, d); if ((int)lane >= d) { xl += a; xe += b; } }
+    uint64_t ol = s_bl + s_wl[warp] + xl - my_l, oe = s_be + s_we[warp] + xe - my_e;
+    for (uint32_t i = wb + lane; i < we; i += 32) {
+        if (T.keys[i] == EMPTY_KEY) continue;
+        uint32_t nin, nout; bool pal, compact;
+        classify(i, nin, nout, pal, compact);
+        const uint64_t *ids = &T.ids[(size_t)i * 8];
+        if (compact) {
+            uint64_t a = ids[0], b = ids[4];
+            if (ol + 2 <= link_cap) { link_msgs[ol] = make_ulonglong2(a, b); link_msgs[ol + 1] = make_ulonglong2(b, a); }
+            ol += 2;
+        } else if (pal) {
+            for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nin; b++) { if (oe < edge_cap) edges[oe] = make_ulonglong2(ids[a], ids[b]); oe++; }
+        } else {
+            for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nout; b++) {
+                if (oe + 2 <= edge_cap) { edges[oe] = make_ulonglong2(ids[a], ids[4 + b]); edges[oe + 1] = make_ulonglong2(ids[4 + b], ids[a]); }
+                oe += 2;
+            }
+        }
+        T.keys[i] = EMPTY_KEY; T.cnt[i] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ generic routing of 16-byte records
+
+// destination = rank field of rec.x (bits 39..32)
+__global__ void __launch_bounds__(256) route_hist(const ulonglong2 *__restrict__ recs, uint64_t n, uint32_t world, unsigned long long *count) {
+    __shared__ uint32_t s_c[MAX_WORLD];
+    if (threadIdx.x < MAX_WORLD) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_c[GID_RANK(recs[i].x)], 1u);
+    __syncthreads();
+    if (threadIdx.x < world && s_c[threadIdx.x]) atomicAdd(&count[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) route_scatter(const ulonglong2 *__restrict__ recs, uint64_t n, uint32_t world, const uint64_t *__restrict__ off,
+                                                     unsigned long long *cursor, ulonglong2 *out) {
+    __shared__ uint32_t s_c[MAX_WORLD];
+    __shared__ uint64_t s_base[MAX_WORLD];
+    const uint64_t per_iter = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t iters = (n + per_iter - 1) / per_iter;
+    for (uint64_t it = 0; it < iters; it++) {
+        uint64_t i = it * per_iter + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        if (threadIdx.x < MAX_WORLD) s_c[threadIdx.x] = 0;
+        __syncthreads();
+        ulonglong2 r = make_ulonglong2(0, 0); uint32_t d = 0, rk = 0; bool ok = i < n;
+        if (ok) { r = recs[i]; d = GID_RANK(r.x); rk = atomicAdd(&s_c[d], 1u); }
+        __syncthreads();
+        if (threadIdx.x < world && s_c[threadIdx.x]) s_base[threadIdx.x] = off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
+        __syncthreads();
+        if (ok) out[s_base[d] + rk] = r;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stage 2 on a shard
+
+// apply link messages (a, b): link64[a.local] = b
+__global__ void __launch_bounds__(256) shard_apply_links(const ulonglong2 *__restrict__ msgs, uint64_t n, uint64_t *link64) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 m = msgs[i];
+        link64[GID_LOCAL(m.x)] = m.y;
+    }
+}
+
+// local view of the links: partners on other GPUs are chain ends for the local ranking
+__global__ void __launch_bounds__(256) shard_local_links(const uint64_t *__restrict__ link64, uint64_t n2, uint32_t rank, uint32_t *link32) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t g = link64[i];
+        link32[i] = (g != NOGID && GID_RANK(g) == rank) ? GID_LOCAL(g) : NOLINK;
+    }
+}
+
+// after local cycle cutting link32 lost some links: mirror that in link64 (a locally cut link must not become a glue link)
+__global__ void __launch_bounds__(256) shard_sync_cut(const uint32_t *__restrict__ link32, uint64_t n2, uint32_t rank, uint64_t *link64) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t g = link64[i];
+        if (g != NOGID && GID_RANK(g) == rank && link32[i] == NOLINK) link64[i] = NOGID;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stage 3: glue of pieces
+
+// piece descriptor exchanged between GPUs (7 x u64)
+struct PieceDesc {
+    uint64_t nbr[2];     // neighbour piece terminus: (global piece id << 1 | terminus), NOGID if none   [0] = at BEGIN, [1] = at END
+    uint64_t term[2];    // gid of the k-mer end at the piece BEGIN / END
+    uint64_t nk;         // k-mers in the piece
+    uint64_t kc;         // abundance sum
+    uint64_t seq_off;    // offset of the piece string in its GPU's piece buffer
+};
+
+// per local piece: termini gids, sizes; neighbour messages for termini with a remote partner
+__global__ void __launch_bounds__(256) glue_describe(uint64_t n_pieces, uint32_t rank, uint64_t piece_base, const uint32_t *__restrict__ term_begin,
+                                                     const uint32_t *__restrict__ term_end, const uint64_t *__restrict__ link64,
+                                                     const uint64_t *__restrict__ seq_off, const unsigned long long *__restrict__ kc, int k,
+                                                     PieceDesc *desc, ulonglong2 *msgs, unsigned long long *n_msgs) {
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n_pieces; q += (uint64_t)gridDim.x * blockDim.x) {
+        PieceDesc d;
+        uint32_t e0 = term_begin[q], e1 = term_end[q];
+        d.term[0] = ((uint64_t)rank << 32) | e0; d.term[1] = ((uint64_t)rank << 32) | e1;
+        d.nbr[0] = d.nbr[1] = NOGID;
+        d.nk = seq_off[q + 1] - seq_off[q] - (uint64_t)(k - 1);
+        d.kc = kc[q]; d.seq_off = seq_off[q];
+        desc[q] = d;
+        uint64_t g0 = link64[e0], g1 = link64[e1];
+        if (g0 != NOGID) { uint64_t pos = atomicAdd(n_msgs, 1ULL); msgs[pos] = make_ulonglong2(g0, ((piece_base + q) << 1) | 0); }
+        if (g1 != NOGID) { uint64_t pos = atomicAdd(n_msgs, 1ULL); msgs[pos] = make_ulonglong2(g1, ((piece_base + q) << 1) | 1); }
+    }
+}
+
+// message (f, their piece terminus): my end f (a terminus of one of my pieces) is glued to that terminus
+__global__ void __launch_bounds__(256) glue_apply_nbr(const ulonglong2 *__restrict__ msgs, uint64_t n, const uint64_t *__restrict__ info,
+                                                      const uint32_t *__restrict__ unitig_of_kmer, PieceDesc *desc) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 m = msgs[i];
+        uint32_t f = GID_LOCAL(m.x);
+        uint32_t q = unitig_of_kmer[f >> 1];
+        int t = ((uint32_t)(info[f >> 1] >> 32) == f) ? 0 : 1;
+        desc[q].nbr[t] = m.y;
+    }
+}
+
+// dense global piece tables from the padded all-gather; plink = piece-terminus links for the replicated ranking
+__global__ void __launch_bounds__(256) glue_build(const PieceDesc *__restrict__ gathered, uint64_t max_p, uint32_t world, const uint64_t *__restrict__ piece_base,
+                                                  uint64_t G, uint32_t *plink, uint32_t *weight) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < G; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r = 0;
+        for (uint32_t j = 1; j < world; j++) if (g >= piece_base[j]) r = j;
+        const PieceDesc &d = gathered[(uint64_t)r * max_p + (g - piece_base[r])];
+        plink[2 * g] = d.nbr[0] == NOGID ? NOLINK : (uint32_t)d.nbr[0];
+        plink[2 * g + 1] = d.nbr[1] == NOGID ? NOLINK : (uint32_t)d.nbr[1];
+        weight[g] = (uint32_t)d.nk;
+    }
+}
+
+__device__ __forceinline__ const PieceDesc &piece_desc(const PieceDesc *gathered, uint64_t max_p, uint32_t world, const uint64_t *piece_base, uint64_t g,
+                                                       uint32_t &r) {
+    r = 0;
+    for (uint32_t j = 1; j < world; j++) if (g >= piece_base[j]) r = j;
+    return gathered[(uint64_t)r * max_p + (g - piece_base[r])];
+}
+
+// weighted variants of the ranking kernels: an element's hop count is the number of k-mers of the pieces AFTER it
+__global__ void __launch_bounds__(256) k6w_init(const uint32_t *__restrict__ link, const uint32_t *__restrict__ weight, uint64_t *pair, uint64_t n2) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t s = link[x ^ 1];
+        pair[x] = s == NOLINK ? K6_TAIL : (((uint64_t)s << 32) | weight[s >> 1]);
+    }
+}
+__global__ void __launch_bounds__(256) k6w_reinit_flagged(const uint8_t *flag, const uint32_t *link, const uint32_t *weight, uint64_t *pair, uint64_t n2) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!flag[x]) continue;
+        uint32_t s = link[x ^ 1];
+        pair[x] = s == NOLINK ? K6_TAIL : (((uint64_t)s << 32) | weight[s >> 1]);
+    }
+}
+// info[g] = (start terminus << 32) | k-mer offset << 1 | reversed ; heads publish the unitig length in nt
+__global__ void __launch_bounds__(256) k6w_finalize(const uint64_t *__restrict__ pair, const uint32_t *__restrict__ weight, uint64_t G, int k, uint64_t *info,
+                                                    uint32_t *head_flag, uint32_t *head_nt) {
+    for (uint64_t v = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; v < G; v += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t p0 = pair[2 * v], p1 = pair[2 * v + 1];
+        uint32_t n0 = (uint32_t)(p0 >> 32), n1 = (uint32_t)(p1 >> 32);
+        uint32_t T0 = (n0 == K6_NIL ? (uint32_t)(2 * v) : n0) ^ 1u, T1 = (n1 == K6_NIL ? (uint32_t)(2 * v + 1) : n1) ^ 1u;
+        uint32_t d0 = (uint32_t)p0 & ~K6_DONE, d1 = (uint32_t)p1 & ~K6_DONE;
+        uint32_t B, pos, rev;
+        if (T1 < T0) { B = T1; pos = d1; rev = 0; } else { B = T0; pos = d0; rev = 1; }
+        info[v] = ((uint64_t)B << 32) | ((uint64_t)pos << 1) | rev;
+        bool head = pos == 0;
+        head_flag[v] = head;
+        head_nt[v] = head ? (d0 + d1 + weight[v] + (uint32_t)(k - 1)) : 0;
+    }
+}
+
+// per piece: unitig id; accumulate unitig KC
+__global__ void __launch_bounds__(256) glue_unitig_of_piece(const uint64_t *__restrict__ pinfo, const uint64_t *__restrict__ uid_scan, uint64_t G,
+                                                            const PieceDesc *__restrict__ gathered, uint64_t max_p, uint32_t world,
+                                                            const uint64_t *__restrict__ piece_base, uint32_t *unitig_of_piece, unsigned long long *kc) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < G; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t B = (uint32_t)(pinfo[g] >> 32);
+        uint32_t u = (uint32_t)uid_scan[B >> 1];
+        unitig_of_piece[g] = u;
+        uint32_t r;
+        const PieceDesc &d = piece_desc(gathered, max_p, world, piece_base, g, r);
+        atomicAdd(&kc[u], (unsigned long long)d.kc);
+    }
+}
+
+// assemble the unitigs this GPU owns (global ids [u_first, u_last)) from the all-gathered piece strings: one warp per piece
+__global__ void __launch_bounds__(256) glue_assemble(uint64_t G, const uint64_t *__restrict__ pinfo, const uint32_t *__restrict__ unitig_of_piece,
+                                                     const uint64_t *__restrict__ nt_scan /*by head piece*/, const PieceDesc *__restrict__ gathered,
+                                                     uint64_t max_p, uint32_t world, const uint64_t *__restrict__ piece_base,
+                                                     const char *__restrict__ all_seq, uint64_t max_nt, uint32_t u_first, uint32_t u_last,
+                                                     uint64_t nt_first, int k, char *seq, uint64_t *seq_off) {
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = lane_id();
+    for (uint64_t g = warp; g < G; g += n_warps) {
+        uint32_t u = unitig_of_piece[g];
+        if (u < u_first || u >= u_last) continue;
+        uint64_t inf = pinfo[g];
+        uint32_t B = (uint32_t)(inf >> 32), pos = (uint32_t)inf >> 1, rev = (uint32_t)inf & 1u;
+        uint32_t r;
+        const PieceDesc &d = piece_desc(gathered, max_p, world, piece_base, g, r);
+        const char *src = all_seq + (uint64_t)r * max_nt + d.seq_off;
+        const uint64_t len = d.nk + (uint64_t)(k - 1);
+        const uint64_t uoff = nt_scan[B >> 1] - nt_first;
+        char *dst = seq + uoff + pos;
+        if (pos == 0 && lane == 0) seq_off[u - u_first] = uoff;
+        for (uint64_t j = lane; j < len; j += 32) {
+            char c = rev ? src[len - 1 - j] : src[j];
+            if (rev) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'A';
+            dst[j] = c;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stage 4 on shards
+
+// edge (e, f) on rank(e): replace e by (unitig(e), is_begin) -> record (f, ue << 1 | e_begin), routed to rank(f) next
+__device__ __forceinline__ void end_to_unitig(uint32_t e, const uint64_t *info, const uint32_t *unitig_of_kmer, uint64_t piece_base_me,
+                                              const uint64_t *pinfo, const uint32_t *unitig_of_piece, uint32_t &u, bool &is_begin) {
+    uint32_t q = unitig_of_kmer[e >> 1];                       // local piece
+    bool piece_begin = (uint32_t)(info[e >> 1] >> 32) == e;    // e is the BEGIN terminus of its piece
+    uint64_t g = piece_base_me + q;
+    uint64_t inf = pinfo[g];
+    uint32_t rev = (uint32_t)inf & 1u;
+    u = unitig_of_piece[g];
+    is_begin = piece_begin != (rev != 0);                      // a reversed piece swaps its termini
+}
+
+__global__ void __launch_bounds__(256) links_annotate_from(ulonglong2 *edges, uint64_t n, const uint64_t *__restrict__ info,
+                                                           const uint32_t *__restrict__ unitig_of_kmer, uint64_t piece_base_me,
+                                                           const uint64_t *__restrict__ pinfo, const uint32_t *__restrict__ unitig_of_piece) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 ed = edges[i];
+        uint32_t u; bool b;
+        end_to_unitig(GID_LOCAL(ed.x), info, unitig_of_kmer, piece_base_me, pinfo, unitig_of_piece, u, b);
+        edges[i] = make_ulonglong2(ed.y, ((uint64_t)u << 1) | (b ? 1 : 0));
+    }
+}
+
+// record (f, ue<<1|e_begin) on rank(f) -> (owner(ue) << 32 | ue,  uf | from_sign << 32 | to_sign << 40)
+__global__ void __launch_bounds__(256) links_annotate_to(ulonglong2 *recs, uint64_t n, const uint64_t *__restrict__ info,
+                                                         const uint32_t *__restrict__ unitig_of_kmer, uint64_t piece_base_me,
+                                                         const uint64_t *__restrict__ pinfo, const uint32_t *__restrict__ unitig_of_piece,
+                                                         uint64_t U_total, uint32_t world) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 r = recs[i];
+        uint32_t uf; bool fb;
+        end_to_unitig(GID_LOCAL(r.x), info, unitig_of_kmer, piece_base_me, pinfo, unitig_of_piece, uf, fb);
+        uint32_t ue = (uint32_t)(r.y >> 1); bool eb = (r.y & 1) != 0;
+        uint64_t owner = ((uint64_t)ue * world) / U_total;
+        uint64_t fs = eb ? '-' : '+', ts = fb ? '+' : '-';
+        recs[i] = make_ulonglong2((owner << 32) | ue, (uint64_t)uf | (fs << 32) | (ts << 40));
+    }
+}
+
+__global__ void __launch_bounds__(256) links_finalize(const ulonglong2 *__restrict__ recs, uint64_t n, uint32_t u_first, LinkRec *out, uint32_t *per_unitig) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        ulonglong2 r = recs[i];
+        LinkRec l;
+        l.from = (uint32_t)r.x; l.to = (uint32_t)r.y; l.from_sign = (uint8_t)(r.y >> 32); l.to_sign = (uint8_t)(r.y >> 40); l.pad0 = l.pad1 = 0;
+        out[i] = l;
+        atomicAdd(&per_unitig[l.from - u_first], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) links_group(const LinkRec *__restrict__ in, uint64_t n, uint32_t u_first, const uint64_t *__restrict__ link_off,
+                                                   uint32_t *cursor, LinkRec *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        LinkRec r = in[i];
+        uint32_t lu = r.from - u_first;
+        out[link_off[lu] + atomicAdd(&cursor[lu], 1u)] = r;
+    }
+}
+
+// nucleotide offset of every unitig (indexed by unitig id) from the scans indexed by head piece
+__global__ void __launch_bounds__(256) glue_unitig_offsets(const uint64_t *__restrict__ pinfo, const uint64_t *__restrict__ uid_scan,
+                                                           const uint64_t *__restrict__ nt_scan, uint64_t G, uint64_t *unt_off) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < G; g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t inf = pinfo[g];
+        if (((uint32_t)inf >> 1) == 0) unt_off[uid_scan[g]] = nt_scan[g];    // head piece (offset 0)
+    }
+}
+
+// edges of locally cut cycles are packed local end ids: make them (gid, gid)
+__global__ void __launch_bounds__(256) shard_local_edges_to_gid(const uint64_t *__restrict__ edges, uint64_t n, uint32_t rank, ulonglong2 *out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t e = edges[i];
+        out[i] = make_ulonglong2(((uint64_t)rank << 32) | (e >> 32), ((uint64_t)rank << 32) | (uint32_t)e);
+    }
+}
+
+// piece-level cycle cuts produce edges between piece termini: translate to k-mer end gids
+__global__ void __launch_bounds__(256) glue_cut_edges(const uint64_t *__restrict__ pedges, uint64_t n, const PieceDesc *__restrict__ gathered, uint64_t max_p,
+                                                      uint32_t world, const uint64_t *__restrict__ piece_base, uint32_t rank, ulonglong2 *edges,
+                                                      uint64_t edge_cap, unsigned long long *n_edges) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t pe = pedges[i];
+        uint32_t a = (uint32_t)(pe >> 32), b = (uint32_t)pe, ra, rb;
+        uint64_t ga = piece_desc(gathered, max_p, world, piece_base, a >> 1, ra).term[a & 1];
+        uint64_t gb = piece_desc(gathered, max_p, world, piece_base, b >> 1, rb).term[b & 1];
+        if (ra != rank) continue;                              // the GPU owning the source end records the edge
+        uint64_t pos = atomicAdd(n_edges, 1ULL);
+        if (pos < edge_cap) edges[pos] = make_ulonglong2(ga, gb);
+    }
+}

@@ -1,0 +1,478 @@
+// shard_host.inl -- host orchestration of the minimizer-sharded multi-GPU path (included by cdbg.cu inside its anonymous
+// namespace).  One context per GPU / process; every shard_* function is a COLLECTIVE: all ranks call it in the same order.
+//
+// Exchanges (NCCL grouped ncclSend/ncclRecv over NVLink, counts first via a small ncclAllGather):
+//   X1  packed canonical k-mers            -> owner(minimizer_k)            (after K1, before counting)
+//   X2  junction end records (key, value)  -> owner(minimizer_{k-1})        (after K3, before the join)
+//   X3  compaction link messages           -> owner of each k-mer end       (after K5)
+//   X4  piece-terminus neighbour messages  -> owner of the partner end      (glue)
+//   AG  piece descriptors + piece strings  -> every GPU                     (glue: replicated piece-level ranking)
+//   X5-X7 edges -> rank(from end) -> rank(to end) -> owner(from unitig)     (links)
+
+#define NK(call)                                                                                                       \
+    do {                                                                                                               \
+        ncclResult_t r_ = (call);                                                                                      \
+        if (r_ != ncclSuccess)                                                                                         \
+            return ctx->fail(CDBG_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_));      \
+    } while (0)
+
+// all-gather `count` u64 host values from every rank: h_out[r * count + i]
+int allgather_host_u64(cdbg_ctx *ctx, const uint64_t *h_in, size_t count, uint64_t *h_out) {
+    int rc;
+    uint64_t *d_in = nullptr, *d_out = nullptr;
+    if ((rc = dalloc(ctx, &d_in, count))) return rc;
+    if ((rc = dalloc(ctx, &d_out, count * ctx->world))) return rc;
+    CK(cudaMemcpyAsync(d_in, h_in, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    NK(ncclAllGather(d_in, d_out, count, ncclUint64, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(h_out, d_out, count * 8 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx, d_in); dfree(ctx, d_out);
+    return CDBG_OK;
+}
+
+// d_send holds the elements for rank 0, then rank 1, ...; send_cnt / recv_cnt are element counts per peer
+int exchange_with_counts(cdbg_ctx *ctx, const void *d_send, const uint64_t *send_cnt, const uint64_t *recv_cnt, size_t esz, void **d_recv,
+                         uint64_t *n_recv) {
+    int rc;
+    uint64_t tot = 0;
+    for (int s = 0; s < ctx->world; s++) tot += recv_cnt[s];
+    uint8_t *recv = nullptr;
+    if ((rc = dalloc(ctx, &recv, tot * esz + 16))) return rc;
+    NK(ncclGroupStart());
+    uint64_t so = 0, ro = 0;
+    for (int peer = 0; peer < ctx->world; peer++) {
+        if (send_cnt[peer]) NK(ncclSend((const uint8_t *)d_send + so * esz, send_cnt[peer] * esz, ncclChar, peer, ctx->comm, ctx->stream));
+        if (recv_cnt[peer]) NK(ncclRecv(recv + ro * esz, recv_cnt[peer] * esz, ncclChar, peer, ctx->comm, ctx->stream));
+        so += send_cnt[peer]; ro += recv_cnt[peer];
+    }
+    NK(ncclGroupEnd());
+    *d_recv = recv; *n_recv = tot;
+    return CDBG_OK;
+}
+
+// route 16-byte records to the rank named in bits 39..32 of rec.x; returns the received records
+int route16(cdbg_ctx *ctx, const ulonglong2 *d_recs, uint64_t n, ulonglong2 **d_out, uint64_t *n_out) {
+    int rc;
+    const int W = ctx->world;
+    unsigned long long *d_cnt = nullptr, *d_cur = nullptr; uint64_t *d_off = nullptr; ulonglong2 *d_sorted = nullptr;
+    if ((rc = dalloc(ctx, &d_cnt, MAX_WORLD))) return rc;
+    if ((rc = dalloc(ctx, &d_cur, MAX_WORLD))) return rc;
+    if ((rc = dalloc(ctx, &d_off, MAX_WORLD + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_sorted, n + 1))) return rc;
+    CK(cudaMemsetAsync(d_cnt, 0, MAX_WORLD * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_cur, 0, MAX_WORLD * 8, ctx->stream));
+    uint64_t h_cnt[MAX_WORLD] = {0}, h_off[MAX_WORLD + 1] = {0};
+    if (n) {
+        LAUNCH(route_hist, grid_for(ctx, n, 256, 4), 256, 0, d_recs, n, (uint32_t)W, d_cnt);
+        CK(cudaMemcpyAsync(h_cnt, d_cnt, W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (int d = 0; d < W; d++) h_off[d + 1] = h_off[d] + h_cnt[d];
+    if (h_off[W] != n) return ctx->fail(CDBG_ERR_INTERNAL, "route16: a record names a rank outside the world");
+    if (n) {
+        CK(cudaMemcpyAsync(d_off, h_off, (W + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(route_scatter, grid_for(ctx, n, 256, 4), 256, 0, d_recs, n, (uint32_t)W, d_off, d_cur, d_sorted);
+    }
+    std::vector<uint64_t> M((size_t)W * W);
+    if ((rc = allgather_host_u64(ctx, h_cnt, W, M.data()))) return rc;
+    uint64_t recv_cnt[MAX_WORLD];
+    for (int s = 0; s < W; s++) recv_cnt[s] = M[(size_t)s * W + ctx->rank];
+    void *recv = nullptr;
+    if ((rc = exchange_with_counts(ctx, d_sorted, h_cnt, recv_cnt, 16, &recv, n_out))) return rc;
+    *d_out = (ulonglong2 *)recv;
+    dfree(ctx, d_cnt); dfree(ctx, d_cur); dfree(ctx, d_off); dfree(ctx, d_sorted);
+    return CDBG_OK;
+}
+
+inline uint32_t table_cap_for(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); }
+
+// ------------------------------------------------------------------------------------------------ stage 1 (sharded)
+
+int shard_stage_count(cdbg_ctx *ctx) {
+    const int W = ctx->world, me = ctx->rank, k = ctx->k;
+    const uint64_t n = ctx->n_bytes;
+    int rc;
+    tstart(ctx, T_COUNT);
+    // global input size -> the same number of local bins on every rank
+    uint64_t all_n[MAX_WORLD], total_bytes = 0;
+    if ((rc = allgather_host_u64(ctx, &n, 1, all_n))) return rc;
+    for (int r = 0; r < W; r++) total_bytes += all_n[r];
+    uint32_t P_local = (uint32_t)std::min<uint64_t>(K1_MAX_BINS / W, std::max<uint64_t>(1, (total_bytes / W * 4 / 5 + 2499999) / 2500000));
+    const uint32_t P = P_local * W;
+    ctx->st.n_count_bins = P_local;
+    uint64_t n_tiles = (n + K1S_TILE - 1) / K1S_TILE;
+
+    unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr; uint64_t *d_bin_off = nullptr;
+    if ((rc = dalloc(ctx, &d_bin_count, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_cursor, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_off, P + 1))) return rc;
+    CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
+    K1SParams kp{};
+    kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.m = ctx->m; kp.world = W; kp.P_local = P_local;
+    kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
+    std::vector<uint64_t> h_cnt(P, 0), h_off(P + 1, 0);
+    CK(cudaFuncSetAttribute(k1s_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(0, P)));
+    CK(cudaFuncSetAttribute(k1s_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(1, P)));
+    if (n_tiles) {
+        tstart(ctx, T_K1H);
+        LAUNCH(k1s_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 4), K1S_THREADS, k1s_smem_bytes(0, P), kp);
+        tstop(ctx, T_K1H);
+        CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t I_out = 0;
+    for (uint32_t b = 0; b < P; b++) { h_off[b] = I_out; I_out += h_cnt[b]; }
+    h_off[P] = I_out;
+    ctx->st.n_instances = I_out;
+    std::vector<uint64_t> all_cnt((size_t)W * P);
+    if ((rc = allgather_host_u64(ctx, h_cnt.data(), P, all_cnt.data()))) return rc;
+
+    uint64_t *d_send = nullptr;
+    if ((rc = dalloc(ctx, &d_send, I_out + 1))) return rc;
+    if (I_out) {
+        CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        kp.out_kmers = d_send;
+        tstart(ctx, T_K1S);
+        LAUNCH(k1s_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1S_THREADS, k1s_smem_bytes(1, P), kp);
+        tstop(ctx, T_K1S);
+    }
+    // X1: k-mers to their counting owner
+    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0}, recv_base[MAX_WORLD + 1] = {0};
+    for (int d = 0; d < W; d++) for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += h_cnt[(size_t)d * P_local + b];
+    for (int s = 0; s < W; s++) for (uint32_t b = 0; b < P_local; b++) recv_cnt[s] += all_cnt[(size_t)s * P + (size_t)me * P_local + b];
+    for (int s = 0; s < W; s++) recv_base[s + 1] = recv_base[s] + recv_cnt[s];
+    void *recv = nullptr; uint64_t I_in = 0;
+    if ((rc = exchange_with_counts(ctx, d_send, send_cnt, recv_cnt, 8, &recv, &I_in))) return rc;
+    uint64_t *d_kmers = (uint64_t *)recv;
+    dfree(ctx, d_send);
+
+    // K2 per local bin; a bin is one run per source rank
+    uint64_t max_bin = 0;
+    std::vector<uint64_t> bin_tot(P_local, 0);
+    for (uint32_t b = 0; b < P_local; b++) { for (int s = 0; s < W; s++) bin_tot[b] += all_cnt[(size_t)s * P + (size_t)me * P_local + b]; max_bin = std::max(max_bin, bin_tot[b]); }
+    uint32_t cap = table_cap_for(max_bin);
+    uint64_t *d_keys = nullptr; uint32_t *d_counts = nullptr;
+    if ((rc = dalloc(ctx, &d_keys, cap))) return rc;
+    if ((rc = dalloc(ctx, &d_counts, cap))) return rc;
+    CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
+    uint64_t solid_cap = std::max<uint64_t>(I_in <= (1ULL << 28) ? I_in : std::max<uint64_t>(I_in / 4, 1ULL << 28), 1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
+        if ((rc = ctr_zero(ctx))) return rc;
+        tstart(ctx, T_K2);
+        std::vector<uint64_t> within(W, 0);
+        for (uint32_t b = 0; b < P_local; b++) {
+            Runs runs{}; runs.n = W; runs.pre[0] = 0;
+            for (int s = 0; s < W; s++) {
+                uint64_t len = all_cnt[(size_t)s * P + (size_t)me * P_local + b];
+                runs.off[s] = recv_base[s] + within[s]; runs.pre[s + 1] = runs.pre[s] + len; within[s] += len;
+            }
+            uint64_t nb = bin_tot[b];
+            if (!nb) continue;
+            uint32_t cap_b = table_cap_for(nb);
+            LAUNCH(k2s_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers, runs, d_keys, d_counts, cap_b, ctx->d_flag);
+            LAUNCH(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers, ctx->d_solid_counts,
+                   solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
+        }
+        tstop(ctx, T_K2);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow");
+        ctx->S = ctx->h_ctr[0];
+        ctx->st.n_distinct = ctx->h_ctr[1];
+        if (ctx->S <= solid_cap) break;
+        if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "solid buffer overflow");
+        dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
+        solid_cap = ctx->S;
+    }
+    ctx->st.n_solid = ctx->S;
+    if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device: shard over more GPUs");
+    dfree(ctx, d_kmers); dfree(ctx, d_keys); dfree(ctx, d_counts);
+    dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+    tstop(ctx, T_COUNT);
+    ctx->stage = ST_COUNTED;
+    return CDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stages 2+3 (sharded)
+
+int shard_stage_compact(cdbg_ctx *ctx) {
+    const int W = ctx->world, me = ctx->rank, k = ctx->k;
+    const uint64_t S = ctx->S, n2 = 2 * S;
+    int rc;
+    tstart(ctx, T_COMPACT);
+    uint64_t all_S[MAX_WORLD], S_total = 0;
+    if ((rc = allgather_host_u64(ctx, &S, 1, all_S))) return rc;
+    for (int r = 0; r < W; r++) S_total += all_S[r];
+
+    // ---- K3: end records, destination-major bins, X2
+    uint32_t P_local = (uint32_t)std::min<uint64_t>(2048 / W, std::max<uint64_t>(1, (2 * S_total / W + 499999) / 500000));
+    const uint32_t P = P_local * W;
+    ctx->st.n_join_bins = P_local;
+    unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;
+    uint64_t *d_bin_off = nullptr, *d_key_s = nullptr, *d_val_s = nullptr;
+    if ((rc = dalloc(ctx, &d_bin_count, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_cursor, P))) return rc;
+    if ((rc = dalloc(ctx, &d_bin_off, P + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_key_s, n2 + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_val_s, n2 + 1))) return rc;
+    CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
+    K3SParams p3{};
+    p3.solid_kmers = ctx->d_solid_kmers; p3.n_solid = S; p3.k = k; p3.m = ctx->m; p3.rank = me; p3.world = W; p3.P_local = P_local;
+    p3.bin_count = d_bin_count; p3.bin_off = d_bin_off; p3.bin_cursor = d_bin_cursor; p3.rec_key = d_key_s; p3.rec_val = d_val_s;
+    std::vector<uint64_t> h_cnt(P, 0), h_off(P + 1, 0);
+    tstart(ctx, T_K3);
+    CK(cudaFuncSetAttribute(k3s_ends<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem_bytes(1, P)));
+    const int g3 = (int)std::max<uint64_t>(1, std::min<uint64_t>((S + K3_TILE - 1) / K3_TILE, (uint64_t)ctx->n_sm * 4));
+    if (S) {
+        LAUNCH(k3s_ends<0>, g3, K3_THREADS, k3_smem_bytes(0, P), p3);
+        CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint64_t acc = 0;
+    for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; }
+    h_off[P] = acc;
+    std::vector<uint64_t> all_cnt((size_t)W * P);
+    if ((rc = allgather_host_u64(ctx, h_cnt.data(), P, all_cnt.data()))) return rc;
+    if (S) {
+        CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k3s_ends<1>, g3, K3_THREADS, k3_smem_bytes(1, P), p3);
+    }
+    tstop(ctx, T_K3);
+    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0}, recv_base[MAX_WORLD + 1] = {0};
+    for (int d = 0; d < W; d++) for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += h_cnt[(size_t)d * P_local + b];
+    for (int s = 0; s < W; s++) for (uint32_t b = 0; b < P_local; b++) recv_cnt[s] += all_cnt[(size_t)s * P + (size_t)me * P_local + b];
+    for (int s = 0; s < W; s++) recv_base[s + 1] = recv_base[s] + recv_cnt[s];
+    void *rk = nullptr, *rv = nullptr; uint64_t T_in = 0, T_in2 = 0;
+    if ((rc = exchange_with_counts(ctx, d_key_s, send_cnt, recv_cnt, 8, &rk, &T_in))) return rc;
+    if ((rc = exchange_with_counts(ctx, d_val_s, send_cnt, recv_cnt, 8, &rv, &T_in2))) return rc;
+    uint64_t *d_rec_key = (uint64_t *)rk, *d_rec_val = (uint64_t *)rv;
+    dfree(ctx, d_key_s); dfree(ctx, d_val_s);
+    ctx->st.n_junction_records = T_in;
+
+    // ---- K5: per-bin join -> link messages + edges (gids)
+    uint64_t max_bin = 0;
+    std::vector<uint64_t> bin_tot(P_local, 0);
+    for (uint32_t b = 0; b < P_local; b++) { for (int s = 0; s < W; s++) bin_tot[b] += all_cnt[(size_t)s * P + (size_t)me * P_local + b]; max_bin = std::max(max_bin, bin_tot[b]); }
+    JoinTable64 T{};
+    uint32_t cap = table_cap_for(max_bin);
+    if ((rc = dalloc(ctx, &T.keys, cap))) return rc;
+    if ((rc = dalloc(ctx, &T.cnt, cap))) return rc;
+    if ((rc = dalloc(ctx, &T.ids, (size_t)cap * 8))) return rc;
+    CK(cudaMemsetAsync(T.keys, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(T.cnt, 0, (size_t)cap * 4, ctx->stream));
+    ulonglong2 *d_link_msgs = nullptr;
+    const uint64_t link_cap = T_in + 16;
+    ctx->sedge_cap = std::max<uint64_t>(T_in / 2, 1 << 16) + 4096;
+    if ((rc = dalloc(ctx, &d_link_msgs, link_cap))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_sedges, ctx->sedge_cap))) return rc;
+    if ((rc = ctr_zero(ctx))) return rc;
+    tstart(ctx, T_K5);
+    {
+        std::vector<uint64_t> within(W, 0);
+        for (uint32_t b = 0; b < P_local; b++) {
+            Runs runs{}; runs.n = W; runs.pre[0] = 0;
+            for (int s = 0; s < W; s++) {
+                uint64_t len = all_cnt[(size_t)s * P + (size_t)me * P_local + b];
+                runs.off[s] = recv_base[s] + within[s]; runs.pre[s + 1] = runs.pre[s] + len; within[s] += len;
+            }
+            uint64_t nb = bin_tot[b];
+            if (!nb) continue;
+            T.cap = table_cap_for(nb);
+            LAUNCH(k5s_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_rec_key, d_rec_val, runs, T, ctx->d_flag);
+            LAUNCH(k5s_resolve, grid_for(ctx, T.cap, 256, 8), 256, 0, T, T.cap, d_link_msgs, link_cap, ctx->d_ctr + 0, ctx->d_sedges, ctx->sedge_cap,
+                   ctx->d_ctr + 1);
+        }
+    }
+    tstop(ctx, T_K5);
+    if ((rc = ctr_read(ctx))) return rc;
+    if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K5 hash table overflow");
+    const uint64_t n_link_msgs = ctx->h_ctr[0];
+    ctx->n_sedges = ctx->h_ctr[1];
+    if (n_link_msgs > link_cap) return ctx->fail(CDBG_ERR_INTERNAL, "link message buffer overflow");
+    if (ctx->n_sedges + 2048 > ctx->sedge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow (%llu edges)", (unsigned long long)ctx->n_sedges);
+    ctx->st.n_compactions = n_link_msgs / 2;
+    dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
+    dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+
+    // ---- X3: link messages to the owners of the ends; local view of the links
+    ulonglong2 *d_msgs_in = nullptr; uint64_t n_msgs_in = 0;
+    if ((rc = route16(ctx, d_link_msgs, n_link_msgs, &d_msgs_in, &n_msgs_in))) return rc;
+    dfree(ctx, d_link_msgs);
+    if ((rc = dalloc(ctx, &ctx->d_link64, n2 + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_link, n2 + 1))) return rc;
+    CK(cudaMemsetAsync(ctx->d_link64, 0xFF, (n2 + 1) * 8, ctx->stream));
+    if (n_msgs_in) LAUNCH(shard_apply_links, grid_for(ctx, n_msgs_in, 256, 8), 256, 0, d_msgs_in, n_msgs_in, ctx->d_link64);
+    dfree(ctx, d_msgs_in);
+    CK(cudaMemsetAsync(ctx->d_link, 0xFF, (n2 + 1) * 4, ctx->stream));
+    if (n2) LAUNCH(shard_local_links, grid_for(ctx, n2, 256, 8), 256, 0, ctx->d_link64, n2, (uint32_t)me, ctx->d_link);
+
+    // ---- stage 2 proper: local ranking -> pieces (the unitigs of this shard), spelled locally
+    uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;
+    ctx->edge_cap = 1 << 16;
+    if ((rc = dalloc(ctx, &ctx->d_edges, ctx->edge_cap))) return rc;
+    ctx->n_edges = 0;
+    tstart(ctx, T_K6R);
+    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, ctx->d_edges, ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
+    if (n2) LAUNCH(shard_sync_cut, grid_for(ctx, n2, 256, 8), 256, 0, ctx->d_link, n2, (uint32_t)me, ctx->d_link64);
+    tstop(ctx, T_K6R);
+    tstart(ctx, T_K6S);
+    uint64_t Pn = 0, piece_nt = 0;
+    if ((rc = number_units(ctx, d_pair, S, nullptr, &ctx->d_info, &d_uid_scan, &d_nt_scan, &Pn, &piece_nt))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_unitig_of_kmer, S + 1))) return rc;
+    ctx->U = Pn; ctx->total_nt = piece_nt;
+    dfree(ctx, d_pair);
+    if ((rc = spell_units(ctx, d_uid_scan, d_nt_scan, true))) return rc;
+    dfree(ctx, d_uid_scan); dfree(ctx, d_nt_scan);
+    // the piece-level arrays move aside; ctx->d_seq etc. will hold the unitigs this GPU owns
+    char *d_pseq = ctx->d_seq; uint64_t *d_pseq_off = ctx->d_seq_off; unsigned long long *d_pkc = ctx->d_kc;
+    ctx->d_seq = nullptr; ctx->d_seq_off = nullptr; ctx->d_kc = nullptr;
+
+    // ---- stage 3: glue.  global piece ids, neighbour messages (X4), all-gather, replicated piece ranking
+    uint64_t all_P[MAX_WORLD], all_nt[MAX_WORLD], piece_base[MAX_WORLD + 1] = {0}, max_p = 1, max_nt = 16;
+    uint64_t mine[2] = {Pn, piece_nt}, both[2 * MAX_WORLD];
+    if ((rc = allgather_host_u64(ctx, mine, 2, both))) return rc;
+    for (int r = 0; r < W; r++) { all_P[r] = both[2 * r]; all_nt[r] = both[2 * r + 1]; piece_base[r + 1] = piece_base[r] + all_P[r]; max_p = std::max(max_p, all_P[r]); max_nt = std::max(max_nt, all_nt[r]); }
+    max_nt = (max_nt + 15) & ~15ULL;
+    const uint64_t G = piece_base[W];
+    if (G >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 pieces");
+    ctx->piece_base_me = piece_base[me];
+    PieceDesc *d_desc = nullptr, *d_desc_all = nullptr; ulonglong2 *d_nmsg = nullptr;
+    if ((rc = dalloc(ctx, &d_desc, max_p))) return rc;
+    if ((rc = dalloc(ctx, &d_desc_all, max_p * W))) return rc;
+    if ((rc = dalloc(ctx, &d_nmsg, 2 * Pn + 1))) return rc;
+    CK(cudaMemsetAsync(d_desc, 0xFF, max_p * sizeof(PieceDesc), ctx->stream));
+    if ((rc = ctr_zero(ctx))) return rc;
+    if (Pn) LAUNCH(glue_describe, grid_for(ctx, Pn, 256, 8), 256, 0, Pn, (uint32_t)me, piece_base[me], ctx->d_term_begin, ctx->d_term_end, ctx->d_link64,
+                   d_pseq_off, d_pkc, k, d_desc, d_nmsg, ctx->d_ctr + 0);
+    if ((rc = ctr_read(ctx))) return rc;
+    const uint64_t n_nmsg = ctx->h_ctr[0];
+    ulonglong2 *d_nmsg_in = nullptr; uint64_t n_nmsg_in = 0;
+    if ((rc = route16(ctx, d_nmsg, n_nmsg, &d_nmsg_in, &n_nmsg_in))) return rc;
+    if (n_nmsg_in) LAUNCH(glue_apply_nbr, grid_for(ctx, n_nmsg_in, 256, 8), 256, 0, d_nmsg_in, n_nmsg_in, ctx->d_info, ctx->d_unitig_of_kmer, d_desc);
+    dfree(ctx, d_nmsg); dfree(ctx, d_nmsg_in);
+    NK(ncclAllGather(d_desc, d_desc_all, max_p * sizeof(PieceDesc), ncclChar, ctx->comm, ctx->stream));
+    char *d_seq_all = nullptr;
+    if ((rc = dalloc(ctx, &d_seq_all, max_nt * W))) return rc;
+    {   // pad my piece strings to max_nt for the all-gather
+        char *d_pad = nullptr;
+        if ((rc = dalloc(ctx, &d_pad, max_nt))) return rc;
+        if (piece_nt) CK(cudaMemcpyAsync(d_pad, d_pseq, piece_nt, cudaMemcpyDeviceToDevice, ctx->stream));
+        NK(ncclAllGather(d_pad, d_seq_all, max_nt, ncclChar, ctx->comm, ctx->stream));
+        dfree(ctx, d_pad);
+    }
+    uint64_t *d_piece_base = nullptr; uint32_t *d_plink = nullptr, *d_weight = nullptr;
+    if ((rc = dalloc(ctx, &d_piece_base, MAX_WORLD + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_plink, 2 * G + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_weight, G + 1))) return rc;
+    CK(cudaMemcpyAsync(d_piece_base, piece_base, (W + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (G) LAUNCH(glue_build, grid_for(ctx, G, 256, 8), 256, 0, d_desc_all, max_p, (uint32_t)W, d_piece_base, G, d_plink, d_weight);
+    uint64_t *d_ppair = nullptr, *d_puid = nullptr, *d_pnt = nullptr, *d_pedges = nullptr; uint64_t n_pedges = 0;
+    const uint64_t pedge_cap = 1 << 16;
+    if ((rc = dalloc(ctx, &d_pedges, pedge_cap))) return rc;
+    if ((rc = run_ranking(ctx, d_plink, G, d_weight, d_pedges, pedge_cap, &n_pedges, &d_ppair))) return rc;
+    uint64_t U_total = 0, nt_total = 0;
+    if ((rc = number_units(ctx, d_ppair, G, d_weight, &ctx->d_pinfo, &d_puid, &d_pnt, &U_total, &nt_total))) return rc;
+    dfree(ctx, d_ppair); dfree(ctx, d_plink);
+    if (U_total >= (1ULL << 32)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^32 unitigs");
+    ctx->U_total = U_total;
+    unsigned long long *d_kc_all = nullptr;
+    if ((rc = dalloc(ctx, &ctx->d_unitig_of_piece, G + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_kc_all, U_total + 1))) return rc;
+    CK(cudaMemsetAsync(d_kc_all, 0, (U_total + 1) * 8, ctx->stream));
+    if (G) LAUNCH(glue_unitig_of_piece, grid_for(ctx, G, 256, 8), 256, 0, ctx->d_pinfo, d_puid, G, d_desc_all, max_p, (uint32_t)W, d_piece_base,
+                  ctx->d_unitig_of_piece, d_kc_all);
+
+    // ---- ownership of the final unitigs: contiguous id ranges; assemble mine from the all-gathered piece strings
+    const uint64_t u_first = ((uint64_t)me * U_total + W - 1) / W, u_last = ((uint64_t)(me + 1) * U_total + W - 1) / W;
+    ctx->u_first = u_first;
+    // nucleotide offset of a unitig = nt_scan at its head piece; find the offsets of u_first and u_last
+    uint64_t *d_unt_off = nullptr;
+    if ((rc = dalloc(ctx, &d_unt_off, U_total + 2))) return rc;
+    if (G) LAUNCH(glue_unitig_offsets, grid_for(ctx, G, 256, 8), 256, 0, ctx->d_pinfo, d_puid, d_pnt, G, d_unt_off);
+    CK(cudaMemcpyAsync(d_unt_off + U_total, &nt_total, 8, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t nt_range[2] = {0, 0};
+    CK(cudaMemcpyAsync(&nt_range[0], d_unt_off + u_first, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&nt_range[1], d_unt_off + u_last, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t U_mine = u_last - u_first, nt_mine = nt_range[1] - nt_range[0];
+    if ((rc = dalloc(ctx, &ctx->d_seq, nt_mine + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_seq_off, U_mine + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_kc, U_mine + 1))) return rc;
+    if (G && U_mine) LAUNCH(glue_assemble, grid_for(ctx, G * 32, 256, 8), 256, 0, G, ctx->d_pinfo, ctx->d_unitig_of_piece, d_pnt, d_desc_all, max_p, (uint32_t)W,
+                            d_piece_base, d_seq_all, max_nt, (uint32_t)u_first, (uint32_t)u_last, nt_range[0], k, ctx->d_seq, ctx->d_seq_off);
+    CK(cudaMemcpyAsync(ctx->d_seq_off + U_mine, &nt_mine, 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (U_mine) CK(cudaMemcpyAsync(ctx->d_kc, d_kc_all + u_first, U_mine * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // nt_mine is a stack variable
+
+    // ---- collect every edge this GPU is responsible for as (from gid, to gid): join edges are already there;
+    //      add the edges of locally cut cycles and of piece-level cut cycles
+    if (ctx->n_edges) {
+        if (ctx->n_sedges + ctx->n_edges > ctx->sedge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow");
+        LAUNCH(shard_local_edges_to_gid, grid_for(ctx, ctx->n_edges, 256, 8), 256, 0, ctx->d_edges, ctx->n_edges, (uint32_t)me, ctx->d_sedges + ctx->n_sedges);
+        ctx->n_sedges += ctx->n_edges;
+    }
+    if (n_pedges) {
+        if ((rc = ctr_zero(ctx))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_ctr + 0, &ctx->n_sedges, 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(glue_cut_edges, grid_for(ctx, n_pedges, 256, 8), 256, 0, d_pedges, n_pedges, d_desc_all, max_p, (uint32_t)W, d_piece_base, (uint32_t)me,
+               ctx->d_sedges, ctx->sedge_cap, ctx->d_ctr + 0);
+        if ((rc = ctr_read(ctx))) return rc;
+        ctx->n_sedges = ctx->h_ctr[0];
+        if (ctx->n_sedges > ctx->sedge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow");
+    }
+    dfree(ctx, d_pedges); dfree(ctx, d_desc); dfree(ctx, d_desc_all); dfree(ctx, d_seq_all); dfree(ctx, d_piece_base); dfree(ctx, d_weight);
+    dfree(ctx, d_puid); dfree(ctx, d_pnt); dfree(ctx, d_kc_all); dfree(ctx, d_unt_off);
+    dfree(ctx, d_pseq); dfree(ctx, d_pseq_off); dfree(ctx, d_pkc);
+    tstop(ctx, T_K6S);
+    ctx->n_pieces = Pn;
+    ctx->U = U_mine; ctx->total_nt = nt_mine;
+    ctx->st.n_unitigs = U_mine; ctx->st.total_nt = nt_mine;
+    tstop(ctx, T_COMPACT);
+    ctx->stage = ST_COMPACTED;
+    return CDBG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage 4 (sharded)
+
+int shard_stage_link(cdbg_ctx *ctx) {
+    int rc;
+    const int W = ctx->world;
+    tstart(ctx, T_LINK);
+    // X5: to the owner of the FROM end, which knows its unitig and whether it is a BEGIN
+    ulonglong2 *a = nullptr, *b = nullptr, *c = nullptr; uint64_t na = 0, nb = 0, nc = 0;
+    if ((rc = route16(ctx, ctx->d_sedges, ctx->n_sedges, &a, &na))) return rc;
+    if (na) LAUNCH(links_annotate_from, grid_for(ctx, na, 256, 8), 256, 0, a, na, ctx->d_info, ctx->d_unitig_of_kmer, ctx->piece_base_me, ctx->d_pinfo,
+                   ctx->d_unitig_of_piece);
+    // X6: to the owner of the TO end
+    if ((rc = route16(ctx, a, na, &b, &nb))) return rc;
+    dfree(ctx, a);
+    if (nb) LAUNCH(links_annotate_to, grid_for(ctx, nb, 256, 8), 256, 0, b, nb, ctx->d_info, ctx->d_unitig_of_kmer, ctx->piece_base_me, ctx->d_pinfo,
+                   ctx->d_unitig_of_piece, std::max<uint64_t>(ctx->U_total, 1), (uint32_t)W);
+    // X7: to the owner of the FROM unitig, grouped CSR there
+    if ((rc = route16(ctx, b, nb, &c, &nc))) return rc;
+    dfree(ctx, b);
+    const uint64_t U = ctx->U;
+    LinkRec *d_tmp = nullptr; uint32_t *d_per = nullptr, *d_cur = nullptr;
+    if ((rc = dalloc(ctx, &ctx->d_links, nc + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_link_off, U + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_tmp, nc + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_per, U + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_cur, U + 1))) return rc;
+    CK(cudaMemsetAsync(d_per, 0, (U + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_cur, 0, (U + 1) * 4, ctx->stream));
+    if (nc) LAUNCH(links_finalize, grid_for(ctx, nc, 256, 8), 256, 0, c, nc, (uint32_t)ctx->u_first, d_tmp, d_per);
+    uint64_t total = 0;
+    if ((rc = exclusive_scan(ctx, d_per, U + 1, ctx->d_link_off, &total))) return rc;
+    if (total != nc) return ctx->fail(CDBG_ERR_INTERNAL, "link grouping lost records");
+    if (nc) LAUNCH(links_group, grid_for(ctx, nc, 256, 8), 256, 0, d_tmp, nc, (uint32_t)ctx->u_first, ctx->d_link_off, d_cur, ctx->d_links);
+    dfree(ctx, c); dfree(ctx, d_tmp); dfree(ctx, d_per); dfree(ctx, d_cur);
+    tstop(ctx, T_LINK);
+    ctx->n_edges = nc;
+    ctx->st.n_links = nc;
+    ctx->stage = ST_LINKED;
+    return CDBG_OK;
+}

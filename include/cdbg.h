@@ -110,6 +110,10 @@ typedef struct {
     uint64_t n_links;
     const cdbg_link_t *links; /* grouped by `from` (CSR); order inside a group is unspecified, as in the reference */
     const uint64_t *link_off; /* [n_unitigs + 1]: links of unitig u = links[link_off[u] .. link_off[u+1]) */
+    /* sharded mode: this context returns the unitigs it owns, global ids first_unitig .. first_unitig + n_unitigs - 1
+     * (local index u <-> global id first_unitig + u); `from`/`to` in links are GLOBAL ids. Single GPU: 0 and n_unitigs. */
+    uint64_t first_unitig;
+    uint64_t n_unitigs_total;
 } cdbg_unitig_view;
 
 int cdbg_create(cdbg_ctx **out, const cdbg_params *params);
@@ -144,6 +148,14 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
  * bytes to device memory owned by the context and returns the device pointer. */
 int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t n_reads, uint32_t err_ppm,
                      uint64_t seed, uint8_t **d_bytes, uint64_t *n_bytes);
+
+/* Sharded (multi-GPU) mode: one context per GPU with params.rank / params.world_size set.  Rank 0 obtains an id with
+ * cdbg_nccl_unique_id and distributes its 128 bytes to the other ranks by any means (torch.distributed, MPI, a file);
+ * every rank then calls cdbg_shard_init (collective).  From then on cdbg_push_reads takes THIS rank's share of the reads and
+ * cdbg_count / cdbg_compact / cdbg_link / cdbg_build are collective calls: k-mers are routed to owner(minimizer) by an NCCL
+ * all-to-all, each GPU compacts its shard, and a second round of exchanges glues the shard-local unitigs and their links. */
+int cdbg_nccl_unique_id(uint8_t *out128);
+int cdbg_shard_init(cdbg_ctx *ctx, const uint8_t *id128);
 
 /* Utility: copy device memory owned by the context to a host buffer (used by tests / bench to fetch synthetic reads). */
 int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes);

@@ -111,6 +111,15 @@ def cases():
                     reads=["ACGTACGTAC", "ACGGTTACGATCGATCGATTTACG", "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNN"]))
     out.append(dict(name="palindrome_k_even", k=6, abundance_min=1, minimizer_size=5,
                     reads=["ACGCGTAAACGCGTTT", "TTAATTAATTAA", "GAATTCGAATTC"]))
+    # cycles whose length is a power of two (pointer doubling lands an element on itself: regression for the K6 tail marker)
+    rng2 = np.random.default_rng(77)
+    for L, k in [(2, 5), (4, 5), (8, 7), (16, 9), (32, 11), (64, 13), (128, 15), (256, 21), (1024, 31)]:
+        if L == 2:
+            g = "AC"            # ACACA / CACAC: a 2-cycle of k-mers
+        else:
+            g = "".join(rng2.choice(list("ACGT"), size=L))
+        reads = [(g * (2 + (k + L) // L))[: L + k - 1 + 3], rc((g * (2 + (k + L) // L))[1: L + k + 5])]
+        out.append(dict(name=f"pow2_cycle_L{L}_k{k}", k=k, abundance_min=1, minimizer_size=min(10, k - 1), reads=reads))
     return out
 
 

@@ -1,0 +1,42 @@
+"""Sharded (multi-GPU) parity: torchrun one process per GPU, every golden case + a C2-like synthetic set, merged shards
+compared with the oracle and the reference's golden output (tests/shard_worker.py).  Needs >= 2 GPUs (NCCL refuses two ranks
+on one device), so on a single-GPU box it is skipped; run it with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_sharded.py -m gpu`."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _world():
+    import torch
+    n = torch.cuda.device_count()
+    return 8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 0
+
+
+def _run(world, names, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "shard_worker.py"), *names]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(l for l in (p.stdout + p.stderr).splitlines() if "shard x" in l or "SHARD_RESULT" in l or "rror" in l)
+    assert p.returncode == 0 and "SHARD_RESULT PASS" in p.stdout, tail[-4000:]
+
+
+def test_sharded_golden_cases():
+    w = _world()
+    if not w:
+        pytest.skip("needs >= 2 GPUs")
+    names = [c["name"] for c in load_golden() if c["unitigs_fa"] is not None]
+    _run(w, names, 29531)
+
+
+def test_sharded_c2_like():
+    w = _world()
+    if not w:
+        pytest.skip("needs >= 2 GPUs")
+    _run(w, ["c2:0.2"], 29532)
