@@ -57,7 +57,7 @@ LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to
 
 EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_count", "cdbg_compact",
            "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_synth_reads",
-           "cdbg_copy_to_host", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init"]
+           "cdbg_copy_to_host", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range"]
 
 _lib = None
 
@@ -84,6 +84,7 @@ def load_library():
     L.cdbg_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, P(UnitigView), P(Stats)]
     L.cdbg_get_solid_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
     L.cdbg_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
+    L.cdbg_synth_reads_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
     L.cdbg_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.cdbg_version.restype = C.c_char_p
     L.cdbg_nccl_unique_id.argtypes = [C.c_void_p]
@@ -253,9 +254,9 @@ class Cdbg:
         self._ck(self.lib.cdbg_build(self.h, C.c_void_p(ptr), n_bytes, location, C.byref(v) if fetch else None, C.byref(s)))
         return v, s
 
-    def synth_reads(self, genome_len: int, read_len: int, n_reads: int, err_ppm: int = 10000, seed: int = 42):
+    def synth_reads(self, genome_len: int, read_len: int, n_reads: int, err_ppm: int = 10000, seed: int = 42, first_read: int = 0):
         p, n = C.c_void_p(), C.c_uint64()
-        self._ck(self.lib.cdbg_synth_reads(self.h, genome_len, read_len, n_reads, err_ppm, seed, C.byref(p), C.byref(n)))
+        self._ck(self.lib.cdbg_synth_reads_range(self.h, genome_len, read_len, first_read, n_reads, err_ppm, seed, C.byref(p), C.byref(n)))
         return p.value, n.value
 
     def copy_to_host(self, dptr: int, n_bytes: int) -> np.ndarray:

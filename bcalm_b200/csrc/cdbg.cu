@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -41,6 +42,8 @@ struct cdbg_ctx {
     cdbg_stats st{};
     Timer tm[T_N];
     uint32_t launches = 0;
+    bool trace = false;            // CDBG_TRACE=1: print a host-side timeline (stream-synchronised, debugging only)
+    double trace_t0 = 0;
 
     // device allocations made through dalloc (freed by reset)
     std::vector<void *> allocs;
@@ -122,6 +125,16 @@ namespace {
         ctx->launches++;                                                       \
         CK(cudaGetLastError());                                                \
     } while (0)
+
+inline double host_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+inline void trace_point(cdbg_ctx *ctx, const char *label) {
+    if (!ctx->trace) return;
+    cudaStreamSynchronize(ctx->stream);
+    double t = host_now();
+    fprintf(stderr, "[cdbg trace r%d] %-28s +%8.3f ms\n", ctx->rank, label, t - ctx->trace_t0);
+    ctx->trace_t0 = t;
+}
+#define TRACE(label) trace_point(ctx, label)
 
 template <typename T>
 int dalloc(cdbg_ctx *ctx, T **p, size_t n_elems) {
@@ -601,6 +614,7 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     ctx->k = params->kmer_size;
     ctx->m = params->minimizer_size > 0 ? params->minimizer_size : 10;
     if (ctx->m > ctx->k - 1) ctx->m = ctx->k - 1;   // ConfigurationAlgorithm.cpp:251
+    ctx->trace = getenv("CDBG_TRACE") != nullptr;
     ctx->amin = (uint32_t)std::max(params->abundance_min, 1);
     ctx->amax = params->abundance_max > 0 ? (uint32_t)params->abundance_max : 0x7FFFFFFFu;
     int ndev = 0;
@@ -783,6 +797,11 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
 
 int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t n_reads, uint32_t err_ppm, uint64_t seed,
                      uint8_t **d_bytes, uint64_t *n_bytes) {
+    return cdbg_synth_reads_range(ctx, genome_len, read_len, 0, n_reads, err_ppm, seed, d_bytes, n_bytes);
+}
+
+int cdbg_synth_reads_range(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t first_read, uint64_t n_reads, uint32_t err_ppm,
+                           uint64_t seed, uint8_t **d_bytes, uint64_t *n_bytes) {
     if (!ctx || !ctx->stream || !d_bytes || !n_bytes) return CDBG_ERR_PARAM;
     if (read_len == 0 || genome_len < read_len) return ctx->fail(CDBG_ERR_PARAM, "bad synthetic read geometry");
     CK(cudaSetDevice(ctx->prm.device));
@@ -793,7 +812,7 @@ int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint
         CK(cudaMalloc(&ctx->d_synth, total + 64));
         ctx->synth_cap = total + 64;
     }
-    if (total) LAUNCH(synth_reads_kernel, grid_for(ctx, total, 256, 16), 256, 0, ctx->d_synth, genome_len, read_len, n_reads, err_ppm, seed);
+    if (total) LAUNCH(synth_reads_kernel, grid_for(ctx, total, 256, 16), 256, 0, ctx->d_synth, genome_len, read_len, first_read, n_reads, err_ppm, seed);
     CK(cudaStreamSynchronize(ctx->stream));
     *d_bytes = ctx->d_synth; *n_bytes = total;
     return CDBG_OK;

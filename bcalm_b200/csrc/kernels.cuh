@@ -763,13 +763,14 @@ __global__ void fill_u64(uint64_t *p, uint64_t n, uint64_t v) {
 // synthetic reads (bench): genome base g(i) = hash(seed, i) & 3 generated on the fly, so no genome array is needed
 __device__ __forceinline__ uint32_t synth_base(uint64_t seed, uint64_t i) { return (uint32_t)(mix64(seed ^ (i * 0x9E3779B97F4A7C15ULL)) >> 61) & 3u; }
 
-__global__ void __launch_bounds__(256) synth_reads_kernel(uint8_t *out, uint64_t genome_len, uint32_t read_len, uint64_t n_reads,
+__global__ void __launch_bounds__(256) synth_reads_kernel(uint8_t *out, uint64_t genome_len, uint32_t read_len, uint64_t first_read, uint64_t n_reads,
                                                           uint32_t err_ppm, uint64_t seed) {
     const char NT[4] = {'A', 'C', 'T', 'G'};
     const uint64_t stride = (uint64_t)read_len + 1;
     const uint64_t total = n_reads * stride;
     for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t r = idx / stride; uint32_t j = (uint32_t)(idx - r * stride);
+        r += first_read;
         if (j == read_len) { out[idx] = '\n'; continue; }
         uint64_t hr = mix64(seed * 0xD1342543DE82EF95ULL + r + 1);
         uint64_t start = hr % (genome_len - read_len + 1);
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(256) synth_reads_kernel(uint8_t *out, uint64_t
         uint64_t gpos = rev ? start + (read_len - 1 - j) : start + j;
         uint32_t b = synth_base(seed, gpos);
         if (rev) b ^= 2u;
-        uint64_t he = mix64((seed + 0x5851F42D4C957F2DULL) ^ (idx * 0xA24BAED4963EE407ULL));
+        uint64_t he = mix64((seed + 0x5851F42D4C957F2DULL) ^ ((r * stride + j) * 0xA24BAED4963EE407ULL));
         if ((uint32_t)(he % 1000000ULL) < err_ppm) b = (b + 1 + (uint32_t)((he >> 40) % 3)) & 3u;
         out[idx] = NT[b];
     }

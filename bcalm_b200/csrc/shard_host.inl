@@ -93,6 +93,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
     const uint64_t n = ctx->n_bytes;
     int rc;
     tstart(ctx, T_COUNT);
+    ctx->trace_t0 = host_now();
     // global input size -> the same number of local bins on every rank
     uint64_t all_n[MAX_WORLD], total_bytes = 0;
     if ((rc = allgather_host_u64(ctx, &n, 1, all_n))) return rc;
@@ -121,6 +122,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    TRACE("k1 hist");
     uint64_t I_out = 0;
     for (uint32_t b = 0; b < P; b++) { h_off[b] = I_out; I_out += h_cnt[b]; }
     h_off[P] = I_out;
@@ -137,6 +139,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
         LAUNCH(k1s_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1S_THREADS, k1s_smem_bytes(1, P), kp);
         tstop(ctx, T_K1S);
     }
+    TRACE("k1 scatter + allgather counts");
     // X1: k-mers to their counting owner
     uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0}, recv_base[MAX_WORLD + 1] = {0};
     for (int d = 0; d < W; d++) for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += h_cnt[(size_t)d * P_local + b];
@@ -147,6 +150,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
     uint64_t *d_kmers = (uint64_t *)recv;
     dfree(ctx, d_send);
 
+    TRACE("X1 kmer exchange");
     // K2 per local bin; a bin is one run per source rank
     uint64_t max_bin = 0;
     std::vector<uint64_t> bin_tot(P_local, 0);
@@ -187,6 +191,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
         dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
         solid_cap = ctx->S;
     }
+    TRACE("k2 count");
     ctx->st.n_solid = ctx->S;
     if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device: shard over more GPUs");
     dfree(ctx, d_kmers); dfree(ctx, d_keys); dfree(ctx, d_counts);
@@ -253,6 +258,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     dfree(ctx, d_key_s); dfree(ctx, d_val_s);
     ctx->st.n_junction_records = T_in;
 
+    TRACE("k3 + X2 record exchange");
     // ---- K5: per-bin join -> link messages + edges (gids)
     uint64_t max_bin = 0;
     std::vector<uint64_t> bin_tot(P_local, 0);
@@ -298,6 +304,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
     dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
 
+    TRACE("k5 join");
     // ---- X3: link messages to the owners of the ends; local view of the links
     ulonglong2 *d_msgs_in = nullptr; uint64_t n_msgs_in = 0;
     if ((rc = route16(ctx, d_link_msgs, n_link_msgs, &d_msgs_in, &n_msgs_in))) return rc;
@@ -310,6 +317,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     CK(cudaMemsetAsync(ctx->d_link, 0xFF, (n2 + 1) * 4, ctx->stream));
     if (n2) LAUNCH(shard_local_links, grid_for(ctx, n2, 256, 8), 256, 0, ctx->d_link64, n2, (uint32_t)me, ctx->d_link);
 
+    TRACE("X3 route link msgs + apply");
     // ---- stage 2 proper: local ranking -> pieces (the unitigs of this shard), spelled locally
     uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;
     ctx->edge_cap = 1 << 16;
@@ -331,6 +339,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     char *d_pseq = ctx->d_seq; uint64_t *d_pseq_off = ctx->d_seq_off; unsigned long long *d_pkc = ctx->d_kc;
     ctx->d_seq = nullptr; ctx->d_seq_off = nullptr; ctx->d_kc = nullptr;
 
+    TRACE("local rank + spell pieces");
     // ---- stage 3: glue.  global piece ids, neighbour messages (X4), all-gather, replicated piece ranking
     uint64_t all_P[MAX_WORLD], all_nt[MAX_WORLD], piece_base[MAX_WORLD + 1] = {0}, max_p = 1, max_nt = 16;
     uint64_t mine[2] = {Pn, piece_nt}, both[2 * MAX_WORLD];
@@ -355,6 +364,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if (n_nmsg_in) LAUNCH(glue_apply_nbr, grid_for(ctx, n_nmsg_in, 256, 8), 256, 0, d_nmsg_in, n_nmsg_in, ctx->d_info, ctx->d_unitig_of_kmer, d_desc);
     dfree(ctx, d_nmsg); dfree(ctx, d_nmsg_in);
     NK(ncclAllGather(d_desc, d_desc_all, max_p * sizeof(PieceDesc), ncclChar, ctx->comm, ctx->stream));
+    TRACE("glue describe + X4 + allgather desc");
     char *d_seq_all = nullptr;
     if ((rc = dalloc(ctx, &d_seq_all, max_nt * W))) return rc;
     {   // pad my piece strings to max_nt for the all-gather
@@ -364,6 +374,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
         NK(ncclAllGather(d_pad, d_seq_all, max_nt, ncclChar, ctx->comm, ctx->stream));
         dfree(ctx, d_pad);
     }
+    TRACE("allgather piece strings");
     uint64_t *d_piece_base = nullptr; uint32_t *d_plink = nullptr, *d_weight = nullptr;
     if ((rc = dalloc(ctx, &d_piece_base, MAX_WORLD + 1))) return rc;
     if ((rc = dalloc(ctx, &d_plink, 2 * G + 1))) return rc;
@@ -386,6 +397,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if (G) LAUNCH(glue_unitig_of_piece, grid_for(ctx, G, 256, 8), 256, 0, ctx->d_pinfo, d_puid, G, d_desc_all, max_p, (uint32_t)W, d_piece_base,
                   ctx->d_unitig_of_piece, d_kc_all);
 
+    TRACE("piece-level ranking");
     // ---- ownership of the final unitigs: contiguous id ranges; assemble mine from the all-gathered piece strings
     const uint64_t u_first = ((uint64_t)me * U_total + W - 1) / W, u_last = ((uint64_t)(me + 1) * U_total + W - 1) / W;
     ctx->u_first = u_first;
@@ -408,6 +420,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if (U_mine) CK(cudaMemcpyAsync(ctx->d_kc, d_kc_all + u_first, U_mine * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // nt_mine is a stack variable
 
+    TRACE("assemble unitigs");
     // ---- collect every edge this GPU is responsible for as (from gid, to gid): join edges are already there;
     //      add the edges of locally cut cycles and of piece-level cut cycles
     if (ctx->n_edges) {
@@ -428,6 +441,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     dfree(ctx, d_puid); dfree(ctx, d_pnt); dfree(ctx, d_kc_all); dfree(ctx, d_unt_off);
     dfree(ctx, d_pseq); dfree(ctx, d_pseq_off); dfree(ctx, d_pkc);
     tstop(ctx, T_K6S);
+    TRACE("edges + cleanup");
     ctx->n_pieces = Pn;
     ctx->U = U_mine; ctx->total_nt = nt_mine;
     ctx->st.n_unitigs = U_mine; ctx->st.total_nt = nt_mine;
@@ -471,6 +485,7 @@ int shard_stage_link(cdbg_ctx *ctx) {
     if (nc) LAUNCH(links_group, grid_for(ctx, nc, 256, 8), 256, 0, d_tmp, nc, (uint32_t)ctx->u_first, ctx->d_link_off, d_cur, ctx->d_links);
     dfree(ctx, c); dfree(ctx, d_tmp); dfree(ctx, d_per); dfree(ctx, d_cur);
     tstop(ctx, T_LINK);
+    TRACE("links (3 routes + group)");
     ctx->n_edges = nc;
     ctx->st.n_links = nc;
     ctx->stage = ST_LINKED;

@@ -58,51 +58,66 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons DURING the timed region, read through NVML (the library behind nvidia-smi: the same
+    clocks.sm / clocks_event_reasons counters) from a thread of this process every 20 ms.  Spawning `nvidia-smi -lms` instead
+    stalls CUDA API calls of the measured process for 100-600 ms per poll on this driver (scripts/dev_sampler.py), which for
+    a 6 ms step would measure the sampler, not the kernels."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, device: int):
         self.device = device
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.h = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: map the CUDA ordinal to the NVML handle through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(torch.cuda.get_device_properties(device), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+                        break
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        while not self.stop_flag:
+            try:
+                self.samples.append((self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM),
+                                     self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join()
+        sm = [a for a, _ in self.samples]
+        mask = 0
+        for _, r in self.samples:
+            mask |= int(r)
+        reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
         try:
-            self.proc.wait(timeout=2)
+            mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            mx = None
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm),
+                "source": "NVML (nvidia-smi's counters), 20 ms period, sampled during the timed region"}
 
 
 def write_fasta_from_bytes(path: str, reads: np.ndarray, read_len: int):
@@ -172,6 +187,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="workload scale (1.0 = C2)")
     ap.add_argument("--cpu-scale", type=float, default=0.5, help="bounded sample for the CPU baseline, fraction of C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (debugging)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,18 +245,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(local_rank)
 
-    g, n_reads = workload(args.scale)
+    # weak scaling: the genome grows with the number of GPUs (5 Mbp per GPU); ONE graph is built by all ranks together, every
+    # rank contributing an equal share of the reads (sharded by minimizer, NCCL all-to-alls inside the library)
+    g, n_reads_total = workload(args.scale * world)
+    n_reads = n_reads_total // world
     n_bases = n_reads * READ_LEN
-    c = Cdbg(k=K, abundance_min=AMIN, device=local_rank)
-    # weak scaling until the sharded path lands: every rank builds the graph of its own genome (independent replicas)
-    ptr, n_bytes = c.synth_reads(g, READ_LEN, n_reads, ERR_PPM, SEED + rank)
+    c = Cdbg(k=K, abundance_min=AMIN, device=local_rank, rank=rank, world_size=world)
+    if world > 1:
+        c.shard_init_torch()
+    ptr, n_bytes = c.synth_reads(g, READ_LEN, n_reads, ERR_PPM, SEED, first_read=rank * n_reads)
 
     # ---- value: reads resident in HBM
     for _ in range(args.warmup):
         c.build_raw(ptr, n_bytes, MEM_DEVICE, fetch=False)
     sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
     t0 = time.perf_counter()
     agg = None
@@ -250,7 +270,6 @@ def main():
         agg = d if agg is None else {k_: (agg[k_] + d[k_] if k_.startswith("ms_") else d[k_]) for k_ in d}
     barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     st = {k_: (agg[k_] / args.steps if k_.startswith("ms_") else agg[k_]) for k_ in agg}
 
     # ---- e2e: pinned host reads -> H2D -> stages -> D2H of the unitig arrays
@@ -265,6 +284,7 @@ def main():
         v, s2 = c.build_raw(hnp.ctypes.data, n_bytes, MEM_HOST, fetch=True)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    clocks = sampler.stop() if rank == 0 else None
     U, nt, nl = v.n_unitigs, v.total_nt, v.n_links
     d2h = nt + (U + 1) * 8 + U * 8 + nl * 12 + (U + 1) * 8
 
@@ -283,10 +303,11 @@ def main():
             "value": total_bases / dt * args.steps / 1e9, "unit": "Gbases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"C2: synthetic {g} bp genome, {n_reads} x {READ_LEN} bp reads, {COVERAGE}x, 1% substitutions, k={K}, "
-                                   f"abundance-min {AMIN}, 1xB200 per rank" + ("" if world == 1 else f" ({world} independent replicas, one genome per rank)"),
+            "config": {"workload": f"C2: synthetic {g} bp genome, {n_reads * world} x {READ_LEN} bp reads, {COVERAGE}x, 1% substitutions, k={K}, "
+                                   f"abundance-min {AMIN}" + ("" if world == 1 else f"; weak scaling: 5 Mbp of genome and 1.5 M reads per GPU, ONE graph "
+                                   f"sharded by minimizer over {world} GPUs (NCCL all-to-all of k-mers, junction records, glue and link records)"),
                        "input_bytes": n_bytes, "l2_note": "input (151 MB) and k-mer stream (840 MB) are larger than the 126 MB L2; no L2 flush needed",
-                       "unitigs": int(st["n_unitigs"]), "links": int(st["n_links"]), "solid_kmers": int(st["n_solid"])},
+                       "unitigs_rank0": int(st["n_unitigs"]), "links_rank0": int(st["n_links"]), "solid_kmers_rank0": int(st["n_solid"])},
             "e2e": {"value": total_bases / dt_e2e * args.steps / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(n_bytes), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": dt_e2e / args.steps * 1e3},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,

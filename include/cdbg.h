@@ -157,6 +157,11 @@ int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint
 int cdbg_nccl_unique_id(uint8_t *out128);
 int cdbg_shard_init(cdbg_ctx *ctx, const uint8_t *id128);
 
+/* Same generator, reads first_read .. first_read + n_reads - 1 of the same read set: lets every rank of a sharded run
+ * generate its own share. */
+int cdbg_synth_reads_range(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t first_read, uint64_t n_reads,
+                           uint32_t err_ppm, uint64_t seed, uint8_t **d_bytes, uint64_t *n_bytes);
+
 /* Utility: copy device memory owned by the context to a host buffer (used by tests / bench to fetch synthetic reads). */
 int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes);
 
