@@ -45,8 +45,10 @@ struct cdbg_ctx {
     bool trace = false;            // CDBG_TRACE=1: print a host-side timeline (stream-synchronised, debugging only)
     double trace_t0 = 0;
 
-    // device allocations made through dalloc (freed by reset)
-    std::vector<void *> allocs;
+    // device block cache behind dalloc/dfree (see dalloc_bytes)
+    struct Block { void *p; size_t cap; bool used; };
+    std::vector<Block> blocks;
+    uint64_t last_n_bytes = 0;
 
     // reads
     uint8_t *d_bytes = nullptr;
@@ -136,21 +138,46 @@ inline void trace_point(cdbg_ctx *ctx, const char *label) {
 }
 #define TRACE(label) trace_point(ctx, label)
 
+// Device memory: a per-context block cache.  Every stage allocates through dalloc/dfree; freed blocks are kept and handed
+// out again (best fit, at most 25% + 1 MB larger than asked), so a repeated build touches the driver allocator only while
+// warming up.  All work of a context is on ONE stream, so reuse right after dfree is safe in stream order -- the semantics of
+// cudaMallocAsync, which this replaced because its pool re-mapped ~GB blocks on every build once NCCL was active (2.4 ms).
+int dalloc_bytes(cdbg_ctx *ctx, void **out, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 256) + 511) & ~size_t(511);
+    int best = -1;
+    for (size_t i = 0; i < ctx->blocks.size(); i++) {
+        const auto &b = ctx->blocks[i];
+        if (b.used || b.cap < bytes || b.cap > bytes + bytes / 4 + (1u << 20)) continue;
+        if (best < 0 || b.cap < ctx->blocks[best].cap) best = (int)i;
+    }
+    if (best >= 0) { ctx->blocks[best].used = true; *out = ctx->blocks[best].p; return CDBG_OK; }
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {   // give cached-but-unused blocks back and retry once
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i < ctx->blocks.size();) {
+            if (!ctx->blocks[i].used) { cudaFree(ctx->blocks[i].p); ctx->blocks.erase(ctx->blocks.begin() + i); } else i++;
+        }
+        CK(cudaMalloc(&q, bytes));
+    }
+    ctx->blocks.push_back({q, bytes, true});
+    *out = q;
+    return CDBG_OK;
+}
+
 template <typename T>
 int dalloc(cdbg_ctx *ctx, T **p, size_t n_elems) {
     void *q = nullptr;
-    size_t bytes = std::max<size_t>(n_elems * sizeof(T), 256);
-    CK(cudaMallocAsync(&q, bytes, ctx->stream));
-    ctx->allocs.push_back(q);
+    int rc = dalloc_bytes(ctx, &q, n_elems * sizeof(T));
     *p = reinterpret_cast<T *>(q);
-    return CDBG_OK;
+    return rc;
 }
 
 template <typename T>
 int dfree(cdbg_ctx *ctx, T *&p) {
     if (!p) return CDBG_OK;
-    auto it = std::find(ctx->allocs.begin(), ctx->allocs.end(), (void *)p);
-    if (it != ctx->allocs.end()) { ctx->allocs.erase(it); CK(cudaFreeAsync(p, ctx->stream)); }
+    for (auto &b : ctx->blocks) if (b.p == (void *)p) { b.used = false; break; }
     p = nullptr;
     return CDBG_OK;
 }
@@ -229,9 +256,7 @@ int exclusive_scan(cdbg_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_
 }
 
 int free_results(cdbg_ctx *ctx) {
-    for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
-    ctx->allocs.clear();
-    if (!ctx->bytes_borrowed) { /* owned buffer was in allocs */ }
+    for (auto &b : ctx->blocks) b.used = false;
     ctx->d_bytes = nullptr; ctx->n_bytes = 0; ctx->cap_bytes = 0; ctx->bytes_borrowed = false;
     ctx->d_solid_kmers = nullptr; ctx->d_solid_counts = nullptr; ctx->S = 0;
     ctx->d_link = nullptr; ctx->d_edges = nullptr; ctx->n_edges = 0; ctx->edge_cap = 0;
@@ -631,10 +656,6 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     CK(cudaGetDeviceProperties(&prop, params->device));
     ctx->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, params->device));
-    uint64_t thresh = ~0ULL;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     CK(cudaMalloc(&ctx->d_ctr, 64 * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->d_flag, 4 * sizeof(int)));
     CK(cudaHostAlloc(&ctx->h_ctr, 80 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -648,6 +669,8 @@ void cdbg_destroy(cdbg_ctx *ctx) {
         free_results(ctx);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->comm) ncclCommDestroy(ctx->comm);
+        for (auto &b : ctx->blocks) cudaFree(b.p);
+        ctx->blocks.clear();
         if (ctx->d_synth) cudaFree(ctx->d_synth);
         if (ctx->d_ctr) cudaFree(ctx->d_ctr);
         if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -707,6 +730,13 @@ int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if (ctx->stage != ST_PUSHED) return ctx->fail(CDBG_ERR_STATE, "cdbg_count needs pushed reads");
     if (ctx->world > 1 && !ctx->comm) return ctx->fail(CDBG_ERR_STATE, "sharded context: call cdbg_shard_init first");
+    if (ctx->last_n_bytes && ctx->last_n_bytes != ctx->n_bytes) {   // a different workload: drop cached blocks of the old sizes
+        cudaStreamSynchronize(ctx->stream);
+        for (size_t i = 0; i < ctx->blocks.size();) {
+            if (!ctx->blocks[i].used) { cudaFree(ctx->blocks[i].p); ctx->blocks.erase(ctx->blocks.begin() + i); } else i++;
+        }
+    }
+    ctx->last_n_bytes = ctx->n_bytes;
     CK(cudaSetDevice(ctx->prm.device));
     int rc = ctx->world > 1 ? shard_stage_count(ctx) : stage_count(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);

@@ -24,11 +24,12 @@ static CDBG_HD uint32_t owner_of_rank(uint32_t minrank, uint32_t world) {
 // smallest canonical m-mer rank of the n-mer x (straightforward form: used per junction record, not per read position)
 static CDBG_HD uint32_t min_rank_of(uint64_t x, int n, int m) {
     const uint64_t mm = kmer_mask(m);
+    const uint64_t rx = revcomp64(x, n);      // the reverse complement of the m-mer at offset j is the m-mer of rx at offset n-m-j
     uint32_t best = 0xFFFFFFFFu;
     for (int j = 0; j + m <= n; j++) {
-        uint64_t mer = (x >> (2 * (n - m - j))) & mm;
-        uint32_t r = mmer_rank((uint32_t)canonical64(mer, m));
-        best = r < best ? r : best;
+        uint32_t f = (uint32_t)((x >> (2 * (n - m - j))) & mm), r = (uint32_t)((rx >> (2 * j)) & mm);
+        uint32_t rk = mmer_rank(f < r ? f : r);
+        best = rk < best ? rk : best;
     }
     return best;
 }
@@ -59,8 +60,9 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
     uint64_t *s_gbase = s_pk + K1S_WORDS;                                      // [P]        MODE 1
     uint64_t *s_c = s_gbase + (MODE == 1 ? P : 0);                             // [K1S_TILE] MODE 1: stashed k-mers
     uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_c + (MODE == 1 ? K1S_TILE : 0));   // [K1S_WORDS]
-    uint32_t *s_R = s_vm + K1S_WORDS;                                          // [K1S_RANKS]
-    uint32_t *s_cnt = s_R + K1S_RANKS;                                         // [P]
+    uint32_t *s_R = s_vm + K1S_WORDS;                                          // [K1S_RANKS] m-mer ranks, then in-block prefix minima
+    uint32_t *s_S = s_R + K1S_RANKS;                                           // [K1S_RANKS] in-block suffix minima
+    uint32_t *s_cnt = s_S + K1S_RANKS;                                         // [P]
     uint32_t *s_cur = s_cnt + P;                                               // [P]        MODE 1
     uint16_t *s_b = reinterpret_cast<uint16_t *>(s_cur + (MODE == 1 ? P : 0)); // [K1S_TILE] MODE 1: stashed bins
     const int t = threadIdx.x, k = p.k, m = p.m, w = k - m + 1;
@@ -79,6 +81,16 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
             s_R[q] = mmer_rank((uint32_t)canonical64(mf, m));
         }
         __syncthreads();
+        // sliding-window minimum (van Herk / Gil-Werman): blocks of w ranks, suffix minima into s_S, prefix minima in place;
+        // min over [q, q+w-1] = min(s_S[q], s_R[q+w-1])
+        for (int b = t; b * w < K1S_RANKS; b += K1S_THREADS) {
+            const int lo = b * w, hi = min(lo + w, K1S_RANKS);
+            uint32_t run = 0xFFFFFFFFu;
+            for (int q = hi - 1; q >= lo; q--) { run = min(run, s_R[q]); s_S[q] = run; }
+            run = 0xFFFFFFFFu;
+            for (int q = lo; q < hi; q++) { run = min(run, s_R[q]); s_R[q] = run; }
+        }
+        __syncthreads();
 #pragma unroll 2
         for (int j = 0; j < K1S_TILE / K1S_THREADS; j++) {
             const int q = t + j * K1S_THREADS;
@@ -90,8 +102,7 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
                 uint64_t fwd = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * k);
                 uint64_t rc = revcomp64(fwd, k);
                 c = fwd < rc ? fwd : rc;
-                uint32_t mr = 0xFFFFFFFFu;
-                for (int d = 0; d < w; d++) mr = min(mr, s_R[q + d]);
+                const uint32_t mr = min(s_S[q], s_R[q + w - 1]);
                 bin = owner_of_rank(mr, p.world) * p.P_local + hash_to_bin(mix64(c), p.P_local);
                 atomicAdd(&s_cnt[bin], 1u);
             }
@@ -122,7 +133,7 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
 }
 
 static inline size_t k1s_smem_bytes(int mode, uint32_t P) {
-    size_t s = (size_t)K1S_WORDS * 8 + (size_t)K1S_WORDS * 4 + (size_t)K1S_RANKS * 4 + (size_t)P * 4;
+    size_t s = (size_t)K1S_WORDS * 8 + (size_t)K1S_WORDS * 4 + 2 * (size_t)K1S_RANKS * 4 + (size_t)P * 4;
     if (mode == 1) s += (size_t)P * 8 + (size_t)K1S_TILE * 8 + (size_t)P * 4 + (size_t)K1S_TILE * 2;
     return s + 32;
 }

@@ -149,6 +149,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
     if ((rc = exchange_with_counts(ctx, d_send, send_cnt, recv_cnt, 8, &recv, &I_in))) return rc;
     uint64_t *d_kmers = (uint64_t *)recv;
     dfree(ctx, d_send);
+    TRACE("  free send buffer");
 
     TRACE("X1 kmer exchange");
     // K2 per local bin; a bin is one run per source rank
@@ -161,11 +162,13 @@ int shard_stage_count(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &d_counts, cap))) return rc;
     CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
+    TRACE("  table alloc + memset");
     uint64_t solid_cap = std::max<uint64_t>(I_in <= (1ULL << 28) ? I_in : std::max<uint64_t>(I_in / 4, 1ULL << 28), 1);
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
         if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
         if ((rc = ctr_zero(ctx))) return rc;
+        TRACE("  solid alloc");
         tstart(ctx, T_K2);
         std::vector<uint64_t> within(W, 0);
         for (uint32_t b = 0; b < P_local; b++) {
