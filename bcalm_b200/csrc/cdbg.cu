@@ -281,7 +281,8 @@ int stage_count(cdbg_ctx *ctx) {
 
     // ---- K1a: histogram over bins
     uint64_t n_tiles = (n + K1_TILE - 1) / K1_TILE;
-    uint32_t P = (uint32_t)std::min<uint64_t>(K1_MAX_BINS, std::max<uint64_t>(1, (n * 4 / 5 + 2499999) / 2500000));
+    const uint64_t bin_target = getenv("CDBG_BIN_TARGET") ? strtoull(getenv("CDBG_BIN_TARGET"), nullptr, 10) : 5000000ULL;   // instances per bin (C2 sweep: 25 bins beat 49 and 13; fewer launches, table still L2 resident)
+    uint32_t P = (uint32_t)std::min<uint64_t>(K1_MAX_BINS, std::max<uint64_t>(1, (n * 4 / 5 + bin_target - 1) / bin_target));
     ctx->st.n_count_bins = P;
     unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;
     uint64_t *d_bin_off = nullptr;
@@ -334,28 +335,45 @@ int stage_count(cdbg_ctx *ctx) {
     CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
 
     uint64_t solid_cap = std::max<uint64_t>(I <= (1ULL << 28) ? I : std::max<uint64_t>(I / 4, 1ULL << 28), 1);
+    // Table sizing: the first bin is sized for the worst case (every instance distinct, 1.5 slots each).  Its measured
+    // distinct/instance ratio r then sizes the other bins at ~2.5 slots per expected distinct k-mer (hash bins are statistically
+    // alike), which shrinks the table scan of k2_emit and its L2 footprint.  If a bin overflows anyway, everything is redone
+    // with worst-case tables (attempt 1).
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
         if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
         if ((rc = ctr_zero(ctx))) return rc;
         tstart(ctx, T_K2);
+        double slots_per_instance = 1.5;
+        bool first = true;
         for (uint32_t b = 0; b < P; b++) {
             uint64_t nb = h_cnt[b];
             if (!nb) continue;
-            uint32_t cap_b = table_cap(nb);
+            uint32_t cap_b = std::min(cap, std::max<uint32_t>(1024, (uint32_t)std::min<double>((double)nb * slots_per_instance + 64.0, 4.0e9) & ~63u));
             LAUNCH(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers + h_off[b], nb, d_keys, d_counts, cap_b, ctx->d_flag);
             LAUNCH(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
                    ctx->d_solid_counts, solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
+            if (first && attempt == 0 && P > 2) {
+                first = false;
+                if ((rc = ctr_read(ctx))) return rc;
+                double r = (double)ctx->h_ctr[1] / (double)nb;
+                slots_per_instance = std::min(1.5, std::max(0.02, 2.5 * r + 0.02));
+            }
         }
         tstop(ctx, T_K2);
         if ((rc = ctr_read(ctx))) return rc;
-        if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow");
+        const bool overflow = ((int *)(ctx->h_ctr + 64))[0] != 0;
+        if (overflow && attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow");
         ctx->S = ctx->h_ctr[0];
         ctx->st.n_distinct = ctx->h_ctr[1];
-        if (ctx->S <= solid_cap) break;
+        if (!overflow && ctx->S <= solid_cap) break;
         if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "solid buffer overflow");
         dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
-        solid_cap = ctx->S;
+        if (!overflow) solid_cap = ctx->S;
+        else {   // a partially filled table may hold stale entries: clear both arrays before the conservative rerun
+            CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
+            CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
+        }
     }
     ctx->st.n_solid = ctx->S;
     if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu): shard over more GPUs", (unsigned long long)ctx->S);
@@ -481,7 +499,8 @@ int stage_compact(cdbg_ctx *ctx) {
     tstart(ctx, T_COMPACT);
 
     // ---- K3: end records, partitioned by hash of the canonical (k-1)-mer
-    uint32_t P = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1, (n2 + 499999) / 500000));
+    const uint64_t join_target = getenv("CDBG_JOIN_TARGET") ? strtoull(getenv("CDBG_JOIN_TARGET"), nullptr, 10) : 500000ULL;   // records per bin
+    uint32_t P = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1, (n2 + join_target - 1) / join_target));
     ctx->st.n_join_bins = P;
     ctx->st.n_junction_records = n2;
     unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;

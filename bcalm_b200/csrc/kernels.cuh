@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ km
             }
             if (cur == key) { atomicAdd(&counts[slot], 1u); break; }
             slot = slot + 1 == cap ? 0 : slot + 1;
-            if (++probes > cap) { *overflow = 1; break; }
+            if (++probes > min(cap, 8192u)) { *overflow = 1; break; }
         }
     }
 }
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ re
                 break;
             }
             slot = slot + 1 == T.cap ? 0 : slot + 1;
-            if (++probes > T.cap) { *overflow = 1; break; }
+            if (++probes > min(T.cap, 8192u)) { *overflow = 1; break; }
         }
     }
 }

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k2s_insert(const uint64_t *__restrict__ k
             }
             if (cur == key) { atomicAdd(&counts[slot], 1u); break; }
             slot = slot + 1 == cap ? 0 : slot + 1;
-            if (++probes > cap) { *overflow = 1; break; }
+            if (++probes > min(cap, 8192u)) { *overflow = 1; break; }
         }
     }
 }
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k5s_insert(const uint64_t *__restrict__ r
                 break;
             }
             slot = slot + 1 == T.cap ? 0 : slot + 1;
-            if (++probes > T.cap) { *overflow = 1; break; }
+            if (++probes > min(T.cap, 8192u)) { *overflow = 1; break; }
         }
     }
 }
