@@ -37,7 +37,7 @@ static CDBG_HD uint32_t min_rank_of(uint64_t x, int n, int m) {
 // ------------------------------------------------------------------------------------------------ K1 (sharded)
 
 constexpr int K1S_THREADS = 256;
-constexpr int K1S_TILE = 4096;                              // positions per tile, lane-consecutive (16 per thread)
+constexpr int K1S_TILE = 2048;                              // positions per tile, lane-consecutive (8 per thread)
 constexpr int K1S_WORDS = K1S_TILE / 32 + 2;                // packed words incl. 64 halo positions
 constexpr int K1S_RANKS = K1S_TILE + 32;                    // m-mer ranks incl. halo (window <= 32)
 
@@ -46,6 +46,8 @@ struct K1SParams {
     int k, m; uint32_t world, P_local;                      // P = world * P_local bins, destination-major
     unsigned long long *bin_count; const uint64_t *bin_off; unsigned long long *bin_cursor;
     uint64_t *out_kmers;
+    uint16_t *pos_bin;                                      // [n_tiles * K1S_TILE] bin of the k-mer starting at each position (0xFFFF = none):
+                                                            // written by the histogram pass, read by the scatter pass
 };
 
 __device__ __forceinline__ uint64_t funnel_left(uint64_t hi, uint64_t lo, int bits) {   // (hi:lo) << bits, top 64 bits; bits in [0, 63]
@@ -58,13 +60,17 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
     const uint32_t P = p.world * p.P_local;
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(smem_raw);                   // [K1S_WORDS]
     uint64_t *s_gbase = s_pk + K1S_WORDS;                                      // [P]        MODE 1
-    uint64_t *s_c = s_gbase + (MODE == 1 ? P : 0);                             // [K1S_TILE] MODE 1: stashed k-mers
-    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_c + (MODE == 1 ? K1S_TILE : 0));   // [K1S_WORDS]
+    uint64_t *s_c = s_gbase + (MODE == 1 ? P : 0);                             // [K1S_TILE] MODE 1: k-mers by position
+    uint64_t *s_stage = s_c + (MODE == 1 ? K1S_TILE : 0);                      // [K1S_TILE] MODE 1: k-mers sorted by bin
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_stage + (MODE == 1 ? K1S_TILE : 0));   // [K1S_WORDS]
     uint32_t *s_R = s_vm + K1S_WORDS;                                          // [K1S_RANKS] m-mer ranks, then in-block prefix minima
     uint32_t *s_S = s_R + K1S_RANKS;                                           // [K1S_RANKS] in-block suffix minima
     uint32_t *s_cnt = s_S + K1S_RANKS;                                         // [P]
-    uint32_t *s_cur = s_cnt + P;                                               // [P]        MODE 1
-    uint16_t *s_b = reinterpret_cast<uint16_t *>(s_cur + (MODE == 1 ? P : 0)); // [K1S_TILE] MODE 1: stashed bins
+    uint32_t *s_off = s_cnt + P;                                               // [P+1]      MODE 1
+    uint32_t *s_cur = s_off + (MODE == 1 ? P + 1 : 0);                         // [P]        MODE 1
+    uint16_t *s_b = reinterpret_cast<uint16_t *>(s_cur + (MODE == 1 ? P : 0)); // [K1S_TILE] MODE 1: bin by position
+    uint16_t *s_sb = s_b + (MODE == 1 ? K1S_TILE : 0);                         // [K1S_TILE] MODE 1: bin by sorted slot
+    __shared__ uint32_t s_warp[K1S_THREADS / 32];
     const int t = threadIdx.x, k = p.k, m = p.m, w = k - m + 1;
 
     if (MODE == 0) { for (uint32_t i = t; i < P; i += K1S_THREADS) s_cnt[i] = 0; __syncthreads(); }
@@ -74,46 +80,79 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
         if (t < K1S_WORDS) { uint64_t pk; uint32_t vm; load_pack32(p.bytes, p.n_bytes, tile_start + (uint64_t)t * 32, pk, vm); s_pk[t] = pk; s_vm[t] = vm; }
         if (MODE == 1) for (uint32_t i = t; i < P; i += K1S_THREADS) s_cnt[i] = 0;
         __syncthreads();
-        // ranks of the canonical m-mers starting at every position of the tile (+ halo)
-        for (int q = t; q < K1S_RANKS; q += K1S_THREADS) {
-            int wi = q >> 5, o = q & 31;
-            uint64_t mf = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * m);
-            s_R[q] = mmer_rank((uint32_t)canonical64(mf, m));
+        if (MODE == 0) {
+            // ranks of the canonical m-mers starting at every position of the tile (+ halo)
+            for (int q = t; q < K1S_RANKS; q += K1S_THREADS) {
+                int wi = q >> 5, o = q & 31;
+                uint64_t mf = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * m);
+                s_R[q] = mmer_rank((uint32_t)canonical64(mf, m));
+            }
+            __syncthreads();
+            // sliding-window minimum (van Herk / Gil-Werman): blocks of w ranks, suffix minima into s_S, prefix minima in place;
+            // min over [q, q+w-1] = min(s_S[q], s_R[q+w-1])
+            for (int b = t; b * w < K1S_RANKS; b += K1S_THREADS) {
+                const int lo = b * w, hi = min(lo + w, K1S_RANKS);
+                uint32_t run = 0xFFFFFFFFu;
+                for (int q = hi - 1; q >= lo; q--) { run = min(run, s_R[q]); s_S[q] = run; }
+                run = 0xFFFFFFFFu;
+                for (int q = lo; q < hi; q++) { run = min(run, s_R[q]); s_R[q] = run; }
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // sliding-window minimum (van Herk / Gil-Werman): blocks of w ranks, suffix minima into s_S, prefix minima in place;
-        // min over [q, q+w-1] = min(s_S[q], s_R[q+w-1])
-        for (int b = t; b * w < K1S_RANKS; b += K1S_THREADS) {
-            const int lo = b * w, hi = min(lo + w, K1S_RANKS);
-            uint32_t run = 0xFFFFFFFFu;
-            for (int q = hi - 1; q >= lo; q--) { run = min(run, s_R[q]); s_S[q] = run; }
-            run = 0xFFFFFFFFu;
-            for (int q = lo; q < hi; q++) { run = min(run, s_R[q]); s_R[q] = run; }
-        }
-        __syncthreads();
 #pragma unroll 2
         for (int j = 0; j < K1S_TILE / K1S_THREADS; j++) {
             const int q = t + j * K1S_THREADS;
             const int wi = q >> 5, o = q & 31;
-            const uint64_t V = (((uint64_t)s_vm[wi] << 32) | s_vm[wi + 1]) << o;
-            const bool valid = ((~V) >> (64 - k)) == 0;
-            uint64_t c = EMPTY_KEY; uint32_t bin = 0;
-            if (valid) {
-                uint64_t fwd = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * k);
-                uint64_t rc = revcomp64(fwd, k);
-                c = fwd < rc ? fwd : rc;
-                const uint32_t mr = min(s_S[q], s_R[q + w - 1]);
-                bin = owner_of_rank(mr, p.world) * p.P_local + hash_to_bin(mix64(c), p.P_local);
-                atomicAdd(&s_cnt[bin], 1u);
+            uint64_t c = EMPTY_KEY; uint32_t bin = 0xFFFFu;
+            if (MODE == 0) {
+                const uint64_t V = (((uint64_t)s_vm[wi] << 32) | s_vm[wi + 1]) << o;
+                if (((~V) >> (64 - k)) == 0) {
+                    uint64_t fwd = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * k);
+                    uint64_t rc = revcomp64(fwd, k);
+                    c = fwd < rc ? fwd : rc;
+                    const uint32_t mr = min(s_S[q], s_R[q + w - 1]);
+                    bin = owner_of_rank(mr, p.world) * p.P_local + hash_to_bin(mix64(c), p.P_local);
+                    atomicAdd(&s_cnt[bin], 1u);
+                }
+                p.pos_bin[tile_start + q] = (uint16_t)bin;
+            } else {
+                bin = p.pos_bin[tile_start + q];
+                if (bin != 0xFFFFu) {
+                    uint64_t fwd = funnel_left(s_pk[wi], s_pk[wi + 1], 2 * o) >> (64 - 2 * k);
+                    uint64_t rc = revcomp64(fwd, k);
+                    c = fwd < rc ? fwd : rc;
+                    atomicAdd(&s_cnt[bin], 1u);
+                }
+                s_c[q] = c; s_b[q] = (uint16_t)bin;
             }
-            if (MODE == 1) { s_c[q] = c; s_b[q] = (uint16_t)bin; }
         }
         __syncthreads();
         if (MODE == 1) {
-            for (uint32_t b = t; b < P; b += K1S_THREADS) {
-                uint32_t cn = s_cnt[b];
-                if (cn) s_gbase[b] = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], (unsigned long long)cn);
-                s_cur[b] = 0;
+            // exclusive scan of the tile's bin counts + one global reservation per non-empty bin
+            {
+                const uint32_t per = (P + K1S_THREADS - 1) / K1S_THREADS;
+                uint32_t b0 = t * per, sum = 0;
+                for (uint32_t j = 0; j < per; j++) if (b0 + j < P) sum += s_cnt[b0 + j];
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+                if (lane_id() == 31) s_warp[t >> 5] = incl;
+                __syncthreads();
+                if (t < 32) {
+                    uint32_t wv = t < K1S_THREADS / 32 ? s_warp[t] : 0, wi2 = wv;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi2, d); if ((int)lane_id() >= d) wi2 += n; }
+                    if (t < K1S_THREADS / 32) s_warp[t] = wi2 - wv;
+                }
+                __syncthreads();
+                uint32_t run = s_warp[t >> 5] + incl - sum;
+                for (uint32_t j = 0; j < per; j++) if (b0 + j < P) {
+                    uint32_t cn = s_cnt[b0 + j];
+                    s_off[b0 + j] = run; s_cur[b0 + j] = run;
+                    if (cn) s_gbase[b0 + j] = p.bin_off[b0 + j] + atomicAdd(&p.bin_cursor[b0 + j], (unsigned long long)cn);
+                    run += cn;
+                }
+                if (t == K1S_THREADS - 1) s_off[P] = run;
             }
             __syncthreads();
             for (int j = 0; j < K1S_TILE / K1S_THREADS; j++) {
@@ -121,7 +160,14 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
                 uint64_t c = s_c[q];
                 if (c == EMPTY_KEY) continue;
                 uint32_t b = s_b[q];
-                p.out_kmers[s_gbase[b] + atomicAdd(&s_cur[b], 1u)] = c;
+                uint32_t pos = atomicAdd(&s_cur[b], 1u);
+                s_stage[pos] = c; s_sb[pos] = (uint16_t)b;
+            }
+            __syncthreads();
+            const uint32_t total = s_off[P];
+            for (uint32_t j = t; j < total; j += K1S_THREADS) {
+                uint32_t b = s_sb[j];
+                p.out_kmers[s_gbase[b] + (j - s_off[b])] = s_stage[j];
             }
             __syncthreads();
         }
@@ -134,7 +180,7 @@ __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
 
 static inline size_t k1s_smem_bytes(int mode, uint32_t P) {
     size_t s = (size_t)K1S_WORDS * 8 + (size_t)K1S_WORDS * 4 + 2 * (size_t)K1S_RANKS * 4 + (size_t)P * 4;
-    if (mode == 1) s += (size_t)P * 8 + (size_t)K1S_TILE * 8 + (size_t)P * 4 + (size_t)K1S_TILE * 2;
+    if (mode == 1) s += (size_t)P * 8 + 2 * (size_t)K1S_TILE * 8 + (size_t)(P + 1) * 4 + (size_t)P * 4 + 2 * (size_t)K1S_TILE * 2;
     return s + 32;
 }
 
@@ -183,6 +229,7 @@ struct K3SParams {
     const uint64_t *solid_kmers; uint64_t n_solid; int k, m; uint32_t rank, world, P_local;
     unsigned long long *bin_count; const uint64_t *bin_off; unsigned long long *bin_cursor;
     uint64_t *rec_key, *rec_val;
+    uint16_t *bins;                  // [2S] bin of every end record: written by the histogram pass, read by the scatter pass
 };
 
 template <int MODE>
@@ -211,8 +258,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3s_ends(K3SParams p) {
                 val[r] = ((uint64_t)p.rank << 32) | (uint32_t)v | ((v & REC_SIDE_OUT) ? SREC_SIDE_OUT : 0) | ((v & REC_PALIN) ? SREC_PALIN : 0);
                 bin[r] = 0xFFFFFFFFu; rnk[r] = 0;
                 if (ok) {
-                    int mm = p.m < p.k - 1 ? p.m : p.k - 1;
-                    bin[r] = owner_of_rank(min_rank_of(key[r], p.k - 1, mm), p.world) * p.P_local + hash_to_bin(mix64(key[r]), p.P_local);
+                    if (MODE == 0) {
+                        int mm = p.m < p.k - 1 ? p.m : p.k - 1;
+                        bin[r] = owner_of_rank(min_rank_of(key[r], p.k - 1, mm), p.world) * p.P_local + hash_to_bin(mix64(key[r]), p.P_local);
+                        p.bins[2 * i + end] = (uint16_t)bin[r];
+                    } else bin[r] = p.bins[2 * i + end];
                     rnk[r] = atomicAdd(&s_cnt[bin[r]], 1u);
                 }
             }
@@ -274,8 +324,9 @@ __global__ void __launch_bounds__(256) k5s_insert(const uint64_t *__restrict__ r
 // Same decision rule as k5_resolve, but the results are MESSAGES because the ends may live on other GPUs:
 //   link message (a, b): "end a is compacted with end b" (emitted twice, once per direction, routed to rank(a));
 //   edge (e, f): unitig-level edge between extremities.  Two-pass warp-chunk scan like k2_emit: count, reserve once per block, write.
-__global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, ulonglong2 *link_msgs, uint64_t link_cap, unsigned long long *n_link_msgs,
-                                                   ulonglong2 *edges, uint64_t edge_cap, unsigned long long *n_edges) {
+__global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, uint32_t rank, uint64_t *link64, ulonglong2 *link_msgs, uint64_t link_cap,
+                                                   unsigned long long *n_link_msgs, ulonglong2 *edges, uint64_t edge_cap, unsigned long long *n_edges,
+                                                   unsigned long long *n_compact) {
     __shared__ uint32_t s_wl[8], s_we[8];
     __shared__ unsigned long long s_bl, s_be;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -288,12 +339,15 @@ __global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, 
         nin = min(c & 0xFFu, 4u); nout = min((c >> 8) & 0xFFu, 4u); pal = (c >> 31) != 0;
         compact = !pal && nin == 1 && nout == 1 && (T.ids[(size_t)i * 8] >> 1) != (T.ids[(size_t)i * 8 + 4] >> 1);
     };
-    uint32_t my_l = 0, my_e = 0;
+    uint32_t my_l = 0, my_e = 0; unsigned long long my_c = 0;
     for (uint32_t i = wb + lane; i < we; i += 32) {
         if (T.keys[i] == EMPTY_KEY) continue;
         uint32_t nin, nout; bool pal, compact;
         classify(i, nin, nout, pal, compact);
-        if (compact) my_l += 2; else my_e += pal ? nin * nin : 2 * nin * nout;
+        if (compact) {   // only the directions whose destination end lives on another GPU become messages
+            my_l += (GID_RANK(T.ids[(size_t)i * 8]) != rank) + (GID_RANK(T.ids[(size_t)i * 8 + 4]) != rank);
+            my_c++;
+        } else my_e += pal ? nin * nin : 2 * nin * nout;
     }
     uint32_t wl = my_l, wed = my_e;
 #pragma unroll
@@ -319,8 +373,8 @@ __global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, 
         const uint64_t *ids = &T.ids[(size_t)i * 8];
         if (compact) {
             uint64_t a = ids[0], b = ids[4];
-            if (ol + 2 <= link_cap) { link_msgs[ol] = make_ulonglong2(a, b); link_msgs[ol + 1] = make_ulonglong2(b, a); }
-            ol += 2;
+            if (GID_RANK(a) == rank) link64[GID_LOCAL(a)] = b; else { if (ol < link_cap) link_msgs[ol] = make_ulonglong2(a, b); ol++; }
+            if (GID_RANK(b) == rank) link64[GID_LOCAL(b)] = a; else { if (ol < link_cap) link_msgs[ol] = make_ulonglong2(b, a); ol++; }
         } else if (pal) {
             for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nin; b++) { if (oe < edge_cap) edges[oe] = make_ulonglong2(ids[a], ids[b]); oe++; }
         } else {
@@ -331,6 +385,7 @@ __global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, 
         }
         T.keys[i] = EMPTY_KEY; T.cnt[i] = 0;
     }
+    block_add(n_compact, my_c);
 }
 
 // ------------------------------------------------------------------------------------------------ generic routing of 16-byte records

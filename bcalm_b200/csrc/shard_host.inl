@@ -98,7 +98,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
     uint64_t all_n[MAX_WORLD], total_bytes = 0;
     if ((rc = allgather_host_u64(ctx, &n, 1, all_n))) return rc;
     for (int r = 0; r < W; r++) total_bytes += all_n[r];
-    uint32_t P_local = (uint32_t)std::min<uint64_t>(K1_MAX_BINS / W, std::max<uint64_t>(1, (total_bytes / W * 4 / 5 + 2499999) / 2500000));
+    uint32_t P_local = (uint32_t)std::min<uint64_t>(K1_MAX_BINS / W, std::max<uint64_t>(1, (total_bytes / W * 4 / 5 + 4999999) / 5000000));
     const uint32_t P = P_local * W;
     ctx->st.n_count_bins = P_local;
     uint64_t n_tiles = (n + K1S_TILE - 1) / K1S_TILE;
@@ -109,7 +109,10 @@ int shard_stage_count(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &d_bin_off, P + 1))) return rc;
     CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
     CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
+    uint16_t *d_pos_bin = nullptr;
+    if ((rc = dalloc(ctx, &d_pos_bin, n_tiles * K1S_TILE + 2))) return rc;
     K1SParams kp{};
+    kp.pos_bin = d_pos_bin;
     kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.m = ctx->m; kp.world = W; kp.P_local = P_local;
     kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
     std::vector<uint64_t> h_cnt(P, 0), h_off(P + 1, 0);
@@ -140,6 +143,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
         tstop(ctx, T_K1S);
     }
     TRACE("k1 scatter + allgather counts");
+    dfree(ctx, d_pos_bin);
     // X1: k-mers to their counting owner
     uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0}, recv_base[MAX_WORLD + 1] = {0};
     for (int d = 0; d < W; d++) for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += h_cnt[(size_t)d * P_local + b];
@@ -171,6 +175,8 @@ int shard_stage_count(cdbg_ctx *ctx) {
         TRACE("  solid alloc");
         tstart(ctx, T_K2);
         std::vector<uint64_t> within(W, 0);
+        double slots_per_instance = 1.5;   // first bin worst case, then sized from its distinct ratio (see stage_count)
+        bool first = true;
         for (uint32_t b = 0; b < P_local; b++) {
             Runs runs{}; runs.n = W; runs.pre[0] = 0;
             for (int s = 0; s < W; s++) {
@@ -179,22 +185,31 @@ int shard_stage_count(cdbg_ctx *ctx) {
             }
             uint64_t nb = bin_tot[b];
             if (!nb) continue;
-            uint32_t cap_b = table_cap_for(nb);
+            uint32_t cap_b = std::min(cap, std::max<uint32_t>(1024, (uint32_t)std::min<double>((double)nb * slots_per_instance + 64.0, 4.0e9) & ~63u));
             LAUNCH(k2s_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers, runs, d_keys, d_counts, cap_b, ctx->d_flag);
             LAUNCH(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers, ctx->d_solid_counts,
                    solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
+            if (first && attempt == 0 && P_local > 2) {
+                first = false;
+                if ((rc = ctr_read(ctx))) return rc;
+                slots_per_instance = std::min(1.5, std::max(0.02, 2.5 * (double)ctx->h_ctr[1] / (double)nb + 0.02));
+            }
         }
         tstop(ctx, T_K2);
         if ((rc = ctr_read(ctx))) return rc;
-        if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow");
+        const bool overflow = ((int *)(ctx->h_ctr + 64))[0] != 0;
+        if (overflow && attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow");
         ctx->S = ctx->h_ctr[0];
         ctx->st.n_distinct = ctx->h_ctr[1];
-        if (ctx->S <= solid_cap) break;
+        if (!overflow && ctx->S <= solid_cap) break;
         if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "solid buffer overflow");
         dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
-        solid_cap = ctx->S;
+        if (!overflow) solid_cap = ctx->S;
+        else {
+            CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
+            CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
+        }
     }
-    TRACE("k2 count");
     ctx->st.n_solid = ctx->S;
     if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device: shard over more GPUs");
     dfree(ctx, d_kmers); dfree(ctx, d_keys); dfree(ctx, d_counts);
@@ -226,11 +241,13 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &d_bin_off, P + 1))) return rc;
     if ((rc = dalloc(ctx, &d_key_s, n2 + 1))) return rc;
     if ((rc = dalloc(ctx, &d_val_s, n2 + 1))) return rc;
+    uint16_t *d_bins3 = nullptr;
+    if ((rc = dalloc(ctx, &d_bins3, n2 + 2))) return rc;
     CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
     CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
     K3SParams p3{};
     p3.solid_kmers = ctx->d_solid_kmers; p3.n_solid = S; p3.k = k; p3.m = ctx->m; p3.rank = me; p3.world = W; p3.P_local = P_local;
-    p3.bin_count = d_bin_count; p3.bin_off = d_bin_off; p3.bin_cursor = d_bin_cursor; p3.rec_key = d_key_s; p3.rec_val = d_val_s;
+    p3.bin_count = d_bin_count; p3.bin_off = d_bin_off; p3.bin_cursor = d_bin_cursor; p3.rec_key = d_key_s; p3.rec_val = d_val_s; p3.bins = d_bins3;
     std::vector<uint64_t> h_cnt(P, 0), h_off(P + 1, 0);
     tstart(ctx, T_K3);
     CK(cudaFuncSetAttribute(k3s_ends<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem_bytes(1, P)));
@@ -258,7 +275,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if ((rc = exchange_with_counts(ctx, d_key_s, send_cnt, recv_cnt, 8, &rk, &T_in))) return rc;
     if ((rc = exchange_with_counts(ctx, d_val_s, send_cnt, recv_cnt, 8, &rv, &T_in2))) return rc;
     uint64_t *d_rec_key = (uint64_t *)rk, *d_rec_val = (uint64_t *)rv;
-    dfree(ctx, d_key_s); dfree(ctx, d_val_s);
+    dfree(ctx, d_key_s); dfree(ctx, d_val_s); dfree(ctx, d_bins3);
     ctx->st.n_junction_records = T_in;
 
     TRACE("k3 + X2 record exchange");
@@ -278,6 +295,8 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     ctx->sedge_cap = std::max<uint64_t>(T_in / 2, 1 << 16) + 4096;
     if ((rc = dalloc(ctx, &d_link_msgs, link_cap))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_sedges, ctx->sedge_cap))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_link64, n2 + 1))) return rc;
+    CK(cudaMemsetAsync(ctx->d_link64, 0xFF, (n2 + 1) * 8, ctx->stream));
     if ((rc = ctr_zero(ctx))) return rc;
     tstart(ctx, T_K5);
     {
@@ -292,8 +311,8 @@ int shard_stage_compact(cdbg_ctx *ctx) {
             if (!nb) continue;
             T.cap = table_cap_for(nb);
             LAUNCH(k5s_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_rec_key, d_rec_val, runs, T, ctx->d_flag);
-            LAUNCH(k5s_resolve, grid_for(ctx, T.cap, 256, 8), 256, 0, T, T.cap, d_link_msgs, link_cap, ctx->d_ctr + 0, ctx->d_sedges, ctx->sedge_cap,
-                   ctx->d_ctr + 1);
+            LAUNCH(k5s_resolve, grid_for(ctx, T.cap, 256, 8), 256, 0, T, T.cap, (uint32_t)me, ctx->d_link64, d_link_msgs, link_cap, ctx->d_ctr + 0,
+                   ctx->d_sedges, ctx->sedge_cap, ctx->d_ctr + 1, ctx->d_ctr + 2);
         }
     }
     tstop(ctx, T_K5);
@@ -303,7 +322,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     ctx->n_sedges = ctx->h_ctr[1];
     if (n_link_msgs > link_cap) return ctx->fail(CDBG_ERR_INTERNAL, "link message buffer overflow");
     if (ctx->n_sedges + 2048 > ctx->sedge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow (%llu edges)", (unsigned long long)ctx->n_sedges);
-    ctx->st.n_compactions = n_link_msgs / 2;
+    ctx->st.n_compactions = ctx->h_ctr[2];
     dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
     dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
 
@@ -312,9 +331,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     ulonglong2 *d_msgs_in = nullptr; uint64_t n_msgs_in = 0;
     if ((rc = route16(ctx, d_link_msgs, n_link_msgs, &d_msgs_in, &n_msgs_in))) return rc;
     dfree(ctx, d_link_msgs);
-    if ((rc = dalloc(ctx, &ctx->d_link64, n2 + 1))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_link, n2 + 1))) return rc;
-    CK(cudaMemsetAsync(ctx->d_link64, 0xFF, (n2 + 1) * 8, ctx->stream));
     if (n_msgs_in) LAUNCH(shard_apply_links, grid_for(ctx, n_msgs_in, 256, 8), 256, 0, d_msgs_in, n_msgs_in, ctx->d_link64);
     dfree(ctx, d_msgs_in);
     CK(cudaMemsetAsync(ctx->d_link, 0xFF, (n2 + 1) * 4, ctx->stream));
