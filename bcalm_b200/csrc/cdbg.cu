@@ -17,6 +17,7 @@
 #include "../../include/cdbg.h"
 #include "kernels.cuh"
 #include "shard.cuh"
+#include "k1_tma.cuh"
 
 namespace {
 
@@ -292,19 +293,33 @@ int stage_count(cdbg_ctx *ctx) {
     CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
     CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
 
+    // K1 runs as the TMA-fed persistent kernel (k1_tma.cuh); CDBG_K1=classic selects the earlier LDG-based kernel for A/B runs
+    const bool use_tma = !(getenv("CDBG_K1") && strcmp(getenv("CDBG_K1"), "classic") == 0);
     K1Params kp{};
     kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.P = P;
     kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
+    K1TParams kt{};
+    kt.bytes = ctx->d_bytes; kt.n_bytes = n; kt.n_tiles = n_tiles; kt.k = k; kt.P = P;
+    kt.bin_count = d_bin_count; kt.bin_off = d_bin_off; kt.bin_cursor = d_bin_cursor; kt.out_kmers = nullptr;
+    uint16_t *d_pos_bin = nullptr;
+    if (use_tma) { if ((rc = dalloc(ctx, &d_pos_bin, n_tiles * K1_TILE + 8))) return rc; }
+    kt.pos_bin = d_pos_bin;
 
     std::vector<uint64_t> h_cnt(P), h_off(P + 1);
     uint64_t I = 0;
     if (n_tiles) {
-        size_t sm0 = k1_smem_bytes(0, P), sm1 = k1_smem_bytes(1, P);
-        CK(cudaFuncSetAttribute(k1_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
-        CK(cudaFuncSetAttribute(k1_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-        int g0 = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6);
         tstart(ctx, T_K1H);
-        LAUNCH(k1_extract<0>, g0, K1_THREADS, sm0, kp);
+        if (use_tma) {
+            size_t sm0 = k1t_smem_bytes(0, P);
+            CK(cudaFuncSetAttribute(k1t_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+            CK(cudaFuncSetAttribute(k1t_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1t_smem_bytes(1, P)));
+            LAUNCH(k1t_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6), K1_THREADS, sm0, kt);
+        } else {
+            size_t sm0 = k1_smem_bytes(0, P), sm1 = k1_smem_bytes(1, P);
+            CK(cudaFuncSetAttribute(k1_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+            CK(cudaFuncSetAttribute(k1_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+            LAUNCH(k1_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6), K1_THREADS, sm0, kp);
+        }
         tstop(ctx, T_K1H);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -318,12 +333,13 @@ int stage_count(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &d_kmers, I + 1))) return rc;
     if (I) {
         CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        kp.out_kmers = d_kmers;
-        int g1 = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2);
+        kp.out_kmers = d_kmers; kt.out_kmers = d_kmers;
         tstart(ctx, T_K1S);
-        LAUNCH(k1_extract<1>, g1, K1_THREADS, k1_smem_bytes(1, P), kp);
+        if (use_tma) LAUNCH(k1t_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1t_smem_bytes(1, P), kt);
+        else LAUNCH(k1_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1_smem_bytes(1, P), kp);
         tstop(ctx, T_K1S);
     }
+    dfree(ctx, d_pos_bin);
 
     // ---- K2: per-bin counting in one L2-resident table
     auto table_cap = [](uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); };

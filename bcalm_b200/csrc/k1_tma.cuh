@@ -1,0 +1,202 @@
+// k1_tma.cuh -- K1 (reads -> canonical k-mers, partitioned) as a persistent kernel fed by the TMA bulk-copy engine.
+//
+// Each CTA walks tiles of 8192 read positions.  One elected thread keeps the NEXT tile's raw bytes in flight with
+// cp.async.bulk (global -> shared, completion signalled on an mbarrier with expect_tx) while all threads work on the current
+// one, so the loads never sit on the critical path and no LSU instructions are spent on the byte stream.
+//   pass 0 (HIST)   : pack ASCII -> 2 bit, roll fwd/rc k-mers, canonical select, 32-bit bin hash; CTA-private histogram in
+//                     shared memory, and the bin of every position is written out (uint16, coalesced 64 B per thread)
+//   pass 1 (SCATTER): reads the bins back (no hashing, no validity logic), counts the tile per bin, reserves one run per
+//                     (tile, bin) with a single global atomic, rolls the k-mers again and counting-sorts them in shared memory so
+//                     that every run leaves the SM as contiguous, coalesced stores.
+#pragma once
+#include "kernels.cuh"
+
+constexpr int K1T_RAW = K1_TILE + 32;       // bytes per tile incl. halo (multiple of 16)
+#define K1_NOBIN 0xFFFFu
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine (SASS: UBLKCP); size and both addresses multiples of 16
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+struct K1TParams {
+    const uint8_t *bytes; uint64_t n_bytes; uint64_t n_tiles;
+    int k; uint32_t P;
+    unsigned long long *bin_count; const uint64_t *bin_off; unsigned long long *bin_cursor;
+    uint64_t *out_kmers;
+    uint16_t *pos_bin;         // [n_tiles * K1_TILE]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS) k1t_extract(K1TParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *s_raw = smem_raw;                                                              // [2][K1T_RAW]  TMA destinations
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * K1T_RAW);                 // [2] mbarriers
+    uint64_t *s_pk = s_bar + 2;                                                             // [THREADS + 2]
+    uint64_t *s_gbase = s_pk + K1_THREADS + 2;                                              // [P]        MODE 1
+    uint64_t *s_stage = s_gbase + (MODE == 1 ? p.P : 0);                                    // [K1_TILE]  MODE 1
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_stage + (MODE == 1 ? K1_TILE : 0));     // [THREADS + 2]
+    uint32_t *s_cnt = s_vm + K1_THREADS + 2;                                                // [P]
+    uint32_t *s_off = s_cnt + p.P;                                                          // [P + 1]    MODE 1
+    uint32_t *s_cur = s_off + (MODE == 1 ? p.P + 1 : 0);                                    // [P]        MODE 1
+    uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_cur + (MODE == 1 ? p.P : 0));           // [K1_TILE]  MODE 1: bin of each staged k-mer
+    __shared__ uint32_t s_warp[K1_THREADS / 32];
+
+    const int t = threadIdx.x, k = p.k;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+
+    auto issue = [&](uint64_t tile, int stage) {      // thread 0 only
+        const uint64_t start = tile * (uint64_t)K1_TILE;
+        if (start + K1T_RAW <= p.n_bytes) {
+            mbar_expect_tx(&s_bar[stage], K1T_RAW);
+            tma_load_1d(s_raw + stage * K1T_RAW, p.bytes + start, K1T_RAW, &s_bar[stage]);
+        } else {                                      // ragged last tile: plain loads, positions past the end read as breaks
+            for (int i = 0; i < K1T_RAW; i++) { uint64_t q = start + i; s_raw[stage * K1T_RAW + i] = q < p.n_bytes ? p.bytes[q] : (uint8_t)'\n'; }
+            mbar_expect_tx(&s_bar[stage], 0);
+        }
+    };
+
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = t; i < p.P; i += K1_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    if (t == 0 && first < p.n_tiles) issue(first, 0);
+
+    uint32_t it = 0;
+    for (uint64_t tile = first; tile < p.n_tiles; tile += stride, it++) {
+        const int stage = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        const uint64_t tile_start = tile * (uint64_t)K1_TILE;
+        if (t == 0 && tile + stride < p.n_tiles) issue(tile + stride, stage ^ 1);   // prefetch the next tile
+        mbar_wait(&s_bar[stage], parity);
+        // ---- phase A: ASCII -> 2 bit from the staged bytes
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + stage * K1T_RAW + t * 32);
+            uint64_t pk; uint32_t vm;
+            pack32(src[0], src[1], pk, vm);
+            s_pk[t] = pk; s_vm[t] = vm;
+            if (t == 0) {
+                const uint4 *h = reinterpret_cast<const uint4 *>(s_raw + stage * K1T_RAW + K1_TILE);
+                pack32(h[0], h[1], pk, vm);
+                s_pk[K1_THREADS] = pk; s_vm[K1_THREADS] = vm;
+            }
+        }
+        __syncthreads();
+        uint64_t hi = s_pk[t], lo = s_pk[t + 1];
+        uint64_t fwd = hi >> (64 - 2 * k);
+        uint64_t rc = revcomp64(fwd, k);
+
+        if (MODE == 0) {
+            const uint64_t V = ((uint64_t)s_vm[t] << 32) | s_vm[t + 1];
+            const uint32_t valid32 = (uint32_t)(kmer_valid_mask(V, k) >> 32);
+            uint32_t packed[K1_PER_THREAD / 2];
+#pragma unroll
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                const uint64_t c = fwd < rc ? fwd : rc;
+                uint32_t bin = hash32_to_bin(bin_hash32(c), p.P);
+                const bool ok = (valid32 >> (31 - i)) & 1;
+                if (ok) atomicAdd(&s_cnt[bin], 1u); else bin = K1_NOBIN;
+                if (i & 1) packed[i >> 1] |= bin << 16; else packed[i >> 1] = bin;
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(p.pos_bin + tile_start + (uint64_t)t * K1_PER_THREAD);
+#pragma unroll
+            for (int v = 0; v < K1_PER_THREAD / 8; v++) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+            __syncthreads();     // s_pk / the raw stage are reused by the next iterations
+        } else {
+            uint32_t packed[K1_PER_THREAD / 2];
+            const uint4 *srcb = reinterpret_cast<const uint4 *>(p.pos_bin + tile_start + (uint64_t)t * K1_PER_THREAD);
+#pragma unroll
+            for (int v = 0; v < K1_PER_THREAD / 8; v++) { uint4 q = __ldg(srcb + v); packed[4 * v] = q.x; packed[4 * v + 1] = q.y; packed[4 * v + 2] = q.z; packed[4 * v + 3] = q.w; }
+            // tile counts per bin (the bins come from pass 0: no hashing here)
+#pragma unroll
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                uint32_t bin = (packed[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+                if (bin != K1_NOBIN) atomicAdd(&s_cnt[bin], 1u);
+            }
+            __syncthreads();
+            {   // exclusive scan of s_cnt + one global reservation per non-empty bin
+                const uint32_t per = (p.P + K1_THREADS - 1) / K1_THREADS;
+                uint32_t b0 = t * per, sum = 0;
+                for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) sum += s_cnt[b0 + j];
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+                if (lane_id() == 31) s_warp[t >> 5] = incl;
+                __syncthreads();
+                if (t < 32) {
+                    uint32_t wv = t < K1_THREADS / 32 ? s_warp[t] : 0, wi = wv;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane_id() >= d) wi += n; }
+                    if (t < K1_THREADS / 32) s_warp[t] = wi - wv;
+                }
+                __syncthreads();
+                uint32_t run = s_warp[t >> 5] + incl - sum;
+                for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) {
+                    uint32_t cn = s_cnt[b0 + j];
+                    s_off[b0 + j] = run; s_cur[b0 + j] = run; s_cnt[b0 + j] = 0;
+                    if (cn) s_gbase[b0 + j] = p.bin_off[b0 + j] + atomicAdd(&p.bin_cursor[b0 + j], (unsigned long long)cn);
+                    run += cn;
+                }
+                if (t == K1_THREADS - 1) s_off[p.P] = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                uint32_t bin = (packed[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+                if (bin != K1_NOBIN) {
+                    uint32_t pos = atomicAdd(&s_cur[bin], 1u);
+                    s_stage[pos] = fwd < rc ? fwd : rc; s_sb[pos] = (uint16_t)bin;
+                }
+            }
+            __syncthreads();
+            const uint32_t total = s_off[p.P];
+            for (uint32_t j = t; j < total; j += K1_THREADS) {
+                uint32_t b = s_sb[j];
+                p.out_kmers[s_gbase[b] + (j - s_off[b])] = s_stage[j];
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == 0) {
+        for (uint32_t i = t; i < p.P; i += K1_THREADS) { uint32_t c = s_cnt[i]; if (c) atomicAdd(&p.bin_count[i], (unsigned long long)c); }
+    }
+}
+
+static inline size_t k1t_smem_bytes(int mode, uint32_t P) {
+    size_t s = 2 * (size_t)K1T_RAW + 16 + (size_t)(K1_THREADS + 2) * 8 + (size_t)(K1_THREADS + 2) * 4 + (size_t)P * 4;
+    if (mode == 1) s += (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(P + 1) * 4 + (size_t)P * 4 + (size_t)K1_TILE * 2;
+    return s + 128;
+}

@@ -66,3 +66,11 @@ static CDBG_HD uint32_t minimizer_of(uint64_t x, int n, int m) {
     }
     return best;
 }
+
+// cheap 32-bit bin hash for K1 (10 integer ops instead of two 64-bit multiplies); independent of table_slot's mix64
+static CDBG_HD uint32_t bin_hash32(uint64_t c) {
+    uint32_t h = ((uint32_t)c * 0x9E3779B1u) ^ ((uint32_t)(c >> 32) * 0x85EBCA77u + 0x165667B1u);
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+static CDBG_HD uint32_t hash32_to_bin(uint32_t h, uint32_t P) { return (uint32_t)(((uint64_t)h * P) >> 32); }
