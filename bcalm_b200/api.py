@@ -57,7 +57,7 @@ LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to
 
 EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_count", "cdbg_compact",
            "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_synth_reads",
-           "cdbg_copy_to_host", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range"]
+           "cdbg_copy_to_host", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range", "cdbg_owner_of", "cdbg_plan_shard_exchange"]
 
 _lib = None
 
@@ -85,6 +85,9 @@ def load_library():
     L.cdbg_get_solid_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
     L.cdbg_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
     L.cdbg_synth_reads_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
+    L.cdbg_owner_of.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint32]
+    L.cdbg_owner_of.restype = C.c_uint32
+    L.cdbg_plan_shard_exchange.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cdbg_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.cdbg_version.restype = C.c_char_p
     L.cdbg_nccl_unique_id.argtypes = [C.c_void_p]
@@ -263,6 +266,23 @@ class Cdbg:
         out = np.empty(n_bytes, np.uint8)
         self._ck(self.lib.cdbg_copy_to_host(self.h, out.ctypes.data, C.c_void_p(dptr), n_bytes))
         return out
+
+
+def owner_of(x: int, n_nt: int, m: int, world: int) -> int:
+    """GPU owning the n_nt-mer x in a `world`-way sharded build (host-side, no GPU needed)."""
+    return int(load_library().cdbg_owner_of(int(x), n_nt, m, world))
+
+
+def plan_shard_exchange(world: int, rank: int, p_local: int, all_cnt: np.ndarray):
+    """-> (send_cnt[world], recv_cnt[world], run_off[p_local, world], run_len[p_local, world]) for `rank`."""
+    a = np.ascontiguousarray(all_cnt, dtype=np.uint64).reshape(-1)
+    assert a.size == world * world * p_local
+    send, recv = np.zeros(world, np.uint64), np.zeros(world, np.uint64)
+    off, ln = np.zeros((p_local, world), np.uint64), np.zeros((p_local, world), np.uint64)
+    rc = load_library().cdbg_plan_shard_exchange(world, rank, p_local, a.ctypes.data, send.ctypes.data, recv.ctypes.data, off.ctypes.data, ln.ctypes.data)
+    if rc != 0:
+        raise CdbgError(rc, "cdbg_plan_shard_exchange: bad arguments")
+    return send, recv, off, ln
 
 
 def merge_shards(graphs) -> Graph:

@@ -905,6 +905,18 @@ int cdbg_shard_init(cdbg_ctx *ctx, const uint8_t *id128) {
     return CDBG_OK;
 }
 
+uint32_t cdbg_owner_of(uint64_t x, int32_t n_nt, int32_t m, uint32_t world) {
+    if (m > n_nt) m = n_nt;
+    return owner_of_rank(min_rank_of(x, n_nt, m), world ? world : 1);
+}
+
+int cdbg_plan_shard_exchange(uint32_t world, uint32_t rank, uint32_t p_local, const uint64_t *all_cnt, uint64_t *send_cnt, uint64_t *recv_cnt,
+                             uint64_t *run_off, uint64_t *run_len) {
+    if (!world || world > MAX_WORLD || rank >= world || !p_local || !all_cnt || !send_cnt || !recv_cnt || !run_off || !run_len) return CDBG_ERR_PARAM;
+    plan_shard_exchange(world, rank, p_local, all_cnt, send_cnt, recv_cnt, run_off, run_len);
+    return CDBG_OK;
+}
+
 int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     CK(cudaSetDevice(ctx->prm.device));

@@ -84,6 +84,26 @@ int route16(cdbg_ctx *ctx, const ulonglong2 *d_recs, uint64_t n, ulonglong2 **d_
     return CDBG_OK;
 }
 
+// Pure planning of a destination-major exchange (no CUDA, no NCCL; exported as cdbg_plan_shard_exchange and exercised by the
+// 2-process gloo test on CPU).  all_cnt[s * P + d * P_local + b] = number of elements rank s holds for (destination d, local bin b),
+// P = world * P_local.  Outputs for rank `me`: elements to send to / receive from every peer, and for each local bin the runs
+// (offset, length) of the receive buffer that make it up, source-major: run_off[b * world + s], run_len[b * world + s].
+inline void plan_shard_exchange(uint32_t world, uint32_t me, uint32_t P_local, const uint64_t *all_cnt, uint64_t *send_cnt, uint64_t *recv_cnt,
+                                uint64_t *run_off, uint64_t *run_len) {
+    const uint64_t P = (uint64_t)world * P_local;
+    std::vector<uint64_t> recv_base(world + 1, 0), within(world, 0);
+    for (uint32_t d = 0; d < world; d++) { send_cnt[d] = 0; for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += all_cnt[(size_t)me * P + (size_t)d * P_local + b]; }
+    for (uint32_t s = 0; s < world; s++) { recv_cnt[s] = 0; for (uint32_t b = 0; b < P_local; b++) recv_cnt[s] += all_cnt[(size_t)s * P + (size_t)me * P_local + b]; }
+    for (uint32_t s = 0; s < world; s++) recv_base[s + 1] = recv_base[s] + recv_cnt[s];
+    for (uint32_t b = 0; b < P_local; b++)
+        for (uint32_t s = 0; s < world; s++) {
+            uint64_t len = all_cnt[(size_t)s * P + (size_t)me * P_local + b];
+            run_off[(size_t)b * world + s] = recv_base[s] + within[s];
+            run_len[(size_t)b * world + s] = len;
+            within[s] += len;
+        }
+}
+
 inline uint32_t table_cap_for(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); }
 
 // ------------------------------------------------------------------------------------------------ stage 1 (sharded)
@@ -145,10 +165,9 @@ int shard_stage_count(cdbg_ctx *ctx) {
     TRACE("k1 scatter + allgather counts");
     dfree(ctx, d_pos_bin);
     // X1: k-mers to their counting owner
-    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0}, recv_base[MAX_WORLD + 1] = {0};
-    for (int d = 0; d < W; d++) for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += h_cnt[(size_t)d * P_local + b];
-    for (int s = 0; s < W; s++) for (uint32_t b = 0; b < P_local; b++) recv_cnt[s] += all_cnt[(size_t)s * P + (size_t)me * P_local + b];
-    for (int s = 0; s < W; s++) recv_base[s + 1] = recv_base[s] + recv_cnt[s];
+    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0};
+    std::vector<uint64_t> run_off((size_t)P_local * W), run_len((size_t)P_local * W);
+    plan_shard_exchange(W, me, P_local, all_cnt.data(), send_cnt, recv_cnt, run_off.data(), run_len.data());
     void *recv = nullptr; uint64_t I_in = 0;
     if ((rc = exchange_with_counts(ctx, d_send, send_cnt, recv_cnt, 8, &recv, &I_in))) return rc;
     uint64_t *d_kmers = (uint64_t *)recv;
@@ -174,15 +193,11 @@ int shard_stage_count(cdbg_ctx *ctx) {
         if ((rc = ctr_zero(ctx))) return rc;
         TRACE("  solid alloc");
         tstart(ctx, T_K2);
-        std::vector<uint64_t> within(W, 0);
         double slots_per_instance = 1.5;   // first bin worst case, then sized from its distinct ratio (see stage_count)
         bool first = true;
         for (uint32_t b = 0; b < P_local; b++) {
             Runs runs{}; runs.n = W; runs.pre[0] = 0;
-            for (int s = 0; s < W; s++) {
-                uint64_t len = all_cnt[(size_t)s * P + (size_t)me * P_local + b];
-                runs.off[s] = recv_base[s] + within[s]; runs.pre[s + 1] = runs.pre[s] + len; within[s] += len;
-            }
+            for (int s = 0; s < W; s++) { runs.off[s] = run_off[(size_t)b * W + s]; runs.pre[s + 1] = runs.pre[s] + run_len[(size_t)b * W + s]; }
             uint64_t nb = bin_tot[b];
             if (!nb) continue;
             uint32_t cap_b = std::min(cap, std::max<uint32_t>(1024, (uint32_t)std::min<double>((double)nb * slots_per_instance + 64.0, 4.0e9) & ~63u));
@@ -267,10 +282,9 @@ int shard_stage_compact(cdbg_ctx *ctx) {
         LAUNCH(k3s_ends<1>, g3, K3_THREADS, k3_smem_bytes(1, P), p3);
     }
     tstop(ctx, T_K3);
-    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0}, recv_base[MAX_WORLD + 1] = {0};
-    for (int d = 0; d < W; d++) for (uint32_t b = 0; b < P_local; b++) send_cnt[d] += h_cnt[(size_t)d * P_local + b];
-    for (int s = 0; s < W; s++) for (uint32_t b = 0; b < P_local; b++) recv_cnt[s] += all_cnt[(size_t)s * P + (size_t)me * P_local + b];
-    for (int s = 0; s < W; s++) recv_base[s + 1] = recv_base[s] + recv_cnt[s];
+    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0};
+    std::vector<uint64_t> run_off((size_t)P_local * W), run_len((size_t)P_local * W);
+    plan_shard_exchange(W, me, P_local, all_cnt.data(), send_cnt, recv_cnt, run_off.data(), run_len.data());
     void *rk = nullptr, *rv = nullptr; uint64_t T_in = 0, T_in2 = 0;
     if ((rc = exchange_with_counts(ctx, d_key_s, send_cnt, recv_cnt, 8, &rk, &T_in))) return rc;
     if ((rc = exchange_with_counts(ctx, d_val_s, send_cnt, recv_cnt, 8, &rv, &T_in2))) return rc;
@@ -300,13 +314,9 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if ((rc = ctr_zero(ctx))) return rc;
     tstart(ctx, T_K5);
     {
-        std::vector<uint64_t> within(W, 0);
         for (uint32_t b = 0; b < P_local; b++) {
             Runs runs{}; runs.n = W; runs.pre[0] = 0;
-            for (int s = 0; s < W; s++) {
-                uint64_t len = all_cnt[(size_t)s * P + (size_t)me * P_local + b];
-                runs.off[s] = recv_base[s] + within[s]; runs.pre[s + 1] = runs.pre[s] + len; within[s] += len;
-            }
+            for (int s = 0; s < W; s++) { runs.off[s] = run_off[(size_t)b * W + s]; runs.pre[s + 1] = runs.pre[s] + run_len[(size_t)b * W + s]; }
             uint64_t nb = bin_tot[b];
             if (!nb) continue;
             T.cap = table_cap_for(nb);

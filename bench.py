@@ -160,6 +160,16 @@ def cpu_baseline_sample(c, scale: float, cores: int):
             "sample": sample + f"; C oracle single thread, {dt:.2f} s, {o.n_unitigs} unitigs"}
 
 
+def load_traffic(name: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel group from the committed `ncu --set full` capture."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["groups"][name]["traffic_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def dominant_kernel(st: dict, n_bytes: int):
     """Pick the kernel group with the largest device time in the step and compute its algorithmic bytes."""
     I, S, w = st["n_instances"], st["n_solid"], 8
@@ -312,7 +322,7 @@ def main():
                     "ms_per_step": dt_e2e / args.steps * 1e3},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes": int(bytes_k), "kernel_ms": ms_k, "peak_source": peak_src,
+                         "traffic": load_traffic(name) if world == 1 else None, "algorithmic_bytes": int(bytes_k), "kernel_ms": ms_k, "peak_source": peak_src,
                          "stage_ms": groups},
             "clocks": clocks,
         }

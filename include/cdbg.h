@@ -162,6 +162,16 @@ int cdbg_shard_init(cdbg_ctx *ctx, const uint8_t *id128);
 int cdbg_synth_reads_range(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t first_read, uint64_t n_reads,
                            uint32_t err_ppm, uint64_t seed, uint8_t **d_bytes, uint64_t *n_bytes);
 
+/* Host-side pieces of the sharded path, callable without a GPU (used by the 2-process gloo tests):
+ *  cdbg_owner_of            GPU that owns the n_nt-mer x (a k-mer for counting, a (k-1)-mer for the junction join):
+ *                           hash(min over its canonical m-mers of mmer_rank) mod world -- the same function the kernels use.
+ *  cdbg_plan_shard_exchange the layout arithmetic of a destination-major all-to-all: from the all-gathered per-(destination, local
+ *                           bin) counts of every rank (all_cnt[s * world*p_local + d * p_local + b]) to this rank's send / receive
+ *                           counts and, per local bin b and source s, the run [run_off, run_off + run_len) of the receive buffer. */
+uint32_t cdbg_owner_of(uint64_t x, int32_t n_nt, int32_t m, uint32_t world);
+int cdbg_plan_shard_exchange(uint32_t world, uint32_t rank, uint32_t p_local, const uint64_t *all_cnt, uint64_t *send_cnt, uint64_t *recv_cnt,
+                             uint64_t *run_off, uint64_t *run_len);
+
 /* Utility: copy device memory owned by the context to a host buffer (used by tests / bench to fetch synthetic reads). */
 int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes);
 
