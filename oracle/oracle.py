@@ -38,14 +38,26 @@ class _Result(C.Structure):
     ]
 
 
+class _ResultW(C.Structure):
+    _fields_ = [
+        ("k", C.c_int),
+        ("n_bases", C.c_uint64), ("n_instances", C.c_uint64), ("n_distinct", C.c_uint64), ("n_solid", C.c_uint64),
+        ("solid_kmers", C.POINTER(C.c_uint64)), ("solid_counts", C.POINTER(C.c_uint32)),
+        ("n_unitigs", C.c_uint64), ("total_nt", C.c_uint64),
+        ("seq", C.POINTER(C.c_char)), ("seq_off", C.POINTER(C.c_uint64)), ("kc", C.POINTER(C.c_uint64)),
+        ("abund", C.POINTER(C.c_uint32)),
+        ("n_links", C.c_uint64), ("links", C.POINTER(_Link)),
+    ]
+
+
 LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to_sign", "u1"), ("pad", "u1", (2,))])
 
 
 def build(force: bool = False) -> str:
     """Compile oracle/cdbg_oracle.c with gcc (seconds)."""
-    src = os.path.join(HERE, "cdbg_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", LIB_PATH, src])
+    srcs = [os.path.join(HERE, "cdbg_oracle.c"), os.path.join(HERE, "cdbg_oracle_wide.c")]
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", LIB_PATH, *srcs])
     return LIB_PATH
 
 
@@ -69,6 +81,9 @@ def lib():
         L.orc_mmer_rank.argtypes = [C.c_uint32]
         L.orc_mmer_rank.restype = C.c_uint32
         L.orc_km_string.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_int]
+        L.orcw_build.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(_ResultW)]
+        L.orcw_build.restype = C.c_int
+        L.orcw_free.argtypes = [C.POINTER(_ResultW)]
         _lib = L
     return _lib
 
@@ -130,6 +145,41 @@ def run(reads, k: int, abundance_min: int = 2, abundance_max: int = 2**31 - 1, s
     finally:
         lib().orc_free(C.byref(res))
     return g
+
+
+def run_wide(reads, k: int, abundance_min: int = 2, abundance_max: int = 2**31 - 1, stages: int = 7) -> Graph:
+    """The multi-word oracle (cdbg_oracle_wide.c), any k <= 127.  solid_kmers has shape (S, 4): little-endian 64-bit words."""
+    b = _as_bytes(reads)
+    res = _ResultW()
+    rc = lib().orcw_build(b.ctypes.data, b.size, k, abundance_min, abundance_max, stages, C.byref(res))
+    if rc != 0:
+        raise RuntimeError(f"orcw_build failed rc={rc}")
+    try:
+        U, S = res.n_unitigs, res.n_solid
+        def arr(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dt).itemsize,)).view(dt).copy()
+        g = Graph(
+            k=k,
+            seq=arr(res.seq, res.total_nt, np.uint8) if stages & 2 else np.zeros(0, np.uint8),
+            seq_off=arr(res.seq_off, U + 1, np.uint64) if stages & 2 else np.zeros(1, np.uint64),
+            kc=arr(res.kc, U, np.uint64),
+            abund=arr(res.abund, S, np.uint32) if stages & 2 else None,
+            links=arr(res.links, res.n_links, LINK_DTYPE),
+            stats=dict(n_bases=res.n_bases, n_instances=res.n_instances, n_distinct=res.n_distinct, n_solid=S,
+                       n_unitigs=U, n_links=res.n_links, total_nt=res.total_nt),
+            solid_kmers=arr(res.solid_kmers, S * 4, np.uint64).reshape(-1, 4),
+            solid_counts=arr(res.solid_counts, S, np.uint32),
+        )
+    finally:
+        lib().orcw_free(C.byref(res))
+    return g
+
+
+def run_any(reads, k: int, abundance_min: int = 2, **kw) -> Graph:
+    """Narrow oracle for k <= 31, wide oracle above."""
+    return run(reads, k, abundance_min, **kw) if k <= 31 else run_wide(reads, k, abundance_min, **kw)
 
 
 def extract(reads, k: int) -> np.ndarray:

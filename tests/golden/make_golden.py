@@ -120,6 +120,19 @@ def cases():
             g = "".join(rng2.choice(list("ACGT"), size=L))
         reads = [(g * (2 + (k + L) // L))[: L + k - 1 + 3], rc((g * (2 + (k + L) // L))[1: L + k + 5])]
         out.append(dict(name=f"pow2_cycle_L{L}_k{k}", k=k, abundance_min=1, minimizer_size=min(10, k - 1), reads=reads))
+    # multi-word k-mers (reference spans 64 / 96 / 128): k = 32 ... 127
+    rng3 = np.random.default_rng(99)
+    for i, (k, glen, rl, cov, a, err) in enumerate([
+        (32, 4000, 100, 20, 2, 0.01), (33, 4000, 100, 20, 2, 0.01), (47, 6000, 120, 25, 2, 0.01), (63, 6000, 150, 25, 2, 0.01),
+        (64, 6000, 150, 25, 2, 0.01), (65, 6000, 150, 25, 2, 0.01), (95, 8000, 200, 30, 2, 0.005), (96, 8000, 200, 30, 2, 0.005),
+        (127, 10000, 250, 30, 2, 0.005), (127, 3000, 250, 12, 1, 0.0), (41, 300, 120, 10, 1, 0.0),
+    ]):
+        reads = synth_reads(rng3, glen, rl, cov, err=err, n_rate=0.001 if i % 3 == 0 else 0.0, circular=(i == 10))
+        out.append(dict(name=f"wide_{i}_k{k}_a{a}", k=k, abundance_min=a, minimizer_size=10, reads=reads))
+    # low-complexity with a wide k: palindromic (k-1)-mers need an odd k
+    for i, (alpha, k, glen) in enumerate([("AT", 33, 400), ("AT", 35, 600), ("ACG", 37, 500)]):
+        reads = synth_reads(rng3, glen, min(glen, 120), 4, err=0.0, alphabet=alpha)
+        out.append(dict(name=f"wide_lowcx_{i}_{alpha}_k{k}", k=k, abundance_min=1, minimizer_size=10, reads=reads))
     return out
 
 

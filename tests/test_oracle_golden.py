@@ -14,10 +14,22 @@ def test_oracle_matches_reference(case):
     if case["unitigs_fa"] is None:
         pytest.skip("reference refused this input: " + case.get("ref_error", ""))
     k = case["k"]
-    g = orc.run(case["reads"], k, case["abundance_min"])
+    g = orc.run_any(case["reads"], k, case["abundance_min"])
     ours = parity.graph_to_records(g)
     ref = parity.parse_unitigs_fa(case["unitigs_fa"])
     d = parity.diff(ours, ref, k)
+    assert d == "", d
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["k"] <= 31], ids=[c["name"] for c in CASES if c["k"] <= 31])
+def test_wide_oracle_equals_narrow_oracle(case):
+    """cdbg_oracle_wide.c (4-word k-mers) must agree with cdbg_oracle.c wherever both apply (k <= 31)."""
+    k = case["k"]
+    a = orc.run(case["reads"], k, case["abundance_min"])
+    b = orc.run_wide(case["reads"], k, case["abundance_min"])
+    assert a.stats == b.stats
+    assert (b.solid_kmers[:, 1:] == 0).all() and (b.solid_kmers[:, 0] == a.solid_kmers).all() and (a.solid_counts == b.solid_counts).all()
+    d = parity.diff(parity.graph_to_records(a), parity.graph_to_records(b), k)
     assert d == "", d
 
 
