@@ -221,10 +221,11 @@ class Cdbg:
     def solid_kmers(self):
         n = C.c_uint64()
         self._ck(self.lib.cdbg_get_solid_kmers(self.h, None, None, 0, C.byref(n)))
-        km = np.empty(n.value, np.uint64)
+        W = 1 if self.k <= 31 else max(2, (2 * self.k + 63) // 64)
+        km = np.empty(n.value * W, np.uint64)
         ct = np.empty(n.value, np.uint32)
         self._ck(self.lib.cdbg_get_solid_kmers(self.h, km.ctypes.data, ct.ctypes.data, n.value, C.byref(n)))
-        return km, ct
+        return (km if W == 1 else km.reshape(-1, W)), ct
 
     def _view_to_graph(self, v: UnitigView, copy: bool = True) -> Graph:
         def arr(ptr, n, dt):

@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "shard.cuh"
 #include "k1_tma.cuh"
+#include "wide.cuh"
 
 namespace {
 
@@ -35,6 +36,7 @@ enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3
 struct cdbg_ctx {
     cdbg_params prm{};
     int k = 0, m = 0;
+    int W = 1;                     // 64-bit words per k-mer: 1 for k <= 31, ceil(2k/64) rounded like the reference spans above
     uint32_t amin = 1, amax = 0x7FFFFFFFu;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
@@ -634,6 +636,7 @@ int stage_link(cdbg_ctx *ctx) {
 }
 
 #include "shard_host.inl"
+#include "wide_host.inl"
 
 void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
     cudaStreamSynchronize(ctx->stream);
@@ -653,7 +656,7 @@ void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
 
 extern "C" {
 
-const char *cdbg_version(void) { return "cdbg_b200 0.1 (sm_100a, k<=31)"; }
+const char *cdbg_version(void) { return "cdbg_b200 0.2 (sm_100a, k<=127)"; }
 
 int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     if (!out || !params) return CDBG_ERR_PARAM;
@@ -662,8 +665,11 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     ctx->prm = *params;
     auto bail = [&](int code) { *out = ctx; return code; };   // caller can still read cdbg_last_error, then destroy
     // span dispatch of the reference (Integer.hpp:77-85): this build instantiates one 64-bit word, k < 32
-    if (params->kmer_size < 4 || params->kmer_size > 31)
-        return bail(ctx->fail(CDBG_ERR_PARAM, "unhandled kmer size %d (this build supports 4 <= k <= 31)", params->kmer_size));
+    if (params->kmer_size < 4 || params->kmer_size > 127)
+        return bail(ctx->fail(CDBG_ERR_PARAM, "unhandled kmer size %d (this build supports 4 <= k <= 127)", params->kmer_size));
+    if (params->kmer_size > 31 && params->world_size > 1)
+        return bail(ctx->fail(CDBG_ERR_PARAM, "k > 31 is not available in sharded mode yet (kmer size %d)", params->kmer_size));
+    ctx->W = params->kmer_size <= 31 ? 1 : std::max(2, (2 * params->kmer_size + 63) / 64);   // k = 32 also takes two words (reference: k < span)
     if (params->abundance_min < 0) return bail(ctx->fail(CDBG_ERR_PARAM, "abundance-min must be >= 0"));
     if (params->world_size > MAX_WORLD || params->world_size < 0 || (params->world_size > 1 && (params->rank < 0 || params->rank >= params->world_size)))
         return bail(ctx->fail(CDBG_ERR_PARAM, "bad rank/world_size %d/%d (at most %d shards)", params->rank, params->world_size, MAX_WORLD));
@@ -773,7 +779,7 @@ int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats) {
     }
     ctx->last_n_bytes = ctx->n_bytes;
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = ctx->world > 1 ? shard_stage_count(ctx) : stage_count(ctx);
+    int rc = ctx->W > 1 ? stage_count_wide_dispatch(ctx) : ctx->world > 1 ? shard_stage_count(ctx) : stage_count(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }
@@ -782,7 +788,7 @@ int cdbg_compact(cdbg_ctx *ctx, cdbg_stats *stats) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if (ctx->stage != ST_COUNTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_compact needs cdbg_count first");
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = ctx->world > 1 ? shard_stage_compact(ctx) : stage_compact(ctx);
+    int rc = ctx->W > 1 ? stage_compact_wide_dispatch(ctx) : ctx->world > 1 ? shard_stage_compact(ctx) : stage_compact(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }
@@ -854,7 +860,7 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
     CK(cudaSetDevice(ctx->prm.device));
     *n = ctx->S;
     uint64_t c = std::min<uint64_t>(cap, ctx->S);
-    if (c && kmers) CK(cudaMemcpyAsync(kmers, ctx->d_solid_kmers, c * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (c && kmers) CK(cudaMemcpyAsync(kmers, ctx->d_solid_kmers, c * 8 * ctx->W, cudaMemcpyDeviceToHost, ctx->stream));
     if (c && counts) CK(cudaMemcpyAsync(counts, ctx->d_solid_counts, c * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return CDBG_OK;

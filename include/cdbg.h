@@ -60,7 +60,8 @@ enum {
 };
 
 typedef struct {
-    int32_t kmer_size;      /* -kmer-size, 4 <= k <= 31 in this build (one 64-bit word; reference span 32) */
+    int32_t kmer_size;      /* -kmer-size, 4 <= k <= 127 (k <= 31: one 64-bit word, the tuned path; 32..127: 2..4 words, like the
+                               reference's spans 64/96/128, G/tools/math/Integer.hpp:77-85) */
     int32_t abundance_min;  /* -abundance-min (solid <=> min <= count <= max) */
     int32_t abundance_max;  /* -abundance-max, 0 means INT32_MAX (the reference default) */
     int32_t minimizer_size; /* -minimizer-size, 0 means default 10 (clamped to k-1 like ConfigurationAlgorithm.cpp:251) */
@@ -138,8 +139,8 @@ int cdbg_build(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int locati
                cdbg_stats *stats);
 
 /* Stage-1 result for parity checks in isolation (like the reference's `dsk/solid` partitions): copies the solid
- * (k-mer, abundance) pairs to host arrays of capacity `cap`; returns the number of solid k-mers in *n. Order is
- * unspecified. */
+ * (k-mer, abundance) pairs to host arrays of capacity `cap` k-mers; returns the number of solid k-mers in *n. Order is
+ * unspecified.  A k-mer takes W = 1 (k <= 31) or max(2, ceil(2k/64)) (k >= 32) little-endian 64-bit words in `kmers`. */
 int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n);
 
 /* Device-side synthetic read generator used by bench.py (inputs resident in HBM when the timed region starts):

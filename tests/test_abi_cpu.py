@@ -65,7 +65,7 @@ def test_create_fails_loudly_without_gpu_or_with_bad_k():
     import torch
     from bcalm_b200.api import Cdbg, CdbgError
     with pytest.raises(CdbgError) as e:
-        Cdbg(k=32)          # reference span list: k < 32 for one word ("unhandled kmer size")
+        Cdbg(k=128)         # reference span list 32/64/96/128: k < 128 ("unhandled kmer size 128")
     assert "unhandled kmer size" in str(e.value)
     with pytest.raises(CdbgError):
         Cdbg(k=3)

@@ -31,7 +31,7 @@ def test_sharded_golden_cases():
     w = _world()
     if not w:
         pytest.skip("needs >= 2 GPUs")
-    names = [c["name"] for c in load_golden() if c["unitigs_fa"] is not None]
+    names = [c["name"] for c in load_golden() if c["unitigs_fa"] is not None and c["k"] <= 31]   # k > 31 is single-GPU only for now
     _run(w, names, 29531)
 
 
