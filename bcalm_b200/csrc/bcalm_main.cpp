@@ -2,7 +2,7 @@
 //
 // Drop-in for the reference CLI on the reads -> unitigs path:
 //   bcalm -in <fasta|fastq[.gz]|comma list|file of files> -kmer-size <k> -abundance-min <a> [-out <prefix>] [-nb-cores n]
-//         [-all-abundance-counts] [-verbose v] [-minimizer-size m] [-abundance-max x]
+//         [-all-abundance-counts] [-edge-km 0|1] [-verbose v] [-minimizer-size m] [-abundance-max x]      (4 <= k <= 127)
 // writes <prefix>.unitigs.fa with prefix = -out, else the basename of -in cut at its last dot, in the current directory
 // (G/debruijn/impl/GraphUnitigs.cpp:888-904, G/system/impl/FileSystemCommon.cpp:115-137), in the reference's header grammar
 //   ><id> LN:i:<len> KC:i:<sum> km:f:<mean, 1 decimal> [L:<+|->:<id>:<+|->]*      (G/bcalm2/bglue_algo.cpp:197-213, LinkTigs.cpp)
@@ -27,6 +27,7 @@ struct Options {
     std::string in, out, out_gfa;
     int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
     bool all_abund = false;
+    bool edge_km = false;   // -edge-km 1: J:<0|1>:<id>:<0|1> tokens instead of L: (G/debruijn/impl/LinkTigs.cpp:380-384,440-444)
 };
 
 [[noreturn]] void die(const std::string &msg) {
@@ -38,7 +39,7 @@ struct Options {
 const char *IGNORED_1[] = {"-max-memory", "-max-disk", "-out-dir", "-out-tmp", "-out-compress", "-storage-type", "-histo2D", "-histo",
                            "-minimizer-type", "-repartition-type", "-bloom", "-debloom", "-debloom-impl", "-branching-nodes",
                            "-topology-stats", "-integer-precision", "-nb-glue-partitions", "-solidity-custom", "-solidity-kind",
-                           "-histo-max", "-solid-kmers-out", "-edge-km"};
+                           "-histo-max", "-solid-kmers-out"};
 const char *IGNORED_0[] = {"-no-mphf", "-kff", "-config-only", "-redo-bcalm", "-skip-bcalm", "-redo-bglue", "-skip-bglue", "-redo-links",
                            "-skip-links"};
 
@@ -52,6 +53,7 @@ void usage() {
            "       -out                  (1 arg) :    output prefix  [default: basename of -in]\n"
            "       -out-gfa              (1 arg) :    also write GFA1 to this file\n"
            "       -all-abundance-counts (0 arg) :    output all k-mer abundance counts instead of mean\n"
+           "       -edge-km              (1 arg) :    edge km representation  [default '0']\n"
            "       -nb-cores             (1 arg) :    number of cores (host parsing threads)  [default '0']\n"
            "       -device               (1 arg) :    CUDA device ordinal  [default '0']\n"
            "       -verbose              (1 arg) :    verbosity level  [default '1']\n"
@@ -79,6 +81,7 @@ Options parse(int argc, char **argv) {
         else if (a == "-verbose") o.verbose = atoi(need("-verbose").c_str());
         else if (a == "-device") o.device = atoi(need("-device").c_str());
         else if (a == "-all-abundance-counts") o.all_abund = true;
+        else if (a == "-edge-km") o.edge_km = atoi(need("-edge-km").c_str()) != 0;
         else if (a == "-help" || a == "-h") { usage(); exit(EXIT_SUCCESS); }
         else {
             bool known = false;
@@ -272,8 +275,13 @@ int main(int argc, char **argv) {
         }
         for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
             const cdbg_link_t &l = v.links[i];
-            text += " L:"; text.push_back((char)l.from_sign); text.push_back(':'); put_u64(text, l.to);
-            text.push_back(':'); text.push_back((char)l.to_sign);
+            if (o.edge_km) {   // J:0 = in-link (leaves the BEGIN), J:1 = out-link; last field 1 when the neighbour is entered at its END
+                text += " J:"; text.push_back(l.from_sign == '-' ? '0' : '1'); text.push_back(':'); put_u64(text, l.to);
+                text.push_back(':'); text.push_back(l.to_sign == '-' ? '1' : '0');
+            } else {
+                text += " L:"; text.push_back((char)l.from_sign); text.push_back(':'); put_u64(text, l.to);
+                text.push_back(':'); text.push_back((char)l.to_sign);
+            }
         }
         text.push_back('\n');
         text.append(v.seq + b, len);

@@ -283,21 +283,49 @@ struct KW3Params {
     uint64_t *rec_val;   // [2S]
 };
 
+// per-tile shared-memory aggregation like k3_ends: the hot per-bin cursors are hit once per (tile, bin)
 template <int W, int MODE>
-__global__ void __launch_bounds__(256) kw3_ends(KW3Params p) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < p.n_solid; i += (uint64_t)gridDim.x * blockDim.x) {
-        KM<W> x = km_load<W>(p.solid_kmers + i * W);
+__global__ void __launch_bounds__(K3_THREADS) kw3_ends(KW3Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? p.P : 0));
+    const int t = threadIdx.x;
+    const uint64_t n_tiles = (p.n_solid + K3_THREADS - 1) / K3_THREADS;
+    for (uint32_t i = t; i < p.P; i += K3_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t i = tile * K3_THREADS + t;
+        const bool ok = i < p.n_solid;
+        KM<W> key[2]; uint64_t val[2]; uint32_t bin[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, rnk[2] = {0, 0};
+        if (ok) {
+            KM<W> x = km_load<W>(p.solid_kmers + i * W);
 #pragma unroll
-        for (int end = 0; end < 2; end++) {
-            KM<W> key; uint64_t val;
-            kmer_end_record_w<W>(x, p.k, end, (uint32_t)i, key, val);
-            uint32_t b = hash_to_bin(km_hash<W>(key), p.P);
-            if (MODE == 0) atomicAdd(&p.bin_count[b], 1ULL);
-            else {
-                uint64_t pos = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], 1ULL);
-                km_store<W>(p.rec_key + pos * W, key); p.rec_val[pos] = val;
+            for (int end = 0; end < 2; end++) {
+                kmer_end_record_w<W>(x, p.k, end, (uint32_t)i, key[end], val[end]);
+                bin[end] = hash_to_bin(km_hash<W>(key[end]), p.P);
+                rnk[end] = atomicAdd(&s_cnt[bin[end]], 1u);
             }
         }
+        if (MODE == 1) {
+            __syncthreads();
+            for (uint32_t b = t; b < p.P; b += K3_THREADS) {
+                uint32_t c = s_cnt[b];
+                if (c) s_base[b] = p.bin_off[b] + atomicAdd(&p.bin_cursor[b], (unsigned long long)c);
+                s_cnt[b] = 0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int end = 0; end < 2; end++) {
+                if (bin[end] == 0xFFFFFFFFu) continue;
+                uint64_t pos = s_base[bin[end]] + rnk[end];
+                km_store<W>(p.rec_key + pos * W, key[end]); p.rec_val[pos] = val[end];
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (uint32_t b = t; b < p.P; b += K3_THREADS) { uint32_t c = s_cnt[b]; if (c) atomicAdd(&p.bin_count[b], (unsigned long long)c); }
     }
 }
 

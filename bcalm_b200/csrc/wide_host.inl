@@ -109,14 +109,16 @@ int stage_compact_wide(cdbg_ctx *ctx) {
     uint64_t max_bin = 0;
     tstart(ctx, T_K3);
     if (S) {
-        LAUNCH((kw3_ends<W, 0>), grid_for(ctx, S, 256, 8), 256, 0, p3);
+        CK(cudaFuncSetAttribute(kw3_ends<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k3_smem_bytes(1, P)));
+        const int g3 = (int)std::max<uint64_t>(1, std::min<uint64_t>((S + K3_THREADS - 1) / K3_THREADS, (uint64_t)ctx->n_sm * 8));
+        LAUNCH((kw3_ends<W, 0>), g3, K3_THREADS, k3_smem_bytes(0, P), p3);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         uint64_t acc = 0;
         for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
         h_off[P] = acc;
         CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH((kw3_ends<W, 1>), grid_for(ctx, S, 256, 8), 256, 0, p3);
+        LAUNCH((kw3_ends<W, 1>), g3, K3_THREADS, k3_smem_bytes(1, P), p3);
     }
     tstop(ctx, T_K3);
 

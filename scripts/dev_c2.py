@@ -5,8 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bcalm_b200.api import Cdbg, MEM_DEVICE
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-G = int(5_000_000 * scale); L = 100; n_reads = int(G * 30 / L)
-c = Cdbg(k=31, abundance_min=2)
+K = int(os.environ.get('DEV_K', '31')); L = int(os.environ.get('DEV_L', '100'))
+G = int(5_000_000 * scale); n_reads = int(G * 30 / L)
+c = Cdbg(k=K, abundance_min=2)
 ptr, n = c.synth_reads(G, L, n_reads, 10000, 42)
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 for it in range(iters):

@@ -37,7 +37,7 @@ def write_fasta(path, reads, width=None):
 
 
 @pytest.mark.parametrize("name", ["tiny_read_k21", "minitip_k21_a1", "circular_test1", "circular_test2_polyA", "pufferize_refs",
-                                  "lowcx_11_ACGT_k7_a2", "reads_3_k31_a2", "reads_1_k21_a2"])
+                                  "lowcx_11_ACGT_k7_a2", "reads_3_k31_a2", "reads_1_k21_a2", "wide_3_k63_a2", "wide_8_k127_a2"])
 def test_cli_matches_reference_golden(cli, tmp_path, name):
     c = CASES[name]
     fa = tmp_path / "input.reads.fa"
@@ -97,3 +97,19 @@ def test_cli_all_abundance_counts_and_gfa(cli, tmp_path):
     assert sum(1 for l in gfa if l.startswith("S\t")) == len(recs)
     assert sum(1 for l in gfa if l.startswith("L\t")) == sum(len(r["links"]) for r in recs)
     assert all(l.endswith("\t14M") for l in gfa if l.startswith("L\t"))
+
+
+def test_cli_edge_km(cli, tmp_path):
+    """-edge-km 1 prints J:<0|1>:<id>:<0|1> instead of L: (LinkTigs.cpp:380-384,440-444): same links, other spelling."""
+    c = CASES["lowcx_11_ACGT_k7_a2"]
+    fa = tmp_path / "e.fa"
+    write_fasta(fa, c["reads"])
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", "7", "-abundance-min", "2", "-edge-km", "1", "-out", str(tmp_path / "j"))
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", "7", "-abundance-min", "2", "-out", str(tmp_path / "l"))
+    import re
+    jt = (tmp_path / "j.unitigs.fa").read_text()
+    assert " L:" not in jt
+    conv = {("0", "1"): "L:-:%s:-", ("0", "0"): "L:-:%s:+", ("1", "0"): "L:+:%s:+", ("1", "1"): "L:+:%s:-"}
+    jt2 = re.sub(r"J:([01]):(\d+):([01])", lambda m: conv[(m.group(1), m.group(3))] % m.group(2), jt)
+    d = parity.diff(parity.parse_unitigs_fa(jt2), parity.parse_unitigs_fa((tmp_path / "l.unitigs.fa").read_text()), 7)
+    assert d == "", d
