@@ -90,6 +90,7 @@ struct cdbg_ctx {
     uint64_t n_sedges = 0, sedge_cap = 0;
     uint64_t *d_pinfo = nullptr;             // [G] replicated piece-level ranking result
     uint32_t *d_unitig_of_piece = nullptr;   // [G]
+    GidTable gid_table{};                    // replicated k-mer-end gid -> piece terminus lookup (glue + links)
     uint64_t piece_base_me = 0, n_pieces = 0, U_total = 0, u_first = 0;
 
     // small device scratch for counters (zeroed per use)
@@ -265,7 +266,7 @@ int free_results(cdbg_ctx *ctx) {
     ctx->d_link = nullptr; ctx->d_edges = nullptr; ctx->n_edges = 0; ctx->edge_cap = 0;
     ctx->d_info = nullptr; ctx->d_unitig_of_kmer = nullptr; ctx->d_seq = nullptr; ctx->d_seq_off = nullptr;
     ctx->d_kc = nullptr; ctx->d_abund = nullptr; ctx->U = 0; ctx->total_nt = 0; ctx->d_links = nullptr; ctx->d_link_off = nullptr; ctx->d_term_begin = nullptr; ctx->d_term_end = nullptr;
-    ctx->d_link64 = nullptr; ctx->d_sedges = nullptr; ctx->n_sedges = 0; ctx->sedge_cap = 0; ctx->d_pinfo = nullptr; ctx->d_unitig_of_piece = nullptr;
+    ctx->d_link64 = nullptr; ctx->d_sedges = nullptr; ctx->n_sedges = 0; ctx->sedge_cap = 0; ctx->d_pinfo = nullptr; ctx->d_unitig_of_piece = nullptr; ctx->gid_table = GidTable{};
     ctx->piece_base_me = 0; ctx->n_pieces = 0; ctx->U_total = 0; ctx->u_first = 0;
     ctx->stage = ST_EMPTY;
     memset(&ctx->st, 0, sizeof ctx->st);

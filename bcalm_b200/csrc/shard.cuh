@@ -458,46 +458,62 @@ struct PieceDesc {
     uint64_t seq_off;    // offset of the piece string in its GPU's piece buffer
 };
 
-// per local piece: termini gids, sizes; neighbour messages for termini with a remote partner
-__global__ void __launch_bounds__(256) glue_describe(uint64_t n_pieces, uint32_t rank, uint64_t piece_base, const uint32_t *__restrict__ term_begin,
+// per local piece: termini gids, partner gids (the k-mer ends on other GPUs its termini are glued to), sizes
+__global__ void __launch_bounds__(256) glue_describe(uint64_t n_pieces, uint32_t rank, const uint32_t *__restrict__ term_begin,
                                                      const uint32_t *__restrict__ term_end, const uint64_t *__restrict__ link64,
                                                      const uint64_t *__restrict__ seq_off, const unsigned long long *__restrict__ kc, int k,
-                                                     PieceDesc *desc, ulonglong2 *msgs, unsigned long long *n_msgs) {
+                                                     PieceDesc *desc) {
     for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < n_pieces; q += (uint64_t)gridDim.x * blockDim.x) {
         PieceDesc d;
         uint32_t e0 = term_begin[q], e1 = term_end[q];
         d.term[0] = ((uint64_t)rank << 32) | e0; d.term[1] = ((uint64_t)rank << 32) | e1;
-        d.nbr[0] = d.nbr[1] = NOGID;
+        d.nbr[0] = link64[e0]; d.nbr[1] = link64[e1];          // NOGID when the terminus is a real chain end
         d.nk = seq_off[q + 1] - seq_off[q] - (uint64_t)(k - 1);
         d.kc = kc[q]; d.seq_off = seq_off[q];
         desc[q] = d;
-        uint64_t g0 = link64[e0], g1 = link64[e1];
-        if (g0 != NOGID) { uint64_t pos = atomicAdd(n_msgs, 1ULL); msgs[pos] = make_ulonglong2(g0, ((piece_base + q) << 1) | 0); }
-        if (g1 != NOGID) { uint64_t pos = atomicAdd(n_msgs, 1ULL); msgs[pos] = make_ulonglong2(g1, ((piece_base + q) << 1) | 1); }
     }
 }
 
-// message (f, their piece terminus): my end f (a terminus of one of my pieces) is glued to that terminus
-__global__ void __launch_bounds__(256) glue_apply_nbr(const ulonglong2 *__restrict__ msgs, uint64_t n, const uint64_t *__restrict__ info,
-                                                      const uint32_t *__restrict__ unitig_of_kmer, PieceDesc *desc) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 m = msgs[i];
-        uint32_t f = GID_LOCAL(m.x);
-        uint32_t q = unitig_of_kmer[f >> 1];
-        int t = ((uint32_t)(info[f >> 1] >> 32) == f) ? 0 : 1;
-        desc[q].nbr[t] = m.y;
+// Replicated lookup table  k-mer-end gid -> global piece terminus id (2 * piece + {0 begin, 1 end}), built on every GPU from the
+// all-gathered descriptors.  It replaces two exchanges: a piece finds its neighbour by looking up its partner gid, and the link
+// stage resolves both ends of an edge locally.
+struct GidTable { uint64_t *keys; uint32_t *vals; uint32_t cap; };
+__device__ __forceinline__ uint32_t gid_lookup(const GidTable &T, uint64_t gid) {
+    uint32_t slot = table_slot(gid, T.cap);
+    for (uint32_t probes = 0; probes <= T.cap; probes++) {
+        uint64_t cur = T.keys[slot];
+        if (cur == gid) return T.vals[slot];
+        if (cur == EMPTY_KEY) return NOLINK;
+        slot = slot + 1 == T.cap ? 0 : slot + 1;
+    }
+    return NOLINK;
+}
+__global__ void __launch_bounds__(256) glue_table_build(const PieceDesc *__restrict__ gathered, uint64_t max_p, uint32_t world,
+                                                        const uint64_t *__restrict__ piece_base, uint64_t G, GidTable T) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < 2 * G; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = x >> 1; const int t = (int)(x & 1);
+        uint32_t r = 0;
+        for (uint32_t j = 1; j < world; j++) if (g >= piece_base[j]) r = j;
+        const uint64_t gid = gathered[(uint64_t)r * max_p + (g - piece_base[r])].term[t];
+        uint32_t slot = table_slot(gid, T.cap);
+        for (;;) {
+            uint64_t cur = atomicCAS((unsigned long long *)&T.keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)gid);
+            if (cur == EMPTY_KEY) { T.vals[slot] = (uint32_t)x; break; }
+            if (cur == gid) break;                                    // every terminus gid is unique: cannot happen
+            slot = slot + 1 == T.cap ? 0 : slot + 1;
+        }
     }
 }
 
 // dense global piece tables from the padded all-gather; plink = piece-terminus links for the replicated ranking
 __global__ void __launch_bounds__(256) glue_build(const PieceDesc *__restrict__ gathered, uint64_t max_p, uint32_t world, const uint64_t *__restrict__ piece_base,
-                                                  uint64_t G, uint32_t *plink, uint32_t *weight) {
+                                                  uint64_t G, GidTable T, uint32_t *plink, uint32_t *weight) {
     for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < G; g += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t r = 0;
         for (uint32_t j = 1; j < world; j++) if (g >= piece_base[j]) r = j;
         const PieceDesc &d = gathered[(uint64_t)r * max_p + (g - piece_base[r])];
-        plink[2 * g] = d.nbr[0] == NOGID ? NOLINK : (uint32_t)d.nbr[0];
-        plink[2 * g + 1] = d.nbr[1] == NOGID ? NOLINK : (uint32_t)d.nbr[1];
+        plink[2 * g] = d.nbr[0] == NOGID ? NOLINK : gid_lookup(T, d.nbr[0]);
+        plink[2 * g + 1] = d.nbr[1] == NOGID ? NOLINK : gid_lookup(T, d.nbr[1]);
         weight[g] = (uint32_t)d.nk;
     }
 }
@@ -584,42 +600,29 @@ __global__ void __launch_bounds__(256) glue_assemble(uint64_t G, const uint64_t 
 
 // ------------------------------------------------------------------------------------------------ stage 4 on shards
 
-// edge (e, f) on rank(e): replace e by (unitig(e), is_begin) -> record (f, ue << 1 | e_begin), routed to rank(f) next
-__device__ __forceinline__ void end_to_unitig(uint32_t e, const uint64_t *info, const uint32_t *unitig_of_kmer, uint64_t piece_base_me,
-                                              const uint64_t *pinfo, const uint32_t *unitig_of_piece, uint32_t &u, bool &is_begin) {
-    uint32_t q = unitig_of_kmer[e >> 1];                       // local piece
-    bool piece_begin = (uint32_t)(info[e >> 1] >> 32) == e;    // e is the BEGIN terminus of its piece
-    uint64_t g = piece_base_me + q;
-    uint64_t inf = pinfo[g];
-    uint32_t rev = (uint32_t)inf & 1u;
+// An edge (e, f) between k-mer ends that are unitig extremities: both ends are piece termini, found in the replicated table; the
+// piece-level ranking (replicated too) says which unitig each terminus belongs to and whether it is the unitig's BEGIN.
+__device__ __forceinline__ bool terminus_to_unitig(uint32_t term, const uint64_t *pinfo, const uint32_t *unitig_of_piece, uint32_t &u, bool &is_begin) {
+    if (term == NOLINK) return false;
+    const uint32_t g = term >> 1;
+    const uint32_t rev = (uint32_t)pinfo[g] & 1u;
     u = unitig_of_piece[g];
-    is_begin = piece_begin != (rev != 0);                      // a reversed piece swaps its termini
+    is_begin = ((term & 1u) == 0) != (rev != 0);               // a reversed piece swaps its termini
+    return true;
 }
 
-__global__ void __launch_bounds__(256) links_annotate_from(ulonglong2 *edges, uint64_t n, const uint64_t *__restrict__ info,
-                                                           const uint32_t *__restrict__ unitig_of_kmer, uint64_t piece_base_me,
-                                                           const uint64_t *__restrict__ pinfo, const uint32_t *__restrict__ unitig_of_piece) {
+// edge (e gid, f gid) -> (owner(ue) << 32 | ue,  uf | from_sign << 32 | to_sign << 40), ready to be routed to the owner of unitig ue
+__global__ void __launch_bounds__(256) links_resolve(ulonglong2 *edges, uint64_t n, GidTable T, const uint64_t *__restrict__ pinfo,
+                                                     const uint32_t *__restrict__ unitig_of_piece, uint64_t U_total, uint32_t world, int *bad) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         ulonglong2 ed = edges[i];
-        uint32_t u; bool b;
-        end_to_unitig(GID_LOCAL(ed.x), info, unitig_of_kmer, piece_base_me, pinfo, unitig_of_piece, u, b);
-        edges[i] = make_ulonglong2(ed.y, ((uint64_t)u << 1) | (b ? 1 : 0));
-    }
-}
-
-// record (f, ue<<1|e_begin) on rank(f) -> (owner(ue) << 32 | ue,  uf | from_sign << 32 | to_sign << 40)
-__global__ void __launch_bounds__(256) links_annotate_to(ulonglong2 *recs, uint64_t n, const uint64_t *__restrict__ info,
-                                                         const uint32_t *__restrict__ unitig_of_kmer, uint64_t piece_base_me,
-                                                         const uint64_t *__restrict__ pinfo, const uint32_t *__restrict__ unitig_of_piece,
-                                                         uint64_t U_total, uint32_t world) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        ulonglong2 r = recs[i];
-        uint32_t uf; bool fb;
-        end_to_unitig(GID_LOCAL(r.x), info, unitig_of_kmer, piece_base_me, pinfo, unitig_of_piece, uf, fb);
-        uint32_t ue = (uint32_t)(r.y >> 1); bool eb = (r.y & 1) != 0;
+        uint32_t ue = 0, uf = 0; bool eb = false, fb = false;
+        bool ok = terminus_to_unitig(gid_lookup(T, ed.x), pinfo, unitig_of_piece, ue, eb) &&
+                  terminus_to_unitig(gid_lookup(T, ed.y), pinfo, unitig_of_piece, uf, fb);
+        if (!ok) { *bad = 1; ue = 0; uf = 0; }
         uint64_t owner = ((uint64_t)ue * world) / U_total;
         uint64_t fs = eb ? '-' : '+', ts = fb ? '+' : '-';
-        recs[i] = make_ulonglong2((owner << 32) | ue, (uint64_t)uf | (fs << 32) | (ts << 40));
+        edges[i] = make_ulonglong2((owner << 32) | ue, (uint64_t)uf | (fs << 32) | (ts << 40));
     }
 }
 

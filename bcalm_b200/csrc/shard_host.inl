@@ -5,9 +5,8 @@
 //   X1  packed canonical k-mers            -> owner(minimizer_k)            (after K1, before counting)
 //   X2  junction end records (key, value)  -> owner(minimizer_{k-1})        (after K3, before the join)
 //   X3  compaction link messages           -> owner of each k-mer end       (after K5)
-//   X4  piece-terminus neighbour messages  -> owner of the partner end      (glue)
-//   AG  piece descriptors + piece strings  -> every GPU                     (glue: replicated piece-level ranking)
-//   X5-X7 edges -> rank(from end) -> rank(to end) -> owner(from unitig)     (links)
+//   AG  piece descriptors + piece strings  -> every GPU                     (glue: replicated gid->terminus table + piece-level ranking)
+//   X4  resolved link records              -> owner(from unitig)            (links; both ends resolved locally through the table)
 
 #define NK(call)                                                                                                       \
     do {                                                                                                               \
@@ -285,10 +284,28 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0};
     std::vector<uint64_t> run_off((size_t)P_local * W), run_len((size_t)P_local * W);
     plan_shard_exchange(W, me, P_local, all_cnt.data(), send_cnt, recv_cnt, run_off.data(), run_len.data());
-    void *rk = nullptr, *rv = nullptr; uint64_t T_in = 0, T_in2 = 0;
-    if ((rc = exchange_with_counts(ctx, d_key_s, send_cnt, recv_cnt, 8, &rk, &T_in))) return rc;
-    if ((rc = exchange_with_counts(ctx, d_val_s, send_cnt, recv_cnt, 8, &rv, &T_in2))) return rc;
-    uint64_t *d_rec_key = (uint64_t *)rk, *d_rec_val = (uint64_t *)rv;
+    // keys and values travel as two segments of ONE exchange: [keys of all bins for peer d | values ...] would need a repack, so
+    // instead both arrays are sent in the same NCCL group (one launch, one synchronisation point)
+    uint64_t *d_rec_key = nullptr, *d_rec_val = nullptr; uint64_t T_in = 0;
+    {
+        for (int sidx = 0; sidx < W; sidx++) T_in += recv_cnt[sidx];
+        if ((rc = dalloc(ctx, &d_rec_key, T_in + 2))) return rc;
+        if ((rc = dalloc(ctx, &d_rec_val, T_in + 2))) return rc;
+        NK(ncclGroupStart());
+        uint64_t so = 0, ro = 0;
+        for (int peer = 0; peer < W; peer++) {
+            if (send_cnt[peer]) {
+                NK(ncclSend(d_key_s + so, send_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
+                NK(ncclSend(d_val_s + so, send_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
+            }
+            if (recv_cnt[peer]) {
+                NK(ncclRecv(d_rec_key + ro, recv_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
+                NK(ncclRecv(d_rec_val + ro, recv_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
+            }
+            so += send_cnt[peer]; ro += recv_cnt[peer];
+        }
+        NK(ncclGroupEnd());
+    }
     dfree(ctx, d_key_s); dfree(ctx, d_val_s); dfree(ctx, d_bins3);
     ctx->st.n_junction_records = T_in;
 
@@ -379,22 +396,14 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     const uint64_t G = piece_base[W];
     if (G >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 pieces");
     ctx->piece_base_me = piece_base[me];
-    PieceDesc *d_desc = nullptr, *d_desc_all = nullptr; ulonglong2 *d_nmsg = nullptr;
+    PieceDesc *d_desc = nullptr, *d_desc_all = nullptr;
     if ((rc = dalloc(ctx, &d_desc, max_p))) return rc;
     if ((rc = dalloc(ctx, &d_desc_all, max_p * W))) return rc;
-    if ((rc = dalloc(ctx, &d_nmsg, 2 * Pn + 1))) return rc;
     CK(cudaMemsetAsync(d_desc, 0xFF, max_p * sizeof(PieceDesc), ctx->stream));
-    if ((rc = ctr_zero(ctx))) return rc;
-    if (Pn) LAUNCH(glue_describe, grid_for(ctx, Pn, 256, 8), 256, 0, Pn, (uint32_t)me, piece_base[me], ctx->d_term_begin, ctx->d_term_end, ctx->d_link64,
-                   d_pseq_off, d_pkc, k, d_desc, d_nmsg, ctx->d_ctr + 0);
-    if ((rc = ctr_read(ctx))) return rc;
-    const uint64_t n_nmsg = ctx->h_ctr[0];
-    ulonglong2 *d_nmsg_in = nullptr; uint64_t n_nmsg_in = 0;
-    if ((rc = route16(ctx, d_nmsg, n_nmsg, &d_nmsg_in, &n_nmsg_in))) return rc;
-    if (n_nmsg_in) LAUNCH(glue_apply_nbr, grid_for(ctx, n_nmsg_in, 256, 8), 256, 0, d_nmsg_in, n_nmsg_in, ctx->d_info, ctx->d_unitig_of_kmer, d_desc);
-    dfree(ctx, d_nmsg); dfree(ctx, d_nmsg_in);
+    if (Pn) LAUNCH(glue_describe, grid_for(ctx, Pn, 256, 8), 256, 0, Pn, (uint32_t)me, ctx->d_term_begin, ctx->d_term_end, ctx->d_link64, d_pseq_off,
+                   d_pkc, k, d_desc);
     NK(ncclAllGather(d_desc, d_desc_all, max_p * sizeof(PieceDesc), ncclChar, ctx->comm, ctx->stream));
-    TRACE("glue describe + X4 + allgather desc");
+    TRACE("glue describe + allgather desc");
     char *d_seq_all = nullptr;
     if ((rc = dalloc(ctx, &d_seq_all, max_nt * W))) return rc;
     {   // pad my piece strings to max_nt for the all-gather
@@ -410,7 +419,15 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &d_plink, 2 * G + 1))) return rc;
     if ((rc = dalloc(ctx, &d_weight, G + 1))) return rc;
     CK(cudaMemcpyAsync(d_piece_base, piece_base, (W + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (G) LAUNCH(glue_build, grid_for(ctx, G, 256, 8), 256, 0, d_desc_all, max_p, (uint32_t)W, d_piece_base, G, d_plink, d_weight);
+    // replicated gid -> piece-terminus table (kept for the link stage)
+    ctx->gid_table.cap = table_cap_for(2 * G + 16);
+    if ((rc = dalloc(ctx, &ctx->gid_table.keys, ctx->gid_table.cap))) return rc;
+    if ((rc = dalloc(ctx, &ctx->gid_table.vals, ctx->gid_table.cap))) return rc;
+    CK(cudaMemsetAsync(ctx->gid_table.keys, 0xFF, (size_t)ctx->gid_table.cap * 8, ctx->stream));
+    if (G) {
+        LAUNCH(glue_table_build, grid_for(ctx, 2 * G, 256, 8), 256, 0, d_desc_all, max_p, (uint32_t)W, d_piece_base, G, ctx->gid_table);
+        LAUNCH(glue_build, grid_for(ctx, G, 256, 8), 256, 0, d_desc_all, max_p, (uint32_t)W, d_piece_base, G, ctx->gid_table, d_plink, d_weight);
+    }
     uint64_t *d_ppair = nullptr, *d_puid = nullptr, *d_pnt = nullptr, *d_pedges = nullptr; uint64_t n_pedges = 0;
     const uint64_t pedge_cap = 1 << 16;
     if ((rc = dalloc(ctx, &d_pedges, pedge_cap))) return rc;
@@ -486,19 +503,18 @@ int shard_stage_link(cdbg_ctx *ctx) {
     int rc;
     const int W = ctx->world;
     tstart(ctx, T_LINK);
-    // X5: to the owner of the FROM end, which knows its unitig and whether it is a BEGIN
-    ulonglong2 *a = nullptr, *b = nullptr, *c = nullptr; uint64_t na = 0, nb = 0, nc = 0;
-    if ((rc = route16(ctx, ctx->d_sedges, ctx->n_sedges, &a, &na))) return rc;
-    if (na) LAUNCH(links_annotate_from, grid_for(ctx, na, 256, 8), 256, 0, a, na, ctx->d_info, ctx->d_unitig_of_kmer, ctx->piece_base_me, ctx->d_pinfo,
-                   ctx->d_unitig_of_piece);
-    // X6: to the owner of the TO end
-    if ((rc = route16(ctx, a, na, &b, &nb))) return rc;
-    dfree(ctx, a);
-    if (nb) LAUNCH(links_annotate_to, grid_for(ctx, nb, 256, 8), 256, 0, b, nb, ctx->d_info, ctx->d_unitig_of_kmer, ctx->piece_base_me, ctx->d_pinfo,
-                   ctx->d_unitig_of_piece, std::max<uint64_t>(ctx->U_total, 1), (uint32_t)W);
-    // X7: to the owner of the FROM unitig, grouped CSR there
-    if ((rc = route16(ctx, b, nb, &c, &nc))) return rc;
-    dfree(ctx, b);
+    // both ends of every edge are resolved through the replicated gid table; one exchange to the owner of the FROM unitig
+    ulonglong2 *c = nullptr; uint64_t nc = 0;
+    if ((rc = ctr_zero(ctx))) return rc;
+    if (ctx->n_sedges) LAUNCH(links_resolve, grid_for(ctx, ctx->n_sedges, 256, 8), 256, 0, ctx->d_sedges, ctx->n_sedges, ctx->gid_table, ctx->d_pinfo,
+                              ctx->d_unitig_of_piece, std::max<uint64_t>(ctx->U_total, 1), (uint32_t)W, ctx->d_flag);
+    if ((rc = route16(ctx, ctx->d_sedges, ctx->n_sedges, &c, &nc))) return rc;
+    {
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (bad) return ctx->fail(CDBG_ERR_INTERNAL, "an edge end is not a piece terminus");
+    }
     const uint64_t U = ctx->U;
     LinkRec *d_tmp = nullptr; uint32_t *d_per = nullptr, *d_cur = nullptr;
     if ((rc = dalloc(ctx, &ctx->d_links, nc + 1))) return rc;
@@ -515,7 +531,7 @@ int shard_stage_link(cdbg_ctx *ctx) {
     if (nc) LAUNCH(links_group, grid_for(ctx, nc, 256, 8), 256, 0, d_tmp, nc, (uint32_t)ctx->u_first, ctx->d_link_off, d_cur, ctx->d_links);
     dfree(ctx, c); dfree(ctx, d_tmp); dfree(ctx, d_per); dfree(ctx, d_cur);
     tstop(ctx, T_LINK);
-    TRACE("links (3 routes + group)");
+    TRACE("links (resolve + 1 route + group)");
     ctx->n_edges = nc;
     ctx->st.n_links = nc;
     ctx->stage = ST_LINKED;
