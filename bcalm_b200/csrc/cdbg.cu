@@ -45,6 +45,7 @@ struct cdbg_ctx {
     cdbg_stats st{};
     Timer tm[T_N];
     uint32_t launches = 0;
+    bool use_pdl = true;           // CDBG_PDL=0 disables programmatic dependent launch (A/B)
     bool trace = false;            // CDBG_TRACE=1: print a host-side timeline (stream-synchronised, debugging only)
     double trace_t0 = 0;
 
@@ -169,6 +170,20 @@ int dalloc_bytes(cdbg_ctx *ctx, void **out, size_t bytes) {
     *out = q;
     return CDBG_OK;
 }
+
+// launch with programmatic stream serialization (the kernel must start with pdl_wait(), see kernels.cuh)
+#define LAUNCH_PDL(kern, grid, block, smem, ...)                                                             \
+    do {                                                                                                     \
+        cudaLaunchConfig_t cfg_ = {};                                                                        \
+        cfg_.gridDim = dim3((unsigned)(grid)); cfg_.blockDim = dim3((unsigned)(block));                      \
+        cfg_.dynamicSmemBytes = (smem); cfg_.stream = ctx->stream;                                           \
+        cudaLaunchAttribute at_[1];                                                                          \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                      \
+        at_[0].val.programmaticStreamSerializationAllowed = ctx->use_pdl ? 1 : 0;                            \
+        cfg_.attrs = at_; cfg_.numAttrs = 1;                                                                 \
+        ctx->launches++;                                                                                     \
+        CK(cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__));                                                    \
+    } while (0)
 
 template <typename T>
 int dalloc(cdbg_ctx *ctx, T **p, size_t n_elems) {
@@ -369,8 +384,8 @@ int stage_count(cdbg_ctx *ctx) {
             uint64_t nb = h_cnt[b];
             if (!nb) continue;
             uint32_t cap_b = std::min(cap, std::max<uint32_t>(1024, (uint32_t)std::min<double>((double)nb * slots_per_instance + 64.0, 4.0e9) & ~63u));
-            LAUNCH(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers + h_off[b], nb, d_keys, d_counts, cap_b, ctx->d_flag);
-            LAUNCH(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
+            LAUNCH_PDL(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers + h_off[b], nb, d_keys, d_counts, cap_b, ctx->d_flag);
+            LAUNCH_PDL(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
                    ctx->d_solid_counts, solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
             if (first && attempt == 0 && P > 2) {
                 first = false;
@@ -412,7 +427,7 @@ int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remainin
     for (int round = 0; round < 80; round += 4) {
         int rc = ctr_zero(ctx);
         if (rc) return rc;
-        for (int j = 0; j < 4; j++) LAUNCH(k6_jump, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, n2, ctx->d_ctr + j);
+        for (int j = 0; j < 4; j++) LAUNCH_PDL(k6_jump, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, n2, ctx->d_ctr + j);
         ctx->st.rank_rounds += 4;
         if ((rc = ctr_read(ctx))) return rc;
         for (int j = 0; j < 4; j++) {
@@ -572,8 +587,8 @@ int stage_compact(cdbg_ctx *ctx) {
             if (!nb) continue;
             uint32_t cap_b = table_cap(nb);
             T.cap = cap_b;
-            LAUNCH(k5_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_rec_key + h_off[b], d_rec_val + h_off[b], nb, T, ctx->d_flag);
-            LAUNCH(k5_resolve, grid_for(ctx, cap_b, 256, 8), 256, 0, T, cap_b, ctx->d_link, ctx->d_edges, ctx->edge_cap, ctx->d_ctr + 0,
+            LAUNCH_PDL(k5_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_rec_key + h_off[b], d_rec_val + h_off[b], nb, T, ctx->d_flag);
+            LAUNCH_PDL(k5_resolve, grid_for(ctx, cap_b, 256, 8), 256, 0, T, cap_b, ctx->d_link, ctx->d_edges, ctx->edge_cap, ctx->d_ctr + 0,
                    ctx->d_ctr + 1);
         }
         tstop(ctx, T_K5);
@@ -682,6 +697,7 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     ctx->m = params->minimizer_size > 0 ? params->minimizer_size : 10;
     if (ctx->m > ctx->k - 1) ctx->m = ctx->k - 1;   // ConfigurationAlgorithm.cpp:251
     ctx->trace = getenv("CDBG_TRACE") != nullptr;
+    ctx->use_pdl = !(getenv("CDBG_PDL") && atoi(getenv("CDBG_PDL")) == 0);
     ctx->amin = (uint32_t)std::max(params->abundance_min, 1);
     ctx->amax = params->abundance_max > 0 ? (uint32_t)params->abundance_max : 0x7FFFFFFFu;
     int ndev = 0;

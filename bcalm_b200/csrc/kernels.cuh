@@ -34,6 +34,14 @@ __device__ __forceinline__ uint64_t warp_append(unsigned long long *cursor, bool
 
 __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) { return *(const volatile uint64_t *)p; }
 
+// Programmatic dependent launch: kernels of the short per-bin loops (K2, K5, K6) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so their CTAs are scheduled while the previous kernel drains; they must
+// wait here before touching anything the predecessor wrote.  A no-op for a normal launch.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // predecessor grid complete and its writes visible
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the successor's CTAs take SM slots as ours retire
+}
+
 // Sum `v` over the block and add it to *dst with ONE atomic per block: a same-address global atomic costs ~4 ns, so
 // per-warp accumulation (thousands of warps per launch) would dominate these short kernels.  All threads must call.
 __device__ __forceinline__ void block_add(unsigned long long *dst, unsigned long long v) {
@@ -265,8 +273,11 @@ static inline size_t k1_smem_bytes(int mode, uint32_t P) {
 // and stays resident in the 126 MB L2.
 __device__ __forceinline__ uint32_t table_slot(uint64_t key, uint32_t cap) { return (uint32_t)(((mix64(key) & 0xFFFFFFFFULL) * cap) >> 32); }
 
+// (Tried: 4 k-mers per thread with their first probes issued together -- 2.16 -> 2.75 ms on C2.  The kernel is bound by L2
+// operation throughput, not by per-thread latency, so more requests in flight only add contention.)
 __global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ kmers, uint64_t n, uint64_t *keys, uint32_t *counts,
                                                  uint32_t cap, int *overflow) {
+    pdl_wait();
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = kmers[i];
         uint32_t slot = table_slot(key, cap);
@@ -293,6 +304,7 @@ constexpr int K2_EMIT_THREADS = 256;
 __global__ void __launch_bounds__(K2_EMIT_THREADS) k2_emit(uint64_t *keys, uint32_t *counts, uint32_t cap, uint32_t amin, uint32_t amax,
                                                            uint64_t *solid_kmers, uint32_t *solid_counts, uint64_t solid_cap,
                                                            unsigned long long *n_solid, unsigned long long *n_distinct) {
+    pdl_wait();
     __shared__ uint32_t s_wsolid[K2_EMIT_THREADS / 32];
     __shared__ unsigned long long s_base;
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -455,6 +467,7 @@ struct JoinTable {
 
 __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ rec_key, const uint64_t *__restrict__ rec_val, uint64_t n,
                                                  JoinTable T, int *overflow) {
+    pdl_wait();
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = rec_key[i], val = rec_val[i];
         uint32_t slot = table_slot(key, T.cap);
@@ -486,6 +499,7 @@ __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ re
 // palindrome) is an edge between unitig extremities (LinkTigs.cpp:365-369,428-432).  Slots are reset for the next bin.
 __global__ void __launch_bounds__(256) k5_resolve(JoinTable T, uint32_t cap, uint32_t *link, uint64_t *edges, uint64_t edge_cap,
                                                   unsigned long long *n_edges, unsigned long long *n_compact) {
+    pdl_wait();
     unsigned long long compact = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
         if (T.keys[i] == EMPTY_KEY) continue;
@@ -539,6 +553,7 @@ __global__ void __launch_bounds__(256) k6_init(const uint32_t *__restrict__ link
 
 
 __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsigned long long *n_updated) {
+    pdl_wait();
     unsigned long long upd = 0;
     for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t p = ld_volatile_u64(&pair[x]);
