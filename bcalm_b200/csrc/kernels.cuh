@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(256) k2_insert(const uint64_t *__restrict__ km
         uint32_t slot = table_slot(key, cap);
         uint32_t probes = 0;
         for (;;) {
+            // load first, CAS only on an empty slot: probing with the CAS itself (2.0 instead of 2.3 L2 operations per instance)
+            // measured slower (2.15 -> 2.23 ms): an L2 atomic costs more than the load it saves
             uint64_t cur = ld_volatile_u64(&keys[slot]);
             if (cur == EMPTY_KEY) {
                 cur = atomicCAS((unsigned long long *)&keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);

@@ -326,7 +326,7 @@ def main():
                          "stage_ms": groups},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU leg runs on rank 0 at N=1 only
             try:
                 out["cpu_baseline"] = cpu_baseline_sample(c, args.cpu_scale, cores)
             except Exception as e:  # never lose the GPU line because the CPU leg failed
