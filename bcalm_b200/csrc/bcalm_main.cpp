@@ -17,6 +17,7 @@
 
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cdbg.h"
@@ -27,6 +28,7 @@ struct Options {
     std::string in, out, out_gfa;
     int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
     bool all_abund = false;
+    bool parse_only = false; // -parse-only: parse the input, print record/byte counts and a checksum, no GPU (host-side tests)
     bool edge_km = false;   // -edge-km 1: J:<0|1>:<id>:<0|1> tokens instead of L: (G/debruijn/impl/LinkTigs.cpp:380-384,440-444)
 };
 
@@ -81,6 +83,7 @@ Options parse(int argc, char **argv) {
         else if (a == "-verbose") o.verbose = atoi(need("-verbose").c_str());
         else if (a == "-device") o.device = atoi(need("-device").c_str());
         else if (a == "-all-abundance-counts") o.all_abund = true;
+        else if (a == "-parse-only") o.parse_only = true;
         else if (a == "-edge-km") o.edge_km = atoi(need("-edge-km").c_str()) != 0;
         else if (a == "-help" || a == "-h") { usage(); exit(EXIT_SUCCESS); }
         else {
@@ -170,6 +173,37 @@ void parse_sequences(const std::vector<char> &in, std::vector<uint8_t> &out, uin
     }
 }
 
+// Parse one file's bytes on `threads` host threads: the buffer is cut at record starts ('>' or, for FASTQ, every 4th line
+// would need a global line count, so FASTQ stays single-threaded unless it is cut at "\n@" followed by a plausible 4-line record),
+// each piece is parsed independently and the pieces are concatenated in order -- byte-identical to the serial parse.
+void parse_sequences_mt(const std::vector<char> &in, std::vector<uint8_t> &out, uint64_t &n_records, int threads) {
+    const size_t n = in.size();
+    if (threads <= 1 || n < (8u << 20) || in[0] != '>') { parse_sequences(in, out, n_records); return; }
+    std::vector<size_t> cut{0};
+    for (int t = 1; t < threads; t++) {
+        size_t p = n / threads * t;
+        while (p < n && !(in[p] == '>' && in[p - 1] == '\n')) p++;      // next FASTA record start
+        if (p < n && p > cut.back()) cut.push_back(p);
+    }
+    cut.push_back(n);
+    const size_t pieces = cut.size() - 1;
+    std::vector<std::vector<uint8_t>> outs(pieces);
+    std::vector<uint64_t> recs(pieces, 0);
+    std::vector<std::thread> pool;
+    for (size_t i = 0; i < pieces; i++)
+        pool.emplace_back([&, i]() {
+            std::vector<char> piece(in.begin() + cut[i], in.begin() + cut[i + 1]);
+            parse_sequences(piece, outs[i], recs[i]);
+        });
+    for (auto &th : pool) th.join();
+    size_t total = out.size();
+    for (auto &o : outs) total += o.size();
+    out.reserve(total);
+    for (size_t i = 0; i < pieces; i++) { out.insert(out.end(), outs[i].begin(), outs[i].end()); n_records += recs[i]; }
+}
+
+static int g_parse_threads = 1;
+
 void load_input(const std::string &spec, std::vector<uint8_t> &stream, uint64_t &n_records, int depth = 0) {
     size_t start = 0;
     while (start <= spec.size()) {
@@ -183,7 +217,7 @@ void load_input(const std::string &spec, std::vector<uint8_t> &stream, uint64_t 
         while (i < buf.size() && (buf[i] == '\n' || buf[i] == '\r' || buf[i] == ' ')) i++;
         if (i == buf.size()) continue;
         if (buf[i] == '>' || buf[i] == '@') {
-            parse_sequences(buf, stream, n_records);
+            parse_sequences_mt(buf, stream, n_records, g_parse_threads);
         } else {
             if (depth > 2) die("file of files nested too deeply: " + path);
             // file of files: one path per line, relative to the list's directory (G/bank/impl/BankAlbum.cpp)
@@ -232,6 +266,15 @@ int main(int argc, char **argv) {
     const double t0 = now_s();
     if (o.verbose) printf("BCALM 2 (B200-native), k=%d abundance-min=%d input=%s\n", o.k, o.amin, o.in.c_str());
 
+    g_parse_threads = o.cores > 0 ? o.cores : (int)std::max(1u, std::thread::hardware_concurrency());
+    if (o.parse_only) {
+        std::vector<uint8_t> st0; uint64_t nrec = 0;
+        load_input(o.in, st0, nrec);
+        uint64_t h = 1469598103934665603ULL;                       // FNV-1a of the nucleotide stream
+        for (uint8_t c : st0) { h ^= c; h *= 1099511628211ULL; }
+        printf("records %llu bytes %llu fnv1a %016llx threads %d\n", (unsigned long long)nrec, (unsigned long long)st0.size(), (unsigned long long)h, g_parse_threads);
+        return EXIT_SUCCESS;
+    }
     cdbg_params prm{};
     prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device;
     prm.flags = (o.all_abund ? CDBG_FLAG_ALL_ABUNDANCE_COUNTS : 0) | (o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0);

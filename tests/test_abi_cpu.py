@@ -95,3 +95,55 @@ def test_cli_version_and_errors():
     assert out.returncode != 0 and "EXCEPTION" in out.stdout
     out = subprocess.run([cli, "-in", "/nonexistent.fa", "-bogus-option", "1"], capture_output=True, text=True)
     assert out.returncode != 0 and "EXCEPTION" in out.stdout
+
+
+def _parse_only(cli, path, *extra):
+    out = subprocess.run([cli, "-in", str(path), "-parse-only", *extra], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    f = [l for l in out.stdout.splitlines() if l.startswith("records ")][-1].split()
+    return int(f[1]), int(f[3]), f[5]
+
+
+def test_cli_input_grammar_host_side(tmp_path):
+    """FASTA (single/multi-line, CRLF), FASTQ, gz, comma list and file of files all yield the same nucleotide stream
+    (G/bank/impl/BankFasta.cpp:390-560; README 'input formats'), checked without a GPU through -parse-only."""
+    import gzip
+    import numpy as np
+    from bcalm_b200 import build
+    build.build_lib()
+    cli = build.build_cli()
+    rng = np.random.default_rng(1)
+    reads = ["".join(rng.choice(list("ACGTN"), size=int(rng.integers(30, 300)), p=[.24, .24, .24, .24, .04])) for _ in range(500)]
+    expected_bytes = sum(len(r) + 1 for r in reads)
+    fa = tmp_path / "a.fa"
+    fa.write_text("".join(f">r{i} some ACGT header\n{r}\n" for i, r in enumerate(reads)))
+    ml = tmp_path / "ml.fasta"
+    ml.write_text("".join(f">r{i}\r\n" + "\r\n".join(r[j:j + 60] for j in range(0, len(r), 60)) + "\r\n" for i, r in enumerate(reads)))
+    fq = tmp_path / "a.fq"
+    fq.write_text("".join(f"@r{i}\n{r}\n+\n{'@' * len(r)}\n" for i, r in enumerate(reads)))   # quality lines starting with '@'
+    gz = tmp_path / "a.fa.gz"
+    with gzip.open(gz, "wt") as f:
+        f.write(fa.read_text())
+    half = tmp_path / "h1.fa"; half2 = tmp_path / "h2.fa"
+    half.write_text("".join(f">r{i}\n{r}\n" for i, r in enumerate(reads[:250])))
+    half2.write_text("".join(f">r{i}\n{r}\n" for i, r in enumerate(reads[250:])))
+    lst = tmp_path / "files.txt"
+    lst.write_text("h1.fa\nh2.fa\n")
+    ref = _parse_only(cli, fa)
+    assert ref[0] == 500 and ref[1] == expected_bytes
+    for p in (ml, fq, gz, lst, f"{half},{half2}"):
+        assert _parse_only(cli, p) == ref, p
+
+
+def test_cli_parallel_parse_is_identical(tmp_path):
+    import numpy as np
+    from bcalm_b200 import build
+    cli = build.build_cli()
+    rng = np.random.default_rng(2)
+    big = tmp_path / "big.fa"
+    with open(big, "w") as f:
+        for i in range(120000):          # ~12 MB: above the threshold for the multi-threaded parse
+            f.write(f">read{i}\n" + "".join(rng.choice(list("ACGT"), size=100)) + "\n")
+    a = _parse_only(cli, big, "-nb-cores", "1")
+    b = _parse_only(cli, big, "-nb-cores", "7")
+    assert a == b and a[0] == 120000
