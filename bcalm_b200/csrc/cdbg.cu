@@ -239,11 +239,6 @@ inline int grid_for(cdbg_ctx *ctx, uint64_t n, int block, int per_sm) {
     return (int)std::max<uint64_t>(1, std::min(need, cap));
 }
 
-uint32_t next_pow2(uint64_t x) {
-    uint64_t p = 1;
-    while (p < x) p <<= 1;
-    return (uint32_t)std::min<uint64_t>(p, 1ULL << 31);
-}
 
 // zero the counter scratch
 int ctr_zero(cdbg_ctx *ctx) {

@@ -141,7 +141,7 @@ struct K1Params {
 // leave the SM as one contiguous run.
 template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS) k1_extract(K1Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     // 8-byte arrays first, then the 4-byte ones
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(smem_raw);                 // [THREADS + 2] packed bases, 32 per word
     uint64_t *s_gbase = s_pk + K1_THREADS + 2;                               // [P]       MODE 1: global base of each bin's run
@@ -405,7 +405,7 @@ constexpr int K3_TILE = K3_THREADS * K3_PER_THREAD;       // 1024 k-mers = 2048 
 // single global atomic, so the hot cursors are hit once per (tile, bin) instead of once per record.
 template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS) k3_ends(K3Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw);                  // [P] MODE 1
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? p.P : 0));   // [P]
     const int t = threadIdx.x;
@@ -773,9 +773,6 @@ __global__ void __launch_bounds__(256) k9_group(const LinkRec *__restrict__ in, 
 
 // ------------------------------------------------------------------------------------------------ misc
 
-__global__ void fill_u64(uint64_t *p, uint64_t n, uint64_t v) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
-}
 
 // synthetic reads (bench): genome base g(i) = hash(seed, i) & 3 generated on the fly, so no genome array is needed
 __device__ __forceinline__ uint32_t synth_base(uint64_t seed, uint64_t i) { return (uint32_t)(mix64(seed ^ (i * 0x9E3779B97F4A7C15ULL)) >> 61) & 3u; }

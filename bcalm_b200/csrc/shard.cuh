@@ -56,7 +56,7 @@ __device__ __forceinline__ uint64_t funnel_left(uint64_t hi, uint64_t lo, int bi
 
 template <int MODE>
 __global__ void __launch_bounds__(K1S_THREADS) k1s_extract(K1SParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t P = p.world * p.P_local;
     uint64_t *s_pk = reinterpret_cast<uint64_t *>(smem_raw);                   // [K1S_WORDS]
     uint64_t *s_gbase = s_pk + K1S_WORDS;                                      // [P]        MODE 1
@@ -234,7 +234,7 @@ struct K3SParams {
 
 template <int MODE>
 __global__ void __launch_bounds__(K3_THREADS) k3s_ends(K3SParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t P = p.world * p.P_local;
     uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? P : 0));

@@ -138,7 +138,7 @@ __device__ __forceinline__ bool nt_valid_dev(uint8_t c) { uint8_t u = c & 0xDF; 
 // MODE 0 histogram, MODE 1 scatter (two rolling sweeps per tile: count, then place into the run reserved per (tile, bin))
 template <int W, int MODE>
 __global__ void __launch_bounds__(KW1_THREADS) kw1_extract(KW1Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *s_raw = smem_raw;                                                             // [TILE + HALO]
     uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw + KW1_TILE + KW1_HALO);       // [P]  MODE 1
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? p.P : 0));        // [P]
@@ -286,7 +286,7 @@ struct KW3Params {
 // per-tile shared-memory aggregation like k3_ends: the hot per-bin cursors are hit once per (tile, bin)
 template <int W, int MODE>
 __global__ void __launch_bounds__(K3_THREADS) kw3_ends(KW3Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *s_base = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_base + (MODE == 1 ? p.P : 0));
     const int t = threadIdx.x;
