@@ -111,31 +111,72 @@ std::string dir_name(const std::string &path) {
     return s == std::string::npos ? std::string(".") : path.substr(0, s);
 }
 
-bool read_whole(const std::string &path, std::vector<char> &buf) {
-    gzFile f = gzopen(path.c_str(), "rb");   // transparently reads plain files too
+// A file's bytes without zero-filling or re-growing: plain files are read in one go into an uninitialised buffer sized from
+// fstat, gzip files (magic 1f 8b) go through zlib with a doubling buffer.
+struct FileBuf {
+    char *p = nullptr; size_t n = 0;
+    ~FileBuf() { free(p); }
+    FileBuf() = default;
+    FileBuf(const FileBuf &) = delete;
+    FileBuf &operator=(const FileBuf &) = delete;
+};
+
+bool read_whole(const std::string &path, FileBuf &buf) {
+    FILE *f = fopen(path.c_str(), "rb");
     if (!f) return false;
-    gzbuffer(f, 1 << 20);
-    buf.clear();
-    size_t cap = 1 << 24;
-    buf.resize(cap);
-    size_t n = 0;
-    for (;;) {
-        if (n == buf.size()) buf.resize(buf.size() * 2);
-        int got = gzread(f, buf.data() + n, (unsigned)std::min<size_t>(buf.size() - n, 1u << 30));
-        if (got < 0) { gzclose(f); return false; }
-        if (got == 0) break;
-        n += (size_t)got;
+    unsigned char magic[2] = {0, 0};
+    size_t got = fread(magic, 1, 2, f);
+    const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (!gz) {
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz < 0) { fclose(f); return false; }
+        buf.p = (char *)malloc((size_t)sz + 1);
+        if (!buf.p) { fclose(f); return false; }
+        buf.n = fread(buf.p, 1, (size_t)sz, f);
+        fclose(f);
+        return true;
     }
-    gzclose(f);
-    buf.resize(n);
+    fclose(f);
+    gzFile g = gzopen(path.c_str(), "rb");
+    if (!g) return false;
+    gzbuffer(g, 1 << 20);
+    size_t cap = 1 << 24;
+    buf.p = (char *)malloc(cap);
+    for (;;) {
+        if (buf.n == cap) { cap *= 2; buf.p = (char *)realloc(buf.p, cap); }
+        if (!buf.p) { gzclose(g); return false; }
+        int r = gzread(g, buf.p + buf.n, (unsigned)std::min<size_t>(cap - buf.n, 1u << 30));
+        if (r < 0) { gzclose(g); return false; }
+        if (r == 0) break;
+        buf.n += (size_t)r;
+    }
+    gzclose(g);
     return true;
 }
 
+// growable byte buffer that does not zero-fill (std::vector<uint8_t>::resize would touch every page twice)
+struct ByteBuf {
+    uint8_t *p = nullptr; size_t n = 0, cap = 0;
+    ~ByteBuf() { free(p); }
+    ByteBuf() = default;
+    ByteBuf(const ByteBuf &) = delete;
+    ByteBuf &operator=(const ByteBuf &) = delete;
+    void reserve(size_t want) { if (want > cap) { cap = std::max(want, cap * 2); p = (uint8_t *)realloc(p, cap); if (!p) { printf("EXCEPTION: out of host memory\n"); exit(EXIT_FAILURE); } } }
+    void append(const uint8_t *src, size_t len) { reserve(n + len); memcpy(p + n, src, len); n += len; }
+    void push(uint8_t c) { reserve(n + 1); p[n++] = c; }
+    uint8_t *data() { return p; }
+    size_t size() const { return n; }
+};
+
 // Append the nucleotide stream of one FASTA/FASTQ buffer to `out`: sequence characters only, one '\n' after each record
 // (multi-line FASTA records are joined: BankFasta.cpp:390-560).
-void parse_sequences(const std::vector<char> &in, std::vector<uint8_t> &out, uint64_t &n_records) {
-    const char *p = in.data(), *e = p + in.size();
-    out.reserve(out.size() + in.size());
+// Writes the nucleotide stream of [begin, e) to dst (which must have room for e - begin + 1 bytes: the output is never longer
+// than the input plus one break) and returns its length.
+size_t parse_sequences_raw(const char *begin, const char *e, uint8_t *dst, uint64_t &n_records) {
+    const char *p = begin;
+    uint8_t *o = dst;
     while (p < e) {
         if (*p == '>') {                                  // FASTA record
             const char *nl = (const char *)memchr(p, '\n', e - p);
@@ -145,10 +186,10 @@ void parse_sequences(const std::vector<char> &in, std::vector<uint8_t> &out, uin
                 const char *le = l ? l : e;
                 size_t len = le - p;
                 if (len && p[len - 1] == '\r') len--;
-                out.insert(out.end(), (const uint8_t *)p, (const uint8_t *)p + len);
+                memcpy(o, p, len); o += len;
                 p = l ? l + 1 : e;
             }
-            out.push_back('\n');
+            *o++ = '\n';
             n_records++;
         } else if (*p == '@') {                           // FASTQ record (4 lines; multi-line FASTQ is not produced by sequencers)
             const char *l1 = (const char *)memchr(p, '\n', e - p);
@@ -158,8 +199,8 @@ void parse_sequences(const std::vector<char> &in, std::vector<uint8_t> &out, uin
             const char *se = l2 ? l2 : e;
             size_t len = se - s;
             if (len && s[len - 1] == '\r') len--;
-            out.insert(out.end(), (const uint8_t *)s, (const uint8_t *)s + len);
-            out.push_back('\n');
+            memcpy(o, s, len); o += len;
+            *o++ = '\n';
             n_records++;
             if (!l2) break;
             const char *l3 = (const char *)memchr(l2 + 1, '\n', e - (l2 + 1));   // '+' line
@@ -171,57 +212,66 @@ void parse_sequences(const std::vector<char> &in, std::vector<uint8_t> &out, uin
             p = nl ? nl + 1 : e;
         }
     }
+    return (size_t)(o - dst);
+}
+
+void parse_sequences(const char *begin, const char *e, ByteBuf &out, uint64_t &n_records) {
+    out.reserve(out.size() + (size_t)(e - begin) + 16);
+    out.n += parse_sequences_raw(begin, e, out.p + out.n, n_records);
 }
 
 // Parse one file's bytes on `threads` host threads: the buffer is cut at record starts ('>' or, for FASTQ, every 4th line
 // would need a global line count, so FASTQ stays single-threaded unless it is cut at "\n@" followed by a plausible 4-line record),
 // each piece is parsed independently and the pieces are concatenated in order -- byte-identical to the serial parse.
-void parse_sequences_mt(const std::vector<char> &in, std::vector<uint8_t> &out, uint64_t &n_records, int threads) {
-    const size_t n = in.size();
-    if (threads <= 1 || n < (8u << 20) || in[0] != '>') { parse_sequences(in, out, n_records); return; }
+void parse_sequences_mt(const FileBuf &in, ByteBuf &out, uint64_t &n_records, int threads) {
+    const size_t n = in.n;
+    const char *b = in.p;
+    if (threads <= 1 || n < (8u << 20) || b[0] != '>') { parse_sequences(b, b + n, out, n_records); return; }
     std::vector<size_t> cut{0};
     for (int t = 1; t < threads; t++) {
         size_t p = n / threads * t;
-        while (p < n && !(in[p] == '>' && in[p - 1] == '\n')) p++;      // next FASTA record start
+        while (p < n && !(b[p] == '>' && b[p - 1] == '\n')) p++;      // next FASTA record start
         if (p < n && p > cut.back()) cut.push_back(p);
     }
     cut.push_back(n);
     const size_t pieces = cut.size() - 1;
-    std::vector<std::vector<uint8_t>> outs(pieces);
+    // every piece writes at its own INPUT offset inside the output reservation (output <= input, so pieces cannot collide),
+    // then the pieces are closed up in order: no per-thread buffers, one pass of page faults shared by all threads
+    out.reserve(out.size() + n + pieces + 16);
+    uint8_t *base = out.p + out.n;
+    std::vector<size_t> len(pieces, 0);
     std::vector<uint64_t> recs(pieces, 0);
     std::vector<std::thread> pool;
-    for (size_t i = 0; i < pieces; i++)
-        pool.emplace_back([&, i]() {
-            std::vector<char> piece(in.begin() + cut[i], in.begin() + cut[i + 1]);
-            parse_sequences(piece, outs[i], recs[i]);
-        });
+    for (size_t i = 0; i < pieces; i++) pool.emplace_back([&, i]() { len[i] = parse_sequences_raw(b + cut[i], b + cut[i + 1], base + cut[i] + i, recs[i]); });
     for (auto &th : pool) th.join();
-    size_t total = out.size();
-    for (auto &o : outs) total += o.size();
-    out.reserve(total);
-    for (size_t i = 0; i < pieces; i++) { out.insert(out.end(), outs[i].begin(), outs[i].end()); n_records += recs[i]; }
+    size_t at = 0;
+    for (size_t i = 0; i < pieces; i++) {
+        if (at != cut[i] + i) memmove(base + at, base + cut[i] + i, len[i]);
+        at += len[i]; n_records += recs[i];
+    }
+    out.n += at;
 }
 
 static int g_parse_threads = 1;
 
-void load_input(const std::string &spec, std::vector<uint8_t> &stream, uint64_t &n_records, int depth = 0) {
+void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, int depth = 0) {
     size_t start = 0;
     while (start <= spec.size()) {
         size_t c = spec.find(',', start);
         std::string path = spec.substr(start, c == std::string::npos ? std::string::npos : c - start);
         start = c == std::string::npos ? spec.size() + 1 : c + 1;
         if (path.empty()) continue;
-        std::vector<char> buf;
+        FileBuf buf;
         if (!read_whole(path, buf)) die("Unable to open file '" + path + "'");
         size_t i = 0;
-        while (i < buf.size() && (buf[i] == '\n' || buf[i] == '\r' || buf[i] == ' ')) i++;
-        if (i == buf.size()) continue;
-        if (buf[i] == '>' || buf[i] == '@') {
+        while (i < buf.n && (buf.p[i] == '\n' || buf.p[i] == '\r' || buf.p[i] == ' ')) i++;
+        if (i == buf.n) continue;
+        if (buf.p[i] == '>' || buf.p[i] == '@') {
             parse_sequences_mt(buf, stream, n_records, g_parse_threads);
         } else {
             if (depth > 2) die("file of files nested too deeply: " + path);
             // file of files: one path per line, relative to the list's directory (G/bank/impl/BankAlbum.cpp)
-            std::string text(buf.begin(), buf.end()), dir = dir_name(path);
+            std::string text(buf.p, buf.p + buf.n), dir = dir_name(path);
             size_t ls = 0;
             while (ls < text.size()) {
                 size_t le = text.find('\n', ls);
@@ -268,10 +318,13 @@ int main(int argc, char **argv) {
 
     g_parse_threads = o.cores > 0 ? o.cores : (int)std::max(1u, std::thread::hardware_concurrency());
     if (o.parse_only) {
-        std::vector<uint8_t> st0; uint64_t nrec = 0;
+        ByteBuf st0; uint64_t nrec = 0;
+        const double tp0 = now_s();
         load_input(o.in, st0, nrec);
+        const double tp1 = now_s();
         uint64_t h = 1469598103934665603ULL;                       // FNV-1a of the nucleotide stream
-        for (uint8_t c : st0) { h ^= c; h *= 1099511628211ULL; }
+        for (size_t i = 0; i < st0.size(); i++) { h ^= st0.p[i]; h *= 1099511628211ULL; }
+        if (o.verbose > 1) printf("parse seconds %.3f\n", tp1 - tp0);
         printf("records %llu bytes %llu fnv1a %016llx threads %d\n", (unsigned long long)nrec, (unsigned long long)st0.size(), (unsigned long long)h, g_parse_threads);
         return EXIT_SUCCESS;
     }
@@ -287,7 +340,7 @@ int main(int argc, char **argv) {
         die(msg);
     }
 
-    std::vector<uint8_t> stream;
+    ByteBuf stream;
     uint64_t n_records = 0;
     load_input(o.in, stream, n_records);
     const double t1 = now_s();
