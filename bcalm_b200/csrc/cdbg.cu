@@ -126,9 +126,15 @@ namespace {
                              __LINE__, #call, cudaGetErrorString(e_));                                             \
     } while (0)
 
+// CDBG_EMU_ACTIVE is only ever defined by tests/emu/cuda_runtime.h (the CPU emulation build used by the no-GPU logic tests)
+#ifdef CDBG_EMU_ACTIVE
+#define KLAUNCH(kern, grid, block, smem, ...) emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); })
+#else
+#define KLAUNCH(kern, grid, block, smem, ...) kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__)
+#endif
 #define LAUNCH(kern, grid, block, smem, ...)                                   \
     do {                                                                       \
-        kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);           \
+        KLAUNCH(kern, grid, block, smem, __VA_ARGS__);                         \
         ctx->launches++;                                                       \
         CK(cudaGetLastError());                                                \
     } while (0)

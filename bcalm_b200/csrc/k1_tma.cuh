@@ -14,6 +14,7 @@
 constexpr int K1T_RAW = K1_TILE + 32;       // bytes per tile incl. halo (multiple of 16)
 #define K1_NOBIN 0xFFFFu
 
+#ifndef CDBG_EMU_ACTIVE
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -39,6 +40,25 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#else
+// CPU emulation build of the tests (tests/emu): an mbarrier is a count of completed phases, a bulk copy is a memcpy that
+// completes the phase it was announced on.  wait(parity) passes once the phase of that parity has completed.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { if (bytes == 0) __atomic_fetch_add(bar, 1, __ATOMIC_SEQ_CST); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (;;) {
+        uint64_t done = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+        if (done > 0 && ((done - 1) & 1) == parity) return;
+        sched_yield();
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    memcpy(dst_smem, src_gmem, bytes);
+    __atomic_fetch_add(bar, 1, __ATOMIC_SEQ_CST);
+}
+__device__ __forceinline__ void mbar_fence_init() {}
+#endif
 
 struct K1TParams {
     const uint8_t *bytes; uint64_t n_bytes; uint64_t n_tiles;
@@ -79,7 +99,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1t_extract(K1TParams p) {
 
     if (t == 0) {
         mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     for (uint32_t i = t; i < p.P; i += K1_THREADS) s_cnt[i] = 0;
     __syncthreads();

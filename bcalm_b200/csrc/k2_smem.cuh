@@ -1,0 +1,271 @@
+// k2_smem.cuh -- K2 (k-mer counting + solidity filter, SURVEY a6/a7: PartitionsCommand.cpp:1600-1805,
+// CountProcessorSolidity.hpp:186-189) as "partition finer, then count in shared memory".
+//
+// The L2 path (k2_insert/k2_emit in kernels.cuh) keeps one hash table per coarse bin resident in L2 and pays ~2.3 L2
+// operations per k-mer instance; it is bound by L2 atomic throughput (6 % of the HBM roofline on C2).  Here the k-mer stream
+// that K1 wrote into P1 coarse bins is split once more, into F fine bins per coarse bin, sized so that the distinct k-mers of a
+// fine bin fit a hash table in SHARED memory; one CTA then owns one fine bin at a time and all probing, CAS and counting are
+// shared-memory operations.  HBM sees three streaming passes instead of table traffic:
+//   k2p_hist     read the stream, histogram of fine bins per coarse bin            I*8 read
+//   k2p_scatter  read it again (L2-warm per coarse bin), tile-local counting sort
+//                in shared memory, one coalesced run per (tile, fine bin)          I*8 read + I*8 write
+//   k2c_count    one CTA per fine bin: stream its k-mers through the table,
+//                then scan the table and emit the solid (k-mer, count) pairs       I*8 read + S*12 write
+// A fine bin whose distinct k-mers do not fit (possible only when the sizing estimate is beaten by skew) is reported in an
+// overflow list and counted by the L2-path kernels afterwards, so the result never depends on the sizing.
+#pragma once
+#include "kernels.cuh"
+
+constexpr int K2P_THREADS = 512;
+constexpr int K2P_PER_THREAD = 16;
+constexpr int K2P_TILE = K2P_THREADS * K2P_PER_THREAD;    // 8192 k-mers per tile
+constexpr int K2P_MAX_F = 1024;                            // fine bins per coarse bin (10 bits in the packed rank word)
+#define K2P_NOKEY 0xFFFFFFFFu
+
+// fine bin inside a coarse bin: the HIGH half of mix64 (K1's coarse bin comes from bin_hash32, the table slot from the LOW half)
+__device__ __forceinline__ uint32_t k2p_fine(uint64_t h, uint32_t F) { return (uint32_t)(((h >> 32) * (uint64_t)F) >> 32); }
+
+struct K2PParams {
+    const uint64_t *kmers;          // [I] K1 output, coarse bin b = [bin_off[b], bin_off[b+1])
+    const uint64_t *bin_off;        // [P1 + 1]
+    const uint32_t *tile_first;     // [P1 + 1] first tile of each coarse bin (tiles never span coarse bins)
+    uint32_t P1, F;
+    uint32_t n_tiles;
+    uint32_t *fine_cnt;             // [P1 * F]     hist: out
+    const uint64_t *fine_off;       // [P1 * F + 1] scatter: exclusive offsets into `out`
+    uint32_t *fine_cursor;          // [P1 * F]     scatter: running cursors, zero-initialised
+    uint64_t *out;                  // [I] scatter: the stream re-ordered by (coarse, fine) bin
+};
+
+// coarse bin that owns `tile`: largest b with tile_first[b] <= tile (empty coarse bins have tile_first[b] == tile_first[b+1])
+__device__ __forceinline__ uint32_t k2p_bin_of_tile(const uint32_t *__restrict__ tile_first, uint32_t P1, uint32_t tile) {
+    uint32_t lo = 0, hi = P1;       // invariant: tile_first[lo] <= tile < tile_first[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (tile_first[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(K2P_THREADS) k2p_hist(K2PParams p) {
+    __shared__ uint32_t s_cnt[K2P_MAX_F];
+    const uint32_t t = threadIdx.x;
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint32_t b = k2p_bin_of_tile(p.tile_first, p.P1, tile);
+        const uint64_t beg = p.bin_off[b] + (uint64_t)(tile - p.tile_first[b]) * K2P_TILE;
+        const uint64_t end = min(beg + (uint64_t)K2P_TILE, p.bin_off[b + 1]);
+        for (uint32_t i = t; i < p.F; i += K2P_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        uint64_t key[K2P_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < K2P_PER_THREAD; j++) {
+            const uint64_t i = beg + (uint64_t)j * K2P_THREADS + t;
+            key[j] = i < end ? p.kmers[i] : EMPTY_KEY;
+        }
+#pragma unroll
+        for (int j = 0; j < K2P_PER_THREAD; j++)
+            if (key[j] != EMPTY_KEY) atomicAdd(&s_cnt[k2p_fine(mix64(key[j]), p.F)], 1u);
+        __syncthreads();
+        // the thread that flushes counter i is the one that zeroes it for the next tile: no barrier needed in between
+        for (uint32_t i = t; i < p.F; i += K2P_THREADS) {
+            const uint32_t c = s_cnt[i];
+            if (c) atomicAdd(&p.fine_cnt[(size_t)b * p.F + i], c);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *s_stage = reinterpret_cast<uint64_t *>(smem_raw);                  // [K2P_TILE] the tile sorted by fine bin
+    uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_stage + K2P_TILE);           // [K2P_TILE] fine bin of each staged k-mer
+    __shared__ uint64_t s_gbase[K2P_MAX_F];                                      // global position of each fine bin's run
+    __shared__ uint32_t s_cnt[K2P_MAX_F];
+    __shared__ uint32_t s_off[K2P_MAX_F + 1];
+    __shared__ uint32_t s_warp[K2P_THREADS / 32];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (p.F + K2P_THREADS - 1) / K2P_THREADS;                  // fine bins scanned per thread (1 or 2)
+
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint32_t b = k2p_bin_of_tile(p.tile_first, p.P1, tile);
+        const uint64_t beg = p.bin_off[b] + (uint64_t)(tile - p.tile_first[b]) * K2P_TILE;
+        const uint64_t end = min(beg + (uint64_t)K2P_TILE, p.bin_off[b + 1]);
+        for (uint32_t i = t; i < p.F; i += K2P_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+
+        // rank of every k-mer inside its fine bin of this tile: one shared-memory atomic per k-mer
+        uint64_t key[K2P_PER_THREAD];
+        uint32_t fr[K2P_PER_THREAD];                                             // rank << 10 | fine bin
+#pragma unroll
+        for (int j = 0; j < K2P_PER_THREAD; j++) {
+            const uint64_t i = beg + (uint64_t)j * K2P_THREADS + t;
+            key[j] = i < end ? p.kmers[i] : EMPTY_KEY;
+        }
+#pragma unroll
+        for (int j = 0; j < K2P_PER_THREAD; j++) {
+            if (key[j] == EMPTY_KEY) { fr[j] = K2P_NOKEY; continue; }
+            const uint32_t f = k2p_fine(mix64(key[j]), p.F);
+            fr[j] = (atomicAdd(&s_cnt[f], 1u) << 10) | f;
+        }
+        __syncthreads();
+
+        // exclusive scan of the tile's fine counts + ONE global reservation per non-empty (tile, fine bin)
+        {
+            const uint32_t b0 = t * per;
+            uint32_t sum = 0;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < p.F) sum += s_cnt[b0 + j];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+            if (lane_id() == 31) s_warp[t >> 5] = incl;
+            __syncthreads();
+            if (t < 32) {
+                uint32_t wv = t < K2P_THREADS / 32 ? s_warp[t] : 0, wi = wv;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane_id() >= d) wi += n; }
+                if (t < K2P_THREADS / 32) s_warp[t] = wi - wv;
+            }
+            __syncthreads();
+            uint32_t run = s_warp[t >> 5] + incl - sum;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < p.F) {
+                const uint32_t cn = s_cnt[b0 + j];
+                s_off[b0 + j] = run;
+                if (cn) {
+                    const size_t g = (size_t)b * p.F + b0 + j;
+                    s_gbase[b0 + j] = p.fine_off[g] + atomicAdd(&p.fine_cursor[g], cn);
+                }
+                run += cn;
+            }
+        }
+        __syncthreads();
+
+        // counting sort into the staging area, then every run leaves as contiguous stores
+#pragma unroll
+        for (int j = 0; j < K2P_PER_THREAD; j++) {
+            if (fr[j] == K2P_NOKEY) continue;
+            const uint32_t f = fr[j] & 1023u, pos = s_off[f] + (fr[j] >> 10);
+            s_stage[pos] = key[j]; s_sb[pos] = (uint16_t)f;
+        }
+        __syncthreads();
+        const uint32_t total = (uint32_t)(end - beg);
+        for (uint32_t j = t; j < total; j += K2P_THREADS) {
+            const uint32_t f = s_sb[j];
+            p.out[s_gbase[f] + (j - s_off[f])] = s_stage[j];
+        }
+        __syncthreads();     // the staging area and the counters are reused by the next tile
+    }
+}
+
+static inline size_t k2p_scatter_smem_bytes() { return (size_t)K2P_TILE * 8 + (size_t)K2P_TILE * 2 + 128; }
+
+// ------------------------------------------------------------------------------------------------ counting in shared memory
+
+struct K2CParams {
+    const uint64_t *kmers;          // the stream ordered by fine bin
+    const uint64_t *fine_off;       // [n_fine + 1]
+    uint32_t n_fine;
+    uint32_t amin, amax;
+    uint64_t *solid_kmers; uint32_t *solid_counts; uint64_t solid_cap;
+    unsigned long long *n_solid, *n_distinct;
+    uint32_t *overflow_list; uint32_t overflow_cap;   // fine bins whose distinct k-mers did not fit the table
+    unsigned long long *n_overflow;
+};
+
+template <int SLOTS> constexpr int k2c_threads() { return SLOTS / 16; }
+template <int SLOTS> static inline size_t k2c_smem_bytes() { return (size_t)SLOTS * 12 + 128; }
+
+// One CTA per fine bin (grid-strided).  Table = SLOTS keys (u64, EMPTY = all ones: never a k-mer for k <= 31) + SLOTS counts.
+// Every warp owns SLOTS/warps consecutive slots for clearing and emitting, so those phases need no barrier between them.
+template <int SLOTS>
+__global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
+    constexpr int T = SLOTS / 16, NW = T / 32, PER_WARP = SLOTS / NW;   // PER_WARP = 512 slots
+    constexpr uint32_t MASK = SLOTS - 1, MAX_PROBES = SLOTS / 8;
+    static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS >= 1024 && T <= 1024, "SLOTS must be a power of two in [1024, 16384]");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_keys + SLOTS);
+    __shared__ uint32_t s_wsolid[32];
+    __shared__ unsigned long long s_base;
+    __shared__ int s_over;
+    const uint32_t t = threadIdx.x, lane = lane_id(), warp = t >> 5;
+    const uint32_t wb = warp * PER_WARP;
+    unsigned long long my_distinct = 0;
+
+    for (uint32_t bin = blockIdx.x; bin < p.n_fine; bin += gridDim.x) {
+        const uint64_t beg = p.fine_off[bin], end = p.fine_off[bin + 1];
+        if (beg == end) continue;                                    // (uniform over the block)
+#pragma unroll 4
+        for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
+        if (t == 0) s_over = 0;
+        __syncthreads();
+
+        // ---- insert: load on the slot, CAS only when it looks empty, count with a shared-memory add
+        for (uint64_t i0 = beg + t; i0 < end; i0 += (uint64_t)T * 4) {
+            uint64_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const uint64_t i = i0 + (uint64_t)u * T; key[u] = i < end ? p.kmers[i] : EMPTY_KEY; }
+            if (*(volatile int *)&s_over) break;                     // someone found the table full: the bin is redone elsewhere
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (key[u] == EMPTY_KEY) continue;
+                uint32_t slot = (uint32_t)mix64(key[u]) & MASK;
+                for (uint32_t probes = 0;;) {
+                    uint64_t cur = ld_volatile_u64(&s_keys[slot]);
+                    if (cur == EMPTY_KEY) {
+                        cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key[u]);
+                        if (cur == EMPTY_KEY) cur = key[u];
+                    }
+                    if (cur == key[u]) { atomicAdd(&s_cnt[slot], 1u); break; }
+                    slot = (slot + 1) & MASK;
+                    if (++probes >= MAX_PROBES) { s_over = 1; break; }
+                }
+            }
+        }
+        __syncthreads();
+        const int over = s_over;
+        __syncthreads();                                             // everyone has read s_over before thread 0 may reset it
+        if (over) {
+            if (t == 0) {
+                unsigned long long pos = atomicAdd(p.n_overflow, 1ULL);
+                if (pos < p.overflow_cap) p.overflow_list[pos] = bin;
+            }
+            continue;
+        }
+
+        // ---- emit: count the solid entries, reserve the output range with ONE global atomic, write ballot-ranked
+        uint32_t my_solid = 0;
+#pragma unroll 4
+        for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
+            const bool occ = s_keys[i] != EMPTY_KEY;
+            const uint32_t c = s_cnt[i];
+            my_distinct += occ;
+            my_solid += occ && c >= p.amin && c <= p.amax;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_solid += __shfl_xor_sync(0xFFFFFFFFu, my_solid, d);
+        if (lane == 0) s_wsolid[warp] = my_solid;
+        __syncthreads();
+        if (t == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < NW; w++) { uint32_t v = s_wsolid[w]; s_wsolid[w] = tot; tot += v; }
+            s_base = tot ? atomicAdd(p.n_solid, (unsigned long long)tot) : 0ULL;
+        }
+        __syncthreads();
+        uint64_t out = s_base + s_wsolid[warp];
+        if (my_solid) {                                              // (uniform over the warp after the reduction)
+            for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
+                const uint64_t key = s_keys[i];
+                const uint32_t c = s_cnt[i];
+                const bool solid = key != EMPTY_KEY && c >= p.amin && c <= p.amax;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, solid);
+                if (solid) {
+                    const uint64_t pos = out + __popc(m & ((1u << lane) - 1));
+                    if (pos < p.solid_cap) { p.solid_kmers[pos] = key; p.solid_counts[pos] = c; }
+                }
+                out += __popc(m);
+            }
+        }
+        // no barrier here: the next iteration's clear touches only this warp's own slots, and s_wsolid / s_base / s_over are
+        // next written after at least two more barriers
+    }
+    block_add(p.n_distinct, my_distinct);
+}

@@ -38,8 +38,10 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) { return 
 // cudaLaunchAttributeProgrammaticStreamSerialization, so their CTAs are scheduled while the previous kernel drains; they must
 // wait here before touching anything the predecessor wrote.  A no-op for a normal launch.
 __device__ __forceinline__ void pdl_wait() {
+#ifndef CDBG_EMU_ACTIVE   // (the CPU emulation build of the tests runs launches back to back)
     asm volatile("griddepcontrol.wait;" ::: "memory");               // predecessor grid complete and its writes visible
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the successor's CTAs take SM slots as ours retire
+#endif
 }
 
 // Sum `v` over the block and add it to *dst with ONE atomic per block: a same-address global atomic costs ~4 ns, so

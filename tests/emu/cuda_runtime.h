@@ -1,0 +1,294 @@
+// tests/emu/cuda_runtime.h -- TEST INFRASTRUCTURE ONLY: a CPU stand-in for <cuda_runtime.h>.
+//
+// tests/emu/build_emu.py compiles the UNCHANGED library sources (bcalm_b200/csrc/*.cu/.cuh/.inl) with g++ and this header
+// first on the include path, giving tests/_emu_build/libcdbg_emu.so: the same host orchestration and the same kernel
+// bodies, with every CUDA thread run by an OS thread.  It exists so that kernel and host LOGIC (indexing, reservations,
+// scans, overflow paths, stage hand-offs) can be checked against the oracle in a container without a GPU.  It is not a
+// product path: nothing under bcalm_b200/ loads it, it says nothing about performance, and it cannot show memory-model or
+// occupancy problems.  The GPU parity tests (-m gpu) remain the gate.
+//
+// Model: one kernel launch = `block` pooled OS threads that run the blocks of the grid one after another (so `__shared__`
+// variables can be plain statics and dynamic shared memory one global buffer).  __syncthreads and the warp collectives are
+// condvar barriers that tolerate threads which have already left the kernel.  The "device" is host memory and every runtime
+// call is synchronous.
+#pragma once
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#define CDBG_EMU_ACTIVE 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+// ------------------------------------------------------------------------------------------------ vector types
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(16))) ulonglong2 { unsigned long long x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
+
+// ------------------------------------------------------------------------------------------------ execution engine
+namespace emu {
+
+struct Barrier {   // generation barrier whose party count can shrink while threads wait (threads that returned from the kernel)
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned expected = 0, arrived = 0;
+    uint64_t gen = 0;
+    void reset(unsigned n) { expected = n; arrived = 0; }
+    void wait() {
+        std::unique_lock<std::mutex> l(m);
+        uint64_t g = gen;
+        if (++arrived >= expected) { arrived = 0; gen++; cv.notify_all(); return; }
+        cv.wait(l, [&] { return gen != g; });
+    }
+    void leave() {
+        std::unique_lock<std::mutex> l(m);
+        if (expected) expected--;
+        if (expected && arrived >= expected) { arrived = 0; gen++; cv.notify_all(); }
+    }
+};
+
+struct Tls { unsigned lane = 0, warp = 0; };
+inline thread_local Tls tls;
+inline void set_builtin(unsigned tid, unsigned bid);
+inline void set_dims(unsigned block, unsigned grid);
+
+constexpr unsigned MAX_THREADS = 1024, MAX_WARPS = MAX_THREADS / 32;
+constexpr size_t DYN_SMEM_BYTES = 256 * 1024;
+
+struct Engine {
+    std::mutex m;
+    std::condition_variable cv_start, cv_done;
+    std::vector<std::thread> workers;
+    uint64_t gen = 0;
+    unsigned done = 0;
+    unsigned grid = 0, block = 0;
+    const std::function<void()> *body = nullptr;
+    Barrier pre, block_bar, warp_bar[MAX_WARPS];
+    uint64_t warp_slot[MAX_WARPS][32];
+    unsigned char *dyn = nullptr;
+    std::mutex launch_mutex;   // one launch at a time (contexts on different host threads serialise here)
+
+    void run(unsigned id) {
+        for (unsigned b = 0; b < grid; b++) {
+            pre.wait();                      // every thread has left the previous block
+            if (id == 0) {
+                block_bar.reset(block);
+                for (unsigned w = 0; w * 32 < block; w++) warp_bar[w].reset(block - w * 32 < 32 ? block - w * 32 : 32);
+            }
+            pre.wait();
+            tls.lane = id & 31; tls.warp = id >> 5;
+            set_builtin(id, b);
+            (*body)();
+            block_bar.leave();
+            warp_bar[id >> 5].leave();
+        }
+    }
+    void worker(unsigned id, uint64_t seen) {
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m);
+                cv_start.wait(l, [&] { return gen != seen; });
+                seen = gen;
+                if (id >= block) continue;
+            }
+            run(id);
+            {
+                std::unique_lock<std::mutex> l(m);
+                if (++done == block) cv_done.notify_one();
+            }
+        }
+    }
+    void launch(unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) {
+        std::lock_guard<std::mutex> one(launch_mutex);
+        if (b == 0 || b > MAX_THREADS || smem > DYN_SMEM_BYTES) { fprintf(stderr, "[emu] bad launch geometry %u x %u, %zu B smem\n", g, b, smem); abort(); }
+        if (g == 0) return;
+        if (!dyn) { if (posix_memalign((void **)&dyn, 1024, DYN_SMEM_BYTES)) abort(); }
+        std::unique_lock<std::mutex> l(m);
+        while (workers.size() < b) {   // new workers start from the current generation: they must not replay an old launch
+            unsigned id = (unsigned)workers.size(); uint64_t g0 = gen;
+            workers.emplace_back([this, id, g0] { worker(id, g0); });
+            workers.back().detach();
+        }
+        grid = g; block = b; body = &fn; done = 0;
+        set_dims(b, g);
+        pre.reset(b);
+        gen++;
+        cv_start.notify_all();
+        cv_done.wait(l, [&] { return done == block; });
+    }
+};
+
+inline Engine &engine() { static Engine *e = new Engine(); return *e; }   // leaked on purpose: its threads are detached
+inline unsigned char *dyn_smem() { return engine().dyn; }
+inline void launch(unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) { engine().launch(g, b, smem, fn); }
+
+template <class T>
+inline T warp_exchange(T v, unsigned src_lane) {
+    static_assert(sizeof(T) <= 8 && std::is_integral<T>::value, "emu shuffles carry integers up to 64 bits");
+    Engine &e = engine();
+    const unsigned w = tls.warp;
+    e.warp_slot[w][tls.lane] = (uint64_t)v;
+    e.warp_bar[w].wait();
+    T r = (T)e.warp_slot[w][src_lane & 31];
+    e.warp_bar[w].wait();
+    return r;
+}
+inline void need_full_mask(unsigned mask) {
+    if (mask != 0xFFFFFFFFu) { fprintf(stderr, "[emu] warp collective with a partial mask %08x is not modelled\n", mask); abort(); }
+}
+
+}  // namespace emu
+
+// the built-in variables are real objects (not macros: cudaLaunchConfig_t has members called gridDim / blockDim)
+inline thread_local dim3 threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+inline void emu::set_builtin(unsigned tid, unsigned bid) { threadIdx = dim3(tid, 0, 0); blockIdx = dim3(bid, 0, 0); }
+inline void emu::set_dims(unsigned block, unsigned grid) { blockDim = dim3(block, 1, 1); gridDim = dim3(grid, 1, 1); }
+
+static inline void __syncthreads() { emu::engine().block_bar.wait(); }
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::need_full_mask(mask); emu::engine().warp_bar[emu::tls.warp].wait(); }
+static inline void __threadfence() { __sync_synchronize(); }
+static inline unsigned __activemask() { return 0xFFFFFFFFu; }
+
+template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) { emu::need_full_mask(mask); return emu::warp_exchange(v, (unsigned)src); }
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T v, int d) { emu::need_full_mask(mask); return emu::warp_exchange(v, emu::tls.lane ^ (unsigned)d); }
+template <class T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned d) {
+    emu::need_full_mask(mask);
+    return emu::warp_exchange(v, emu::tls.lane >= d ? emu::tls.lane - d : emu::tls.lane);
+}
+template <class T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned d) {
+    emu::need_full_mask(mask);
+    return emu::warp_exchange(v, emu::tls.lane + d < 32 ? emu::tls.lane + d : emu::tls.lane);
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
+    emu::need_full_mask(mask);
+    emu::Engine &e = emu::engine();
+    const unsigned w = emu::tls.warp;
+    e.warp_slot[w][emu::tls.lane] = pred ? 1 : 0;
+    e.warp_bar[w].wait();
+    unsigned r = 0;
+    const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
+    for (unsigned i = 0; i < lanes; i++) r |= (unsigned)e.warp_slot[w][i] << i;
+    e.warp_bar[w].wait();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ intrinsics
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned __vcmpeq4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) if (((a >> (8 * i)) & 0xFF) == ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
+    return r;
+}
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
+
+template <class A, class B> static inline typename std::common_type<A, B>::type min(A a, B b) { typedef typename std::common_type<A, B>::type T; return (T)a < (T)b ? (T)a : (T)b; }
+template <class A, class B> static inline typename std::common_type<A, B>::type max(A a, B b) { typedef typename std::common_type<A, B>::type T; return (T)a > (T)b ? (T)a : (T)b; }
+
+template <class T, class V> static inline T atomicAdd(T *p, V v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class V> static inline T atomicSub(T *p, V v) { return __atomic_fetch_sub(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class V> static inline T atomicOr(T *p, V v) { return __atomic_fetch_or(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class V> static inline T atomicAnd(T *p, V v) { return __atomic_fetch_and(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class V> static inline T atomicExch(T *p, V v) { return __atomic_exchange_n(p, (T)v, __ATOMIC_SEQ_CST); }
+template <class T, class V> static inline T atomicMin(T *p, V v) {
+    T cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while ((T)v < cur && !__atomic_compare_exchange_n(p, &cur, (T)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return cur;
+}
+template <class T, class V> static inline T atomicMax(T *p, V v) {
+    T cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while ((T)v > cur && !__atomic_compare_exchange_n(p, &cur, (T)v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return cur;
+}
+template <class T, class A, class B> static inline T atomicCAS(T *p, A cmp, B val) {
+    T expected = (T)cmp;
+    __atomic_compare_exchange_n(p, &expected, (T)val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;
+}
+
+// ------------------------------------------------------------------------------------------------ runtime API
+typedef enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorUnknown = 999 } cudaError_t;
+typedef void *cudaStream_t;
+struct emuEvent { timespec t; };
+typedef emuEvent *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
+enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 4 };
+struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes = 0; cudaStream_t stream = nullptr; cudaLaunchAttribute *attrs = nullptr; unsigned numAttrs = 0; };
+struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
+
+static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+    const char *s = getenv("CDBG_EMU_SMS");
+    p->multiProcessorCount = s ? atoi(s) : 2;
+    snprintf(p->name, sizeof p->name, "CPU emulation (tests/emu)");
+    return cudaSuccess;
+}
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
+    void *q = nullptr;
+    if (posix_memalign(&q, 512, (n + 511) & ~size_t(511))) { *p = nullptr; return cudaErrorMemoryAllocation; }
+    memset(q, 0xCD, (n + 511) & ~size_t(511));   // poison: device memory is not zero-initialised
+    *p = (T *)q;
+    return cudaSuccess;
+}
+template <class T> static inline cudaError_t cudaFree(T *p) { free((void *)p); return cudaSuccess; }
+template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { return cudaMalloc(p, n); }
+template <class T> static inline cudaError_t cudaFreeHost(T *p) { free((void *)p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { memmove(dst, src, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *dst, int v, size_t n, cudaStream_t) { memset(dst, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { clock_gettime(CLOCK_MONOTONIC, &e->t); return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    *ms = (float)((b->t.tv_sec - a->t.tv_sec) * 1e3 + (b->t.tv_nsec - a->t.tv_nsec) * 1e-6);
+    return cudaSuccess;
+}
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
+template <class... Params, class... Args>
+static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void (*kern)(Params...), Args &&...args) {
+    std::tuple<typename std::decay<Params>::type...> a{static_cast<typename std::decay<Params>::type>(args)...};
+    emu::launch(cfg->gridDim.x, cfg->blockDim.x, cfg->dynamicSmemBytes, [&] { std::apply(kern, a); });
+    return cudaSuccess;
+}
