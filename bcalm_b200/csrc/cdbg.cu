@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <time.h>
 
 #include <algorithm>
@@ -18,6 +19,7 @@
 #include "kernels.cuh"
 #include "shard.cuh"
 #include "k1_tma.cuh"
+#include "k2_smem.cuh"
 #include "wide.cuh"
 
 namespace {
@@ -293,6 +295,131 @@ int free_results(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stage 1
 
+// Sizing of the shared-memory K2 variant.  slots = table size per CTA, fill = k-mer INSTANCES per slot a fine bin is sized for
+// (0.7 keeps the load factor <= ~0.75 even if every instance is a distinct k-mer; 30x data has ~0.3 distinct per instance).
+struct K2SmemPlan { bool enabled; uint32_t slots; double fill; uint32_t P1; };
+
+K2SmemPlan k2_smem_plan(uint64_t n_bytes) {
+    K2SmemPlan pl{};
+    const char *mode = getenv("CDBG_K2");
+    pl.enabled = mode && strcmp(mode, "smem") == 0;   // default: the L2 path (the shared-memory variant has not been timed on a GPU yet)
+    pl.slots = getenv("CDBG_K2S_SLOTS") ? (uint32_t)atoi(getenv("CDBG_K2S_SLOTS")) : 8192u;
+    if (pl.slots != 4096 && pl.slots != 8192 && pl.slots != 16384) pl.slots = 8192;
+    pl.fill = getenv("CDBG_K2S_FILL") ? atof(getenv("CDBG_K2S_FILL")) : 0.7;
+    if (!(pl.fill >= 0.05 && pl.fill <= 8.0)) pl.fill = 0.7;
+    const double per_fine = pl.fill * pl.slots;
+    const double n_fine = std::max(1.0, (double)n_bytes * 0.8 / per_fine);
+    uint64_t p1 = (uint64_t)ceil(sqrt(n_fine));
+    if (getenv("CDBG_K2S_P1")) p1 = strtoull(getenv("CDBG_K2S_P1"), nullptr, 10);
+    pl.P1 = (uint32_t)std::min<uint64_t>(K1_MAX_BINS, std::max<uint64_t>(1, p1));
+    return pl;
+}
+
+// K2 with shared-memory tables: fine histogram -> scan -> fine scatter -> one CTA per fine bin (k2_smem.cuh).  d_kmers holds the
+// I instances in P coarse bins (h_cnt, d_bin_off).  Leaves ctx->d_solid_kmers / d_solid_counts / S like the L2 path.
+int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_kmers, uint64_t I, uint32_t P, const std::vector<uint64_t> &h_cnt,
+                        const uint64_t *d_bin_off) {
+    int rc;
+    const double per_fine = pl.fill * pl.slots;
+    const uint32_t F = (uint32_t)std::min<uint64_t>(K2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)I / (per_fine * P))));
+    const uint64_t NF = (uint64_t)P * F;
+    std::vector<uint32_t> h_tile_first(P + 1);
+    uint64_t tiles = 0;
+    for (uint32_t b = 0; b < P; b++) { h_tile_first[b] = (uint32_t)tiles; tiles += (h_cnt[b] + K2P_TILE - 1) / K2P_TILE; }
+    h_tile_first[P] = (uint32_t)tiles;
+    if (tiles >= (1ULL << 32)) return ctx->fail(CDBG_ERR_PARAM, "too many k-mer tiles for one device");
+
+    uint32_t *d_tile_first = nullptr, *d_fine_cnt = nullptr, *d_fine_cursor = nullptr, *d_over = nullptr;
+    uint64_t *d_fine_off = nullptr, *d_kmers2 = nullptr;
+    if ((rc = dalloc(ctx, &d_tile_first, P + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_cnt, NF + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_cursor, NF + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_off, NF + 2))) return rc;
+    if ((rc = dalloc(ctx, &d_kmers2, I + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_over, NF + 1))) return rc;
+    CK(cudaMemsetAsync(d_fine_cnt, 0, (NF + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_fine_cursor, 0, (NF + 1) * 4, ctx->stream));
+    CK(cudaMemcpyAsync(d_tile_first, h_tile_first.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    tstart(ctx, T_K2);
+    K2PParams pp{};
+    pp.kmers = d_kmers; pp.bin_off = d_bin_off; pp.tile_first = d_tile_first; pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out = d_kmers2;
+    if (tiles) {
+        LAUNCH(k2p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 4), K2P_THREADS, 0, pp);
+        uint64_t total = 0;
+        if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;   // entry NF = I
+        if (total != I) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost k-mers (%llu != %llu)", (unsigned long long)total, (unsigned long long)I);
+        CK(cudaFuncSetAttribute(k2p_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2p_scatter_smem_bytes()));
+        LAUNCH(k2p_scatter, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K2P_THREADS, k2p_scatter_smem_bytes(), pp);
+    } else {
+        CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
+    }
+    TRACE("K2 fine partition");
+
+    uint64_t solid_cap = std::max<uint64_t>(I <= (1ULL << 28) ? I : std::max<uint64_t>(I / 4, 1ULL << 28), 1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
+        if ((rc = ctr_zero(ctx))) return rc;
+        K2CParams cp{};
+        cp.kmers = d_kmers2; cp.fine_off = d_fine_off; cp.n_fine = (uint32_t)NF; cp.amin = ctx->amin; cp.amax = ctx->amax;
+        cp.solid_kmers = ctx->d_solid_kmers; cp.solid_counts = ctx->d_solid_counts; cp.solid_cap = solid_cap;
+        cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.overflow_list = d_over; cp.overflow_cap = (uint32_t)NF; cp.n_overflow = ctx->d_ctr + 2;
+        if (I) {
+            if (pl.slots == 4096) {
+                CK(cudaFuncSetAttribute(k2c_count<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<4096>()));
+                LAUNCH(k2c_count<4096>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * 4), k2c_threads<4096>(), k2c_smem_bytes<4096>(), cp);
+            } else if (pl.slots == 8192) {
+                CK(cudaFuncSetAttribute(k2c_count<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<8192>()));
+                LAUNCH(k2c_count<8192>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * 2), k2c_threads<8192>(), k2c_smem_bytes<8192>(), cp);
+            } else {
+                CK(cudaFuncSetAttribute(k2c_count<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<16384>()));
+                LAUNCH(k2c_count<16384>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm), k2c_threads<16384>(), k2c_smem_bytes<16384>(), cp);
+            }
+        }
+        if ((rc = ctr_read(ctx))) return rc;
+        const uint64_t n_over = ctx->h_ctr[2];
+        if (n_over) {
+            // fine bins that did not fit a shared-memory table: count them with the L2-path kernels, one bin at a time
+            std::vector<uint32_t> h_over(n_over);
+            std::vector<uint64_t> h_fine_off(NF + 1);
+            CK(cudaMemcpyAsync(h_over.data(), d_over, n_over * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(h_fine_off.data(), d_fine_off, (NF + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            uint64_t worst = 0;
+            for (uint32_t j : h_over) worst = std::max(worst, h_fine_off[j + 1] - h_fine_off[j]);
+            const uint32_t cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (worst * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u);
+            uint64_t *d_keys = nullptr; uint32_t *d_counts = nullptr;
+            if ((rc = dalloc(ctx, &d_keys, cap))) return rc;
+            if ((rc = dalloc(ctx, &d_counts, cap))) return rc;
+            CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
+            CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
+            for (uint32_t j : h_over) {
+                const uint64_t nb = h_fine_off[j + 1] - h_fine_off[j];
+                const uint32_t cap_b = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1024, (nb * 3 / 2 + 63) & ~63ULL));
+                LAUNCH_PDL(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers2 + h_fine_off[j], nb, d_keys, d_counts, cap_b, ctx->d_flag);
+                LAUNCH_PDL(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
+                           ctx->d_solid_counts, solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
+            }
+            if ((rc = ctr_read(ctx))) return rc;
+            dfree(ctx, d_keys); dfree(ctx, d_counts);
+            if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow (fallback of the shared-memory variant)");
+        }
+        ctx->S = ctx->h_ctr[0];
+        ctx->st.n_distinct = ctx->h_ctr[1];
+        if (ctx->S <= solid_cap) break;
+        if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "solid buffer overflow");
+        dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
+        solid_cap = ctx->S;
+    }
+    tstop(ctx, T_K2);
+    ctx->st.n_solid = ctx->S;
+    if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu): shard over more GPUs", (unsigned long long)ctx->S);
+    dfree(ctx, d_tile_first); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off); dfree(ctx, d_kmers2); dfree(ctx, d_over);
+    return CDBG_OK;
+}
+
 int stage_count(cdbg_ctx *ctx) {
     const int k = ctx->k;
     const uint64_t n = ctx->n_bytes;
@@ -303,6 +430,11 @@ int stage_count(cdbg_ctx *ctx) {
     uint64_t n_tiles = (n + K1_TILE - 1) / K1_TILE;
     const uint64_t bin_target = getenv("CDBG_BIN_TARGET") ? strtoull(getenv("CDBG_BIN_TARGET"), nullptr, 10) : 5000000ULL;   // instances per bin (C2 sweep: 25 bins beat 49 and 13; fewer launches, table still L2 resident)
     uint32_t P = (uint32_t)std::min<uint64_t>(K1_MAX_BINS, std::max<uint64_t>(1, (n * 4 / 5 + bin_target - 1) / bin_target));
+    // K2 variant: "l2" = one L2-resident table per coarse bin (k2_insert/k2_emit); "smem" = fine partition + shared-memory
+    // tables (k2_smem.cuh).  With shared-memory tables the coarse fan-out P and the fine fan-out F split the total number of
+    // fine bins about evenly, so that both partition passes write runs of similar length.
+    K2SmemPlan k2s = k2_smem_plan(n);
+    if (k2s.enabled) P = k2s.P1;
     ctx->st.n_count_bins = P;
     unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;
     uint64_t *d_bin_off = nullptr;
@@ -359,6 +491,16 @@ int stage_count(cdbg_ctx *ctx) {
         tstop(ctx, T_K1S);
     }
     dfree(ctx, d_pos_bin);
+
+    // ---- K2, shared-memory variant (falls through to the L2 path when a coarse bin is too large for 32-bit fine counters)
+    if (k2s.enabled && max_bin < (1ULL << 32)) {
+        if ((rc = stage_count_k2_smem(ctx, k2s, d_kmers, I, P, h_cnt, d_bin_off))) return rc;
+        dfree(ctx, d_kmers);
+        dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+        tstop(ctx, T_COUNT);
+        ctx->stage = ST_COUNTED;
+        return CDBG_OK;
+    }
 
     // ---- K2: per-bin counting in one L2-resident table
     auto table_cap = [](uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); };
