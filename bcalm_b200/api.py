@@ -37,7 +37,9 @@ class Stats(C.Structure):
                                            "n_compactions", "n_cycles", "n_unitigs", "total_nt", "n_links")] + \
                [(n, C.c_uint32) for n in ("n_count_bins", "n_join_bins", "rank_rounds", "kernel_launches")] + \
                [(n, C.c_float) for n in ("ms_push", "ms_count", "ms_compact", "ms_link", "ms_fetch", "ms_k1_hist",
-                                         "ms_k1_scatter", "ms_k2", "ms_k3", "ms_k5", "ms_k6_rank", "ms_k6_spell")]
+                                         "ms_k1_scatter", "ms_k2", "ms_k3", "ms_k5", "ms_k6_rank", "ms_k6_spell",
+                                         "ms_k2_hist", "ms_k2_scatter", "ms_k2_table")] + \
+               [(n, C.c_uint32) for n in ("n_k2_splits", "k1_fallback", "zero_copy")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -57,7 +59,7 @@ LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to
 
 EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_count", "cdbg_compact",
            "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_synth_reads",
-           "cdbg_copy_to_host", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range", "cdbg_owner_of", "cdbg_plan_shard_exchange"]
+           "cdbg_copy_to_host", "cdbg_host_alloc", "cdbg_host_free", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range", "cdbg_owner_of", "cdbg_plan_shard_exchange"]
 
 _lib = None
 
@@ -89,6 +91,10 @@ def load_library():
     L.cdbg_owner_of.restype = C.c_uint32
     L.cdbg_plan_shard_exchange.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.cdbg_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.cdbg_host_alloc.argtypes = [C.c_uint64]
+    L.cdbg_host_alloc.restype = C.c_void_p
+    L.cdbg_host_free.argtypes = [C.c_void_p]
+    L.cdbg_host_free.restype = None
     L.cdbg_version.restype = C.c_char_p
     L.cdbg_nccl_unique_id.argtypes = [C.c_void_p]
     L.cdbg_shard_init.argtypes = [C.c_void_p, C.c_void_p]

@@ -31,7 +31,7 @@ struct Timer {
 
 enum Stage { ST_EMPTY = 0, ST_PUSHED, ST_COUNTED, ST_COMPACTED, ST_LINKED };
 
-enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3, T_K5, T_K6R, T_K6S, T_N };
+enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3, T_K5, T_K6R, T_K6S, T_K2H, T_K2S, T_K2C, T_N };
 
 }  // namespace
 
@@ -60,6 +60,8 @@ struct cdbg_ctx {
     uint8_t *d_bytes = nullptr;
     uint64_t n_bytes = 0, cap_bytes = 0;
     bool bytes_borrowed = false;
+    bool bytes_hostmapped = false;        // d_bytes is pinned HOST memory (cdbg_build zero-copy): only k1t_single may read it
+    const uint8_t *h_bytes_src = nullptr; // the caller's host pointer behind it
     uint8_t *d_synth = nullptr;   // owned by the context across resets (bench input)
     uint64_t synth_cap = 0;
 
@@ -279,7 +281,7 @@ int exclusive_scan(cdbg_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_
 
 int free_results(cdbg_ctx *ctx) {
     for (auto &b : ctx->blocks) b.used = false;
-    ctx->d_bytes = nullptr; ctx->n_bytes = 0; ctx->cap_bytes = 0; ctx->bytes_borrowed = false;
+    ctx->d_bytes = nullptr; ctx->n_bytes = 0; ctx->cap_bytes = 0; ctx->bytes_borrowed = false; ctx->bytes_hostmapped = false; ctx->h_bytes_src = nullptr;
     ctx->d_solid_kmers = nullptr; ctx->d_solid_counts = nullptr; ctx->S = 0;
     ctx->d_link = nullptr; ctx->d_edges = nullptr; ctx->n_edges = 0; ctx->edge_cap = 0;
     ctx->d_info = nullptr; ctx->d_unitig_of_kmer = nullptr; ctx->d_seq = nullptr; ctx->d_seq_off = nullptr;
@@ -295,18 +297,19 @@ int free_results(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stage 1
 
-// Sizing of the shared-memory K2 variant.  slots = table size per CTA, fill = k-mer INSTANCES per slot a fine bin is sized for
-// (0.7 keeps the load factor <= ~0.75 even if every instance is a distinct k-mer; 30x data has ~0.3 distinct per instance).
+// Sizing of the shared-memory K2 variant.  slots = table size per CTA, fill = k-mer INSTANCES per slot a fine bin is sized for:
+// 1.5 suits sequencing coverage (30x data has ~0.3 distinct k-mers per instance, i.e. a load factor below 0.5); when an input
+// has more distinct k-mers than that, k2c_count splits the affected bins on the fly, so the value is a tuning knob only.
 struct K2SmemPlan { bool enabled; uint32_t slots; double fill; uint32_t P1; };
 
 K2SmemPlan k2_smem_plan(uint64_t n_bytes) {
     K2SmemPlan pl{};
     const char *mode = getenv("CDBG_K2");
-    pl.enabled = mode && strcmp(mode, "smem") == 0;   // default: the L2 path (the shared-memory variant has not been timed on a GPU yet)
+    pl.enabled = !(mode && strcmp(mode, "l2") == 0);  // default: shared-memory tables (C2 on a B200: K2 2.15 -> 1.52 ms); CDBG_K2=l2 for A/B
     pl.slots = getenv("CDBG_K2S_SLOTS") ? (uint32_t)atoi(getenv("CDBG_K2S_SLOTS")) : 8192u;
     if (pl.slots != 4096 && pl.slots != 8192 && pl.slots != 16384) pl.slots = 8192;
-    pl.fill = getenv("CDBG_K2S_FILL") ? atof(getenv("CDBG_K2S_FILL")) : 0.7;
-    if (!(pl.fill >= 0.05 && pl.fill <= 8.0)) pl.fill = 0.7;
+    pl.fill = getenv("CDBG_K2S_FILL") ? atof(getenv("CDBG_K2S_FILL")) : 1.5;
+    if (!(pl.fill >= 0.05 && pl.fill <= 8.0)) pl.fill = 1.5;
     const double per_fine = pl.fill * pl.slots;
     const double n_fine = std::max(1.0, (double)n_bytes * 0.8 / per_fine);
     uint64_t p1 = (uint64_t)ceil(sqrt(n_fine));
@@ -318,7 +321,7 @@ K2SmemPlan k2_smem_plan(uint64_t n_bytes) {
 // K2 with shared-memory tables: fine histogram -> scan -> fine scatter -> one CTA per fine bin (k2_smem.cuh).  d_kmers holds the
 // I instances in P coarse bins (h_cnt, d_bin_off).  Leaves ctx->d_solid_kmers / d_solid_counts / S like the L2 path.
 int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_kmers, uint64_t I, uint32_t P, const std::vector<uint64_t> &h_cnt,
-                        const uint64_t *d_bin_off) {
+                        const std::vector<uint64_t> &h_off) {
     int rc;
     const double per_fine = pl.fill * pl.slots;
     const uint32_t F = (uint32_t)std::min<uint64_t>(K2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)I / (per_fine * P))));
@@ -329,29 +332,36 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     h_tile_first[P] = (uint32_t)tiles;
     if (tiles >= (1ULL << 32)) return ctx->fail(CDBG_ERR_PARAM, "too many k-mer tiles for one device");
 
-    uint32_t *d_tile_first = nullptr, *d_fine_cnt = nullptr, *d_fine_cursor = nullptr, *d_over = nullptr;
-    uint64_t *d_fine_off = nullptr, *d_kmers2 = nullptr;
+    uint32_t *d_tile_first = nullptr, *d_fine_cnt = nullptr, *d_fine_cursor = nullptr;
+    uint64_t *d_fine_off = nullptr, *d_kmers2 = nullptr, *d_bin_range = nullptr;
+    std::vector<uint64_t> h_range(2 * (size_t)P);   // [begin of bin 0..P-1 | end of bin 0..P-1] inside d_kmers
+    for (uint32_t b = 0; b < P; b++) { h_range[b] = h_off[b]; h_range[P + b] = h_off[b] + h_cnt[b]; }
+    if ((rc = dalloc(ctx, &d_bin_range, 2 * (size_t)P))) return rc;
+    CK(cudaMemcpyAsync(d_bin_range, h_range.data(), 2 * (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = dalloc(ctx, &d_tile_first, P + 1))) return rc;
     if ((rc = dalloc(ctx, &d_fine_cnt, NF + 1))) return rc;
     if ((rc = dalloc(ctx, &d_fine_cursor, NF + 1))) return rc;
     if ((rc = dalloc(ctx, &d_fine_off, NF + 2))) return rc;
     if ((rc = dalloc(ctx, &d_kmers2, I + 1))) return rc;
-    if ((rc = dalloc(ctx, &d_over, NF + 1))) return rc;
     CK(cudaMemsetAsync(d_fine_cnt, 0, (NF + 1) * 4, ctx->stream));
     CK(cudaMemsetAsync(d_fine_cursor, 0, (NF + 1) * 4, ctx->stream));
     CK(cudaMemcpyAsync(d_tile_first, h_tile_first.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
 
     tstart(ctx, T_K2);
     K2PParams pp{};
-    pp.kmers = d_kmers; pp.bin_off = d_bin_off; pp.tile_first = d_tile_first; pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    pp.kmers = d_kmers; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first; pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
     pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out = d_kmers2;
     if (tiles) {
+        tstart(ctx, T_K2H);
         LAUNCH(k2p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 4), K2P_THREADS, 0, pp);
+        tstop(ctx, T_K2H);
         uint64_t total = 0;
         if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;   // entry NF = I
         if (total != I) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost k-mers (%llu != %llu)", (unsigned long long)total, (unsigned long long)I);
         CK(cudaFuncSetAttribute(k2p_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2p_scatter_smem_bytes()));
+        tstart(ctx, T_K2S);
         LAUNCH(k2p_scatter, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K2P_THREADS, k2p_scatter_smem_bytes(), pp);
+        tstop(ctx, T_K2S);
     } else {
         CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
     }
@@ -365,7 +375,8 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
         K2CParams cp{};
         cp.kmers = d_kmers2; cp.fine_off = d_fine_off; cp.n_fine = (uint32_t)NF; cp.amin = ctx->amin; cp.amax = ctx->amax;
         cp.solid_kmers = ctx->d_solid_kmers; cp.solid_counts = ctx->d_solid_counts; cp.solid_cap = solid_cap;
-        cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.overflow_list = d_over; cp.overflow_cap = (uint32_t)NF; cp.n_overflow = ctx->d_ctr + 2;
+        cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
+        tstart(ctx, T_K2C);
         if (I) {
             if (pl.slots == 4096) {
                 CK(cudaFuncSetAttribute(k2c_count<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<4096>()));
@@ -378,34 +389,10 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
                 LAUNCH(k2c_count<16384>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm), k2c_threads<16384>(), k2c_smem_bytes<16384>(), cp);
             }
         }
+        tstop(ctx, T_K2C);
         if ((rc = ctr_read(ctx))) return rc;
-        const uint64_t n_over = ctx->h_ctr[2];
-        if (n_over) {
-            // fine bins that did not fit a shared-memory table: count them with the L2-path kernels, one bin at a time
-            std::vector<uint32_t> h_over(n_over);
-            std::vector<uint64_t> h_fine_off(NF + 1);
-            CK(cudaMemcpyAsync(h_over.data(), d_over, n_over * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(h_fine_off.data(), d_fine_off, (NF + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            uint64_t worst = 0;
-            for (uint32_t j : h_over) worst = std::max(worst, h_fine_off[j + 1] - h_fine_off[j]);
-            const uint32_t cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (worst * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u);
-            uint64_t *d_keys = nullptr; uint32_t *d_counts = nullptr;
-            if ((rc = dalloc(ctx, &d_keys, cap))) return rc;
-            if ((rc = dalloc(ctx, &d_counts, cap))) return rc;
-            CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
-            CK(cudaMemsetAsync(d_counts, 0, (size_t)cap * 4, ctx->stream));
-            for (uint32_t j : h_over) {
-                const uint64_t nb = h_fine_off[j + 1] - h_fine_off[j];
-                const uint32_t cap_b = (uint32_t)std::min<uint64_t>(cap, std::max<uint64_t>(1024, (nb * 3 / 2 + 63) & ~63ULL));
-                LAUNCH_PDL(k2_insert, grid_for(ctx, nb, 256, 8), 256, 0, d_kmers2 + h_fine_off[j], nb, d_keys, d_counts, cap_b, ctx->d_flag);
-                LAUNCH_PDL(k2_emit, grid_for(ctx, cap_b, 256, 8), 256, 0, d_keys, d_counts, cap_b, ctx->amin, ctx->amax, ctx->d_solid_kmers,
-                           ctx->d_solid_counts, solid_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
-            }
-            if ((rc = ctr_read(ctx))) return rc;
-            dfree(ctx, d_keys); dfree(ctx, d_counts);
-            if (((int *)(ctx->h_ctr + 64))[0]) return ctx->fail(CDBG_ERR_INTERNAL, "K2 hash table overflow (fallback of the shared-memory variant)");
-        }
+        if (((int *)(ctx->h_ctr + 64))[1]) return ctx->fail(CDBG_ERR_INTERNAL, "K2: a fine bin does not fit a shared-memory table after %d splits", K2C_MAX_LEVEL);
+        ctx->st.n_k2_splits = ctx->h_ctr[2];
         ctx->S = ctx->h_ctr[0];
         ctx->st.n_distinct = ctx->h_ctr[1];
         if (ctx->S <= solid_cap) break;
@@ -416,7 +403,7 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     tstop(ctx, T_K2);
     ctx->st.n_solid = ctx->S;
     if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu): shard over more GPUs", (unsigned long long)ctx->S);
-    dfree(ctx, d_tile_first); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off); dfree(ctx, d_kmers2); dfree(ctx, d_over);
+    dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off); dfree(ctx, d_kmers2);
     return CDBG_OK;
 }
 
@@ -444,57 +431,107 @@ int stage_count(cdbg_ctx *ctx) {
     CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
     CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
 
-    // K1 runs as the TMA-fed persistent kernel (k1_tma.cuh); CDBG_K1=classic selects the earlier LDG-based kernel for A/B runs
-    const bool use_tma = !(getenv("CDBG_K1") && strcmp(getenv("CDBG_K1"), "classic") == 0);
-    K1Params kp{};
-    kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.P = P;
-    kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
-    K1TParams kt{};
-    kt.bytes = ctx->d_bytes; kt.n_bytes = n; kt.n_tiles = n_tiles; kt.k = k; kt.P = P;
-    kt.bin_count = d_bin_count; kt.bin_off = d_bin_off; kt.bin_cursor = d_bin_cursor; kt.out_kmers = nullptr;
-    uint16_t *d_pos_bin = nullptr;
-    if (use_tma) { if ((rc = dalloc(ctx, &d_pos_bin, n_tiles * K1_TILE + 8))) return rc; }
-    kt.pos_bin = d_pos_bin;
+    // K1 variants (CDBG_K1): default "single" = one pass into fixed-capacity bin regions (k1t_single), falling back to the exact
+    // two-pass TMA kernels ("twopass": histogram, then scatter) when a bin outgrows its region; "classic" = the earlier LDG-based
+    // two-pass kernel, kept for A/B runs.
+    const char *k1mode = getenv("CDBG_K1");
+    const bool use_classic = k1mode && strcmp(k1mode, "classic") == 0;
+    bool use_single = !use_classic && !(k1mode && strcmp(k1mode, "twopass") == 0);
+    const bool use_tma = !use_classic;
 
-    std::vector<uint64_t> h_cnt(P), h_off(P + 1);
-    uint64_t I = 0;
-    if (n_tiles) {
-        tstart(ctx, T_K1H);
-        if (use_tma) {
-            size_t sm0 = k1t_smem_bytes(0, P);
-            CK(cudaFuncSetAttribute(k1t_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
-            CK(cudaFuncSetAttribute(k1t_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1t_smem_bytes(1, P)));
-            LAUNCH(k1t_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6), K1_THREADS, sm0, kt);
-        } else {
-            size_t sm0 = k1_smem_bytes(0, P), sm1 = k1_smem_bytes(1, P);
-            CK(cudaFuncSetAttribute(k1_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
-            CK(cudaFuncSetAttribute(k1_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-            LAUNCH(k1_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6), K1_THREADS, sm0, kp);
-        }
-        tstop(ctx, T_K1H);
-        CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    uint64_t max_bin = 0;
-    for (uint32_t b = 0; b < P; b++) { h_off[b] = I; I += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
-    h_off[P] = I;
-    ctx->st.n_instances = I;
-
+    std::vector<uint64_t> h_cnt(P), h_off(P + 1);   // per coarse bin: number of k-mers, start inside d_kmers (regions may have gaps)
+    uint64_t I = 0, max_bin = 0;
     uint64_t *d_kmers = nullptr;
-    if ((rc = dalloc(ctx, &d_kmers, I + 1))) return rc;
-    if (I) {
-        CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        kp.out_kmers = d_kmers; kt.out_kmers = d_kmers;
+
+    if (use_single && n_tiles) {
+        // every bin gets the mean number of POSITIONS per bin plus 3 % and a constant: instances <= positions, so a bin only
+        // overflows when repeated k-mers pile up in it
+        const uint64_t slack = getenv("CDBG_K1_SLACK") ? strtoull(getenv("CDBG_K1_SLACK"), nullptr, 10) : 16384;   // (tests shrink it to force the fallback)
+        const uint64_t bin_cap = ((n / P + n / P / 32 + slack) + 31) & ~31ULL;
+        if ((rc = dalloc(ctx, &d_kmers, (uint64_t)P * bin_cap + 1))) return rc;
+        if ((rc = ctr_zero(ctx))) return rc;
+        K1XParams kx{};
+        kx.bytes = ctx->d_bytes; kx.n_bytes = n; kx.n_tiles = n_tiles; kx.k = k; kx.P = P;
+        kx.bin_cap = bin_cap; kx.bin_cursor = d_bin_cursor; kx.out_kmers = d_kmers; kx.overflow = ctx->d_flag + 2;
+        // the ragged last tiles are read with plain loads: keep them in device memory when the reads are mapped host memory
+        kx.tail_start = n > 2 * (uint64_t)K1T_RAW ? ((n - 2 * (uint64_t)K1T_RAW) & ~15ULL) : 0;
+        uint8_t *d_tail = nullptr;
+        if (ctx->bytes_hostmapped) {
+            if ((rc = dalloc(ctx, &d_tail, n - kx.tail_start + 16))) return rc;
+            CK(cudaMemcpyAsync(d_tail, ctx->h_bytes_src + kx.tail_start, n - kx.tail_start, cudaMemcpyHostToDevice, ctx->stream));
+            kx.tail = d_tail;
+        } else kx.tail = ctx->d_bytes + kx.tail_start;
         tstart(ctx, T_K1S);
-        if (use_tma) LAUNCH(k1t_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1t_smem_bytes(1, P), kt);
-        else LAUNCH(k1_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1_smem_bytes(1, P), kp);
+        CK(cudaFuncSetAttribute(k1t_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1x_smem_bytes(P)));
+        LAUNCH(k1t_single, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1x_smem_bytes(P), kx);
         tstop(ctx, T_K1S);
+        CK(cudaMemcpyAsync(h_cnt.data(), d_bin_cursor, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = ctr_read(ctx))) return rc;
+        dfree(ctx, d_tail);
+        if (((int *)(ctx->h_ctr + 64))[2]) {   // a bin outgrew its region: redo with exact offsets
+            dfree(ctx, d_kmers);
+            CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
+            use_single = false;
+            ctx->st.k1_fallback = 1;
+        } else {
+            for (uint32_t b = 0; b < P; b++) { h_off[b] = (uint64_t)b * bin_cap; I += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
+            h_off[P] = (uint64_t)P * bin_cap;
+        }
     }
-    dfree(ctx, d_pos_bin);
+    if (ctx->bytes_hostmapped && !(use_single && n_tiles)) {
+        // the two-pass kernels read the input twice: bring it into HBM first
+        uint8_t *nb = nullptr;
+        if ((rc = dalloc(ctx, &nb, n + 64))) return rc;
+        CK(cudaMemcpyAsync(nb, ctx->h_bytes_src, n, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->d_bytes = nb; ctx->cap_bytes = n; ctx->bytes_borrowed = false; ctx->bytes_hostmapped = false;
+    }
+
+    if (!(use_single && n_tiles)) {
+        K1Params kp{};
+        kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.P = P;
+        kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
+        K1TParams kt{};
+        kt.bytes = ctx->d_bytes; kt.n_bytes = n; kt.n_tiles = n_tiles; kt.k = k; kt.P = P;
+        kt.bin_count = d_bin_count; kt.bin_off = d_bin_off; kt.bin_cursor = d_bin_cursor; kt.out_kmers = nullptr;
+        uint16_t *d_pos_bin = nullptr;
+        if (use_tma) { if ((rc = dalloc(ctx, &d_pos_bin, n_tiles * K1_TILE + 8))) return rc; }
+        kt.pos_bin = d_pos_bin;
+        if (n_tiles) {
+            tstart(ctx, T_K1H);
+            if (use_tma) {
+                size_t sm0 = k1t_smem_bytes(0, P);
+                CK(cudaFuncSetAttribute(k1t_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+                CK(cudaFuncSetAttribute(k1t_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1t_smem_bytes(1, P)));
+                LAUNCH(k1t_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6), K1_THREADS, sm0, kt);
+            } else {
+                size_t sm0 = k1_smem_bytes(0, P), sm1 = k1_smem_bytes(1, P);
+                CK(cudaFuncSetAttribute(k1_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0));
+                CK(cudaFuncSetAttribute(k1_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+                LAUNCH(k1_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 6), K1_THREADS, sm0, kp);
+            }
+            tstop(ctx, T_K1H);
+            CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        } else std::fill(h_cnt.begin(), h_cnt.end(), 0);
+        I = 0; max_bin = 0;
+        for (uint32_t b = 0; b < P; b++) { h_off[b] = I; I += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
+        h_off[P] = I;
+        if ((rc = dalloc(ctx, &d_kmers, I + 1))) return rc;
+        if (I) {
+            CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            kp.out_kmers = d_kmers; kt.out_kmers = d_kmers;
+            tstart(ctx, T_K1S);
+            if (use_tma) LAUNCH(k1t_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1t_smem_bytes(1, P), kt);
+            else LAUNCH(k1_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1_smem_bytes(1, P), kp);
+            tstop(ctx, T_K1S);
+        }
+        dfree(ctx, d_pos_bin);
+    }
+    ctx->st.n_instances = I;
 
     // ---- K2, shared-memory variant (falls through to the L2 path when a coarse bin is too large for 32-bit fine counters)
     if (k2s.enabled && max_bin < (1ULL << 32)) {
-        if ((rc = stage_count_k2_smem(ctx, k2s, d_kmers, I, P, h_cnt, d_bin_off))) return rc;
+        if ((rc = stage_count_k2_smem(ctx, k2s, d_kmers, I, P, h_cnt, h_off))) return rc;
         dfree(ctx, d_kmers);
         dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
         tstop(ctx, T_COUNT);
@@ -806,6 +843,7 @@ void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
     s.ms_link = tread(ctx, T_LINK); s.ms_fetch = tread(ctx, T_FETCH);
     s.ms_k1_hist = tread(ctx, T_K1H); s.ms_k1_scatter = tread(ctx, T_K1S); s.ms_k2 = tread(ctx, T_K2);
     s.ms_k3 = tread(ctx, T_K3); s.ms_k5 = tread(ctx, T_K5); s.ms_k6_rank = tread(ctx, T_K6R); s.ms_k6_spell = tread(ctx, T_K6S);
+    s.ms_k2_hist = tread(ctx, T_K2H); s.ms_k2_scatter = tread(ctx, T_K2S); s.ms_k2_table = tread(ctx, T_K2C);
     if (out) *out = s;
 }
 
@@ -1002,10 +1040,29 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
     return CDBG_OK;
 }
 
+// cdbg_build with reads in PINNED host memory: instead of an H2D copy followed by K1, the single-pass K1 reads the host buffer
+// in place (its TMA bulk loads go over PCIe), so the transfer and the extraction are one step.  Only inside cdbg_build: the call
+// is blocking, so the caller's buffer is guaranteed to stay valid while the kernel reads it.
+static bool try_zero_copy(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes) {
+    const char *z = getenv("CDBG_ZEROCOPY"), *k1 = getenv("CDBG_K1"), *zmin = getenv("CDBG_ZEROCOPY_MIN");
+    const uint64_t min_bytes = zmin ? strtoull(zmin, nullptr, 10) : (1u << 20);   // small inputs: a plain copy is as good
+    if (ctx->W != 1 || ctx->world != 1 || n_bytes < min_bytes || n_bytes == 0 || (reinterpret_cast<uintptr_t>(bytes) & 15)) return false;
+    if ((z && atoi(z) == 0) || (k1 && strcmp(k1, "single") != 0)) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    ctx->d_bytes = static_cast<uint8_t *>(at.devicePointer);
+    ctx->h_bytes_src = bytes;
+    ctx->n_bytes = n_bytes; ctx->bytes_borrowed = true; ctx->bytes_hostmapped = true;
+    ctx->stage = ST_PUSHED;
+    return true;
+}
+
 int cdbg_build(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int location, cdbg_unitig_view *view, cdbg_stats *stats) {
     int rc;
     if ((rc = cdbg_reset(ctx))) return rc;
-    if ((rc = cdbg_push_reads(ctx, bytes, n_bytes, location))) return rc;
+    if (location == CDBG_MEM_HOST && bytes && try_zero_copy(ctx, bytes, n_bytes)) ctx->st.zero_copy = 1;
+    else if ((rc = cdbg_push_reads(ctx, bytes, n_bytes, location))) return rc;
     if ((rc = cdbg_count(ctx, nullptr))) return rc;
     if ((rc = cdbg_compact(ctx, nullptr))) return rc;
     if ((rc = cdbg_link(ctx, nullptr))) return rc;
@@ -1082,6 +1139,14 @@ int cdbg_plan_shard_exchange(uint32_t world, uint32_t rank, uint32_t p_local, co
     plan_shard_exchange(world, rank, p_local, all_cnt, send_cnt, recv_cnt, run_off, run_len);
     return CDBG_OK;
 }
+
+void *cdbg_host_alloc(uint64_t n_bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n_bytes ? n_bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void cdbg_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;

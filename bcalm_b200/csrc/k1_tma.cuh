@@ -220,3 +220,169 @@ static inline size_t k1t_smem_bytes(int mode, uint32_t P) {
     if (mode == 1) s += (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(P + 1) * 4 + (size_t)P * 4 + (size_t)K1_TILE * 2;
     return s + 128;
 }
+
+// ------------------------------------------------------------------------------------------------ single pass
+//
+// k1t_single: the same extraction in ONE pass over the reads.  Hash bins are statistically alike, so instead of counting
+// first (pass 0 above) every bin gets a fixed region of `bin_cap` k-mers (mean + slack, the host sizes it from the byte count)
+// and tiles reserve their runs from per-bin cursors directly.  A bin that outgrows its region (possible only with heavily
+// repeated k-mers) raises *overflow and the host redoes stage 1 with the exact two-pass kernels -- the result never depends
+// on the estimate.  Per tile: pack, roll + hash once (the rank inside the tile's bin comes back from the counting atomic and
+// stays in a register with the bin), scan + one global reservation per (tile, bin), roll again into the staging area at
+// offset + rank, coalesced run stores.  Compared with the two passes this reads the input once (which is what allows `bytes`
+// to be pinned HOST memory read over PCIe by the TMA engine: the H2D copy and K1 become one step), and it neither writes nor
+// re-reads the per-position bins.
+struct K1XParams {
+    const uint8_t *bytes;            // device memory, or pinned host memory mapped into the device address space
+    const uint8_t *tail;             // device copy of bytes[tail_start, n_bytes): the ragged last tiles are read from here
+    uint64_t tail_start;
+    uint64_t n_bytes, n_tiles;
+    int k; uint32_t P;
+    uint64_t bin_cap;                // bin b owns out_kmers[b * bin_cap, (b + 1) * bin_cap)
+    unsigned long long *bin_cursor;  // [P] zero-initialised; ends as the bin counts
+    uint64_t *out_kmers;
+    int *overflow;
+};
+
+#define K1X_NONE 0xFFFFFFFFu
+#define K1X_SKIP 0xFFFFFFFFFFFFFFFFULL
+
+__global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *s_raw = smem_raw;                                                              // [2][K1T_RAW]  TMA destinations
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * K1T_RAW);                 // [2] mbarriers
+    uint64_t *s_pk = s_bar + 2;                                                             // [THREADS + 2]
+    uint64_t *s_gbase = s_pk + K1_THREADS + 2;                                              // [P]
+    uint64_t *s_stage = s_gbase + p.P;                                                      // [K1_TILE]
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_stage + K1_TILE);                       // [THREADS + 2]
+    uint32_t *s_cnt = s_vm + K1_THREADS + 2;                                                // [P]
+    uint32_t *s_off = s_cnt + p.P;                                                          // [P + 1]
+    uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_off + p.P + 1);                         // [K1_TILE] bin of each staged k-mer
+    __shared__ uint32_t s_warp[K1_THREADS / 32];
+
+    const int t = threadIdx.x, k = p.k;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+
+    auto issue = [&](uint64_t tile, int stage) {      // thread 0 only
+        const uint64_t start = tile * (uint64_t)K1_TILE;
+        if (start + K1T_RAW <= p.n_bytes) {
+            mbar_expect_tx(&s_bar[stage], K1T_RAW);
+            tma_load_1d(s_raw + stage * K1T_RAW, p.bytes + start, K1T_RAW, &s_bar[stage]);
+        } else {                                      // ragged last tiles: plain loads from the device-resident tail
+            for (int i = 0; i < K1T_RAW; i++) { uint64_t q = start + i; s_raw[stage * K1T_RAW + i] = q < p.n_bytes ? p.tail[q - p.tail_start] : (uint8_t)'\n'; }
+            mbar_expect_tx(&s_bar[stage], 0);
+        }
+    };
+
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    for (uint32_t i = t; i < p.P; i += K1_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    if (t == 0 && first < p.n_tiles) issue(first, 0);
+
+    uint32_t it = 0;
+    for (uint64_t tile = first; tile < p.n_tiles; tile += stride, it++) {
+        const int stage = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        if (t == 0 && tile + stride < p.n_tiles) issue(tile + stride, stage ^ 1);   // prefetch the next tile
+        mbar_wait(&s_bar[stage], parity);
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + stage * K1T_RAW + t * 32);
+            uint64_t pk; uint32_t vm;
+            pack32(src[0], src[1], pk, vm);
+            s_pk[t] = pk; s_vm[t] = vm;
+            if (t == 0) {
+                const uint4 *h = reinterpret_cast<const uint4 *>(s_raw + stage * K1T_RAW + K1_TILE);
+                pack32(h[0], h[1], pk, vm);
+                s_pk[K1_THREADS] = pk; s_vm[K1_THREADS] = vm;
+            }
+        }
+        __syncthreads();
+        const uint64_t hi0 = s_pk[t], lo0 = s_pk[t + 1];
+        const uint64_t V = ((uint64_t)s_vm[t] << 32) | s_vm[t + 1];
+        const uint32_t valid32 = (uint32_t)(kmer_valid_mask(V, k) >> 32);
+
+        // ---- sweep 1: bin of every valid position + its rank inside the tile's bin (one shared-memory atomic)
+        uint32_t br[K1_PER_THREAD];                   // rank << 11 | bin   (P <= 2048, rank < 8192)
+        {
+            uint64_t hi = hi0, lo = lo0;
+            uint64_t fwd = hi >> (64 - 2 * k);
+            uint64_t rc = revcomp64(fwd, k);
+#pragma unroll
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                const uint64_t c = fwd < rc ? fwd : rc;
+                const uint32_t bin = hash32_to_bin(bin_hash32(c), p.P);
+                br[i] = ((valid32 >> (31 - i)) & 1) ? ((atomicAdd(&s_cnt[bin], 1u) << 11) | bin) : K1X_NONE;
+            }
+        }
+        __syncthreads();
+        {   // exclusive scan of s_cnt + one global reservation per non-empty bin, checked against the bin's region
+            const uint32_t per = (p.P + K1_THREADS - 1) / K1_THREADS;
+            uint32_t b0 = t * per, sum = 0;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) sum += s_cnt[b0 + j];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+            if (lane_id() == 31) s_warp[t >> 5] = incl;
+            __syncthreads();
+            if (t < 32) {
+                uint32_t wv = t < K1_THREADS / 32 ? s_warp[t] : 0, wi = wv;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane_id() >= d) wi += n; }
+                if (t < K1_THREADS / 32) s_warp[t] = wi - wv;
+            }
+            __syncthreads();
+            uint32_t run = s_warp[t >> 5] + incl - sum;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) {
+                const uint32_t cn = s_cnt[b0 + j];
+                s_off[b0 + j] = run; s_cnt[b0 + j] = 0;
+                if (cn) {
+                    const unsigned long long old = atomicAdd(&p.bin_cursor[b0 + j], (unsigned long long)cn);
+                    if (old + cn > p.bin_cap) { *p.overflow = 1; s_gbase[b0 + j] = K1X_SKIP; }
+                    else s_gbase[b0 + j] = (uint64_t)(b0 + j) * p.bin_cap + old;
+                }
+                run += cn;
+            }
+            if (t == K1_THREADS - 1) s_off[p.P] = run;
+        }
+        __syncthreads();
+        // ---- sweep 2: roll again, counting-sort into the staging area
+        {
+            uint64_t hi = hi0, lo = lo0;
+            uint64_t fwd = hi >> (64 - 2 * k);
+            uint64_t rc = revcomp64(fwd, k);
+#pragma unroll
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                if (br[i] != K1X_NONE) {
+                    const uint32_t bin = br[i] & 2047u, pos = s_off[bin] + (br[i] >> 11);
+                    s_stage[pos] = fwd < rc ? fwd : rc; s_sb[pos] = (uint16_t)bin;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_off[p.P];
+        for (uint32_t j = t; j < total; j += K1_THREADS) {
+            const uint32_t b = s_sb[j];
+            const uint64_t g = s_gbase[b];
+            if (g != K1X_SKIP) p.out_kmers[g + (j - s_off[b])] = s_stage[j];
+        }
+        __syncthreads();
+    }
+}
+
+static inline size_t k1x_smem_bytes(uint32_t P) {
+    return 2 * (size_t)K1T_RAW + 16 + (size_t)(K1_THREADS + 2) * 8 + (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(K1_THREADS + 2) * 4 +
+           (size_t)P * 4 + (size_t)(P + 1) * 4 + (size_t)K1_TILE * 2 + 128;
+}

@@ -11,8 +11,8 @@
 //                in shared memory, one coalesced run per (tile, fine bin)          I*8 read + I*8 write
 //   k2c_count    one CTA per fine bin: stream its k-mers through the table,
 //                then scan the table and emit the solid (k-mer, count) pairs       I*8 read + S*12 write
-// A fine bin whose distinct k-mers do not fit (possible only when the sizing estimate is beaten by skew) is reported in an
-// overflow list and counted by the L2-path kernels afterwards, so the result never depends on the sizing.
+// A fine bin whose distinct k-mers do not fit its table is split further inside k2c_count (see there), so the result never
+// depends on the sizing estimate.
 #pragma once
 #include "kernels.cuh"
 
@@ -26,8 +26,8 @@ constexpr int K2P_MAX_F = 1024;                            // fine bins per coar
 __device__ __forceinline__ uint32_t k2p_fine(uint64_t h, uint32_t F) { return (uint32_t)(((h >> 32) * (uint64_t)F) >> 32); }
 
 struct K2PParams {
-    const uint64_t *kmers;          // [I] K1 output, coarse bin b = [bin_off[b], bin_off[b+1])
-    const uint64_t *bin_off;        // [P1 + 1]
+    const uint64_t *kmers;          // K1 output, coarse bin b = [bin_beg[b], bin_end[b]) (regions may have gaps)
+    const uint64_t *bin_beg, *bin_end;   // [P1] each
     const uint32_t *tile_first;     // [P1 + 1] first tile of each coarse bin (tiles never span coarse bins)
     uint32_t P1, F;
     uint32_t n_tiles;
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(K2P_THREADS) k2p_hist(K2PParams p) {
     const uint32_t t = threadIdx.x;
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t b = k2p_bin_of_tile(p.tile_first, p.P1, tile);
-        const uint64_t beg = p.bin_off[b] + (uint64_t)(tile - p.tile_first[b]) * K2P_TILE;
-        const uint64_t end = min(beg + (uint64_t)K2P_TILE, p.bin_off[b + 1]);
+        const uint64_t beg = p.bin_beg[b] + (uint64_t)(tile - p.tile_first[b]) * K2P_TILE;
+        const uint64_t end = min(beg + (uint64_t)K2P_TILE, p.bin_end[b]);
         for (uint32_t i = t; i < p.F; i += K2P_THREADS) s_cnt[i] = 0;
         __syncthreads();
         uint64_t key[K2P_PER_THREAD];
@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t b = k2p_bin_of_tile(p.tile_first, p.P1, tile);
-        const uint64_t beg = p.bin_off[b] + (uint64_t)(tile - p.tile_first[b]) * K2P_TILE;
-        const uint64_t end = min(beg + (uint64_t)K2P_TILE, p.bin_off[b + 1]);
+        const uint64_t beg = p.bin_beg[b] + (uint64_t)(tile - p.tile_first[b]) * K2P_TILE;
+        const uint64_t end = min(beg + (uint64_t)K2P_TILE, p.bin_end[b]);
         for (uint32_t i = t; i < p.F; i += K2P_THREADS) s_cnt[i] = 0;
         __syncthreads();
 
@@ -166,19 +166,26 @@ struct K2CParams {
     uint32_t amin, amax;
     uint64_t *solid_kmers; uint32_t *solid_counts; uint64_t solid_cap;
     unsigned long long *n_solid, *n_distinct;
-    uint32_t *overflow_list; uint32_t overflow_cap;   // fine bins whose distinct k-mers did not fit the table
-    unsigned long long *n_overflow;
+    unsigned long long *n_splits;   // statistics: how many times a (part of a) fine bin had to be split
+    int *failed;                    // set when a fine bin still does not fit after K2C_MAX_LEVEL splits (host reports an error)
 };
+
+constexpr int K2C_MAX_LEVEL = 10;   // a fine bin is split into at most 2^10 parts by further hash bits
 
 template <int SLOTS> constexpr int k2c_threads() { return SLOTS / 16; }
 template <int SLOTS> static inline size_t k2c_smem_bytes() { return (size_t)SLOTS * 12 + 128; }
 
 // One CTA per fine bin (grid-strided).  Table = SLOTS keys (u64, EMPTY = all ones: never a k-mer for k <= 31) + SLOTS counts.
 // Every warp owns SLOTS/warps consecutive slots for clearing and emitting, so those phases need no barrier between them.
+//
+// Sizing is only an estimate (the number of DISTINCT k-mers of a bin is not known in advance), so the kernel adapts: new keys
+// are tallied while inserting, and when the table passes 3/4 full the pass is abandoned BEFORE anything was emitted and the
+// (part of the) bin is redone as two halves selected by one more hash bit, each half a full pass over the bin's k-mers (they
+// are L2-warm).  Low-coverage input (every instance distinct) therefore costs one extra read per bin instead of failing.
 template <int SLOTS>
 __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
     constexpr int T = SLOTS / 16, NW = T / 32, PER_WARP = SLOTS / NW;   // PER_WARP = 512 slots
-    constexpr uint32_t MASK = SLOTS - 1, MAX_PROBES = SLOTS / 8;
+    constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
     static_assert((SLOTS & (SLOTS - 1)) == 0 && SLOTS >= 1024 && T <= 1024, "SLOTS must be a power of two in [1024, 16384]");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);
@@ -186,86 +193,101 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
     __shared__ uint32_t s_wsolid[32];
     __shared__ unsigned long long s_base;
     __shared__ int s_over;
+    __shared__ uint32_t s_fill;
     const uint32_t t = threadIdx.x, lane = lane_id(), warp = t >> 5;
     const uint32_t wb = warp * PER_WARP;
-    unsigned long long my_distinct = 0;
+    unsigned long long my_distinct = 0, my_splits = 0;
 
     for (uint32_t bin = blockIdx.x; bin < p.n_fine; bin += gridDim.x) {
         const uint64_t beg = p.fine_off[bin], end = p.fine_off[bin + 1];
         if (beg == end) continue;                                    // (uniform over the block)
+        // work stack of (level << 16 | part): the k-mers of this bin whose hash bits 16.. (level of them) equal `part`.
+        // Every thread keeps the same copy: all decisions below are uniform over the block.
+        uint32_t stk[K2C_MAX_LEVEL + 2];
+        int sp = 0;
+        stk[sp++] = 0;
+        while (sp) {
+            const uint32_t item = stk[--sp], level = item >> 16, part = item & 0xFFFFu, sel_mask = (1u << level) - 1u;
 #pragma unroll 4
-        for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
-        if (t == 0) s_over = 0;
-        __syncthreads();
+            for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
+            if (t == 0) { s_over = 0; s_fill = 0; }
+            __syncthreads();
 
-        // ---- insert: load on the slot, CAS only when it looks empty, count with a shared-memory add
-        for (uint64_t i0 = beg + t; i0 < end; i0 += (uint64_t)T * 4) {
-            uint64_t key[4];
+            // ---- insert: load on the slot, CAS only when it looks empty, count with a shared-memory add
+            for (uint64_t base = beg + warp * 32; base < end; base += (uint64_t)T * 4) {     // warp-uniform trip count
+                uint64_t key[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const uint64_t i = i0 + (uint64_t)u * T; key[u] = i < end ? p.kmers[i] : EMPTY_KEY; }
-            if (*(volatile int *)&s_over) break;                     // someone found the table full: the bin is redone elsewhere
+                for (int u = 0; u < 4; u++) { const uint64_t i = base + lane + (uint64_t)u * T; key[u] = i < end ? p.kmers[i] : EMPTY_KEY; }
+                if (__any_sync(0xFFFFFFFFu, *(volatile int *)&s_over)) break;     // table (nearly) full: this pass is abandoned
+                uint32_t fresh = 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (key[u] == EMPTY_KEY) continue;
-                uint32_t slot = (uint32_t)mix64(key[u]) & MASK;
-                for (uint32_t probes = 0;;) {
-                    uint64_t cur = ld_volatile_u64(&s_keys[slot]);
-                    if (cur == EMPTY_KEY) {
-                        cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key[u]);
-                        if (cur == EMPTY_KEY) cur = key[u];
+                for (int u = 0; u < 4; u++) {
+                    if (key[u] == EMPTY_KEY) continue;
+                    const uint64_t h = mix64(key[u]);
+                    if ((((uint32_t)h >> 16) & sel_mask) != part) continue;
+                    uint32_t slot = (uint32_t)h & MASK;
+                    for (uint32_t probes = 0;;) {
+                        uint64_t cur = ld_volatile_u64(&s_keys[slot]);
+                        if (cur == EMPTY_KEY) {
+                            cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key[u]);
+                            if (cur == EMPTY_KEY) { cur = key[u]; fresh++; }
+                        }
+                        if (cur == key[u]) { atomicAdd(&s_cnt[slot], 1u); break; }
+                        slot = (slot + 1) & MASK;
+                        if (++probes >= (uint32_t)SLOTS) { s_over = 1; break; }
                     }
-                    if (cur == key[u]) { atomicAdd(&s_cnt[slot], 1u); break; }
-                    slot = (slot + 1) & MASK;
-                    if (++probes >= MAX_PROBES) { s_over = 1; break; }
                 }
+                fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+                if (lane == 0 && fresh && atomicAdd(&s_fill, fresh) + fresh > FILL_LIMIT) s_over = 1;
             }
-        }
-        __syncthreads();
-        const int over = s_over;
-        __syncthreads();                                             // everyone has read s_over before thread 0 may reset it
-        if (over) {
-            if (t == 0) {
-                unsigned long long pos = atomicAdd(p.n_overflow, 1ULL);
-                if (pos < p.overflow_cap) p.overflow_list[pos] = bin;
+            __syncthreads();
+            const int over = s_over;
+            __syncthreads();                                         // everyone has read s_over before thread 0 may reset it
+            if (over) {
+                my_splits += t == 0;
+                if (level >= (uint32_t)K2C_MAX_LEVEL) { if (t == 0) *p.failed = 1; break; }
+                stk[sp++] = ((level + 1) << 16) | part;
+                stk[sp++] = ((level + 1) << 16) | part | (1u << level);
+                continue;
             }
-            continue;
-        }
 
-        // ---- emit: count the solid entries, reserve the output range with ONE global atomic, write ballot-ranked
-        uint32_t my_solid = 0;
+            // ---- emit: count the solid entries, reserve the output range with ONE global atomic, write ballot-ranked
+            uint32_t my_solid = 0;
 #pragma unroll 4
-        for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
-            const bool occ = s_keys[i] != EMPTY_KEY;
-            const uint32_t c = s_cnt[i];
-            my_distinct += occ;
-            my_solid += occ && c >= p.amin && c <= p.amax;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) my_solid += __shfl_xor_sync(0xFFFFFFFFu, my_solid, d);
-        if (lane == 0) s_wsolid[warp] = my_solid;
-        __syncthreads();
-        if (t == 0) {
-            uint32_t tot = 0;
-            for (int w = 0; w < NW; w++) { uint32_t v = s_wsolid[w]; s_wsolid[w] = tot; tot += v; }
-            s_base = tot ? atomicAdd(p.n_solid, (unsigned long long)tot) : 0ULL;
-        }
-        __syncthreads();
-        uint64_t out = s_base + s_wsolid[warp];
-        if (my_solid) {                                              // (uniform over the warp after the reduction)
             for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
-                const uint64_t key = s_keys[i];
+                const bool occ = s_keys[i] != EMPTY_KEY;
                 const uint32_t c = s_cnt[i];
-                const bool solid = key != EMPTY_KEY && c >= p.amin && c <= p.amax;
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, solid);
-                if (solid) {
-                    const uint64_t pos = out + __popc(m & ((1u << lane) - 1));
-                    if (pos < p.solid_cap) { p.solid_kmers[pos] = key; p.solid_counts[pos] = c; }
-                }
-                out += __popc(m);
+                my_distinct += occ;
+                my_solid += occ && c >= p.amin && c <= p.amax;
             }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) my_solid += __shfl_xor_sync(0xFFFFFFFFu, my_solid, d);
+            if (lane == 0) s_wsolid[warp] = my_solid;
+            __syncthreads();
+            if (t == 0) {
+                uint32_t tot = 0;
+                for (int w = 0; w < NW; w++) { uint32_t v = s_wsolid[w]; s_wsolid[w] = tot; tot += v; }
+                s_base = tot ? atomicAdd(p.n_solid, (unsigned long long)tot) : 0ULL;
+            }
+            __syncthreads();
+            uint64_t out = s_base + s_wsolid[warp];
+            if (my_solid) {                                          // (uniform over the warp after the reduction)
+                for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
+                    const uint64_t key = s_keys[i];
+                    const uint32_t c = s_cnt[i];
+                    const bool solid = key != EMPTY_KEY && c >= p.amin && c <= p.amax;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, solid);
+                    if (solid) {
+                        const uint64_t pos = out + __popc(m & ((1u << lane) - 1));
+                        if (pos < p.solid_cap) { p.solid_kmers[pos] = key; p.solid_counts[pos] = c; }
+                    }
+                    out += __popc(m);
+                }
+            }
+            // no barrier here: the next pass's clear touches only this warp's own slots, and s_wsolid / s_base / s_over / s_fill
+            // are next written after at least two more barriers
         }
-        // no barrier here: the next iteration's clear touches only this warp's own slots, and s_wsolid / s_base / s_over are
-        // next written after at least two more barriers
     }
     block_add(p.n_distinct, my_distinct);
+    block_add(p.n_splits, my_splits);
 }

@@ -88,6 +88,10 @@ typedef struct {
     uint32_t kernel_launches; /* kernels launched by the library since cdbg_create / the last cdbg_reset */
     float ms_push, ms_count, ms_compact, ms_link, ms_fetch; /* device time per stage, CUDA events */
     float ms_k1_hist, ms_k1_scatter, ms_k2, ms_k3, ms_k5, ms_k6_rank, ms_k6_spell; /* inside the stages */
+    float ms_k2_hist, ms_k2_scatter, ms_k2_table; /* inside K2 (shared-memory variant): fine histogram, fine scatter, table pass */
+    uint32_t n_k2_splits;   /* K2 (shared-memory variant): table passes abandoned and redone as two halves */
+    uint32_t k1_fallback;   /* 1 when the single-pass K1 overflowed a bin region and stage 1 was redone with the exact two-pass kernels */
+    uint32_t zero_copy;     /* 1 when cdbg_build read pinned host memory directly from K1 (no separate H2D copy) */
 } cdbg_stats;
 
 typedef struct {
@@ -172,6 +176,13 @@ int cdbg_synth_reads_range(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len
 uint32_t cdbg_owner_of(uint64_t x, int32_t n_nt, int32_t m, uint32_t world);
 int cdbg_plan_shard_exchange(uint32_t world, uint32_t rank, uint32_t p_local, const uint64_t *all_cnt, uint64_t *send_cnt, uint64_t *recv_cnt,
                              uint64_t *run_off, uint64_t *run_len);
+
+/* Pinned (page-locked) host memory for read buffers.  cdbg_push_reads copies from pinned memory at full PCIe speed, and
+ * cdbg_build does not copy at all when `bytes` is pinned and 16-byte aligned (memory from here, cudaHostAlloc, or a pinned
+ * torch tensor): the extraction kernel reads the buffer in place over PCIe (cdbg_stats.zero_copy says whether that happened).
+ * Returns NULL on failure. */
+void *cdbg_host_alloc(uint64_t n_bytes);
+void cdbg_host_free(void *p);
 
 /* Utility: copy device memory owned by the context to a host buffer (used by tests / bench to fetch synthetic reads). */
 int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_bytes);

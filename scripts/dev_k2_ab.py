@@ -26,23 +26,24 @@ n_reads = int(G * 30 / L)
 TUNABLES = ("CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_JOIN_TARGET", "CDBG_BIN_TARGET", "CDBG_K1")
 
 CONFIGS = [
-    ("default (L2 tables)", {}),
-    ("smem 8192 fill 0.7", {"CDBG_K2": "smem"}),
-    ("smem 8192 fill 1.5", {"CDBG_K2": "smem", "CDBG_K2S_FILL": "1.5"}),
-    ("smem 8192 fill 2.2", {"CDBG_K2": "smem", "CDBG_K2S_FILL": "2.2"}),
-    ("smem 4096 fill 0.7", {"CDBG_K2": "smem", "CDBG_K2S_SLOTS": "4096"}),
-    ("smem 4096 fill 1.5", {"CDBG_K2": "smem", "CDBG_K2S_SLOTS": "4096", "CDBG_K2S_FILL": "1.5"}),
-    ("smem 16384 fill 0.7", {"CDBG_K2": "smem", "CDBG_K2S_SLOTS": "16384"}),
-    ("smem 16384 fill 1.5", {"CDBG_K2": "smem", "CDBG_K2S_SLOTS": "16384", "CDBG_K2S_FILL": "1.5"}),
-    ("smem 16384 fill 2.2", {"CDBG_K2": "smem", "CDBG_K2S_SLOTS": "16384", "CDBG_K2S_FILL": "2.2"}),
-    ("smem 8192 fill 1.5 P1=64", {"CDBG_K2": "smem", "CDBG_K2S_FILL": "1.5", "CDBG_K2S_P1": "64"}),
-    ("smem 8192 fill 1.5 P1=256", {"CDBG_K2": "smem", "CDBG_K2S_FILL": "1.5", "CDBG_K2S_P1": "256"}),
-    ("smem 8192 fill 6 (forces the overflow fallback)", {"CDBG_K2": "smem", "CDBG_K2S_FILL": "6"}),
-    ("join target 1M", {"CDBG_JOIN_TARGET": "1000000"}),
-    ("join target 2M", {"CDBG_JOIN_TARGET": "2000000"}),
-    ("join target 4M", {"CDBG_JOIN_TARGET": "4000000"}),
-    ("join target 250k", {"CDBG_JOIN_TARGET": "250000"}),
+    ("round-start defaults: K1 twopass, K2 l2", {"CDBG_K1": "twopass", "CDBG_K2": "l2"}),
+    ("K1 twopass, K2 smem", {"CDBG_K1": "twopass"}),
+    ("K1 single, K2 l2", {"CDBG_K2": "l2"}),
+    ("default: K1 single, K2 smem 8192/1.5", {}),
+    ("K1 single P1=64", {"CDBG_K2S_P1": "64"}),
+    ("K1 single P1=160", {"CDBG_K2S_P1": "160"}),
+    ("smem 8192 fill 1.0", {"CDBG_K2S_FILL": "1.0"}),
+    ("smem 8192 fill 1.9", {"CDBG_K2S_FILL": "1.9"}),
+    ("smem 16384 fill 1.5", {"CDBG_K2S_SLOTS": "16384"}),
+    ("smem 8192 fill 4 (splits)", {"CDBG_K2S_FILL": "4"}),
+    ("K1 slack 0, P1=100 (may fall back)", {"CDBG_K1_SLACK": "0", "CDBG_K2S_P1": "100"}),
 ]
+E2E_CONFIGS = [
+    ("e2e round-start defaults (copy, twopass, l2)", {"CDBG_K1": "twopass", "CDBG_K2": "l2", "CDBG_ZEROCOPY": "0"}),
+    ("e2e copy + single + smem", {"CDBG_ZEROCOPY": "0"}),
+    ("e2e zero-copy + single + smem (default)", {}),
+]
+TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK")
 
 
 def say(*a):
@@ -81,7 +82,8 @@ for name, env in CONFIGS:
             same = "SAME" if (summary == base[2] and np.array_equal(km, base[0]) and np.array_equal(ct, base[1])) else "DIFFERENT"
         say(f"{name:50s} {same:9s} total {tot:6.3f} ms | K1 {st['ms_k1_hist']:.3f}+{st['ms_k1_scatter']:.3f} K2 {st['ms_k2']:.3f} K3 {st['ms_k3']:.3f} "
             f"K5 {st['ms_k5']:.3f} K6 {st['ms_k6_rank']:.3f}+{st['ms_k6_spell']:.3f} link {st['ms_link']:.3f} | bins {st['n_count_bins']}/{st['n_join_bins']} "
-            f"launches {st['kernel_launches']} | S,D,U,nt,links,KC = {summary}")
+            f"launches {st['kernel_launches']} | K2 parts hist {st['ms_k2_hist']:.3f} scatter {st['ms_k2_scatter']:.3f} table {st['ms_k2_table']:.3f} "
+            f"splits {st['n_k2_splits']} k1fb {st['k1_fallback']} | S,D,U,nt,links,KC = {summary}")
     except Exception as e:  # keep going: one bad configuration must not cost the whole call
         say(f"{name:50s} FAILED: {e}")
         try:
@@ -90,4 +92,31 @@ for name, env in CONFIGS:
             pass
         c = Cdbg(k=K, abundance_min=2)
         ptr, n = c.synth_reads(G, L, n_reads, 10000, 42)
+
+# ---- end to end through cdbg_build with the reads in pinned host memory (H2D inside the timed region, result fetched)
+import ctypes as C  # noqa: E402
+
+lib = api.load_library()
+hptr = lib.cdbg_host_alloc(n)
+assert hptr, "pinned allocation failed"
+c._ck(lib.cdbg_copy_to_host(c.h, C.c_void_p(hptr), C.c_void_p(ptr), n))
+for name, env in E2E_CONFIGS:
+    for k_ in TUNABLES:
+        os.environ.pop(k_, None)
+    os.environ.update(env)
+    try:
+        ts = []
+        for it in range(7):
+            t0 = time.perf_counter()
+            v, s = c.build_raw(hptr, n, 0, fetch=True)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        st = c.stats()
+        ts = sorted(ts[2:])
+        ok = (int(st["n_solid"]), int(v.n_unitigs), int(v.n_links)) == (base[2][0], base[2][2], base[2][4]) if base else None
+        say(f"{name:50s} wall min {ts[0]:.3f} median {ts[len(ts) // 2]:.3f} ms -> {n_reads * L / ts[len(ts) // 2] / 1e6:.2f} Gbases/s | zero_copy {st['zero_copy']} "
+            f"push {st['ms_push']:.3f} count {st['ms_count']:.3f} (K1 {st['ms_k1_hist']:.3f}+{st['ms_k1_scatter']:.3f}) compact {st['ms_compact']:.3f} link {st['ms_link']:.3f} "
+            f"fetch {st['ms_fetch']:.3f} | same counts: {ok}")
+    except Exception as e:
+        say(f"{name:50s} FAILED: {e}")
+lib.cdbg_host_free(C.c_void_p(hptr))
 say(f"# done in {time.time() - T0:.1f} s")

@@ -198,6 +198,21 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+    emu::need_full_mask(mask);
+    emu::Engine &e = emu::engine();
+    const unsigned w = emu::tls.warp;
+    e.warp_slot[w][emu::tls.lane] = v;
+    e.warp_bar[w].wait();
+    unsigned r = 0;
+    const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
+    for (unsigned i = 0; i < lanes; i++) r += (unsigned)e.warp_slot[w][i];
+    e.warp_bar[w].wait();
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ intrinsics
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
@@ -282,6 +297,16 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cud
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { clock_gettime(CLOCK_MONOTONIC, &e->t); return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
     *ms = (float)((b->t.tv_sec - a->t.tv_sec) * 1e3 + (b->t.tv_nsec - a->t.tv_nsec) * 1e-6);
+    return cudaSuccess;
+}
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type; int device; void *devicePointer; void *hostPointer; };
+// CDBG_EMU_PINNED=1 makes every host pointer look pinned + mapped, so that the zero-copy path of cdbg_build can be exercised
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p) {
+    const char *s = getenv("CDBG_EMU_PINNED");
+    const bool pinned = s && atoi(s) != 0;
+    a->type = pinned ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
+    a->device = 0; a->devicePointer = pinned ? const_cast<void *>(p) : nullptr; a->hostPointer = const_cast<void *>(p);
     return cudaSuccess;
 }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }

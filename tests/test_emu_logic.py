@@ -1,0 +1,156 @@
+"""Kernel and host LOGIC of the CUDA library checked without a GPU.
+
+tests/emu builds the unchanged library sources against a CPU stand-in for the CUDA runtime (every CUDA thread is an OS
+thread, see tests/emu/cuda_runtime.h) and these tests push golden cases through that build via the normal ctypes mirror, for
+the default configuration and for the variants / rare paths that the GPU suite reaches only through environment knobs:
+the two K1 kernels behind the single-pass one (its overflow fallback), the split path of the shared-memory K2, the L2-table
+K2, zero-copy input.  This is test infrastructure: it proves indexing, reservations and stage hand-offs, not performance and
+not the GPU memory model -- the `-m gpu` parity tests remain the gate for the product.
+"""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+from bcalm_b200 import api, parity  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ to build the CPU emulation of the library")
+
+with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+    GOLDEN = {c["name"]: c for c in json.load(f)}
+
+KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
+         "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    import build_emu
+    path = build_emu.build()
+    saved = (api.LIB_PATH, api._lib)
+    api.LIB_PATH, api._lib = path, None
+    yield path
+    api.LIB_PATH, api._lib = saved
+
+
+@pytest.fixture()
+def knobs(monkeypatch):
+    for k in KNOBS:
+        monkeypatch.delenv(k, raising=False)
+
+    def set_(**kw):
+        for k, v in kw.items():
+            monkeypatch.setenv(k, str(v))
+    return set_
+
+
+def run_case(case, **kw):
+    with api.Cdbg(k=case["k"], abundance_min=case["abundance_min"], device=0, **kw) as c:
+        return c.build(case["reads"])
+
+
+def check_against_golden(g, case):
+    d = parity.diff(parity.graph_to_records(g), parity.parse_unitigs_fa(case["unitigs_fa"]), case["k"])
+    assert d == "", d
+
+
+SMALL = ["tiny_read_k21", "tiny_read_k13", "minitip_k21_a1", "minitip_k21_a2", "circular_test1", "circular_test2_polyA",
+         "circular_test3_onebucket", "pufferize_refs", "lowcx_0_AT_k5_a1", "lowcx_3_AT_k9_a1", "lowcx_5_ACG_k5_a1", "lowcx_7_ACGT_k6_a1",
+         "lowcx_12_AT_k6_a1", "lowcx_14_ACGT_k4_a1", "circular_genome_0_k7", "circular_genome_1_k11", "reads_6_k31_a1", "reads_7_k31_a1",
+         "short_reads_only", "palindrome_k_even", "pow2_cycle_L2_k5", "pow2_cycle_L16_k9", "pow2_cycle_L256_k21", "wide_10_k41_a1",
+         "wide_lowcx_0_AT_k33"]
+MEDIUM = ["reads_0_k15_a2", "reads_5_k25_a1", "lowcx_8_ACGT_k8_a1"]
+
+
+@pytest.mark.parametrize("name", SMALL + MEDIUM)
+def test_default_configuration_matches_reference_output(emu_lib, knobs, name):
+    g = run_case(GOLDEN[name])
+    check_against_golden(g, GOLDEN[name])
+
+
+VARIANTS = {
+    "k1_twopass_tma": dict(CDBG_K1="twopass"),
+    "k1_classic_ldg": dict(CDBG_K1="classic"),
+    "k2_l2_tables": dict(CDBG_K2="l2"),
+    "k2_l2_many_bins": dict(CDBG_K2="l2", CDBG_BIN_TARGET=3000),
+    "k2_smem_many_fine_bins": dict(CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=0.05),
+    "k2_smem_16384": dict(CDBG_K2S_SLOTS=16384, CDBG_K2S_FILL=0.2),
+    "k2_smem_forced_splits": dict(CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
+    "k1_many_coarse_bins": dict(CDBG_K2S_P1=37),
+    "zero_copy_input": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0),
+    "no_pdl": dict(CDBG_PDL=0),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+@pytest.mark.parametrize("name", ["minitip_k21_a1", "circular_test2_polyA", "reads_0_k15_a2", "reads_5_k25_a1"])
+def test_variants_match_reference_output(emu_lib, knobs, variant, name):
+    knobs(**VARIANTS[variant])
+    g = run_case(GOLDEN[name])
+    check_against_golden(g, GOLDEN[name])
+    if variant == "zero_copy_input":
+        assert g.stats["zero_copy"] == 1
+    if variant == "k2_smem_forced_splits" and name.startswith("reads_"):
+        assert g.stats["n_k2_splits"] > 0
+
+
+def _repeats_input():
+    """One heavily repeated k-mer family (poly-A reads) next to ordinary reads: the repeated k-mer lands in one bin."""
+    rng = np.random.default_rng(7)
+    genome = "".join("ACGT"[i] for i in rng.integers(0, 4, 600))
+    reads = ["A" * 100] * 300 + [genome[i:i + 80] for i in range(0, 520, 3)] * 2
+    return reads
+
+
+def test_k1_single_pass_overflow_falls_back_to_exact_two_pass(emu_lib, knobs):
+    reads = _repeats_input()
+    knobs(CDBG_K2S_P1=8, CDBG_K1_SLACK=0)
+    with api.Cdbg(k=21, abundance_min=2, device=0) as c:
+        g = c.build(reads)
+    assert g.stats["k1_fallback"] == 1
+    o = orc.run(reads, 21, 2)
+    d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), 21)
+    assert d == "", d
+
+
+def test_zero_copy_overflow_falls_back_with_a_copy(emu_lib, knobs):
+    reads = _repeats_input()
+    knobs(CDBG_K2S_P1=8, CDBG_K1_SLACK=0, CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0)
+    with api.Cdbg(k=21, abundance_min=2, device=0) as c:
+        g = c.build(reads)
+    assert g.stats["k1_fallback"] == 1 and g.stats["zero_copy"] == 1
+    o = orc.run(reads, 21, 2)
+    d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), 21)
+    assert d == "", d
+
+
+def test_stage_one_in_isolation_matches_oracle_counts(emu_lib, knobs):
+    case = GOLDEN["reads_0_k15_a2"]
+    with api.Cdbg(k=case["k"], abundance_min=case["abundance_min"], device=0) as c:
+        c.push_reads(case["reads"])
+        st = c.count()
+        km, ct = c.solid_kmers()
+    o = orc.run(case["reads"], case["k"], case["abundance_min"])
+    assert st["n_solid"] == len(km)
+    order = np.argsort(km)
+    assert int(ct.sum()) == int(np.asarray(o.kc).sum())
+    assert len(np.unique(km)) == len(km) and np.all(km[order][1:] > km[order][:-1])
+
+
+def test_repeated_builds_on_one_context_are_identical(emu_lib, knobs):
+    case = GOLDEN["reads_6_k31_a1"]
+    with api.Cdbg(k=case["k"], abundance_min=case["abundance_min"], device=0) as c:
+        a = c.build(case["reads"])
+        b = c.build(case["reads"])
+    assert parity.diff(parity.graph_to_records(a), parity.graph_to_records(b), case["k"]) == ""
+    check_against_golden(b, case)
