@@ -20,6 +20,7 @@
 #include "shard.cuh"
 #include "k1_tma.cuh"
 #include "k2_smem.cuh"
+#include "k5_smem.cuh"
 #include "wide.cuh"
 
 namespace {
@@ -706,6 +707,92 @@ int spell_units(cdbg_ctx *ctx, const uint64_t *d_uid_scan, const uint64_t *d_nt_
     return CDBG_OK;
 }
 
+#ifndef K5_SMEM_DEFAULT
+#define K5_SMEM_DEFAULT 0   // the shared-memory join is opt-in (CDBG_K5=smem) until it has been timed on a GPU
+#endif
+
+// K5 with shared-memory tables: fine histogram -> scan -> fine scatter -> one CTA per fine bin (k5_smem.cuh).  The end records are
+// in P coarse bins (h_cnt, h_off).  Leaves ctx->d_link (pre-allocated) / d_edges / n_edges like the L2 path.
+int stage_compact_k5_smem(cdbg_ctx *ctx, uint32_t slots, double per_fine, const uint64_t *d_rec_key, const uint64_t *d_rec_val, uint32_t P,
+                          const std::vector<uint64_t> &h_cnt, const std::vector<uint64_t> &h_off) {
+    int rc;
+    const uint64_t S = ctx->S, n2 = 2 * S;
+    const uint32_t F = (uint32_t)std::min<uint64_t>(K5P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)n2 / (per_fine * P))));
+    const uint64_t NF = (uint64_t)P * F;
+    std::vector<uint32_t> h_tile_first(P + 1);
+    std::vector<uint64_t> h_range(2 * (size_t)P);
+    uint64_t tiles = 0;
+    for (uint32_t b = 0; b < P; b++) {
+        h_tile_first[b] = (uint32_t)tiles; tiles += (h_cnt[b] + K5P_TILE - 1) / K5P_TILE;
+        h_range[b] = h_off[b]; h_range[P + b] = h_off[b] + h_cnt[b];
+    }
+    h_tile_first[P] = (uint32_t)tiles;
+    if (tiles >= (1ULL << 32) || NF >= (1ULL << 32)) return ctx->fail(CDBG_ERR_PARAM, "too many end-record tiles for one device");
+
+    uint32_t *d_tile_first = nullptr, *d_fine_cnt = nullptr, *d_fine_cursor = nullptr;
+    uint64_t *d_fine_off = nullptr, *d_key2 = nullptr, *d_val2 = nullptr, *d_bin_range = nullptr;
+    if ((rc = dalloc(ctx, &d_bin_range, 2 * (size_t)P))) return rc;
+    if ((rc = dalloc(ctx, &d_tile_first, P + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_cnt, NF + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_cursor, NF + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_off, NF + 2))) return rc;
+    if ((rc = dalloc(ctx, &d_key2, n2 + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_val2, n2 + 1))) return rc;
+    CK(cudaMemsetAsync(d_fine_cnt, 0, (NF + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_fine_cursor, 0, (NF + 1) * 4, ctx->stream));
+    CK(cudaMemcpyAsync(d_bin_range, h_range.data(), 2 * (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tile_first, h_tile_first.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    tstart(ctx, T_K5);
+    K5PParams pp{};
+    pp.key = d_rec_key; pp.val = d_rec_val; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first;
+    pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out_key = d_key2; pp.out_val = d_val2;
+    if (tiles) {
+        LAUNCH(k5p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 8), K5P_THREADS, 0, pp);
+        uint64_t total = 0;
+        if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;
+        if (total != n2) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost end records (%llu != %llu)", (unsigned long long)total, (unsigned long long)n2);
+        CK(cudaFuncSetAttribute(k5p_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5p_scatter_smem_bytes()));
+        LAUNCH(k5p_scatter, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K5P_THREADS, k5p_scatter_smem_bytes(), pp);
+    } else {
+        CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
+    }
+
+    ctx->edge_cap = std::max<uint64_t>(S / 2, 1 << 16);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = dalloc(ctx, &ctx->d_edges, ctx->edge_cap))) return rc;
+        CK(cudaMemsetAsync(ctx->d_link, 0xFF, (n2 + 1) * 4, ctx->stream));
+        if ((rc = ctr_zero(ctx))) return rc;
+        K5CParams cp{};
+        cp.key = d_key2; cp.val = d_val2; cp.fine_off = d_fine_off; cp.n_fine = (uint32_t)NF;
+        cp.link = ctx->d_link; cp.edges = ctx->d_edges; cp.edge_cap = ctx->edge_cap;
+        cp.n_edges = ctx->d_ctr + 0; cp.n_compact = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
+        if (n2) {
+            if (slots == 4096) {
+                CK(cudaFuncSetAttribute(k5c_join<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5c_smem_bytes<4096>()));
+                LAUNCH(k5c_join<4096>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm), K5C_THREADS, k5c_smem_bytes<4096>(), cp);
+            } else {
+                CK(cudaFuncSetAttribute(k5c_join<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5c_smem_bytes<2048>()));
+                LAUNCH(k5c_join<2048>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * 2), K5C_THREADS, k5c_smem_bytes<2048>(), cp);
+            }
+        }
+        if (attempt == 0) tstop(ctx, T_K5);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (((int *)(ctx->h_ctr + 64))[1]) return ctx->fail(CDBG_ERR_INTERNAL, "K5: a fine bin does not fit a shared-memory table after %d splits", K5C_MAX_LEVEL);
+        ctx->n_edges = ctx->h_ctr[0];
+        ctx->st.n_compactions = ctx->h_ctr[1];
+        ctx->st.n_k5_splits = ctx->h_ctr[2];
+        if (ctx->n_edges + 2048 <= ctx->edge_cap) break;   // room for the two edges of every cut cycle
+        if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow");
+        dfree(ctx, ctx->d_edges);
+        ctx->edge_cap = ctx->n_edges + std::max<uint64_t>(ctx->n_edges / 8, 1 << 16);
+    }
+    dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off);
+    dfree(ctx, d_key2); dfree(ctx, d_val2);
+    return CDBG_OK;
+}
+
 int stage_compact(cdbg_ctx *ctx) {
     const int k = ctx->k;
     const uint64_t S = ctx->S, n2 = 2 * S;
@@ -715,6 +802,19 @@ int stage_compact(cdbg_ctx *ctx) {
     // ---- K3: end records, partitioned by hash of the canonical (k-1)-mer
     const uint64_t join_target = getenv("CDBG_JOIN_TARGET") ? strtoull(getenv("CDBG_JOIN_TARGET"), nullptr, 10) : 500000ULL;   // records per bin
     uint32_t P = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1, (n2 + join_target - 1) / join_target));
+    // K5 variant (CDBG_K5): "l2" = one L2-resident join table per coarse bin; "smem" = fine partition + shared-memory tables
+    // (k5_smem.cuh): the coarse and the fine fan-out split the number of fine bins evenly, as for K2.
+    const char *k5mode = getenv("CDBG_K5");
+    const bool k5_smem = K5_SMEM_DEFAULT ? !(k5mode && strcmp(k5mode, "l2") == 0) : (k5mode && strcmp(k5mode, "smem") == 0);
+    const uint32_t k5_slots = getenv("CDBG_K5S_SLOTS") && atoi(getenv("CDBG_K5S_SLOTS")) == 4096 ? 4096u : 2048u;
+    double k5_fill = getenv("CDBG_K5S_FILL") ? atof(getenv("CDBG_K5S_FILL")) : 1.0;   // end records per table slot (2 records per key are typical)
+    if (!(k5_fill >= 0.05 && k5_fill <= 8.0)) k5_fill = 1.0;
+    const double k5_per_fine = k5_fill * k5_slots;
+    if (k5_smem) {
+        uint64_t p1 = (uint64_t)ceil(sqrt(std::max(1.0, (double)n2 / k5_per_fine)));
+        if (getenv("CDBG_K5S_P1")) p1 = strtoull(getenv("CDBG_K5S_P1"), nullptr, 10);
+        P = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(1, p1));
+    }
     ctx->st.n_join_bins = P;
     ctx->st.n_junction_records = n2;
     unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr;
@@ -748,6 +848,11 @@ int stage_compact(cdbg_ctx *ctx) {
 
     // ---- K5: per-bin join
     if ((rc = dalloc(ctx, &ctx->d_link, n2 + 1))) return rc;
+    if (k5_smem && max_bin < (1ULL << 32)) {
+        if ((rc = stage_compact_k5_smem(ctx, k5_slots, k5_per_fine, d_rec_key, d_rec_val, P, h_cnt, h_off))) return rc;
+        dfree(ctx, d_rec_key); dfree(ctx, d_rec_val);
+        dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+    } else {
     auto table_cap = [](uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); };
     uint32_t cap = table_cap(max_bin);
     JoinTable T{};
@@ -784,6 +889,7 @@ int stage_compact(cdbg_ctx *ctx) {
     }
     dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
     dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+    }
 
     // ---- K6: list ranking + unitig numbering
     uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;

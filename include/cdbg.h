@@ -92,6 +92,7 @@ typedef struct {
     uint32_t n_k2_splits;   /* K2 (shared-memory variant): table passes abandoned and redone as two halves */
     uint32_t k1_fallback;   /* 1 when the single-pass K1 overflowed a bin region and stage 1 was redone with the exact two-pass kernels */
     uint32_t zero_copy;     /* 1 when cdbg_build read pinned host memory directly from K1 (no separate H2D copy) */
+    uint32_t n_k5_splits;   /* K5 (shared-memory variant): join passes abandoned and redone as two halves */
 } cdbg_stats;
 
 typedef struct {
