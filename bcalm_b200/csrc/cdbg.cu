@@ -298,6 +298,14 @@ int free_results(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stage 1
 
+#ifndef RANK_MATCH_DEFAULT
+#define RANK_MATCH_DEFAULT 0   // tile-local ranks by match.any instead of shared-memory atomics: opt-in (CDBG_RANK=match) until timed on a GPU
+#endif
+bool rank_by_match() {
+    const char *r = getenv("CDBG_RANK");
+    return RANK_MATCH_DEFAULT ? !(r && strcmp(r, "atomic") == 0) : (r && strcmp(r, "match") == 0);
+}
+
 // Sizing of the shared-memory K2 variant.  slots = table size per CTA, fill = k-mer INSTANCES per slot a fine bin is sized for:
 // 1.5 suits sequencing coverage (30x data has ~0.3 distinct k-mers per instance, i.e. a load factor below 0.5); when an input
 // has more distinct k-mers than that, k2c_count splits the affected bins on the fly, so the value is a tuning knob only.
@@ -359,9 +367,16 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
         uint64_t total = 0;
         if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;   // entry NF = I
         if (total != I) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost k-mers (%llu != %llu)", (unsigned long long)total, (unsigned long long)I);
-        CK(cudaFuncSetAttribute(k2p_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2p_scatter_smem_bytes()));
+        const bool match = rank_by_match() && F <= K2P_MATCH_MAX_F;
+        const size_t sm = k2p_scatter_smem_bytes(F, match);
         tstart(ctx, T_K2S);
-        LAUNCH(k2p_scatter, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K2P_THREADS, k2p_scatter_smem_bytes(), pp);
+        if (match) {
+            CK(cudaFuncSetAttribute(k2p_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            LAUNCH(k2p_scatter<true>, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K2P_THREADS, sm, pp);
+        } else {
+            CK(cudaFuncSetAttribute(k2p_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            LAUNCH(k2p_scatter<false>, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K2P_THREADS, sm, pp);
+        }
         tstop(ctx, T_K2S);
     } else {
         CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
@@ -462,9 +477,16 @@ int stage_count(cdbg_ctx *ctx) {
             CK(cudaMemcpyAsync(d_tail, ctx->h_bytes_src + kx.tail_start, n - kx.tail_start, cudaMemcpyHostToDevice, ctx->stream));
             kx.tail = d_tail;
         } else kx.tail = ctx->d_bytes + kx.tail_start;
+        const bool match = rank_by_match() && P <= K1X_MATCH_MAX_P;
+        const size_t sm = k1x_smem_bytes(P, match);
         tstart(ctx, T_K1S);
-        CK(cudaFuncSetAttribute(k1t_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1x_smem_bytes(P)));
-        LAUNCH(k1t_single, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1x_smem_bytes(P), kx);
+        if (match) {
+            CK(cudaFuncSetAttribute(k1t_single<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            LAUNCH(k1t_single<true>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, sm, kx);
+        } else {
+            CK(cudaFuncSetAttribute(k1t_single<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            LAUNCH(k1t_single<false>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, sm, kx);
+        }
         tstop(ctx, T_K1S);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_cursor, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         if ((rc = ctr_read(ctx))) return rc;

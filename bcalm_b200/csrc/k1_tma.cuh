@@ -247,6 +247,13 @@ struct K1XParams {
 #define K1X_NONE 0xFFFFFFFFu
 #define K1X_SKIP 0xFFFFFFFFFFFFFFFFULL
 
+// MATCH = true ranks the positions of a tile inside their bin without atomics: lanes of a warp that hit the same bin find each
+// other with match.any, the first of them bumps a counter that is private to (bin, warp) with a plain read-modify-write, and the
+// per-warp counts are prefix-summed per bin before the second sweep.  (A shared-memory atomic that returns a value costs more than
+// one that does not; this trades it for match + shuffle.)  Needs P * 8 warp counters in shared memory: P <= K1X_MATCH_MAX_P.
+constexpr uint32_t K1X_MATCH_MAX_P = 512;
+
+template <bool MATCH>
 __global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t *s_raw = smem_raw;                                                              // [2][K1T_RAW]  TMA destinations
@@ -257,10 +264,13 @@ __global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
     uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_stage + K1_TILE);                       // [THREADS + 2]
     uint32_t *s_cnt = s_vm + K1_THREADS + 2;                                                // [P]
     uint32_t *s_off = s_cnt + p.P;                                                          // [P + 1]
-    uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_off + p.P + 1);                         // [K1_TILE] bin of each staged k-mer
+    uint32_t *s_wc = s_off + p.P + 1;                                                       // [P * 8] MATCH: per (bin, warp) counters
+    uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_wc + (MATCH ? p.P * (K1_THREADS / 32) : 0));   // [K1_TILE] bin of each staged k-mer
     __shared__ uint32_t s_warp[K1_THREADS / 32];
+    constexpr uint32_t NW = K1_THREADS / 32;
 
     const int t = threadIdx.x, k = p.k;
+    const uint32_t lane = lane_id(), warp = (uint32_t)t >> 5;
     const uint64_t first = blockIdx.x, stride = gridDim.x;
 
     auto issue = [&](uint64_t tile, int stage) {      // thread 0 only
@@ -279,6 +289,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
         mbar_fence_init();
     }
     for (uint32_t i = t; i < p.P; i += K1_THREADS) s_cnt[i] = 0;
+    if (MATCH) for (uint32_t i = t; i < p.P * NW; i += K1_THREADS) s_wc[i] = 0;
     __syncthreads();
     if (t == 0 && first < p.n_tiles) issue(first, 0);
 
@@ -319,10 +330,30 @@ __global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
                 }
                 const uint64_t c = fwd < rc ? fwd : rc;
                 const uint32_t bin = hash32_to_bin(bin_hash32(c), p.P);
-                br[i] = ((valid32 >> (31 - i)) & 1) ? ((atomicAdd(&s_cnt[bin], 1u) << 11) | bin) : K1X_NONE;
+                const bool ok = (valid32 >> (31 - i)) & 1;
+                if (!MATCH) {
+                    br[i] = ok ? ((atomicAdd(&s_cnt[bin], 1u) << 11) | bin) : K1X_NONE;
+                } else {
+                    const unsigned m = __match_any_sync(0xFFFFFFFFu, ok ? bin : K1X_NONE);
+                    const int leader = __ffs(m) - 1;
+                    uint32_t base = 0;
+                    if (ok && (int)lane == leader) { base = s_wc[bin * NW + warp]; s_wc[bin * NW + warp] = base + __popc(m); }
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    br[i] = ok ? (((base + __popc(m & ((1u << lane) - 1))) << 11) | bin) : K1X_NONE;
+                    __syncwarp();
+                }
             }
         }
         __syncthreads();
+        if (MATCH) {   // per bin: prefix over the warps' counts (becomes each warp's base), total into s_cnt
+            for (uint32_t b = t; b < p.P; b += K1_THREADS) {
+                uint32_t run = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < NW; w++) { const uint32_t c = s_wc[b * NW + w]; s_wc[b * NW + w] = run; run += c; }
+                s_cnt[b] = run;
+            }
+            __syncthreads();
+        }
         {   // exclusive scan of s_cnt + one global reservation per non-empty bin, checked against the bin's region
             const uint32_t per = (p.P + K1_THREADS - 1) / K1_THREADS;
             uint32_t b0 = t * per, sum = 0;
@@ -366,7 +397,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
                     rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
                 }
                 if (br[i] != K1X_NONE) {
-                    const uint32_t bin = br[i] & 2047u, pos = s_off[bin] + (br[i] >> 11);
+                    const uint32_t bin = br[i] & 2047u, pos = s_off[bin] + (br[i] >> 11) + (MATCH ? s_wc[bin * NW + warp] : 0u);
                     s_stage[pos] = fwd < rc ? fwd : rc; s_sb[pos] = (uint16_t)bin;
                 }
             }
@@ -378,11 +409,12 @@ __global__ void __launch_bounds__(K1_THREADS) k1t_single(K1XParams p) {
             const uint64_t g = s_gbase[b];
             if (g != K1X_SKIP) p.out_kmers[g + (j - s_off[b])] = s_stage[j];
         }
+        if (MATCH) for (uint32_t i = t; i < p.P * NW; i += K1_THREADS) s_wc[i] = 0;   // (sweep 2 is behind the barrier above)
         __syncthreads();
     }
 }
 
-static inline size_t k1x_smem_bytes(uint32_t P) {
-    return 2 * (size_t)K1T_RAW + 16 + (size_t)(K1_THREADS + 2) * 8 + (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(K1_THREADS + 2) * 4 +
+static inline size_t k1x_smem_bytes(uint32_t P, bool match) {
+    return (match ? (size_t)P * (K1_THREADS / 32) * 4 : 0) + 2 * (size_t)K1T_RAW + 16 + (size_t)(K1_THREADS + 2) * 8 + (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(K1_THREADS + 2) * 4 +
            (size_t)P * 4 + (size_t)(P + 1) * 4 + (size_t)K1_TILE * 2 + 128;
 }

@@ -74,16 +74,24 @@ __global__ void __launch_bounds__(K2P_THREADS) k2p_hist(K2PParams p) {
     }
 }
 
+// MATCH = true: ranks without atomics (match.any inside the warp + counters private to (fine bin, warp)), see k1t_single.
+constexpr uint32_t K2P_MATCH_MAX_F = 256;
+
+template <bool MATCH>
 __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *s_stage = reinterpret_cast<uint64_t *>(smem_raw);                  // [K2P_TILE] the tile sorted by fine bin
     uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_stage + K2P_TILE);           // [K2P_TILE] fine bin of each staged k-mer
+    uint32_t *s_wc = reinterpret_cast<uint32_t *>(s_sb + K2P_TILE);              // [F * 16] MATCH: per (fine bin, warp) counters
+    constexpr uint32_t NW = K2P_THREADS / 32;
     __shared__ uint64_t s_gbase[K2P_MAX_F];                                      // global position of each fine bin's run
     __shared__ uint32_t s_cnt[K2P_MAX_F];
     __shared__ uint32_t s_off[K2P_MAX_F + 1];
     __shared__ uint32_t s_warp[K2P_THREADS / 32];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (p.F + K2P_THREADS - 1) / K2P_THREADS;                  // fine bins scanned per thread (1 or 2)
+    const uint32_t lane = lane_id(), warp = t >> 5;
+    if (MATCH) { for (uint32_t i = t; i < p.F * NW; i += K2P_THREADS) s_wc[i] = 0; }
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t b = k2p_bin_of_tile(p.tile_first, p.P1, tile);
@@ -102,11 +110,32 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
         }
 #pragma unroll
         for (int j = 0; j < K2P_PER_THREAD; j++) {
-            if (key[j] == EMPTY_KEY) { fr[j] = K2P_NOKEY; continue; }
-            const uint32_t f = k2p_fine(mix64(key[j]), p.F);
-            fr[j] = (atomicAdd(&s_cnt[f], 1u) << 10) | f;
+            if (!MATCH) {
+                if (key[j] == EMPTY_KEY) { fr[j] = K2P_NOKEY; continue; }
+                const uint32_t f = k2p_fine(mix64(key[j]), p.F);
+                fr[j] = (atomicAdd(&s_cnt[f], 1u) << 10) | f;
+            } else {   // (every lane takes part: the tile's ragged end is warp-divergent otherwise)
+                const bool ok = key[j] != EMPTY_KEY;
+                const uint32_t f = ok ? k2p_fine(mix64(key[j]), p.F) : K2P_NOKEY;
+                const unsigned m = __match_any_sync(0xFFFFFFFFu, f);
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if (ok && (int)lane == leader) { base = s_wc[f * NW + warp]; s_wc[f * NW + warp] = base + __popc(m); }
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                fr[j] = ok ? (((base + __popc(m & ((1u << lane) - 1))) << 10) | f) : K2P_NOKEY;
+                __syncwarp();
+            }
         }
         __syncthreads();
+        if (MATCH) {   // per fine bin: prefix over the warps' counts (each warp's base), total into s_cnt
+            for (uint32_t f = t; f < p.F; f += K2P_THREADS) {
+                uint32_t run = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < NW; w++) { const uint32_t c = s_wc[f * NW + w]; s_wc[f * NW + w] = run; run += c; }
+                s_cnt[f] = run;
+            }
+            __syncthreads();
+        }
 
         // exclusive scan of the tile's fine counts + ONE global reservation per non-empty (tile, fine bin)
         {
@@ -142,7 +171,7 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
 #pragma unroll
         for (int j = 0; j < K2P_PER_THREAD; j++) {
             if (fr[j] == K2P_NOKEY) continue;
-            const uint32_t f = fr[j] & 1023u, pos = s_off[f] + (fr[j] >> 10);
+            const uint32_t f = fr[j] & 1023u, pos = s_off[f] + (fr[j] >> 10) + (MATCH ? s_wc[f * NW + warp] : 0u);
             s_stage[pos] = key[j]; s_sb[pos] = (uint16_t)f;
         }
         __syncthreads();
@@ -151,11 +180,14 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
             const uint32_t f = s_sb[j];
             p.out[s_gbase[f] + (j - s_off[f])] = s_stage[j];
         }
+        if (MATCH) { for (uint32_t i = t; i < p.F * NW; i += K2P_THREADS) s_wc[i] = 0; }   // (the staging loop is behind the barrier above)
         __syncthreads();     // the staging area and the counters are reused by the next tile
     }
 }
 
-static inline size_t k2p_scatter_smem_bytes() { return (size_t)K2P_TILE * 8 + (size_t)K2P_TILE * 2 + 128; }
+static inline size_t k2p_scatter_smem_bytes(uint32_t F, bool match) {
+    return (size_t)K2P_TILE * 8 + (size_t)K2P_TILE * 2 + (match ? (size_t)F * (K2P_THREADS / 32) * 4 : 0) + 128;
+}
 
 // ------------------------------------------------------------------------------------------------ counting in shared memory
 

@@ -198,6 +198,18 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+    emu::need_full_mask(mask);
+    emu::Engine &e = emu::engine();
+    const unsigned w = emu::tls.warp;
+    e.warp_slot[w][emu::tls.lane] = v;
+    e.warp_bar[w].wait();
+    unsigned r = 0;
+    const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
+    for (unsigned i = 0; i < lanes; i++) if ((unsigned)e.warp_slot[w][i] == v) r |= 1u << i;
+    e.warp_bar[w].wait();
+    return r;
+}
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
 static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
