@@ -623,12 +623,47 @@ int stage_count(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stages 2+3
 
+#ifndef K6_LIST_DEFAULT
+#define K6_LIST_DEFAULT 0   // pointer jumping over shrinking lists of moving elements: opt-in (CDBG_K6=list) until timed on a GPU
+#endif
+
 int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remaining) {
     // pointer jumping until no element moves (paths done) or the number of moving elements stops shrinking (cycles)
     uint64_t prev = ~0ULL;
     *remaining = 0;
+    const char *mode = getenv("CDBG_K6");
+    const bool use_list = (K6_LIST_DEFAULT ? !(mode && strcmp(mode, "full") == 0) : (mode && strcmp(mode, "list") == 0)) && n2 < (1ULL << 32);
+    int rc;
+    if (use_list) {
+        // rounds come in batches of 4; the last round of a batch writes the list of elements that moved, the next batch walks it
+        uint32_t *d_list[2] = {nullptr, nullptr};
+        if ((rc = dalloc(ctx, &d_list[0], n2 + 1))) return rc;
+        if ((rc = dalloc(ctx, &d_list[1], n2 + 1))) return rc;
+        const uint32_t *in_list = nullptr;
+        uint64_t n_cur = n2;
+        int result = -1;
+        for (int round = 0, batch = 0; round < 80 && result < 0; round += 4, batch++) {
+            if ((rc = ctr_zero(ctx))) return rc;
+            uint32_t *out_list = d_list[batch & 1];
+            for (int j = 0; j < 4; j++)
+                LAUNCH_PDL(k6_jump_list, grid_for(ctx, n_cur, 256, 8), 256, 0, d_pair, in_list, n_cur, j == 3 ? out_list : (uint32_t *)nullptr, ctx->d_ctr + 4,
+                           ctx->d_ctr + j);
+            ctx->st.rank_rounds += 4;
+            if ((rc = ctr_read(ctx))) return rc;
+            for (int j = 0; j < 4 && result < 0; j++) {
+                uint64_t c = ctx->h_ctr[j];
+                if (c == 0) { *remaining = 0; result = 0; }
+                else if (c == prev) { *remaining = c; result = 0; }
+                prev = c;
+            }
+            in_list = out_list; n_cur = ctx->h_ctr[4];
+        }
+        dfree(ctx, d_list[0]); dfree(ctx, d_list[1]);
+        if (result == 0) return CDBG_OK;
+        return ctx->fail(CDBG_ERR_INTERNAL, "list ranking did not converge");
+    }
     for (int round = 0; round < 80; round += 4) {
-        int rc = ctr_zero(ctx);
+        rc = ctr_zero(ctx);
         if (rc) return rc;
         for (int j = 0; j < 4; j++) LAUNCH_PDL(k6_jump, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, n2, ctx->d_ctr + j);
         ctx->st.rank_rounds += 4;

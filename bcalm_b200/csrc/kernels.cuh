@@ -572,6 +572,52 @@ __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsi
     block_add(n_updated, upd);
 }
 
+// Variant that walks a LIST of still-moving elements instead of the whole array (in_list == nullptr: all x < n), and can emit
+// the elements that moved -- exactly the ones that may move again -- as the next list (out_list != nullptr; one reservation
+// atomic per block).  After a few rounds only the elements far from a tail are left, so later rounds touch a small fraction.
+// (An element whose next became the tail is simply not listed again; it stays without its DONE bit, which nothing relies on.)
+__global__ void __launch_bounds__(256) k6_jump_list(uint64_t *pair, const uint32_t *__restrict__ in_list, uint64_t n, uint32_t *out_list,
+                                                    unsigned long long *n_out, unsigned long long *n_updated) {
+    pdl_wait();
+    __shared__ uint32_t s_wcnt[8];
+    __shared__ unsigned long long s_obase;
+    unsigned long long upd = 0;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < n; base += (uint64_t)gridDim.x * blockDim.x) {   // block-uniform
+        const uint64_t i = base + threadIdx.x;
+        bool moved = false;
+        uint32_t x = 0;
+        if (i < n) {
+            x = in_list ? in_list[i] : (uint32_t)i;
+            uint64_t p = ld_volatile_u64(&pair[x]);
+            if (!((uint32_t)p & K6_DONE)) {
+                uint32_t nx = (uint32_t)(p >> 32);
+                uint64_t q = ld_volatile_u64(&pair[nx]);
+                uint32_t n2_ = (uint32_t)(q >> 32);
+                if (n2_ == K6_NIL) *(volatile uint64_t *)&pair[x] = p | K6_DONE;
+                else {
+                    *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p + (uint32_t)q) & ~K6_DONE);
+                    moved = true; upd++;
+                }
+            }
+        }
+        if (out_list) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, moved);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t tot = 0;
+                for (int w = 0; w < 8; w++) { uint32_t v = s_wcnt[w]; s_wcnt[w] = tot; tot += v; }
+                s_obase = tot ? atomicAdd(n_out, (unsigned long long)tot) : 0ULL;
+            }
+            __syncthreads();
+            if (moved) out_list[s_obase + s_wcnt[warp] + __popc(m & ((1u << lane) - 1))] = x;
+            __syncthreads();
+        }
+    }
+    block_add(n_updated, upd);
+}
+
 // ---- cycles: elements that never reach a tail.  Find the smallest k-mer index on each cycle by pointer doubling with a
 // running minimum, cut the link at that k-mer's left end (the reference cuts wherever its scan order happens to close
 // the cycle: bglue_algo.cpp:400-416), record the two edges of the cut junction, and re-rank the affected elements.

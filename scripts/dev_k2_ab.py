@@ -26,24 +26,27 @@ n_reads = int(G * 30 / L)
 TUNABLES = ("CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_JOIN_TARGET", "CDBG_BIN_TARGET", "CDBG_K1")
 
 CONFIGS = [
-    ("round-start defaults: K1 twopass, K2 l2", {"CDBG_K1": "twopass", "CDBG_K2": "l2"}),
-    ("K1 twopass, K2 smem", {"CDBG_K1": "twopass"}),
-    ("K1 single, K2 l2", {"CDBG_K2": "l2"}),
-    ("default: K1 single, K2 smem 8192/1.5", {}),
-    ("K1 single P1=64", {"CDBG_K2S_P1": "64"}),
-    ("K1 single P1=160", {"CDBG_K2S_P1": "160"}),
-    ("smem 8192 fill 1.0", {"CDBG_K2S_FILL": "1.0"}),
-    ("smem 8192 fill 1.9", {"CDBG_K2S_FILL": "1.9"}),
-    ("smem 16384 fill 1.5", {"CDBG_K2S_SLOTS": "16384"}),
-    ("smem 8192 fill 4 (splits)", {"CDBG_K2S_FILL": "4"}),
-    ("K1 slack 0, P1=100 (may fall back)", {"CDBG_K1_SLACK": "0", "CDBG_K2S_P1": "100"}),
+    ("default: K1 single, K2 smem, K5 l2, atomic ranks", {}),
+    ("ranks by match.any", {"CDBG_RANK": "match"}),
+    ("K5 smem 2048/1.0", {"CDBG_K5": "smem"}),
+    ("K5 smem 2048/0.7", {"CDBG_K5": "smem", "CDBG_K5S_FILL": "0.7"}),
+    ("K5 smem 2048/1.4", {"CDBG_K5": "smem", "CDBG_K5S_FILL": "1.4"}),
+    ("K5 smem 4096/1.0", {"CDBG_K5": "smem", "CDBG_K5S_SLOTS": "4096"}),
+    ("K5 smem 2048/1.0 P1=32", {"CDBG_K5": "smem", "CDBG_K5S_P1": "32"}),
+    ("K5 smem + match ranks", {"CDBG_K5": "smem", "CDBG_RANK": "match"}),
+    ("K6 over lists", {"CDBG_K6": "list"}),
+    ("K5 smem + K6 lists", {"CDBG_K5": "smem", "CDBG_K6": "list"}),
+    ("K5 smem + K6 lists + match ranks", {"CDBG_K5": "smem", "CDBG_K6": "list", "CDBG_RANK": "match"}),
+    ("round-start: K1 twopass, K2 l2, K5 l2", {"CDBG_K1": "twopass", "CDBG_K2": "l2"}),
 ]
 E2E_CONFIGS = [
-    ("e2e round-start defaults (copy, twopass, l2)", {"CDBG_K1": "twopass", "CDBG_K2": "l2", "CDBG_ZEROCOPY": "0"}),
-    ("e2e copy + single + smem", {"CDBG_ZEROCOPY": "0"}),
-    ("e2e zero-copy + single + smem (default)", {}),
+    ("e2e default (zero-copy, single, K2 smem, K5 l2)", {}),
+    ("e2e + K5 smem", {"CDBG_K5": "smem"}),
+    ("e2e + K5 smem + K6 lists", {"CDBG_K5": "smem", "CDBG_K6": "list"}),
+    ("e2e + K5 smem + K6 lists + match ranks", {"CDBG_K5": "smem", "CDBG_K6": "list", "CDBG_RANK": "match"}),
+    ("e2e round-start (copy, twopass, l2)", {"CDBG_K1": "twopass", "CDBG_K2": "l2", "CDBG_ZEROCOPY": "0"}),
 ]
-TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK")
+TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK", "CDBG_K5", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_K5S_P1", "CDBG_RANK", "CDBG_K6")
 
 
 def say(*a):
@@ -83,7 +86,7 @@ for name, env in CONFIGS:
         say(f"{name:50s} {same:9s} total {tot:6.3f} ms | K1 {st['ms_k1_hist']:.3f}+{st['ms_k1_scatter']:.3f} K2 {st['ms_k2']:.3f} K3 {st['ms_k3']:.3f} "
             f"K5 {st['ms_k5']:.3f} K6 {st['ms_k6_rank']:.3f}+{st['ms_k6_spell']:.3f} link {st['ms_link']:.3f} | bins {st['n_count_bins']}/{st['n_join_bins']} "
             f"launches {st['kernel_launches']} | K2 parts hist {st['ms_k2_hist']:.3f} scatter {st['ms_k2_scatter']:.3f} table {st['ms_k2_table']:.3f} "
-            f"splits {st['n_k2_splits']} k1fb {st['k1_fallback']} | S,D,U,nt,links,KC = {summary}")
+            f"splits {st['n_k2_splits']}/{st['n_k5_splits']} k1fb {st['k1_fallback']} rounds {st['rank_rounds']} | S,D,U,nt,links,KC = {summary}")
     except Exception as e:  # keep going: one bad configuration must not cost the whole call
         say(f"{name:50s} FAILED: {e}")
         try:
