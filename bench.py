@@ -12,7 +12,7 @@ compaction -> unitigs -> links over that read set.
   e2e   : the same pass through the C ABI with HOST buffers: pinned host reads -> H2D -> all stages -> D2H of the unitig
           arrays (sequences, offsets, KC, links) inside the timed region.
   roofline : the dominant kernel group of the step (by CUDA-event time measured inside the library on its own stream),
-          algorithmic bytes per SURVEY.md 8d / DESIGN.md.
+          algorithmic bytes per SURVEY.md 8d / DESIGN.md; for the K2 group also its three kernels one by one (`k2_kernels`).
   cpu_baseline : the real reference binary (oracle/_ref/bcalm, kind "reference") -- or the C oracle (kind "port") when the
           binary is absent -- on a bounded sample of the same workload, all host cores.
 
@@ -161,31 +161,41 @@ def cpu_baseline_sample(c, scale: float, cores: int):
 
 
 def load_traffic(name: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel group from the committed `ncu --set full` capture."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)["groups"][name]["traffic_bytes_per_step"]
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernel group from the committed `ncu --set full` captures."""
+    for fn in ("r01b_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                return json.load(f)["groups"][name]["traffic_bytes_per_step"]
+        except Exception:
+            continue
+    return None
 
 
 def dominant_kernel(st: dict, n_bytes: int):
-    """Pick the kernel group with the largest device time in the step and compute its algorithmic bytes."""
+    """Pick the kernel group with the largest device time in the step and compute its algorithmic bytes.
+    Also returns, for the K2 group, the three kernels it consists of with their own algorithmic bytes."""
     I, S, w = st["n_instances"], st["n_solid"], 8
     T = st["n_junction_records"]
-    groups = {
-        "K1 extract (hist pass)": (st["ms_k1_hist"], n_bytes),
-        "K1 extract (scatter pass)": (st["ms_k1_scatter"], n_bytes + I * w),
-        "K2 count (insert+emit, all bins)": (st["ms_k2"], I * w + S * (w + 4)),
-        "K3 end records (hist+scatter)": (st["ms_k3"], 2 * S * (w + 4) + T * 16),
-        "K5 junction join (insert+resolve, all bins)": (st["ms_k5"], T * 16 + 2 * S * 4),
-        "K6 list ranking": (st["ms_k6_rank"], 2 * S * 4 + 2 * S * 8 * 2),
-        "K6/K8 numbering + spelling": (st["ms_k6_spell"], S * (w + 4) + 2 * S * 8 + st["total_nt"] + st["n_unitigs"] * 16),
-    }
+    single = st["ms_k1_hist"] == 0
+    k2_smem = st.get("ms_k2_table", 0) > 0
+    groups = {}
+    if single:
+        groups["K1 extract (single pass)"] = (st["ms_k1_scatter"], n_bytes + I * w)
+    else:
+        groups["K1 extract (hist pass)"] = (st["ms_k1_hist"], n_bytes)
+        groups["K1 extract (scatter pass)"] = (st["ms_k1_scatter"], n_bytes + I * w)
+    groups["K2 count (fine partition + shared-memory tables)" if k2_smem else "K2 count (insert+emit, all bins)"] = (st["ms_k2"], I * w + S * (w + 4))
+    groups["K3 end records (hist+scatter)"] = (st["ms_k3"], 2 * S * (w + 4) + T * 16)
+    groups["K5 junction join"] = (st["ms_k5"], T * 16 + 2 * S * 4)
+    groups["K6 list ranking"] = (st["ms_k6_rank"], 2 * S * 4 + 2 * S * 8 * 2)
+    groups["K6/K8 numbering + spelling"] = (st["ms_k6_spell"], S * (w + 4) + 2 * S * 8 + st["total_nt"] + st["n_unitigs"] * 16)
     name = max(groups, key=lambda k_: groups[k_][0])
     ms, nbytes = groups[name]
-    return name, ms, nbytes, {k_: round(v[0], 4) for k_, v in groups.items()}
+    kernels = None
+    if k2_smem:
+        kernels = {"k2p_hist": (st["ms_k2_hist"], I * w), "k2p_scatter": (st["ms_k2_scatter"], 2 * I * w),
+                   "k2c_count": (st["ms_k2_table"], I * w + S * (w + 4))}
+    return name, ms, nbytes, {k_: round(v[0], 4) for k_, v in groups.items()}, kernels
 
 
 def main():
@@ -305,7 +315,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        name, ms_k, bytes_k, groups = dominant_kernel(st, n_bytes)
+        name, ms_k, bytes_k, groups, k2_kernels = dominant_kernel(st, n_bytes)
         achieved = bytes_k / (ms_k / 1e3) / 1e9 if ms_k > 0 else 0.0
         total_bases = n_bases * world
         out = {
@@ -319,11 +329,16 @@ def main():
                        "input_bytes": n_bytes, "l2_note": "input (151 MB) and k-mer stream (840 MB) are larger than the 126 MB L2; no L2 flush needed",
                        "unitigs_rank0": int(st["n_unitigs"]), "links_rank0": int(st["n_links"]), "solid_kmers_rank0": int(st["n_solid"])},
             "e2e": {"value": total_bases / dt_e2e * args.steps / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": int(n_bytes), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": dt_e2e / args.steps * 1e3},
+                    "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "zero_copy": bool(s2.zero_copy),
+                    "note": "zero_copy: the pinned host reads are not copied first; the extraction kernel's TMA loads read them in place over PCIe, so the "
+                            "h2d bytes cross the bus inside K1" if s2.zero_copy else "host reads copied H2D (cudaMemcpyAsync), then the stages"},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(name) if world == 1 else None, "algorithmic_bytes": int(bytes_k), "kernel_ms": ms_k, "peak_source": peak_src,
-                         "stage_ms": groups},
+                         "stage_ms": groups,
+                         "k2_kernels": None if not k2_kernels else {k_: {"ms": round(m_, 4), "algorithmic_bytes": int(b_), "achieved": round(b_ / (m_ / 1e3) / 1e9, 1) if m_ > 0 else None,
+                                                                        "frac": round(b_ / (m_ / 1e3) / 1e9 / peak, 4) if m_ > 0 else None} for k_, (m_, b_) in k2_kernels.items()}},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:   # the CPU leg runs on rank 0 at N=1 only

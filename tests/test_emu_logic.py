@@ -3,8 +3,8 @@
 tests/emu builds the unchanged library sources against a CPU stand-in for the CUDA runtime (every CUDA thread is an OS
 thread, see tests/emu/cuda_runtime.h) and these tests push golden cases through that build via the normal ctypes mirror, for
 the default configuration and for the variants / rare paths that the GPU suite reaches only through environment knobs:
-the two K1 kernels behind the single-pass one (its overflow fallback), the split path of the shared-memory K2, the L2-table
-K2, zero-copy input.  This is test infrastructure: it proves indexing, reservations and stage hand-offs, not performance and
+the two K1 kernels behind the single-pass one (its overflow fallback), the split paths of the shared-memory K2 and K5, the
+L2-table K2 and K5, match-based ranks, list-based pointer jumping, zero-copy input.  This is test infrastructure: it proves indexing, reservations and stage hand-offs, not performance and
 not the GPU memory model -- the `-m gpu` parity tests remain the gate for the product.
 """
 from __future__ import annotations
@@ -30,7 +30,8 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
     GOLDEN = {c["name"]: c for c in json.load(f)}
 
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
-         "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL")
+         "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
+         "CDBG_RANK", "CDBG_K6")
 
 
 @pytest.fixture(scope="module")
@@ -69,7 +70,7 @@ SMALL = ["tiny_read_k21", "tiny_read_k13", "minitip_k21_a1", "minitip_k21_a2", "
          "lowcx_12_AT_k6_a1", "lowcx_14_ACGT_k4_a1", "circular_genome_0_k7", "circular_genome_1_k11", "reads_6_k31_a1", "reads_7_k31_a1",
          "short_reads_only", "palindrome_k_even", "pow2_cycle_L2_k5", "pow2_cycle_L16_k9", "pow2_cycle_L256_k21", "wide_10_k41_a1",
          "wide_lowcx_0_AT_k33"]
-MEDIUM = ["reads_0_k15_a2", "reads_5_k25_a1", "lowcx_8_ACGT_k8_a1"]
+MEDIUM = ["reads_5_k25_a1", "lowcx_8_ACGT_k8_a1"]
 
 
 @pytest.mark.parametrize("name", SMALL + MEDIUM)
@@ -89,11 +90,17 @@ VARIANTS = {
     "k1_many_coarse_bins": dict(CDBG_K2S_P1=37),
     "zero_copy_input": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0),
     "no_pdl": dict(CDBG_PDL=0),
+    "k5_l2_tables": dict(CDBG_K5="l2"),
+    "k5_l2_many_bins": dict(CDBG_K5="l2", CDBG_JOIN_TARGET=500),
+    "k5_smem_many_fine_bins": dict(CDBG_K5S_FILL=0.05, CDBG_K5S_P1=7),
+    "k5_smem_forced_splits": dict(CDBG_K5S_FILL=8, CDBG_K5S_SLOTS=4096),
+    "ranks_by_match": dict(CDBG_RANK="match", CDBG_K2S_P1=9),
+    "k6_over_lists": dict(CDBG_K6="list"),
 }
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
-@pytest.mark.parametrize("name", ["minitip_k21_a1", "circular_test2_polyA", "reads_0_k15_a2", "reads_5_k25_a1"])
+@pytest.mark.parametrize("name", ["circular_test1", "lowcx_3_AT_k9_a1", "reads_0_k15_a2"])
 def test_variants_match_reference_output(emu_lib, knobs, variant, name):
     knobs(**VARIANTS[variant])
     g = run_case(GOLDEN[name])
@@ -102,6 +109,8 @@ def test_variants_match_reference_output(emu_lib, knobs, variant, name):
         assert g.stats["zero_copy"] == 1
     if variant == "k2_smem_forced_splits" and name.startswith("reads_"):
         assert g.stats["n_k2_splits"] > 0
+    if variant == "k5_smem_forced_splits" and name.startswith("reads_"):
+        assert g.stats["n_k5_splits"] > 0
 
 
 def _repeats_input():
