@@ -22,6 +22,13 @@ struct NcclApi {
 
     bool load() {
         if (handle) return true;
+#ifdef CDBG_EMU_ACTIVE   // CPU emulation build of the tests: ranks are threads of one process, see tests/emu/nccl.h
+        handle = this;
+        GetUniqueId = emu_ncclGetUniqueId; CommInitRank = emu_ncclCommInitRank; CommDestroy = emu_ncclCommDestroy;
+        AllGather = emu_ncclAllGather; Send = emu_ncclSend; Recv = emu_ncclRecv; GroupStart = emu_ncclGroupStart; GroupEnd = emu_ncclGroupEnd;
+        GetErrorString = emu_ncclGetErrorString;
+        return true;
+#endif
         const char *names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char *n : names) { handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
         if (!handle) { error = "cannot dlopen libnccl.so.2"; return false; }
