@@ -298,6 +298,9 @@ int free_results(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stage 1
 
+#ifndef K2C_FLAT_DEFAULT
+#define K2C_FLAT_DEFAULT 0   // flat (one probe step per iteration) insert loop of k2c_count: opt-in (CDBG_K2C=flat) until timed on a GPU
+#endif
 #ifndef RANK_MATCH_DEFAULT
 #define RANK_MATCH_DEFAULT 0   // tile-local ranks by match.any instead of shared-memory atomics: opt-in (CDBG_RANK=match) until timed on a GPU
 #endif
@@ -394,16 +397,17 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
         cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
         tstart(ctx, T_K2C);
         if (I) {
-            if (pl.slots == 4096) {
-                CK(cudaFuncSetAttribute(k2c_count<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<4096>()));
-                LAUNCH(k2c_count<4096>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * 4), k2c_threads<4096>(), k2c_smem_bytes<4096>(), cp);
-            } else if (pl.slots == 8192) {
-                CK(cudaFuncSetAttribute(k2c_count<8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<8192>()));
-                LAUNCH(k2c_count<8192>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * 2), k2c_threads<8192>(), k2c_smem_bytes<8192>(), cp);
-            } else {
-                CK(cudaFuncSetAttribute(k2c_count<16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<16384>()));
-                LAUNCH(k2c_count<16384>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm), k2c_threads<16384>(), k2c_smem_bytes<16384>(), cp);
-            }
+#define K2C_LAUNCH(SL, FL, PER_SM)                                                                                                          \
+    do {                                                                                                                                    \
+        CK(cudaFuncSetAttribute(k2c_count<SL, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<SL>()));                 \
+        LAUNCH((k2c_count<SL, FL>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * (PER_SM)), k2c_threads<SL>(), k2c_smem_bytes<SL>(), cp); \
+    } while (0)
+            const char *k2c = getenv("CDBG_K2C");
+            const bool flat = K2C_FLAT_DEFAULT ? !(k2c && strcmp(k2c, "nested") == 0) : (k2c && strcmp(k2c, "flat") == 0);
+            if (pl.slots == 4096) { if (flat) K2C_LAUNCH(4096, true, 4); else K2C_LAUNCH(4096, false, 4); }
+            else if (pl.slots == 8192) { if (flat) K2C_LAUNCH(8192, true, 2); else K2C_LAUNCH(8192, false, 2); }
+            else { if (flat) K2C_LAUNCH(16384, true, 1); else K2C_LAUNCH(16384, false, 1); }
+#undef K2C_LAUNCH
         }
         tstop(ctx, T_K2C);
         if ((rc = ctr_read(ctx))) return rc;

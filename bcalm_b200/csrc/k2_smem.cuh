@@ -214,7 +214,14 @@ template <int SLOTS> static inline size_t k2c_smem_bytes() { return (size_t)SLOT
 // are tallied while inserting, and when the table passes 3/4 full the pass is abandoned BEFORE anything was emitted and the
 // (part of the) bin is redone as two halves selected by one more hash bit, each half a full pass over the bin's k-mers (they
 // are L2-warm).  Low-coverage input (every instance distinct) therefore costs one extra read per bin instead of failing.
-template <int SLOTS>
+//
+// FLAT = true is a second form of the insert loop (same table, same result).  In the nested form every lane probes for ITS key
+// until it is placed, so a warp waits for its slowest lane at every key: ncu shows 16.6 of 32 lanes active on average and
+// 38 % of the warp-instructions issued for fewer than 4 lanes (the tail of the probe-length distribution).  The flat form does
+// ONE probe step per iteration and a lane that has placed its key takes its next one immediately (keys are prefetched two
+// ahead into registers), so lanes drift apart across keys instead of idling: the warp runs for max-over-lanes of the SUM of
+// probe lengths instead of the sum of the per-key maxima.
+template <int SLOTS, bool FLAT>
 __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
     constexpr int T = SLOTS / 16, NW = T / 32, PER_WARP = SLOTS / NW;   // PER_WARP = 512 slots
     constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
@@ -246,6 +253,7 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
             __syncthreads();
 
             // ---- insert: load on the slot, CAS only when it looks empty, count with a shared-memory add
+            if (!FLAT)
             for (uint64_t base = beg + warp * 32; base < end; base += (uint64_t)T * 4) {     // warp-uniform trip count
                 uint64_t key[4];
 #pragma unroll
@@ -271,6 +279,45 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
                 }
                 fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
                 if (lane == 0 && fresh && atomicAdd(&s_fill, fresh) + fresh > FILL_LIMIT) s_over = 1;
+            }
+            if (FLAT) {
+                uint64_t nxt = beg + t;                                   // index of the next key to load; this thread owns beg + t + j*T
+                uint64_t q0 = nxt < end ? p.kmers[nxt] : EMPTY_KEY; nxt += T;
+                uint64_t q1 = nxt < end ? p.kmers[nxt] : EMPTY_KEY; nxt += T;
+                uint64_t cur = EMPTY_KEY;
+                uint32_t slot = 0, probes = 0, fresh = 0;
+                bool have = false, drained = false;
+                for (uint32_t iter = 0;; iter++) {
+                    if (!have && !drained) {                              // take the next key of this thread that belongs to this pass
+                        cur = q0; q0 = q1; q1 = nxt < end ? p.kmers[nxt] : EMPTY_KEY; nxt += T;
+                        if (cur == EMPTY_KEY) drained = true;
+                        else {
+                            const uint64_t h = mix64(cur);
+                            if ((((uint32_t)h >> 16) & sel_mask) == part) { slot = (uint32_t)h & MASK; probes = 0; have = true; }
+                        }
+                    }
+                    if (have) {                                           // one probe step
+                        uint64_t c = ld_volatile_u64(&s_keys[slot]);
+                        if (c == EMPTY_KEY) {
+                            c = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)cur);
+                            if (c == EMPTY_KEY) { c = cur; fresh++; }
+                        }
+                        if (c == cur) { atomicAdd(&s_cnt[slot], 1u); have = false; }
+                        else {
+                            slot = (slot + 1) & MASK;
+                            if (++probes >= (uint32_t)SLOTS) { s_over = 1; have = false; drained = true; }
+                        }
+                    }
+                    if ((iter & 7u) == 7u) {                              // tally the new keys, look at the overflow flag (warp-uniform)
+                        const uint32_t f = __reduce_add_sync(0xFFFFFFFFu, fresh);
+                        fresh = 0;
+                        if (lane == 0 && f && atomicAdd(&s_fill, f) + f > FILL_LIMIT) s_over = 1;
+                        if (__any_sync(0xFFFFFFFFu, *(volatile int *)&s_over)) break;
+                    }
+                    if (!__any_sync(0xFFFFFFFFu, have || !drained)) break;
+                }
+                const uint32_t f = __reduce_add_sync(0xFFFFFFFFu, fresh);
+                if (lane == 0 && f && atomicAdd(&s_fill, f) + f > FILL_LIMIT) s_over = 1;
             }
             __syncthreads();
             const int over = s_over;
