@@ -298,6 +298,9 @@ int free_results(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stage 1
 
+#ifndef K1_512_DEFAULT
+#define K1_512_DEFAULT 0   // k1t_single with 512 threads x 16 positions (twice the resident warps): opt-in (CDBG_K1_THREADS=512) until timed on a GPU
+#endif
 #ifndef K2C_FLAT_DEFAULT
 #define K2C_FLAT_DEFAULT 0   // flat (one probe step per iteration) insert loop of k2c_count: opt-in (CDBG_K2C=flat) until timed on a GPU
 #endif
@@ -483,8 +486,13 @@ int stage_count(cdbg_ctx *ctx) {
         } else kx.tail = ctx->d_bytes + kx.tail_start;
         const bool match = rank_by_match() && P <= K1X_MATCH_MAX_P;
         const size_t sm = k1x_smem_bytes(P, match);
+        const char *k1t = getenv("CDBG_K1_THREADS");
+        const bool wide_cta = K1_512_DEFAULT ? !(k1t && atoi(k1t) == 256) : (k1t && atoi(k1t) == 512);
         tstart(ctx, T_K1S);
-        if (match) {
+        if (wide_cta && !match) {
+            CK(cudaFuncSetAttribute(k1t_single512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            LAUNCH(k1t_single512, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1H_THREADS, sm, kx);
+        } else if (match) {
             CK(cudaFuncSetAttribute(k1t_single<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             LAUNCH(k1t_single<true>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, sm, kx);
         } else {

@@ -418,3 +418,147 @@ static inline size_t k1x_smem_bytes(uint32_t P, bool match) {
     return (match ? (size_t)P * (K1_THREADS / 32) * 4 : 0) + 2 * (size_t)K1T_RAW + 16 + (size_t)(K1_THREADS + 2) * 8 + (size_t)P * 8 + (size_t)K1_TILE * 8 + (size_t)(K1_THREADS + 2) * 4 +
            (size_t)P * 4 + (size_t)(P + 1) * 4 + (size_t)K1_TILE * 2 + 128;
 }
+
+// ------------------------------------------------------------------------------------------------ single pass, 512 threads
+//
+// k1t_single512: the same kernel with 512 threads per 8192-position tile, 16 positions per thread, capped at 64 registers so that
+// two CTAs (32 warps) are resident per SM instead of 16 warps.  ncu on k1t_single: IPC 1.85, 23 % occupancy, the top stall is
+// `wait` (dependent ALU chains of the rolling k-mer and the hash) -- more resident warps is the direct remedy.  Thread t owns
+// positions [16t, 16t + 16): its 46 bases come from the packed words t/2 and t/2 + 1, shifted by half a word for odd t.
+constexpr int K1H_THREADS = 512;
+constexpr int K1H_PER_THREAD = K1_TILE / K1H_THREADS;     // 16
+
+__global__ void __launch_bounds__(K1H_THREADS, 2) k1t_single512(K1XParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t *s_raw = smem_raw;                                                              // [2][K1T_RAW]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * K1T_RAW);                 // [2]
+    uint64_t *s_pk = s_bar + 2;                                                             // [256 + 2] packed bases, 32 per word
+    uint64_t *s_gbase = s_pk + K1_THREADS + 2;                                              // [P]
+    uint64_t *s_stage = s_gbase + p.P;                                                      // [K1_TILE]
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_stage + K1_TILE);                       // [256 + 2]
+    uint32_t *s_cnt = s_vm + K1_THREADS + 2;                                                // [P]
+    uint32_t *s_off = s_cnt + p.P;                                                          // [P + 1]
+    uint16_t *s_sb = reinterpret_cast<uint16_t *>(s_off + p.P + 1);                         // [K1_TILE]
+    __shared__ uint32_t s_warp[K1H_THREADS / 32];
+
+    const int t = threadIdx.x, k = p.k;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+
+    auto issue = [&](uint64_t tile, int stage) {      // thread 0 only
+        const uint64_t start = tile * (uint64_t)K1_TILE;
+        if (start + K1T_RAW <= p.n_bytes) {
+            mbar_expect_tx(&s_bar[stage], K1T_RAW);
+            tma_load_1d(s_raw + stage * K1T_RAW, p.bytes + start, K1T_RAW, &s_bar[stage]);
+        } else {
+            for (int i = 0; i < K1T_RAW; i++) { uint64_t q = start + i; s_raw[stage * K1T_RAW + i] = q < p.n_bytes ? p.tail[q - p.tail_start] : (uint8_t)'\n'; }
+            mbar_expect_tx(&s_bar[stage], 0);
+        }
+    };
+
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    for (uint32_t i = t; i < p.P; i += K1H_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    if (t == 0 && first < p.n_tiles) issue(first, 0);
+
+    uint32_t it = 0;
+    for (uint64_t tile = first; tile < p.n_tiles; tile += stride, it++) {
+        const int stage = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        if (t == 0 && tile + stride < p.n_tiles) issue(tile + stride, stage ^ 1);
+        mbar_wait(&s_bar[stage], parity);
+        if (t <= K1_THREADS) {                        // 256 words of the tile + the halo word
+            const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + stage * K1T_RAW + t * 32);
+            uint64_t pk; uint32_t vm;
+            pack32(src[0], src[1], pk, vm);
+            s_pk[t] = pk; s_vm[t] = vm;
+        }
+        __syncthreads();
+        const int w = t >> 1;
+        uint64_t hi0, lo0, V;
+        if (t & 1) {
+            hi0 = (s_pk[w] << 32) | (s_pk[w + 1] >> 32); lo0 = s_pk[w + 1] << 32;
+            V = ((uint64_t)s_vm[w] << 48) | ((uint64_t)s_vm[w + 1] << 16);
+        } else {
+            hi0 = s_pk[w]; lo0 = s_pk[w + 1];
+            V = ((uint64_t)s_vm[w] << 32) | s_vm[w + 1];
+        }
+        const uint32_t valid16 = (uint32_t)(kmer_valid_mask(V, k) >> 48);   // bit (15-i): k-mer at position 16t + i valid
+
+        uint32_t br[K1H_PER_THREAD];                  // rank << 11 | bin
+        {
+            uint64_t hi = hi0, lo = lo0;
+            uint64_t fwd = hi >> (64 - 2 * k);
+            uint64_t rc = revcomp64(fwd, k);
+#pragma unroll
+            for (int i = 0; i < K1H_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                const uint64_t c = fwd < rc ? fwd : rc;
+                const uint32_t bin = hash32_to_bin(bin_hash32(c), p.P);
+                br[i] = ((valid16 >> (15 - i)) & 1) ? ((atomicAdd(&s_cnt[bin], 1u) << 11) | bin) : K1X_NONE;
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t per = (p.P + K1H_THREADS - 1) / K1H_THREADS;
+            uint32_t b0 = t * per, sum = 0;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) sum += s_cnt[b0 + j];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane_id() >= d) incl += n; }
+            if (lane_id() == 31) s_warp[t >> 5] = incl;
+            __syncthreads();
+            if (t < 32) {
+                uint32_t wv = t < K1H_THREADS / 32 ? s_warp[t] : 0, wi = wv;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xFFFFFFFFu, wi, d); if ((int)lane_id() >= d) wi += n; }
+                if (t < K1H_THREADS / 32) s_warp[t] = wi - wv;
+            }
+            __syncthreads();
+            uint32_t run = s_warp[t >> 5] + incl - sum;
+            for (uint32_t j = 0; j < per; j++) if (b0 + j < p.P) {
+                const uint32_t cn = s_cnt[b0 + j];
+                s_off[b0 + j] = run; s_cnt[b0 + j] = 0;
+                if (cn) {
+                    const unsigned long long old = atomicAdd(&p.bin_cursor[b0 + j], (unsigned long long)cn);
+                    if (old + cn > p.bin_cap) { *p.overflow = 1; s_gbase[b0 + j] = K1X_SKIP; }
+                    else s_gbase[b0 + j] = (uint64_t)(b0 + j) * p.bin_cap + old;
+                }
+                run += cn;
+            }
+            if (t == K1H_THREADS - 1) s_off[p.P] = run;
+        }
+        __syncthreads();
+        {
+            uint64_t hi = hi0, lo = lo0;
+            uint64_t fwd = hi >> (64 - 2 * k);
+            uint64_t rc = revcomp64(fwd, k);
+#pragma unroll
+            for (int i = 0; i < K1H_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                if (br[i] != K1X_NONE) {
+                    const uint32_t bin = br[i] & 2047u, pos = s_off[bin] + (br[i] >> 11);
+                    s_stage[pos] = fwd < rc ? fwd : rc; s_sb[pos] = (uint16_t)bin;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t total = s_off[p.P];
+        for (uint32_t j = t; j < total; j += K1H_THREADS) {
+            const uint32_t b = s_sb[j];
+            const uint64_t g = s_gbase[b];
+            if (g != K1X_SKIP) p.out_kmers[g + (j - s_off[b])] = s_stage[j];
+        }
+        __syncthreads();
+    }
+}
