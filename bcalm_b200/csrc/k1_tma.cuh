@@ -50,7 +50,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (;;) {
         uint64_t done = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
         if (done > 0 && ((done - 1) & 1) == parity) return;
-        sched_yield();
+        emu::yield_now();
     }
 }
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

@@ -7,10 +7,9 @@
 // product path: nothing under bcalm_b200/ loads it, it says nothing about performance, and it cannot show memory-model or
 // occupancy problems.  The GPU parity tests (-m gpu) remain the gate.
 //
-// Model: one kernel launch = `block` pooled OS threads that run the blocks of the grid one after another (so `__shared__`
-// variables can be plain statics and dynamic shared memory one global buffer).  __syncthreads and the warp collectives are
-// condvar barriers that tolerate threads which have already left the kernel.  The "device" is host memory and every runtime
-// call is synchronous.
+// Model: the blocks of a launch run one after another (so `__shared__` variables can be plain statics and dynamic shared memory
+// one global buffer); inside a block every CUDA thread is a fiber (default) or an OS thread (CDBG_EMU_ENGINE=threads), see
+// "execution engine" below.  The "device" is host memory and every runtime call is synchronous.
 #pragma once
 #include <pthread.h>
 #include <stdint.h>
@@ -50,9 +49,26 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 
 // ------------------------------------------------------------------------------------------------ execution engine
+//
+// Two engines behind one interface.  "fibers" (default): the CUDA threads of a block are user-level contexts that one OS thread
+// switches between (a 20-instruction x86-64 context switch, ucontext elsewhere); a thread runs until it blocks in __syncthreads
+// or a warp collective.  Fast -- a barrier is a handful of switches instead of hundreds of futex wake-ups -- and deterministic,
+// and a kernel that can never make progress is reported as a deadlock instead of hanging.  "threads" (CDBG_EMU_ENGINE=threads):
+// one OS thread per CUDA thread, truly concurrent, so shared-memory and global atomics really race; slow.
+#if !defined(__x86_64__)
+#include <ucontext.h>
+#endif
 namespace emu {
 
-struct Barrier {   // generation barrier whose party count can shrink while threads wait (threads that returned from the kernel)
+constexpr unsigned MAX_THREADS = 1024, MAX_WARPS = MAX_THREADS / 32;
+constexpr size_t DYN_SMEM_BYTES = 256 * 1024, FIBER_STACK = 96 * 1024;
+
+struct Tls { unsigned lane = 0, warp = 0; };
+inline thread_local Tls tls;
+inline void set_builtin(unsigned tid, unsigned bid);
+inline void set_dims(unsigned block, unsigned grid);
+
+struct Barrier {   // OS-thread generation barrier whose party count can shrink (threads that returned from the kernel)
     std::mutex m;
     std::condition_variable cv;
     unsigned expected = 0, arrived = 0;
@@ -71,27 +87,118 @@ struct Barrier {   // generation barrier whose party count can shrink while thre
     }
 };
 
-struct Tls { unsigned lane = 0, warp = 0; };
-inline thread_local Tls tls;
-inline void set_builtin(unsigned tid, unsigned bid);
-inline void set_dims(unsigned block, unsigned grid);
+struct FBarrier { unsigned expected = 0, arrived = 0; uint64_t gen = 0; };   // the same for fibers (single OS thread: no locking)
 
-constexpr unsigned MAX_THREADS = 1024, MAX_WARPS = MAX_THREADS / 32;
-constexpr size_t DYN_SMEM_BYTES = 256 * 1024;
+#if defined(__x86_64__)
+extern "C" void emu_ctx_switch(void **save_sp, void *load_sp);
+__asm__(".text\n.p2align 4\n.globl emu_ctx_switch\n.type emu_ctx_switch,@function\nemu_ctx_switch:\n"
+        "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+        "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
+        "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
+        ".size emu_ctx_switch,.-emu_ctx_switch\n");
+#endif
+
+struct Fiber {
+#if defined(__x86_64__)
+    void *sp = nullptr;
+#else
+    ucontext_t uc;
+#endif
+    bool done = false;
+    const uint64_t *wait_gen = nullptr;   // blocked until *wait_gen != wait_val
+    uint64_t wait_val = 0;
+};
 
 struct Engine {
+    // ---- common
+    unsigned grid = 0, block = 0;
+    const std::function<void()> *body = nullptr;
+    uint64_t warp_slot[MAX_WARPS][32];
+    unsigned char *dyn = nullptr;
+    std::mutex launch_mutex;   // one launch at a time (contexts on different host threads serialise here)
+    bool use_threads = false;
+
+    // ---- fibers
+    std::vector<Fiber> fib;
+    unsigned char *stacks = nullptr;
+    unsigned cur = 0, alive = 0;
+    FBarrier fblock, fwarp[MAX_WARPS];
+#if defined(__x86_64__)
+    void *sched_sp = nullptr;
+#else
+    ucontext_t sched_uc;
+#endif
+    static void fiber_main();
+    void to_fiber(unsigned i) {
+        cur = i;
+        tls.lane = i & 31; tls.warp = i >> 5;
+#if defined(__x86_64__)
+        emu_ctx_switch(&sched_sp, fib[i].sp);
+#else
+        swapcontext(&sched_uc, &fib[i].uc);
+#endif
+    }
+    void to_scheduler() {
+#if defined(__x86_64__)
+        emu_ctx_switch(&fib[cur].sp, sched_sp);
+#else
+        swapcontext(&fib[cur].uc, &sched_uc);
+#endif
+    }
+    void fwait(FBarrier &b) {
+        if (++b.arrived >= b.expected) { b.arrived = 0; b.gen++; return; }
+        Fiber &f = fib[cur];
+        f.wait_gen = &b.gen; f.wait_val = b.gen;
+        to_scheduler();
+    }
+    static void fleave(FBarrier &b) {
+        if (b.expected) b.expected--;
+        if (b.expected && b.arrived >= b.expected) { b.arrived = 0; b.gen++; }
+    }
+    void run_block_fibers(unsigned bidx) {
+        if (!stacks) { if (posix_memalign((void **)&stacks, 4096, (size_t)MAX_THREADS * FIBER_STACK)) abort(); }
+        fib.assign(block, Fiber());
+        fblock = FBarrier(); fblock.expected = block;
+        for (unsigned w = 0; w * 32 < block; w++) { fwarp[w] = FBarrier(); fwarp[w].expected = block - w * 32 < 32 ? block - w * 32 : 32; }
+        for (unsigned i = 0; i < block; i++) {
+            unsigned char *top = stacks + (size_t)(i + 1) * FIBER_STACK;
+#if defined(__x86_64__)
+            void **sp = (void **)top;
+            *(--sp) = nullptr;                       // keeps the entry aligned like after a call
+            *(--sp) = (void *)&Engine::fiber_main;   // `ret` of the first switch lands here
+            for (int r = 0; r < 6; r++) *(--sp) = nullptr;
+            fib[i].sp = sp;
+#else
+            getcontext(&fib[i].uc);
+            fib[i].uc.uc_stack.ss_sp = top - FIBER_STACK; fib[i].uc.uc_stack.ss_size = FIBER_STACK; fib[i].uc.uc_link = nullptr;
+            makecontext(&fib[i].uc, (void (*)()) & Engine::fiber_main, 0);
+#endif
+        }
+        alive = block;
+        while (alive) {
+            bool progressed = false;
+            for (unsigned i = 0; i < block; i++) {
+                Fiber &f = fib[i];
+                if (f.done || (f.wait_gen && *f.wait_gen == f.wait_val)) continue;
+                f.wait_gen = nullptr;
+                set_builtin(i, bidx);
+                to_fiber(i);
+                progressed = true;
+            }
+            if (!progressed) {
+                fprintf(stderr, "[emu] deadlock in block %u: %u of %u threads are blocked in a barrier or warp collective that the others never reach\n", bidx, alive, block);
+                abort();
+            }
+        }
+    }
+
+    // ---- OS threads
     std::mutex m;
     std::condition_variable cv_start, cv_done;
     std::vector<std::thread> workers;
     uint64_t gen = 0;
     unsigned done = 0;
-    unsigned grid = 0, block = 0;
-    const std::function<void()> *body = nullptr;
     Barrier pre, block_bar, warp_bar[MAX_WARPS];
-    uint64_t warp_slot[MAX_WARPS][32];
-    unsigned char *dyn = nullptr;
-    std::mutex launch_mutex;   // one launch at a time (contexts on different host threads serialise here)
-
     void run(unsigned id) {
         for (unsigned b = 0; b < grid; b++) {
             pre.wait();                      // every thread has left the previous block
@@ -122,39 +229,68 @@ struct Engine {
             }
         }
     }
+
     void launch(unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) {
         std::lock_guard<std::mutex> one(launch_mutex);
         if (b == 0 || b > MAX_THREADS || smem > DYN_SMEM_BYTES) { fprintf(stderr, "[emu] bad launch geometry %u x %u, %zu B smem\n", g, b, smem); abort(); }
         if (g == 0) return;
-        if (!dyn) { if (posix_memalign((void **)&dyn, 1024, DYN_SMEM_BYTES)) abort(); }
+        if (!dyn) {
+            if (posix_memalign((void **)&dyn, 1024, DYN_SMEM_BYTES)) abort();
+            const char *e = getenv("CDBG_EMU_ENGINE");
+            use_threads = e && strcmp(e, "threads") == 0;
+        }
+        grid = g; block = b; body = &fn;
+        set_dims(b, g);
+        if (!use_threads) {
+            for (unsigned bidx = 0; bidx < g; bidx++) run_block_fibers(bidx);
+            return;
+        }
         std::unique_lock<std::mutex> l(m);
         while (workers.size() < b) {   // new workers start from the current generation: they must not replay an old launch
             unsigned id = (unsigned)workers.size(); uint64_t g0 = gen;
             workers.emplace_back([this, id, g0] { worker(id, g0); });
             workers.back().detach();
         }
-        grid = g; block = b; body = &fn; done = 0;
-        set_dims(b, g);
+        done = 0;
         pre.reset(b);
         gen++;
         cv_start.notify_all();
         cv_done.wait(l, [&] { return done == block; });
     }
+
+    // ---- what the intrinsics call
+    void sync_block() { if (use_threads) block_bar.wait(); else fwait(fblock); }
+    void sync_warp() { if (use_threads) warp_bar[tls.warp].wait(); else fwait(fwarp[tls.warp]); }
+    void yield_now() {   // a spin-wait on memory another CUDA thread writes must let that thread run
+        if (use_threads) sched_yield(); else { fib[cur].wait_gen = nullptr; to_scheduler(); }
+    }
 };
 
-inline Engine &engine() { static Engine *e = new Engine(); return *e; }   // leaked on purpose: its threads are detached
+inline Engine &engine() { static Engine *e = new Engine(); return *e; }   // leaked on purpose: worker threads are detached
+inline void Engine::fiber_main() {
+    Engine &e = engine();
+    (*e.body)();
+    Fiber &f = e.fib[e.cur];
+    f.done = true;
+    e.alive--;
+    fleave(e.fblock);
+    fleave(e.fwarp[e.cur >> 5]);
+    e.to_scheduler();
+    abort();   // a finished fiber is never resumed
+}
 inline unsigned char *dyn_smem() { return engine().dyn; }
 inline void launch(unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) { engine().launch(g, b, smem, fn); }
+inline void yield_now() { engine().yield_now(); }
 
 template <class T>
 inline T warp_exchange(T v, unsigned src_lane) {
     static_assert(sizeof(T) <= 8 && std::is_integral<T>::value, "emu shuffles carry integers up to 64 bits");
     Engine &e = engine();
-    const unsigned w = tls.warp;
-    e.warp_slot[w][tls.lane] = (uint64_t)v;
-    e.warp_bar[w].wait();
+    const unsigned w = tls.warp, lane = tls.lane;
+    e.warp_slot[w][lane] = (uint64_t)v;
+    e.sync_warp();
     T r = (T)e.warp_slot[w][src_lane & 31];
-    e.warp_bar[w].wait();
+    e.sync_warp();
     return r;
 }
 inline void need_full_mask(unsigned mask) {
@@ -170,8 +306,8 @@ inline dim3 blockDim, gridDim;
 inline void emu::set_builtin(unsigned tid, unsigned bid) { threadIdx = dim3(tid, 0, 0); blockIdx = dim3(bid, 0, 0); }
 inline void emu::set_dims(unsigned block, unsigned grid) { blockDim = dim3(block, 1, 1); gridDim = dim3(grid, 1, 1); }
 
-static inline void __syncthreads() { emu::engine().block_bar.wait(); }
-static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::need_full_mask(mask); emu::engine().warp_bar[emu::tls.warp].wait(); }
+static inline void __syncthreads() { emu::engine().sync_block(); }
+static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::need_full_mask(mask); emu::engine().sync_warp(); }
 static inline void __threadfence() { __sync_synchronize(); }
 static inline unsigned __activemask() { return 0xFFFFFFFFu; }
 
@@ -190,11 +326,11 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     emu::Engine &e = emu::engine();
     const unsigned w = emu::tls.warp;
     e.warp_slot[w][emu::tls.lane] = pred ? 1 : 0;
-    e.warp_bar[w].wait();
+    e.sync_warp();
     unsigned r = 0;
     const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
     for (unsigned i = 0; i < lanes; i++) r |= (unsigned)e.warp_slot[w][i] << i;
-    e.warp_bar[w].wait();
+    e.sync_warp();
     return r;
 }
 
@@ -203,11 +339,11 @@ static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
     emu::Engine &e = emu::engine();
     const unsigned w = emu::tls.warp;
     e.warp_slot[w][emu::tls.lane] = v;
-    e.warp_bar[w].wait();
+    e.sync_warp();
     unsigned r = 0;
     const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
     for (unsigned i = 0; i < lanes; i++) if ((unsigned)e.warp_slot[w][i] == v) r |= 1u << i;
-    e.warp_bar[w].wait();
+    e.sync_warp();
     return r;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
@@ -217,11 +353,11 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     emu::Engine &e = emu::engine();
     const unsigned w = emu::tls.warp;
     e.warp_slot[w][emu::tls.lane] = v;
-    e.warp_bar[w].wait();
+    e.sync_warp();
     unsigned r = 0;
     const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
     for (unsigned i = 0; i < lanes; i++) r += (unsigned)e.warp_slot[w][i];
-    e.warp_bar[w].wait();
+    e.sync_warp();
     return r;
 }
 

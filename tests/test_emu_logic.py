@@ -65,15 +65,7 @@ def check_against_golden(g, case):
     assert d == "", d
 
 
-SMALL = ["tiny_read_k21", "tiny_read_k13", "minitip_k21_a1", "minitip_k21_a2", "circular_test1", "circular_test2_polyA",
-         "circular_test3_onebucket", "pufferize_refs", "lowcx_0_AT_k5_a1", "lowcx_3_AT_k9_a1", "lowcx_5_ACG_k5_a1", "lowcx_7_ACGT_k6_a1",
-         "lowcx_12_AT_k6_a1", "lowcx_14_ACGT_k4_a1", "circular_genome_0_k7", "circular_genome_1_k11", "reads_6_k31_a1", "reads_7_k31_a1",
-         "short_reads_only", "palindrome_k_even", "pow2_cycle_L2_k5", "pow2_cycle_L16_k9", "pow2_cycle_L256_k21", "wide_10_k41_a1",
-         "wide_lowcx_0_AT_k33"]
-MEDIUM = ["reads_5_k25_a1", "lowcx_8_ACGT_k8_a1"]
-
-
-@pytest.mark.parametrize("name", SMALL + MEDIUM)
+@pytest.mark.parametrize("name", sorted(GOLDEN))
 def test_default_configuration_matches_reference_output(emu_lib, knobs, name):
     g = run_case(GOLDEN[name])
     check_against_golden(g, GOLDEN[name])
@@ -103,7 +95,8 @@ VARIANTS = {
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
-@pytest.mark.parametrize("name", ["circular_test1", "lowcx_3_AT_k9_a1", "reads_0_k15_a2"])
+@pytest.mark.parametrize("name", ["circular_test1", "circular_test2_polyA", "lowcx_3_AT_k9_a1", "lowcx_8_ACGT_k8_a1", "palindrome_k_even",
+                                  "pow2_cycle_L256_k21", "reads_0_k15_a2", "reads_3_k31_a2", "reads_5_k25_a1"])
 def test_variants_match_reference_output(emu_lib, knobs, variant, name):
     knobs(**VARIANTS[variant])
     g = run_case(GOLDEN[name])
@@ -114,6 +107,64 @@ def test_variants_match_reference_output(emu_lib, knobs, variant, name):
         assert g.stats["n_k2_splits"] > 0
     if variant == "k5_smem_forced_splits" and name.startswith("reads_"):
         assert g.stats["n_k5_splits"] > 0
+
+
+def _synthetic_reads(genome_len, read_len, coverage, err, seed):
+    """Sequencing-like reads (both strands, substitution errors) over a random genome, as in bench.py's workload."""
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 4, genome_len)
+    n = genome_len * coverage // read_len
+    starts = rng.integers(0, genome_len - read_len + 1, n)
+    comp = np.array([3, 2, 1, 0])
+    reads = []
+    for st_ in starts:
+        r = genome[st_:st_ + read_len].copy()
+        if rng.random() < 0.5:
+            r = comp[r[::-1]]
+        e = rng.random(read_len) < err
+        r[e] = (r[e] + rng.integers(1, 4, int(e.sum()))) % 4
+        reads.append("".join("ACGT"[i] for i in r))
+    return reads
+
+
+@pytest.mark.parametrize("variant", ["default", "k2c_flat_insert_loop", "k1_512_threads", "k2_l2_tables", "k5_l2_tables", "k1_twopass_tma",
+                                     "k2_smem_forced_splits", "k5_smem_forced_splits"])
+def test_larger_synthetic_read_set_matches_oracle(emu_lib, knobs, variant):
+    """40 kbp genome, 100 bp reads at 30x with 1 % errors (1.2 Mbases): several tiles, coarse and fine bins, real branching."""
+    if variant != "default":
+        knobs(**VARIANTS[variant])
+    reads = _synthetic_reads(40_000, 100, 30, 0.01, 11)
+    with api.Cdbg(k=31, abundance_min=2, device=0) as c:
+        g = c.build(reads)
+    o = orc.run(reads, 31, 2)
+    assert g.stats["n_solid"] == o.stats["n_solid"]
+    d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), 31)
+    assert d == "", d
+
+
+def test_truly_concurrent_engine_smoke():
+    """The default emulator engine runs the CUDA threads of a block as fibers of one OS thread.  Run a few cases once with one OS
+    thread per CUDA thread as well (real races on the shared-memory and global atomics), in a subprocess: the engine is chosen
+    at the first launch of a process."""
+    import subprocess
+    code = (
+        "import json, os, sys\n"
+        f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, 'tests', 'emu'))\n"
+        "import build_emu\n"
+        "from bcalm_b200 import api, parity\n"
+        "api.LIB_PATH = build_emu.build()\n"
+        f"cases = {{c['name']: c for c in json.load(open(os.path.join({ROOT!r}, 'tests', 'golden', 'golden.json')))}}\n"
+        "for n in ('minitip_k21_a1', 'circular_test1', 'reads_0_k15_a2'):\n"
+        "    c = cases[n]\n"
+        "    with api.Cdbg(k=c['k'], abundance_min=c['abundance_min'], device=0) as x:\n"
+        "        g = x.build(c['reads'])\n"
+        "    assert parity.diff(parity.graph_to_records(g), parity.parse_unitigs_fa(c['unitigs_fa']), c['k']) == '', n\n"
+        "print('ok')\n")
+    env = dict(os.environ, CDBG_EMU_ENGINE="threads")
+    for k_ in KNOBS:
+        env.pop(k_, None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
 def _repeats_input():
