@@ -58,7 +58,7 @@ class UnitigView(C.Structure):
 LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to_sign", "u1"), ("pad", "u1", (2,))])
 
 EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_count", "cdbg_compact",
-           "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_synth_reads",
+           "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_set_solid_kmers", "cdbg_synth_reads",
            "cdbg_copy_to_host", "cdbg_host_alloc", "cdbg_host_free", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range", "cdbg_owner_of", "cdbg_plan_shard_exchange"]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library():
     L.cdbg_get_unitigs.argtypes = [C.c_void_p, P(UnitigView)]
     L.cdbg_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, P(UnitigView), P(Stats)]
     L.cdbg_get_solid_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
+    L.cdbg_set_solid_kmers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     L.cdbg_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
     L.cdbg_synth_reads_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, P(C.c_void_p), P(C.c_uint64)]
     L.cdbg_owner_of.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_uint32]
@@ -232,6 +233,14 @@ class Cdbg:
         ct = np.empty(n.value, np.uint32)
         self._ck(self.lib.cdbg_get_solid_kmers(self.h, km.ctypes.data, ct.ctypes.data, n.value, C.byref(n)))
         return (km if W == 1 else km.reshape(-1, W)), ct
+
+    def set_solid_kmers(self, kmers, counts):
+        """Start from counted k-mers instead of reads (k <= 31): uint64 k-mers in either orientation, uint32 abundances."""
+        km = np.ascontiguousarray(kmers, dtype=np.uint64)
+        ct = np.ascontiguousarray(counts, dtype=np.uint32)
+        if km.shape != ct.shape or km.ndim != 1:
+            raise ValueError("kmers and counts must be 1-D arrays of the same length")
+        self._ck(self.lib.cdbg_set_solid_kmers(self.h, km.ctypes.data, ct.ctypes.data, km.size, MEM_HOST))
 
     def _view_to_graph(self, v: UnitigView, copy: bool = True) -> Graph:
         def arr(ptr, n, dt):

@@ -17,6 +17,7 @@
 
 #include <chrono>
 #include <string>
+#include <algorithm>
 #include <thread>
 #include <vector>
 
@@ -26,6 +27,8 @@ namespace {
 
 struct Options {
     std::string in, out, out_gfa;
+    std::string solid_in;   // -solid-kmers-in: start from counted k-mers ("KMER count" lines: dsk2ascii / jellyfish dump -c / kmc dump)
+    std::string solid_out;  // -solid-kmers-out: also write the solid k-mers of this run in the same format
     int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
     bool all_abund = false;
     bool parse_only = false; // -parse-only: parse the input, print record/byte counts and a checksum, no GPU (host-side tests)
@@ -41,7 +44,7 @@ struct Options {
 const char *IGNORED_1[] = {"-max-memory", "-max-disk", "-out-dir", "-out-tmp", "-out-compress", "-storage-type", "-histo2D", "-histo",
                            "-minimizer-type", "-repartition-type", "-bloom", "-debloom", "-debloom-impl", "-branching-nodes",
                            "-topology-stats", "-integer-precision", "-nb-glue-partitions", "-solidity-custom", "-solidity-kind",
-                           "-histo-max", "-solid-kmers-out"};
+                           "-histo-max"};
 const char *IGNORED_0[] = {"-no-mphf", "-kff", "-config-only", "-redo-bcalm", "-skip-bcalm", "-redo-bglue", "-skip-bglue", "-redo-links",
                            "-skip-links"};
 
@@ -54,6 +57,9 @@ void usage() {
            "       -minimizer-size       (1 arg) :    size of a minimizer  [default '10']\n"
            "       -out                  (1 arg) :    output prefix  [default: basename of -in]\n"
            "       -out-gfa              (1 arg) :    also write GFA1 to this file\n"
+           "       -solid-kmers-in       (1 arg) :    start from counted k-mers instead of reads: text lines 'KMER count' (dsk2ascii,\n"
+           "                                          jellyfish dump -c, kmc dump); -abundance-min/-max are applied; -in is then optional\n"
+           "       -solid-kmers-out      (1 arg) :    also write the solid k-mers of this run as 'KMER count' lines\n"
            "       -all-abundance-counts (0 arg) :    output all k-mer abundance counts instead of mean\n"
            "       -edge-km              (1 arg) :    edge km representation  [default '0']\n"
            "       -nb-cores             (1 arg) :    number of cores (host parsing threads)  [default '0']\n"
@@ -75,6 +81,8 @@ Options parse(int argc, char **argv) {
         if (a == "-in") o.in = need("-in");
         else if (a == "-out") o.out = need("-out");
         else if (a == "-out-gfa") o.out_gfa = need("-out-gfa");
+        else if (a == "-solid-kmers-in") o.solid_in = need("-solid-kmers-in");
+        else if (a == "-solid-kmers-out") o.solid_out = need("-solid-kmers-out");
         else if (a == "-kmer-size") o.k = atoi(need("-kmer-size").c_str());
         else if (a == "-abundance-min") o.amin = atoi(need("-abundance-min").c_str());
         else if (a == "-abundance-max") { long long v = atoll(need("-abundance-max").c_str()); o.amax = v >= 2147483647LL ? 0 : (int)v; }
@@ -93,7 +101,8 @@ Options parse(int argc, char **argv) {
             if (!known) { usage(); die("Unknown parameter '" + a + "'"); }
         }
     }
-    if (o.in.empty()) { usage(); die("Option '-in' is mandatory"); }
+    if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
+    if (!o.solid_in.empty() && o.k > 31) die("-solid-kmers-in needs -kmer-size <= 31");
     return o;
 }
 
@@ -307,6 +316,69 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 }  // namespace
 
+// "KMER count" lines -> packed canonical k-mers (A=0 C=1 T=2 G=3, first nucleotide most significant) + abundances.  A dump made
+// without canonical counting lists both orientations of a k-mer: their counts are added.  The abundance filter is applied here.
+void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vector<uint32_t> &counts) {
+    FileBuf in;
+    if (!read_whole(o.solid_in, in)) die("Unable to open file '" + o.solid_in + "'");
+    const int k = o.k;
+    std::vector<std::pair<uint64_t, uint64_t>> rec;
+    const char *p = in.p, *e = in.p + in.n;
+    uint64_t line = 0;
+    while (p < e) {
+        line++;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+        const char *le = nl ? nl : e;
+        const char *q = p;
+        while (q < le && (*q == ' ' || *q == '\t')) q++;
+        if (q < le && *q != '#' && *q != '\r') {
+            uint64_t x = 0, r = 0;
+            int len = 0;
+            for (; q < le && *q != ' ' && *q != '\t' && *q != '\r'; q++, len++) {
+                const char c = *q & 0xDF;
+                if (len >= k) die("k-mer longer than -kmer-size in '" + o.solid_in + "' line " + std::to_string(line));
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') die("bad nucleotide in '" + o.solid_in + "' line " + std::to_string(line));
+                const uint64_t code = ((uint64_t)c >> 1) & 3;
+                x = (x << 2) | code;
+                r = (r >> 2) | ((code ^ 2) << (2 * (k - 1)));
+            }
+            if (len != k) die("k-mer length differs from -kmer-size in '" + o.solid_in + "' line " + std::to_string(line));
+            while (q < le && (*q == ' ' || *q == '\t')) q++;
+            if (q >= le || *q < '0' || *q > '9') die("missing count in '" + o.solid_in + "' line " + std::to_string(line));
+            uint64_t c = 0;
+            for (; q < le && *q >= '0' && *q <= '9'; q++) c = std::min<uint64_t>(c * 10 + (uint64_t)(*q - '0'), 1ULL << 40);
+            rec.emplace_back(x < r ? x : r, c);
+        }
+        p = nl ? nl + 1 : e;
+    }
+    std::sort(rec.begin(), rec.end());
+    const uint64_t amax = o.amax > 0 ? (uint64_t)o.amax : 2147483647ULL, amin = (uint64_t)std::max(o.amin, 1);
+    for (size_t i = 0; i < rec.size();) {
+        size_t j = i; uint64_t c = 0;
+        for (; j < rec.size() && rec[j].first == rec[i].first; j++) c += rec[j].second;
+        if (c >= amin && c <= amax) { kmers.push_back(rec[i].first); counts.push_back((uint32_t)c); }
+        i = j;
+    }
+}
+
+void write_counted_kmers(const std::string &path, cdbg_ctx *ctx, int k) {
+    uint64_t n = 0;
+    if (cdbg_get_solid_kmers(ctx, nullptr, nullptr, 0, &n) != CDBG_OK) die(cdbg_last_error(ctx));
+    std::vector<uint64_t> km(n + 1); std::vector<uint32_t> ct(n + 1);
+    if (cdbg_get_solid_kmers(ctx, km.data(), ct.data(), n, &n) != CDBG_OK) die(cdbg_last_error(ctx));
+    std::string text;
+    text.reserve(n * (size_t)(k + 12));
+    const char NT[4] = {'A', 'C', 'T', 'G'};
+    for (uint64_t i = 0; i < n; i++) {
+        for (int j = k - 1; j >= 0; j--) text.push_back(NT[(km[i] >> (2 * j)) & 3]);
+        text.push_back(' '); put_u64(text, ct[i]); text.push_back('\n');
+    }
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) die("Unable to open output file '" + path + "'");
+    fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && (strcmp(argv[1], "-version") == 0 || strcmp(argv[1], "-v") == 0)) {
         printf("BCALM 2 (B200-native cdbg), version v2.2.3-compatible\nUsing %s\n", cdbg_version());
@@ -342,16 +414,28 @@ int main(int argc, char **argv) {
 
     ByteBuf stream;
     uint64_t n_records = 0;
-    load_input(o.in, stream, n_records);
-    const double t1 = now_s();
-
     cdbg_unitig_view v{};
     cdbg_stats st{};
-    rc = cdbg_build(ctx, stream.data(), stream.size(), CDBG_MEM_HOST, &v, &st);
+    double t1;
+    if (!o.solid_in.empty()) {   // stages 2-4 only, from counted k-mers
+        std::vector<uint64_t> km; std::vector<uint32_t> ct;
+        load_counted_kmers(o, km, ct);
+        t1 = now_s();
+        rc = cdbg_set_solid_kmers(ctx, km.data(), ct.data(), km.size(), CDBG_MEM_HOST);
+        if (rc == CDBG_OK) rc = cdbg_compact(ctx, nullptr);
+        if (rc == CDBG_OK) rc = cdbg_link(ctx, nullptr);
+        if (rc == CDBG_OK) rc = cdbg_get_unitigs(ctx, &v);
+        if (rc == CDBG_OK) rc = cdbg_get_stats(ctx, &st);
+    } else {
+        load_input(o.in, stream, n_records);
+        t1 = now_s();
+        rc = cdbg_build(ctx, stream.data(), stream.size(), CDBG_MEM_HOST, &v, &st);
+    }
     if (rc != CDBG_OK) { std::string msg = cdbg_last_error(ctx); cdbg_destroy(ctx); die(msg); }
     const double t2 = now_s();
+    if (!o.solid_out.empty()) write_counted_kmers(o.solid_out, ctx, o.k);
 
-    const std::string prefix = o.out.empty() ? base_name(o.in) : o.out;
+    const std::string prefix = !o.out.empty() ? o.out : base_name(o.in.empty() ? o.solid_in : o.in);
     const std::string out_path = prefix + ".unitigs.fa";
     const int k = o.k;
     std::string text;

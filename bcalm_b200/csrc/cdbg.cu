@@ -1258,6 +1258,31 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
     return CDBG_OK;
 }
 
+int cdbg_set_solid_kmers(cdbg_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, uint64_t n, int location) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if ((!kmers || !counts) && n) return ctx->fail(CDBG_ERR_PARAM, "null k-mer / count pointer");
+    if (ctx->W != 1 || ctx->world != 1) return ctx->fail(CDBG_ERR_PARAM, "cdbg_set_solid_kmers needs k <= 31 on a single-GPU context");
+    if (ctx->stage != ST_EMPTY) return ctx->fail(CDBG_ERR_STATE, "cdbg_set_solid_kmers on a context that already holds reads or results: call cdbg_reset first");
+    if (n >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu)", (unsigned long long)n);
+    CK(cudaSetDevice(ctx->prm.device));
+    int rc;
+    tstart(ctx, T_COUNT);
+    if ((rc = dalloc(ctx, &ctx->d_solid_kmers, n + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_solid_counts, n + 1))) return rc;
+    const cudaMemcpyKind kind = location == CDBG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->d_solid_kmers, kmers, n * 8, kind, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_solid_counts, counts, n * 4, kind, ctx->stream));
+        LAUNCH(k2_canonicalise, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));   // the caller may free its arrays when this returns
+    tstop(ctx, T_COUNT);
+    ctx->S = n;
+    ctx->st.n_solid = n; ctx->st.n_distinct = n;
+    ctx->stage = ST_COUNTED;
+    return CDBG_OK;
+}
+
 int cdbg_synth_reads(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len, uint64_t n_reads, uint32_t err_ppm, uint64_t seed,
                      uint8_t **d_bytes, uint64_t *n_bytes) {
     return cdbg_synth_reads_range(ctx, genome_len, read_len, 0, n_reads, err_ppm, seed, d_bytes, n_bytes);

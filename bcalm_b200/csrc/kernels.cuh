@@ -366,6 +366,12 @@ __global__ void __launch_bounds__(K2_EMIT_THREADS) k2_emit(uint64_t *keys, uint3
     block_add(n_distinct, (unsigned long long)my_distinct);
 }
 
+// counted k-mers handed in from outside (cdbg_set_solid_kmers): bring every k-mer to the canonical orientation of this encoding
+__global__ void __launch_bounds__(256) k2_canonicalise(uint64_t *kmers, uint64_t n, int k) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        kmers[i] = canonical64(kmers[i] & kmer_mask(k), k);
+}
+
 // ------------------------------------------------------------------------------------------------ K3: junction end records
 
 // A solid canonical k-mer x has two ends.  Each end is keyed by the canonical form c of its (k-1)-mer and lies on one SIDE

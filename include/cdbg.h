@@ -13,6 +13,8 @@
  *   cdbg_count           SortingCountAlgorithm<span>::execute + the ICountProcessor chain Solidity -> Dump
  *                        (G/kmer/impl/SortingCountAlgorithm.cpp:636-781, G/kmer/api/ICountProcessor.hpp:105-173,
  *                         G/kmer/impl/CountProcessorSolidity.hpp:186-189, CountProcessorDump.hpp:148-152)
+ *   cdbg_set_solid_kmers the "solid k-mers already on disk" entry of the same class (GraphUnitigs.cpp:884-951: a `.h5` with a
+ *                        dsk/solid group skips the counting step)
  *   cdbg_compact         bcalm2<SPAN>() + bglue<SPAN>()  (G/bcalm2/bcalm_algo.hpp:29-38, G/bcalm2/bglue_algo.hpp:147-155)
  *   cdbg_link            link_tigs<SPAN>()               (G/debruijn/impl/LinkTigs.hpp:33)
  *   cdbg_get_unitigs     the <prefix>.unitigs.fa content (G/bcalm2/bglue_algo.hpp:73-90 BufferedFasta,
@@ -147,6 +149,13 @@ int cdbg_build(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int locati
  * (k-mer, abundance) pairs to host arrays of capacity `cap` k-mers; returns the number of solid k-mers in *n. Order is
  * unspecified.  A k-mer takes W = 1 (k <= 31) or max(2, ceil(2k/64)) (k >= 32) little-endian 64-bit words in `kmers`. */
 int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint64_t cap, uint64_t *n);
+
+/* The same hand-off in the other direction (start from counted k-mers, like the reference resuming from the solid
+ * k-mers of its `.h5`, GraphUnitigs.cpp:884-951): install `n` solid (k-mer, abundance) pairs -- e.g. a DSK / KMC / Jellyfish dump
+ * after the caller's abundance filter -- and continue with cdbg_compact / cdbg_link.  K-mers are 2 bits per nucleotide, first
+ * nucleotide most significant, A=0 C=1 T=2 G=3, in either orientation (they are canonicalised on the device); every canonical
+ * k-mer must occur once.  k <= 31, single GPU, on an empty context (after cdbg_create or cdbg_reset). */
+int cdbg_set_solid_kmers(cdbg_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, uint64_t n, int location);
 
 /* Device-side synthetic read generator used by bench.py (inputs resident in HBM when the timed region starts):
  * uniform random genome of `genome_len` nt from `seed`, `n_reads` reads of `read_len` nt, uniform start, random strand,

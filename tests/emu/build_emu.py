@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "bcalm_b200", "csrc")
 OUT = os.path.join(ROOT, "tests", "_emu_build")          # two levels below the root, like csrc (relative include of include/cdbg.h)
 LIB = os.path.join(OUT, "libcdbg_emu.so")
+CLI = os.path.join(OUT, "bcalm_emu")                      # the unchanged command line tool linked against the emulated library
 
 _DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];")
 
@@ -39,6 +40,8 @@ def build(force: bool = False) -> str:
     cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-fno-strict-aliasing", "-w",
            "-I", HERE, "-o", LIB, os.path.join(OUT, "cdbg.cu"), "-ldl"]
     subprocess.check_call(cmd)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", CLI, os.path.join(CSRC, "bcalm_main.cpp"), "-L" + OUT, "-lcdbg_emu",
+                           "-Wl,-rpath,$ORIGIN", "-lz", "-lpthread"])
     return LIB
 
 

@@ -210,6 +210,30 @@ def test_stage_one_in_isolation_matches_oracle_counts(emu_lib, knobs):
     assert len(np.unique(km)) == len(km) and np.all(km[order][1:] > km[order][:-1])
 
 
+def test_counted_kmers_hand_off_through_the_abi(emu_lib, knobs):
+    """cdbg_set_solid_kmers: stage 1 result of one context (half of the k-mers flipped to the other strand) -> stages 2-4 of another."""
+    case = GOLDEN["reads_3_k31_a2"]
+    k = case["k"]
+    with api.Cdbg(k=k, abundance_min=case["abundance_min"], device=0) as a:
+        a.push_reads(case["reads"])
+        a.count()
+        km, ct = a.solid_kmers()
+    rc = np.zeros_like(km)
+    for i in range(k):
+        rc = (rc << np.uint64(2)) | (((km >> np.uint64(2 * i)) & np.uint64(3)) ^ np.uint64(2))
+    mixed = np.where(np.arange(len(km)) % 2 == 0, rc, km)
+    with api.Cdbg(k=k, abundance_min=1, device=0) as b:
+        b.set_solid_kmers(mixed, ct)
+        b.compact()
+        b.link()
+        g = b.unitigs()
+        with pytest.raises(api.CdbgError):
+            b.set_solid_kmers(mixed, ct)          # not on a context that already holds results
+    check_against_golden(g, case)
+    with api.Cdbg(k=63, abundance_min=1, device=0) as w, pytest.raises(api.CdbgError):
+        w.set_solid_kmers(km, ct)                 # k <= 31 only
+
+
 def test_repeated_builds_on_one_context_are_identical(emu_lib, knobs):
     case = GOLDEN["reads_6_k31_a1"]
     with api.Cdbg(k=case["k"], abundance_min=case["abundance_min"], device=0) as c:
