@@ -57,7 +57,7 @@ class UnitigView(C.Structure):
 
 LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to_sign", "u1"), ("pad", "u1", (2,))])
 
-EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_count", "cdbg_compact",
+EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_push_sequence_text", "cdbg_get_pushed_reads", "cdbg_count", "cdbg_compact",
            "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_set_solid_kmers", "cdbg_synth_reads",
            "cdbg_copy_to_host", "cdbg_host_alloc", "cdbg_host_free", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range", "cdbg_owner_of", "cdbg_plan_shard_exchange"]
 
@@ -80,6 +80,8 @@ def load_library():
     L.cdbg_last_error.argtypes = [C.c_void_p]
     L.cdbg_last_error.restype = C.c_char_p
     L.cdbg_push_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    L.cdbg_get_pushed_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
+    L.cdbg_push_sequence_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, P(C.c_uint64)]
     for n in ("cdbg_count", "cdbg_compact", "cdbg_link", "cdbg_get_stats"):
         getattr(L, n).argtypes = [C.c_void_p, P(Stats)]
     L.cdbg_get_unitigs.argtypes = [C.c_void_p, P(UnitigView)]
@@ -201,6 +203,21 @@ class Cdbg:
         b = _as_u8(reads)
         self._keep = b
         self._ck(self.lib.cdbg_push_reads(self.h, b.ctypes.data, b.size, MEM_HOST))
+
+    def push_sequence_text(self, text) -> int:
+        """Raw FASTA / FASTQ text (bytes of the file) parsed on the GPU; returns the number of records."""
+        b = _as_u8(text)
+        self._keep = b
+        n = C.c_uint64()
+        self._ck(self.lib.cdbg_push_sequence_text(self.h, b.ctypes.data, b.size, MEM_HOST, C.byref(n)))
+        return int(n.value)
+
+    def pushed_reads(self) -> bytes:
+        n = C.c_uint64()
+        self._ck(self.lib.cdbg_get_pushed_reads(self.h, None, 0, C.byref(n)))
+        buf = np.empty(n.value, np.uint8)
+        self._ck(self.lib.cdbg_get_pushed_reads(self.h, buf.ctypes.data, n.value, C.byref(n)))
+        return buf.tobytes()
 
     def push_device(self, dptr: int, n_bytes: int):
         self._ck(self.lib.cdbg_push_reads(self.h, C.c_void_p(dptr), n_bytes, MEM_DEVICE))

@@ -32,6 +32,7 @@ struct Options {
     int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
     bool all_abund = false;
     bool parse_only = false; // -parse-only: parse the input, print record/byte counts and a checksum, no GPU (host-side tests)
+    bool gpu_parse = false; // -gpu-parse 1: ship the file bytes and strip headers / quality lines on the GPU (cdbg_push_sequence_text)
     bool edge_km = false;   // -edge-km 1: J:<0|1>:<id>:<0|1> tokens instead of L: (G/debruijn/impl/LinkTigs.cpp:380-384,440-444)
 };
 
@@ -64,6 +65,7 @@ void usage() {
            "       -edge-km              (1 arg) :    edge km representation  [default '0']\n"
            "       -nb-cores             (1 arg) :    number of cores (host parsing threads)  [default '0']\n"
            "       -device               (1 arg) :    CUDA device ordinal  [default '0']\n"
+           "       -gpu-parse            (1 arg) :    parse FASTA/FASTQ text on the GPU instead of the host  [default '0']\n"
            "       -verbose              (1 arg) :    verbosity level  [default '1']\n"
            "       -version              (0 arg) :    version\n"
            "       -help                 (0 arg) :    help\n"
@@ -92,6 +94,7 @@ Options parse(int argc, char **argv) {
         else if (a == "-device") o.device = atoi(need("-device").c_str());
         else if (a == "-all-abundance-counts") o.all_abund = true;
         else if (a == "-parse-only") o.parse_only = true;
+        else if (a == "-gpu-parse") o.gpu_parse = atoi(need("-gpu-parse").c_str()) != 0;
         else if (a == "-edge-km") o.edge_km = atoi(need("-edge-km").c_str()) != 0;
         else if (a == "-help" || a == "-h") { usage(); exit(EXIT_SUCCESS); }
         else {
@@ -262,6 +265,7 @@ void parse_sequences_mt(const FileBuf &in, ByteBuf &out, uint64_t &n_records, in
 }
 
 static int g_parse_threads = 1;
+static cdbg_ctx *g_gpu_parse_ctx = nullptr;   // -gpu-parse 1: files are pushed as text and parsed on the device
 
 void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, int depth = 0) {
     size_t start = 0;
@@ -276,7 +280,13 @@ void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, i
         while (i < buf.n && (buf.p[i] == '\n' || buf.p[i] == '\r' || buf.p[i] == ' ')) i++;
         if (i == buf.n) continue;
         if (buf.p[i] == '>' || buf.p[i] == '@') {
-            parse_sequences_mt(buf, stream, n_records, g_parse_threads);
+            bool done = false;
+            if (g_gpu_parse_ctx) {   // the library refuses text it cannot parse exactly (e.g. multi-line FASTQ): then the host parser takes it
+                uint64_t nrec = 0;
+                done = cdbg_push_sequence_text(g_gpu_parse_ctx, (const uint8_t *)buf.p + i, buf.n - i, CDBG_MEM_HOST, &nrec) == CDBG_OK;
+                if (done) n_records += nrec;
+            }
+            if (!done) parse_sequences_mt(buf, stream, n_records, g_parse_threads);
         } else {
             if (depth > 2) die("file of files nested too deeply: " + path);
             // file of files: one path per line, relative to the list's directory (G/bank/impl/BankAlbum.cpp)
@@ -422,6 +432,16 @@ int main(int argc, char **argv) {
         load_counted_kmers(o, km, ct);
         t1 = now_s();
         rc = cdbg_set_solid_kmers(ctx, km.data(), ct.data(), km.size(), CDBG_MEM_HOST);
+        if (rc == CDBG_OK) rc = cdbg_compact(ctx, nullptr);
+        if (rc == CDBG_OK) rc = cdbg_link(ctx, nullptr);
+        if (rc == CDBG_OK) rc = cdbg_get_unitigs(ctx, &v);
+        if (rc == CDBG_OK) rc = cdbg_get_stats(ctx, &st);
+    } else if (o.gpu_parse) {
+        g_gpu_parse_ctx = ctx;
+        load_input(o.in, stream, n_records);           // GPU-parsed files are already on the device; `stream` holds the rest
+        t1 = now_s();
+        rc = stream.size() || n_records == 0 ? cdbg_push_reads(ctx, stream.data(), stream.size(), CDBG_MEM_HOST) : CDBG_OK;
+        if (rc == CDBG_OK) rc = cdbg_count(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_compact(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_link(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_get_unitigs(ctx, &v);

@@ -21,6 +21,7 @@
 #include "k1_tma.cuh"
 #include "k2_smem.cuh"
 #include "k5_smem.cuh"
+#include "parse.cuh"
 #include "wide.cuh"
 
 namespace {
@@ -1137,6 +1138,87 @@ int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int l
     }
     tstop(ctx, T_PUSH);
     ctx->stage = ST_PUSHED;
+    return CDBG_OK;
+}
+
+int cdbg_push_sequence_text(cdbg_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int location, uint64_t *n_records) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if (n_records) *n_records = 0;
+    if (!text && n_bytes) return ctx->fail(CDBG_ERR_PARAM, "null text pointer");
+    if (ctx->stage > ST_PUSHED) return ctx->fail(CDBG_ERR_STATE, "push after count: call cdbg_reset first");
+    if (n_bytes == 0) return CDBG_OK;
+    CK(cudaSetDevice(ctx->prm.device));
+    const uint64_t n_tiles = (n_bytes + PARSE_TILE - 1) / PARSE_TILE;
+    if (n_tiles >= (1ULL << 32)) return ctx->fail(CDBG_ERR_PARAM, "text too large for one push (%llu bytes): push it in pieces cut at record starts", (unsigned long long)n_bytes);
+    int rc;
+    uint8_t first = 0;
+    if (location == CDBG_MEM_DEVICE) {
+        CK(cudaMemcpyAsync(&first, text, 1, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else first = text[0];
+    if (first != '>' && first != '@') return ctx->fail(CDBG_ERR_PARAM, "text does not start with a FASTA ('>') or FASTQ ('@') record");
+    const int fmt = first == '>' ? PARSE_FASTA : PARSE_FASTQ;
+
+    uint8_t *d_text = nullptr, *d_fn = nullptr, *d_state = nullptr, *d_out = nullptr;
+    uint32_t *d_cnt = nullptr; uint64_t *d_off = nullptr;
+    const uint8_t *src = text;
+    if (location != CDBG_MEM_DEVICE) {
+        if ((rc = dalloc(ctx, &d_text, n_bytes + 64))) return rc;
+        CK(cudaMemcpyAsync(d_text, text, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        src = d_text;
+    }
+    if ((rc = dalloc(ctx, &d_fn, n_tiles + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_state, n_tiles + 2))) return rc;
+    if ((rc = dalloc(ctx, &d_cnt, n_tiles + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_off, n_tiles + 2))) return rc;
+    if ((rc = dalloc(ctx, &d_out, n_bytes + 64))) return rc;
+    if ((rc = ctr_zero(ctx))) return rc;
+    ParseParams pp{};
+    pp.text = src; pp.n = n_bytes; pp.n_tiles = (uint32_t)n_tiles; pp.tile_fn = d_fn; pp.tile_state = d_state; pp.tile_cnt = d_cnt;
+    pp.tile_off = d_off; pp.out = d_out; pp.n_records = ctx->d_ctr + 0; pp.bad = ctx->d_flag + 3;
+    const int grid = (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 8);
+    uint64_t total = 0;
+    if (fmt == PARSE_FASTA) {
+        LAUNCH(parse_tile_fn<PARSE_FASTA>, grid, PARSE_THREADS, 0, pp);
+        LAUNCH(parse_tile_states, 1, PARSE_THREADS, 0, pp, fmt);
+        LAUNCH((parse_emit<PARSE_FASTA, false>), grid, PARSE_THREADS, 0, pp);
+        if ((rc = exclusive_scan(ctx, d_cnt, n_tiles, d_off, &total))) return rc;
+        LAUNCH((parse_emit<PARSE_FASTA, true>), grid, PARSE_THREADS, 0, pp);
+    } else {
+        LAUNCH(parse_tile_fn<PARSE_FASTQ>, grid, PARSE_THREADS, 0, pp);
+        LAUNCH(parse_tile_states, 1, PARSE_THREADS, 0, pp, fmt);
+        LAUNCH((parse_emit<PARSE_FASTQ, false>), grid, PARSE_THREADS, 0, pp);
+        if ((rc = exclusive_scan(ctx, d_cnt, n_tiles, d_off, &total))) return rc;
+        LAUNCH((parse_emit<PARSE_FASTQ, true>), grid, PARSE_THREADS, 0, pp);
+    }
+    uint8_t final_state = 0;
+    CK(cudaMemcpyAsync(&final_state, d_state + n_tiles, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = ctr_read(ctx))) return rc;
+    bool bad = ((int *)(ctx->h_ctr + 64))[3] != 0;
+    if (fmt == PARSE_FASTQ && final_state != 3) bad = true;                      // the last record is incomplete
+    // the record that is still open at the end of the text gets its '\n'
+    if (!bad && fmt == PARSE_FASTA && final_state != 0) {
+        CK(cudaMemsetAsync(d_out + total, '\n', 1, ctx->stream));
+        total++;
+    }
+    dfree(ctx, d_text); dfree(ctx, d_fn); dfree(ctx, d_state); dfree(ctx, d_cnt); dfree(ctx, d_off);
+    if (bad) { dfree(ctx, d_out); return ctx->fail(CDBG_ERR_PARAM, "FASTQ text is not in strict 4-line records (multi-line FASTQ or stray lines): parse it on the host"); }
+    if (n_records) *n_records = ctx->h_ctr[0];
+    // hand the nucleotide stream to the normal path; as the first push it is used in place (the block stays allocated until reset)
+    const bool in_place = ctx->stage == ST_EMPTY;
+    rc = cdbg_push_reads(ctx, d_out, total, CDBG_MEM_DEVICE);
+    if (!in_place || rc != CDBG_OK) dfree(ctx, d_out);
+    return rc;
+}
+
+int cdbg_get_pushed_reads(cdbg_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n) {
+    if (!ctx || !ctx->stream || !n) return CDBG_ERR_PARAM;
+    if (ctx->bytes_hostmapped) return ctx->fail(CDBG_ERR_STATE, "the reads of a zero-copy build stay in the caller's buffer");
+    CK(cudaSetDevice(ctx->prm.device));
+    *n = ctx->n_bytes;
+    const uint64_t c = std::min<uint64_t>(cap, ctx->n_bytes);
+    if (c && dst) CK(cudaMemcpyAsync(dst, ctx->d_bytes, c, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return CDBG_OK;
 }
 

@@ -135,6 +135,17 @@ const char *cdbg_last_error(const cdbg_ctx *ctx);
  * cdbg_count returns). */
 int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int location);
 
+/* Append reads given as raw FASTA or FASTQ TEXT (the bytes of the file, after gunzip): headers, '+' and quality lines are
+ * removed and multi-line records joined ON THE GPU (a parallel scan over the parser's state-transition functions, parse.cuh),
+ * replacing the host-side Bank parser (G/bank/impl/BankFasta.cpp:390-560) for this path.  The text must start at a record
+ * ('>' or '@'); FASTQ must be in strict 4-line records, otherwise CDBG_ERR_PARAM is returned and nothing is appended (parse
+ * such input on the host and use cdbg_push_reads).  *n_records (optional) receives the number of records. */
+int cdbg_push_sequence_text(cdbg_ctx *ctx, const uint8_t *text, uint64_t n_bytes, int location, uint64_t *n_records);
+
+/* The nucleotide stream pushed so far (after GPU parsing, with the break bytes between pushes), copied to `dst` (capacity `cap`);
+ * *n receives its length.  For inspection and tests. */
+int cdbg_get_pushed_reads(cdbg_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n);
+
 int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats);   /* stage 1: K1 extract + K2 count + solidity filter */
 int cdbg_compact(cdbg_ctx *ctx, cdbg_stats *stats); /* stages 2+3: K3-K5 junction join, K6/K8 chain + spell */
 int cdbg_link(cdbg_ctx *ctx, cdbg_stats *stats);    /* stage 4: K9 links */
