@@ -13,6 +13,7 @@ compaction -> unitigs -> links over that read set.
           arrays (sequences, offsets, KC, links) inside the timed region.
   roofline : the dominant kernel group of the step (by CUDA-event time measured inside the library on its own stream),
           algorithmic bytes per SURVEY.md 8d / DESIGN.md; for the K2 group also its three kernels one by one (`k2_kernels`).
+  file_to_file : the same workload through the CLI, FASTA file -> unitigs.fa (what the reference arm measures), N=1 only.
   cpu_baseline : the real reference binary (oracle/_ref/bcalm, kind "reference") -- or the C oracle (kind "port") when the
           binary is absent -- on a bounded sample of the same workload, all host cores.
 
@@ -160,6 +161,31 @@ def cpu_baseline_sample(c, scale: float, cores: int):
             "sample": sample + f"; C oracle single thread, {dt:.2f} s, {o.n_unitigs} unitigs"}
 
 
+def file_to_file_sample(reads: np.ndarray, n_bases: int):
+    """The same workload through the bcalm-compatible CLI, FASTA file -> <prefix>.unitigs.fa (process start, CUDA context, file read,
+    host parse, H2D, stages, D2H, formatting and write all inside): the variant SURVEY 8d asks for next to resident -> resident, and
+    the like-for-like of the reference arm, which is file -> file too."""
+    cli = os.path.join(ROOT, "bcalm_b200", "bcalm")
+    if not os.path.exists(cli):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        fa = os.path.join(d, "reads.fa")
+        write_fasta_from_bytes(fa, reads, READ_LEN)
+        best, log = None, []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            p = subprocess.run([cli, "-in", fa, "-kmer-size", str(K), "-abundance-min", str(AMIN), "-out", os.path.join(d, "out")],
+                               capture_output=True, text=True, cwd=d)
+            dt = time.perf_counter() - t0
+            if p.returncode != 0:
+                return {"value": None, "unit": "Gbases/s", "note": "CLI failed: " + p.stdout[-200:]}
+            if best is None or dt < best:
+                best, log = dt, [ln for ln in p.stdout.splitlines() if ln.startswith("wall s")]
+        return {"value": n_bases / best / 1e9, "unit": "Gbases/s", "seconds": best, "fasta_bytes": os.path.getsize(fa),
+                "cli_split": log[0] if log else None,
+                "note": "bcalm_b200/bcalm -in reads.fa -> out.unitigs.fa, best of 2 runs, page cache warm; includes process start and CUDA context creation"}
+
+
 def load_traffic(name: str):
     """dram__bytes_read.sum + dram__bytes_write.sum of the kernel group from the committed `ncu --set full` captures."""
     for fn in ("r01b_traffic.json", "r01_traffic.json"):
@@ -207,6 +233,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="workload scale (1.0 = C2)")
     ap.add_argument("--cpu-scale", type=float, default=0.5, help="bounded sample for the CPU baseline, fraction of C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-to-file", action="store_true", help="skip the CLI file -> file sample")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region (debugging)")
     args = ap.parse_args()
 
@@ -341,6 +368,11 @@ def main():
                                                                         "frac": round(b_ / (m_ / 1e3) / 1e9 / peak, 4) if m_ > 0 else None} for k_, (m_, b_) in k2_kernels.items()}},
             "clocks": clocks,
         }
+        if not args.no_file_to_file and world == 1:
+            try:
+                out["file_to_file"] = file_to_file_sample(c.copy_to_host(ptr, n_bytes), n_bases)
+            except Exception as e:  # a reported extra, never a reason to lose the line
+                out["file_to_file"] = {"value": None, "unit": "Gbases/s", "note": f"failed: {e}"}
         if not args.no_cpu_baseline and world == 1:   # the CPU leg runs on rank 0 at N=1 only
             try:
                 out["cpu_baseline"] = cpu_baseline_sample(c, args.cpu_scale, cores)
