@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(K5C_THREADS) k5c_join(K5CParams p) {
                 uint32_t fresh = 0;
 #pragma unroll
                 for (int u = 0; u < 2; u++) {
-                    if (key[u] == EMPTY_KEY) continue;
+                    if (key[u] == EMPTY_KEY || (val[u] & REC_SKIP)) continue;      // (REC_SKIP: second end of a self-complementary k-mer)
                     const uint64_t h = mix64(key[u]);
                     if ((((uint32_t)h >> 16) & sel_mask) != part) continue;
                     uint32_t slot = (uint32_t)h & MASK;
@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(K5C_THREADS) k5c_join(K5CParams p) {
                             const uint32_t old = atomicAdd(&s_cnt[slot], use_out ? 0x100u : 0x1u);
                             if (pal) atomicOr(&s_cnt[slot], 0x80000000u);
                             const uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
-                            if (pos < 4) s_ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val[u];
+                            if (pos < 4) {
+                                s_ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val[u];
+                                if (val[u] & REC_BOTH) atomicOr(&s_cnt[slot], 1u << ((use_out ? JOIN_BOTH_SHIFT_OUT : JOIN_BOTH_SHIFT_IN) + pos));
+                            }
                             break;
                         }
                         slot = (slot + 1) & MASK;
@@ -248,9 +251,14 @@ __global__ void __launch_bounds__(K5C_THREADS) k5c_join(K5CParams p) {
                 uint32_t nin = c & 0xFF, nout = (c >> 8) & 0xFF; const bool pal = (c >> 31) != 0;
                 if (nin > 4) nin = 4;
                 if (nout > 4) nout = 4;
-                const uint4 vin = *reinterpret_cast<const uint4 *>(&s_ids[(size_t)i * 8]);
-                const uint4 vout = *reinterpret_cast<const uint4 *>(&s_ids[(size_t)i * 8 + 4]);
-                const uint32_t in[4] = {vin.x, vin.y, vin.z, vin.w}, out[4] = {vout.x, vout.y, vout.z, vout.w};
+                uint32_t in[5], out[5];
+                {
+                    const uint4 vin = *reinterpret_cast<const uint4 *>(&s_ids[(size_t)i * 8]);
+                    const uint4 vout = *reinterpret_cast<const uint4 *>(&s_ids[(size_t)i * 8 + 4]);
+                    const uint32_t sin[4] = {vin.x, vin.y, vin.z, vin.w}, sout[4] = {vout.x, vout.y, vout.z, vout.w};
+                    nin = join_expand_side(sin, nin, (c >> JOIN_BOTH_SHIFT_IN) & 0xFu, in);
+                    nout = join_expand_side(sout, nout, (c >> JOIN_BOTH_SHIFT_OUT) & 0xFu, out);
+                }
                 if (!pal && nin == 1 && nout == 1 && (in[0] >> 1) != (out[0] >> 1)) {
                     p.link[in[0]] = out[0]; p.link[out[0]] = in[0];
                     compact++;

@@ -380,6 +380,26 @@ __global__ void __launch_bounds__(256) k2_canonicalise(uint64_t *kmers, uint64_t
 //   record value: bits 31..0 = end id (2*kmer_index + {0: left end, 1: right end}), bit 32 = side (0 IN, 1 OUT), bit 33 = palindrome
 #define REC_SIDE_OUT (1ULL << 32)
 #define REC_PALIN (1ULL << 33)
+// A k-mer that is its own reverse complement (even k only) has BOTH its ends on the same side of the same junction (its suffix
+// is the reverse complement of its prefix).  With such a k-mer a side can hold 5 ends -- 4 extensions of which one is the
+// palindrome, counted twice -- one more than the 4 id slots per side.  So the two ends travel as ONE record: the left end's
+// record carries REC_BOTH and stands for ends 2v and 2v+1, the right end's record carries REC_SKIP and is ignored by the join;
+// the table remembers which stored ids are such pairs in bits 16..19 (IN list) / 20..23 (OUT list) of its counter word.
+#define REC_BOTH (1ULL << 34)
+#define REC_SKIP (1ULL << 35)
+#define JOIN_BOTH_SHIFT_IN 16
+#define JOIN_BOTH_SHIFT_OUT 20
+
+// ids of one side of a junction with the (2v, 2v+1) pairs written out; at most 4 stored ids, at most one of them a pair
+template <class ID>
+__device__ __forceinline__ uint32_t join_expand_side(const ID *ids, uint32_t n, uint32_t both_mask, ID *out) {
+    uint32_t m = 0;
+    for (uint32_t a = 0; a < n; a++) {
+        out[m++] = ids[a];
+        if ((both_mask >> a) & 1u) out[m++] = ids[a] ^ (ID)1;
+    }
+    return m;
+}
 
 __device__ __forceinline__ void kmer_end_record(uint64_t x, int k, int end, uint32_t idx, uint64_t &key, uint64_t &val) {
     const int k1 = k - 1;
@@ -391,6 +411,7 @@ __device__ __forceinline__ void kmer_end_record(uint64_t x, int k, int end, uint
     // right end: suffix -> the k-mer ends with c (IN) when canonical, else rc(k-mer) begins with c (OUT)
     bool out = (end == 0) ? canon_fwd : !canon_fwd;
     val = (uint64_t)(2u * idx + (uint32_t)end) | (out ? REC_SIDE_OUT : 0) | (e == r ? REC_PALIN : 0);
+    if (!(k & 1) && x == revcomp64(x, k)) val |= end == 0 ? REC_BOTH : REC_SKIP;
 }
 
 struct K3Params {
@@ -480,6 +501,7 @@ __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ re
     pdl_wait();
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = rec_key[i], val = rec_val[i];
+        if (val & REC_SKIP) continue;
         uint32_t slot = table_slot(key, T.cap);
         uint32_t probes = 0;
         for (;;) {
@@ -495,7 +517,10 @@ __global__ void __launch_bounds__(256) k5_insert(const uint64_t *__restrict__ re
                 uint32_t old = atomicAdd(&T.cnt[slot], use_out ? 0x100u : 0x1u);
                 if (pal) atomicOr(&T.cnt[slot], 0x80000000u);
                 uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
-                if (pos < 4) T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val;
+                if (pos < 4) {
+                    T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val;
+                    if (val & REC_BOTH) atomicOr(&T.cnt[slot], 1u << ((use_out ? JOIN_BOTH_SHIFT_OUT : JOIN_BOTH_SHIFT_IN) + pos));
+                }
                 break;
             }
             slot = slot + 1 == T.cap ? 0 : slot + 1;
@@ -517,11 +542,14 @@ __global__ void __launch_bounds__(256) k5_resolve(JoinTable T, uint32_t cap, uin
         T.keys[i] = EMPTY_KEY; T.cnt[i] = 0;
         uint32_t nin = c & 0xFF, nout = (c >> 8) & 0xFF; bool pal = (c >> 31) != 0;
         if (nin > 4) nin = 4; if (nout > 4) nout = 4;
-        uint32_t in[4], out[4];
-        const uint4 vin = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8]);
-        const uint4 vout = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8 + 4]);
-        in[0] = vin.x; in[1] = vin.y; in[2] = vin.z; in[3] = vin.w;
-        out[0] = vout.x; out[1] = vout.y; out[2] = vout.z; out[3] = vout.w;
+        uint32_t in[5], out[5];
+        {
+            const uint4 vin = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8]);
+            const uint4 vout = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8 + 4]);
+            const uint32_t sin[4] = {vin.x, vin.y, vin.z, vin.w}, sout[4] = {vout.x, vout.y, vout.z, vout.w};
+            nin = join_expand_side(sin, nin, (c >> JOIN_BOTH_SHIFT_IN) & 0xFu, in);
+            nout = join_expand_side(sout, nout, (c >> JOIN_BOTH_SHIFT_OUT) & 0xFu, out);
+        }
         if (!pal && nin == 1 && nout == 1 && (in[0] >> 1) != (out[0] >> 1)) {
             link[in[0]] = out[0]; link[out[0]] = in[0];
             compact++;

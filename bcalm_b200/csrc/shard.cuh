@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(256) k2s_insert(const uint64_t *__restrict__ k
 // record value: bits 39..0 = gid of the k-mer end, bit 62 = side OUT, bit 63 = palindrome
 #define SREC_SIDE_OUT (1ULL << 62)
 #define SREC_PALIN (1ULL << 63)
+#define SREC_BOTH (1ULL << 61)   // see REC_BOTH / REC_SKIP in kernels.cuh
+#define SREC_SKIP (1ULL << 60)
 
 struct K3SParams {
     const uint64_t *solid_kmers; uint64_t n_solid; int k, m; uint32_t rank, world, P_local;
@@ -255,7 +257,8 @@ __global__ void __launch_bounds__(K3_THREADS) k3s_ends(K3SParams p) {
                 const int r = 2 * j + end;
                 uint64_t v;
                 kmer_end_record(x, p.k, end, (uint32_t)i, key[r], v);
-                val[r] = ((uint64_t)p.rank << 32) | (uint32_t)v | ((v & REC_SIDE_OUT) ? SREC_SIDE_OUT : 0) | ((v & REC_PALIN) ? SREC_PALIN : 0);
+                val[r] = ((uint64_t)p.rank << 32) | (uint32_t)v | ((v & REC_SIDE_OUT) ? SREC_SIDE_OUT : 0) | ((v & REC_PALIN) ? SREC_PALIN : 0) |
+                         ((v & REC_BOTH) ? SREC_BOTH : 0) | ((v & REC_SKIP) ? SREC_SKIP : 0);
                 bin[r] = 0xFFFFFFFFu; rnk[r] = 0;
                 if (ok) {
                     if (MODE == 0) {
@@ -300,6 +303,7 @@ __global__ void __launch_bounds__(256) k5s_insert(const uint64_t *__restrict__ r
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t src = runs_index(runs, i);
         const uint64_t key = rec_key[src], val = rec_val[src];
+        if (val & SREC_SKIP) continue;
         uint32_t slot = table_slot(key, T.cap), probes = 0;
         for (;;) {
             uint64_t cur = ld_volatile_u64(&T.keys[slot]);
@@ -312,7 +316,10 @@ __global__ void __launch_bounds__(256) k5s_insert(const uint64_t *__restrict__ r
                 uint32_t old = atomicAdd(&T.cnt[slot], use_out ? 0x100u : 0x1u);
                 if (pal) atomicOr(&T.cnt[slot], 0x80000000u);
                 uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
-                if (pos < 4) T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = val & GID_MASK;
+                if (pos < 4) {
+                    T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = val & GID_MASK;
+                    if (val & SREC_BOTH) atomicOr(&T.cnt[slot], 1u << ((use_out ? JOIN_BOTH_SHIFT_OUT : JOIN_BOTH_SHIFT_IN) + pos));
+                }
                 break;
             }
             slot = slot + 1 == T.cap ? 0 : slot + 1;
@@ -334,16 +341,19 @@ __global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, 
     const uint32_t per_warp = ((cap + n_warps - 1) / n_warps + 31u) & ~31u;
     const uint32_t gw = blockIdx.x * 8 + warp;
     const uint32_t wb = (uint32_t)min((uint64_t)cap, (uint64_t)gw * per_warp), we = (uint32_t)min((uint64_t)cap, (uint64_t)wb + per_warp);
-    auto classify = [&](uint32_t i, uint32_t &nin, uint32_t &nout, bool &pal, bool &compact) {
+    // counts with the (2v, 2v+1) pairs of self-complementary k-mers written out (REC_BOTH); bin/bout say which stored ids are pairs
+    auto classify = [&](uint32_t i, uint32_t &nin, uint32_t &nout, bool &pal, bool &compact, uint32_t &sin, uint32_t &sout, uint32_t &bin_, uint32_t &bout) {
         uint32_t c = T.cnt[i];
-        nin = min(c & 0xFFu, 4u); nout = min((c >> 8) & 0xFFu, 4u); pal = (c >> 31) != 0;
+        sin = min(c & 0xFFu, 4u); sout = min((c >> 8) & 0xFFu, 4u); pal = (c >> 31) != 0;
+        bin_ = (c >> JOIN_BOTH_SHIFT_IN) & ((1u << sin) - 1u); bout = (c >> JOIN_BOTH_SHIFT_OUT) & ((1u << sout) - 1u);
+        nin = sin + __popc(bin_); nout = sout + __popc(bout);
         compact = !pal && nin == 1 && nout == 1 && (T.ids[(size_t)i * 8] >> 1) != (T.ids[(size_t)i * 8 + 4] >> 1);
     };
     uint32_t my_l = 0, my_e = 0; unsigned long long my_c = 0;
     for (uint32_t i = wb + lane; i < we; i += 32) {
         if (T.keys[i] == EMPTY_KEY) continue;
-        uint32_t nin, nout; bool pal, compact;
-        classify(i, nin, nout, pal, compact);
+        uint32_t nin, nout, sin, sout, bin_, bout; bool pal, compact;
+        classify(i, nin, nout, pal, compact, sin, sout, bin_, bout);
         if (compact) {   // only the directions whose destination end lives on another GPU become messages
             my_l += (GID_RANK(T.ids[(size_t)i * 8]) != rank) + (GID_RANK(T.ids[(size_t)i * 8 + 4]) != rank);
             my_c++;
@@ -368,18 +378,21 @@ __global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, 
     uint64_t ol = s_bl + s_wl[warp] + xl - my_l, oe = s_be + s_we[warp] + xe - my_e;
     for (uint32_t i = wb + lane; i < we; i += 32) {
         if (T.keys[i] == EMPTY_KEY) continue;
-        uint32_t nin, nout; bool pal, compact;
-        classify(i, nin, nout, pal, compact);
+        uint32_t nin, nout, sin, sout, bin_, bout; bool pal, compact;
+        classify(i, nin, nout, pal, compact, sin, sout, bin_, bout);
         const uint64_t *ids = &T.ids[(size_t)i * 8];
+        uint64_t ein[5], eout[5];
+        join_expand_side(ids, sin, bin_, ein);
+        join_expand_side(ids + 4, sout, bout, eout);
         if (compact) {
             uint64_t a = ids[0], b = ids[4];
             if (GID_RANK(a) == rank) link64[GID_LOCAL(a)] = b; else { if (ol < link_cap) link_msgs[ol] = make_ulonglong2(a, b); ol++; }
             if (GID_RANK(b) == rank) link64[GID_LOCAL(b)] = a; else { if (ol < link_cap) link_msgs[ol] = make_ulonglong2(b, a); ol++; }
         } else if (pal) {
-            for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nin; b++) { if (oe < edge_cap) edges[oe] = make_ulonglong2(ids[a], ids[b]); oe++; }
+            for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nin; b++) { if (oe < edge_cap) edges[oe] = make_ulonglong2(ein[a], ein[b]); oe++; }
         } else {
             for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nout; b++) {
-                if (oe + 2 <= edge_cap) { edges[oe] = make_ulonglong2(ids[a], ids[4 + b]); edges[oe + 1] = make_ulonglong2(ids[4 + b], ids[a]); }
+                if (oe + 2 <= edge_cap) { edges[oe] = make_ulonglong2(ein[a], eout[b]); edges[oe + 1] = make_ulonglong2(eout[b], ein[a]); }
                 oe += 2;
             }
         }

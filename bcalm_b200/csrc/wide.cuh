@@ -274,6 +274,7 @@ __device__ __forceinline__ void kmer_end_record_w(const KM<W> &x, int k, int end
     const bool canon_fwd = lt || eq;
     const bool out = (end == 0) ? canon_fwd : !canon_fwd;
     val = (uint64_t)(2u * idx + (uint32_t)end) | (out ? REC_SIDE_OUT : 0) | (eq ? REC_PALIN : 0);
+    if (!(k & 1) && km_eq<W>(x, km_revcomp<W>(x, k))) val |= end == 0 ? REC_BOTH : REC_SKIP;   // see REC_BOTH in kernels.cuh
 }
 
 struct KW3Params {
@@ -339,13 +340,17 @@ __global__ void __launch_bounds__(256) kw5_insert(const uint64_t *__restrict__ r
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         KM<W> key = km_load<W>(rec_key + i * W);
         const uint64_t val = rec_val[i];
+        if (val & REC_SKIP) continue;
         uint32_t slot = wide_find_or_insert<W>(key, km_hash<W>(key) * 0x9E3779B97F4A7C15ULL + 0x7F4A7C15ULL, T.tags, T.keys, T.cap);
         if (slot == 0xFFFFFFFFu) { *overflow = 1; continue; }
         const bool pal = (val & REC_PALIN) != 0, use_out = (val & REC_SIDE_OUT) != 0 && !pal;
         uint32_t old = atomicAdd(&T.cnt[slot], use_out ? 0x100u : 0x1u);
         if (pal) atomicOr(&T.cnt[slot], 0x80000000u);
         uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
-        if (pos < 4) T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val;
+        if (pos < 4) {
+            T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = (uint32_t)val;
+            if (val & REC_BOTH) atomicOr(&T.cnt[slot], 1u << ((use_out ? JOIN_BOTH_SHIFT_OUT : JOIN_BOTH_SHIFT_IN) + pos));
+        }
     }
 }
 
@@ -358,11 +363,14 @@ __global__ void __launch_bounds__(256) kw5_resolve(JoinTableW T, uint32_t cap, u
         uint32_t c = T.cnt[i];
         T.tags[i] = TAG_EMPTY; T.cnt[i] = 0;
         uint32_t nin = min(c & 0xFFu, 4u), nout = min((c >> 8) & 0xFFu, 4u); bool pal = (c >> 31) != 0;
-        uint32_t in[4], out[4];
-        const uint4 vin = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8]);
-        const uint4 vout = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8 + 4]);
-        in[0] = vin.x; in[1] = vin.y; in[2] = vin.z; in[3] = vin.w;
-        out[0] = vout.x; out[1] = vout.y; out[2] = vout.z; out[3] = vout.w;
+        uint32_t in[5], out[5];
+        {
+            const uint4 vin = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8]);
+            const uint4 vout = *reinterpret_cast<const uint4 *>(&T.ids[(size_t)i * 8 + 4]);
+            const uint32_t sin[4] = {vin.x, vin.y, vin.z, vin.w}, sout[4] = {vout.x, vout.y, vout.z, vout.w};
+            nin = join_expand_side(sin, nin, (c >> JOIN_BOTH_SHIFT_IN) & 0xFu, in);
+            nout = join_expand_side(sout, nout, (c >> JOIN_BOTH_SHIFT_OUT) & 0xFu, out);
+        }
         if (!pal && nin == 1 && nout == 1 && (in[0] >> 1) != (out[0] >> 1)) { link[in[0]] = out[0]; link[out[0]] = in[0]; compact++; continue; }
         uint32_t ne = pal ? nin * nin : 2 * nin * nout;
         if (ne == 0) continue;

@@ -133,6 +133,16 @@ def cases():
     for i, (alpha, k, glen) in enumerate([("AT", 33, 400), ("AT", 35, 600), ("ACG", 37, 500)]):
         reads = synth_reads(rng3, glen, min(glen, 120), 4, err=0.0, alphabet=alpha)
         out.append(dict(name=f"wide_lowcx_{i}_{alpha}_k{k}", k=k, abundance_min=1, minimizer_size=10, reads=reads))
+    # even k, dense graphs: a k-mer that is its own reverse complement has BOTH ends on the same side of one junction, so a
+    # junction side can carry 5 ends (4 extensions, the self-complementary one twice).  Found by fuzzing the CUDA path against
+    # the oracle: the join tables used to keep 4 ids per side.  (own generator: the cases above keep their random streams)
+    rng4 = np.random.default_rng(2024)
+    for name, alpha, k, glen, m in [("even_k_dense_k4", "ACGT", 4, 3000, 3), ("even_k_dense_k6", "ACGT", 6, 30000, 5),
+                                    ("even_k_dense_AT_k8", "AT", 8, 3000, 5), ("even_k_dense_ACG_k6", "ACG", 6, 5000, 5)]:
+        g = "".join(rng4.choice(list(alpha), size=glen))
+        out.append(dict(name=name, k=k, abundance_min=1, minimizer_size=m, reads=[g[: glen // 2 + k], rc(g[glen // 2:])]))
+    reads = synth_reads(rng4, 6000, 90, 25, err=0.01)
+    out.append(dict(name="even_k_reads_k20_a2", k=20, abundance_min=2, minimizer_size=10, reads=reads))
     return out
 
 

@@ -1,0 +1,95 @@
+"""Randomised parity sweep of the CUDA path (under the CPU emulator) against the oracle: small k (even and odd), low-complexity
+alphabets, reads of exactly k / k+1 nucleotides, N's and lower case, byte streams that end within a few bytes of a tile edge,
+and a randomly chosen kernel configuration per case (default, the L2-table and two-pass variants, the opt-in variants, tiny
+fine bins, forced splits, zero-copy input, and the sharded path over 2-3 emulated ranks).  Seeded, so a failure reproduces.
+This sweep is what found the 5-ends-per-junction-side case of even k (tests/golden: even_k_dense_*)."""
+from __future__ import annotations
+
+import os
+import random
+import shutil
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+from bcalm_b200 import api, parity  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from test_emu_sharded import sharded_build  # noqa: E402
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ to build the CPU emulation of the library")
+
+CONFIGS = [{}, {"CDBG_K1": "twopass"}, {"CDBG_K1": "classic"}, {"CDBG_K2": "l2"}, {"CDBG_K5": "l2"}, {"CDBG_K2C": "flat"}, {"CDBG_K1_THREADS": "512"},
+           {"CDBG_K6": "list"}, {"CDBG_RANK": "match", "CDBG_K2S_P1": "6"}, {"CDBG_EMU_PINNED": "1", "CDBG_ZEROCOPY_MIN": "0"},
+           {"CDBG_K2S_P1": "7", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"CDBG_K5S_P1": "5", "CDBG_K5S_FILL": "0.05"},
+           {"CDBG_K2S_FILL": "8", "CDBG_K2S_SLOTS": "4096", "CDBG_K5S_FILL": "8"}, {"shards": 2}, {"shards": 3}]
+KNOBS = sorted({k for c in CONFIGS for k in c if k.startswith("CDBG_")})
+COMP = str.maketrans("ACGTacgt", "TGCAtgca")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    import build_emu
+    path = build_emu.build()
+    saved = (api.LIB_PATH, api._lib)
+    api.LIB_PATH, api._lib = path, None
+    yield path
+    api.LIB_PATH, api._lib = saved
+
+
+def make_case(rng: random.Random):
+    k = rng.choice([4, 5, 6, 7, 8, 11, 15, 20, 21, 25, 31, 31, 31])
+    alpha = rng.choice(["ACGT", "ACGT", "AT", "ACG", "ACGTN", "ACGTacgt"])
+    glen = rng.choice([50, 300, 2000, 9000, 20000])
+    letters = "ACGT" if alpha in ("ACGTN", "ACGTacgt") else alpha
+    genome = "".join(rng.choice(letters) for _ in range(glen))
+    L = rng.choice([k, k + 1, 40, 100, 150, 251])
+    cov = rng.choice([1, 3, 8])
+    reads = []
+    for _ in range(max(1, glen * cov // L)):
+        s = rng.randrange(0, max(1, glen - L + 1))
+        r = genome[s:s + L]
+        if rng.random() < 0.5:
+            r = r[::-1].translate(COMP)
+        if alpha == "ACGTN" and rng.random() < 0.3:
+            p = rng.randrange(len(r)); r = r[:p] + "N" + r[p + 1:]
+        if alpha == "ACGTacgt" and rng.random() < 0.5:
+            r = r.lower()
+        if rng.random() < 0.02 and len(r) > 2:
+            p = rng.randrange(len(r)); r = r[:p] + rng.choice("ACGT") + r[p + 1:]
+        reads.append(r)
+    if rng.random() < 0.4:   # end the byte stream within +-40 bytes of a tile edge (8192-byte tiles, 32-byte halo)
+        tot = sum(len(r) + 1 for r in reads)
+        target = (tot // 8192 + 1) * 8192 + rng.randint(-40, 40)
+        while tot < target - 1:
+            r = genome[:min(len(genome), target - 1 - tot)] or "A"
+            reads.append(r); tot += len(r) + 1
+    return k, rng.choice([1, 1, 2, 3]), reads, rng.choice(CONFIGS)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_inputs_and_configurations_match_the_oracle(emu_lib, monkeypatch, seed):
+    rng = random.Random(1000 + seed)
+    for it in range(40):
+        k, amin, reads, cfg = make_case(rng)
+        for name in KNOBS:
+            monkeypatch.delenv(name, raising=False)
+        for name, v in cfg.items():
+            if name.startswith("CDBG_"):
+                monkeypatch.setenv(name, v)
+        o = orc.run(reads, k, amin)
+        if "shards" in cfg:
+            g, parts = sharded_build(reads, k, amin, cfg["shards"])
+            n_solid = sum(p.stats["n_solid"] for p in parts)
+        else:
+            with api.Cdbg(k=k, abundance_min=amin, device=0) as c:
+                g = c.build(reads)
+            n_solid = g.stats["n_solid"]
+            assert g.stats["n_instances"] == o.stats["n_instances"] and g.stats["n_distinct"] == o.stats["n_distinct"], (seed, it, k, cfg)
+        assert n_solid == o.stats["n_solid"], (seed, it, k, amin, cfg)
+        d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k)
+        assert d == "", (seed, it, k, amin, cfg, d[:400])
