@@ -487,8 +487,9 @@ static inline size_t k3_smem_bytes(int mode, uint32_t P) { return (size_t)P * 4 
 
 // ------------------------------------------------------------------------------------------------ K5: junction join
 
-// table entry: key, packed counters (IN count in bits 7..0, OUT count in bits 15..8, palindrome flag bit 31) and up to 4 end
-// ids per side.  A (k-1)-mer has at most 4 IN and 4 OUT ends (one per extension base).
+// table entry: key, packed counters (IN count in bits 7..0, OUT count in bits 15..8, REC_BOTH masks in bits 16..23, palindrome
+// flag bit 31) and up to 4 end ids per side.  A (k-1)-mer has at most 4 k-mers on each side (one per extension base); the one
+// case of 5 ENDS on a side (even k, one of the 4 k-mers is its own reverse complement) is stored as 4 ids + a pair flag.
 struct JoinTable {
     uint64_t *keys;     // [cap]
     uint32_t *cnt;      // [cap]
