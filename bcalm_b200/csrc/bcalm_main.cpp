@@ -32,6 +32,7 @@ struct Options {
     int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
     bool all_abund = false;
     bool parse_only = false; // -parse-only: parse the input, print record/byte counts and a checksum, no GPU (host-side tests)
+    int nb_gpus = 1;        // -nb-gpus N: one context per GPU (threads of this process), the graph sharded by minimizer over them
     bool gpu_parse = false; // -gpu-parse 1: ship the file bytes and strip headers / quality lines on the GPU (cdbg_push_sequence_text)
     bool edge_km = false;   // -edge-km 1: J:<0|1>:<id>:<0|1> tokens instead of L: (G/debruijn/impl/LinkTigs.cpp:380-384,440-444)
 };
@@ -65,6 +66,7 @@ void usage() {
            "       -edge-km              (1 arg) :    edge km representation  [default '0']\n"
            "       -nb-cores             (1 arg) :    number of cores (host parsing threads)  [default '0']\n"
            "       -device               (1 arg) :    CUDA device ordinal  [default '0']\n"
+           "       -nb-gpus              (1 arg) :    number of GPUs (devices -device .. -device+N-1), one shard each, NCCL between them  [default '1']\n"
            "       -gpu-parse            (1 arg) :    parse FASTA/FASTQ text on the GPU instead of the host  [default '0']\n"
            "       -verbose              (1 arg) :    verbosity level  [default '1']\n"
            "       -version              (0 arg) :    version\n"
@@ -92,6 +94,7 @@ Options parse(int argc, char **argv) {
         else if (a == "-nb-cores") o.cores = atoi(need("-nb-cores").c_str());
         else if (a == "-verbose") o.verbose = atoi(need("-verbose").c_str());
         else if (a == "-device") o.device = atoi(need("-device").c_str());
+        else if (a == "-nb-gpus") o.nb_gpus = atoi(need("-nb-gpus").c_str());
         else if (a == "-all-abundance-counts") o.all_abund = true;
         else if (a == "-parse-only") o.parse_only = true;
         else if (a == "-gpu-parse") o.gpu_parse = atoi(need("-gpu-parse").c_str()) != 0;
@@ -106,6 +109,9 @@ Options parse(int argc, char **argv) {
     }
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
     if (!o.solid_in.empty() && o.k > 31) die("-solid-kmers-in needs -kmer-size <= 31");
+    if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
+    if (o.nb_gpus > 1 && (o.k > 31 || o.all_abund || !o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse))
+        die("-nb-gpus > 1 supports -kmer-size <= 31 without -all-abundance-counts / -solid-kmers-in / -solid-kmers-out / -gpu-parse");
     return o;
 }
 
@@ -389,6 +395,145 @@ void write_counted_kmers(const std::string &path, cdbg_ctx *ctx, int k) {
     fclose(f);
 }
 
+// <prefix>.unitigs.fa (and GFA1) from one view, or from the views of a sharded run in the order of their global unitig ids
+void write_outputs(const Options &o, const std::vector<const cdbg_unitig_view *> &views, const std::string &out_path, cdbg_ctx *ctx_for_cleanup) {
+    const int k = o.k;
+    uint64_t total_nt = 0, n_unitigs = 0, n_links = 0;
+    for (const cdbg_unitig_view *vp : views) { total_nt += vp->total_nt; n_unitigs += vp->n_unitigs; n_links += vp->n_links; }
+    std::string text;
+    text.reserve(total_nt + n_unitigs * 64 + n_links * 16 + 64);
+    for (const cdbg_unitig_view *vp : views) {
+        const cdbg_unitig_view &v = *vp;
+        for (uint64_t u = 0; u < v.n_unitigs; u++) {
+            const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
+            const uint32_t *ab = v.abund ? v.abund + (b - u * (uint64_t)(k - 1)) : nullptr;
+            text.push_back('>'); put_u64(text, v.first_unitig + u);
+            text += " LN:i:"; put_u64(text, len);
+            if (o.all_abund && ab) {
+                text += " ab:Z:";
+                for (uint64_t i = 0; i < nk; i++) { put_u64(text, ab[i]); text.push_back(' '); }
+            } else {
+                text += " KC:i:"; put_u64(text, v.kc[u]);
+                text += " km:f:"; put_km(text, v.kc[u], nk, ab);
+                text.push_back(' ');
+            }
+            for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
+                const cdbg_link_t &l = v.links[i];
+                if (o.edge_km) {   // J:0 = in-link (leaves the BEGIN), J:1 = out-link; last field 1 when the neighbour is entered at its END
+                    text += " J:"; text.push_back(l.from_sign == '-' ? '0' : '1'); text.push_back(':'); put_u64(text, l.to);
+                    text.push_back(':'); text.push_back(l.to_sign == '-' ? '1' : '0');
+                } else {
+                    text += " L:"; text.push_back((char)l.from_sign); text.push_back(':'); put_u64(text, l.to);
+                    text.push_back(':'); text.push_back((char)l.to_sign);
+                }
+            }
+            text.push_back('\n');
+            text.append(v.seq + b, len);
+            text.push_back('\n');
+        }
+    }
+    FILE *f = fopen(out_path.c_str(), "wb");
+    if (!f) { if (ctx_for_cleanup) cdbg_destroy(ctx_for_cleanup); die("Unable to open output file '" + out_path + "'"); }
+    fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
+
+    if (!o.out_gfa.empty()) {   // GFA1, same records as scripts/convertToGFA.py:74,97-114
+        std::string g;
+        g.reserve(text.size() + n_links * 24);
+        g += "H\tVN:Z:1.0\tks:i:"; put_u64(g, (uint64_t)k); g.push_back('\n');
+        for (const cdbg_unitig_view *vp : views) {
+            const cdbg_unitig_view &v = *vp;
+            for (uint64_t u = 0; u < v.n_unitigs; u++) {
+                const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
+                g += "S\t"; put_u64(g, v.first_unitig + u); g.push_back('\t'); g.append(v.seq + b, len);
+                g += "\tLN:i:"; put_u64(g, len); g += "\tKC:i:"; put_u64(g, v.kc[u]); g += "\tkm:f:"; put_km(g, v.kc[u], nk, nullptr);
+                g.push_back('\n');
+            }
+        }
+        for (const cdbg_unitig_view *vp : views) {
+            const cdbg_unitig_view &v = *vp;
+            for (uint64_t u = 0; u < v.n_unitigs; u++)
+                for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
+                    const cdbg_link_t &l = v.links[i];
+                    g += "L\t"; put_u64(g, v.first_unitig + u); g.push_back('\t'); g.push_back((char)l.from_sign); g.push_back('\t'); put_u64(g, l.to);
+                    g.push_back('\t'); g.push_back((char)l.to_sign); g.push_back('\t'); put_u64(g, (uint64_t)(k - 1)); g += "M\n";
+                }
+        }
+        FILE *gf = fopen(o.out_gfa.c_str(), "wb");
+        if (!gf) { if (ctx_for_cleanup) cdbg_destroy(ctx_for_cleanup); die("Unable to open output file '" + o.out_gfa + "'"); }
+        fwrite(g.data(), 1, g.size(), gf);
+        fclose(gf);
+    }
+}
+
+// -nb-gpus N: the reads are dealt round-robin (by record) to N contexts, one per GPU, each driven by its own thread; the library
+// shards the graph by minimizer and exchanges k-mers, junction records, glue and link records over NCCL; every context returns
+// the unitigs whose global ids fall in its range.
+int run_sharded(const Options &o, ByteBuf &stream, uint64_t n_records, double t0) {
+    const int N = o.nb_gpus;
+    std::vector<ByteBuf> share(N);
+    {
+        const uint8_t *p = stream.data(), *e = p + stream.size();
+        uint64_t r = 0;
+        for (ByteBuf &sb : share) sb.reserve(stream.size() / N + 4096);
+        while (p < e) {
+            const uint8_t *nl = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+            const uint8_t *le = nl ? nl + 1 : e;
+            share[r % N].append(p, (size_t)(le - p));
+            r++; p = le;
+        }
+    }
+    const double t1 = now_s();
+    std::vector<cdbg_ctx *> ctx(N, nullptr);
+    auto destroy_all = [&]() { for (cdbg_ctx *c : ctx) if (c) cdbg_destroy(c); };
+    for (int r = 0; r < N; r++) {
+        cdbg_params prm{};
+        prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device + r;
+        prm.flags = o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0;
+        prm.rank = r; prm.world_size = N;
+        if (cdbg_create(&ctx[r], &prm) != CDBG_OK) {
+            std::string msg = ctx[r] ? cdbg_last_error(ctx[r]) : "cdbg_create failed";
+            destroy_all();
+            die(msg);
+        }
+    }
+    uint8_t id[128];
+    if (cdbg_nccl_unique_id(id) != CDBG_OK) { destroy_all(); die("NCCL is not available (cdbg_nccl_unique_id failed)"); }
+    std::vector<cdbg_unitig_view> view(N);
+    std::vector<cdbg_stats> st(N);
+    std::vector<int> rcs(N, CDBG_OK);
+    std::vector<std::thread> pool;
+    for (int r = 0; r < N; r++)
+        pool.emplace_back([&, r]() {
+            int rc = cdbg_shard_init(ctx[r], id);
+            if (rc == CDBG_OK) rc = cdbg_build(ctx[r], share[r].data(), share[r].size(), CDBG_MEM_HOST, &view[r], &st[r]);
+            rcs[r] = rc;
+        });
+    for (auto &th : pool) th.join();
+    for (int r = 0; r < N; r++)
+        if (rcs[r] != CDBG_OK) { std::string msg = cdbg_last_error(ctx[r]); destroy_all(); die(msg); }
+    const double t2 = now_s();
+    std::vector<const cdbg_unitig_view *> views;
+    for (int r = 0; r < N; r++) views.push_back(&view[r]);
+    std::sort(views.begin(), views.end(), [](const cdbg_unitig_view *a, const cdbg_unitig_view *b) {
+        return a->first_unitig != b->first_unitig ? a->first_unitig < b->first_unitig : a->n_unitigs < b->n_unitigs; });
+    const std::string prefix = !o.out.empty() ? o.out : base_name(o.in);
+    const std::string out_path = prefix + ".unitigs.fa";
+    write_outputs(o, views, out_path, nullptr);
+    const double t3 = now_s();
+    if (o.verbose) {
+        uint64_t inst = 0, solid = 0, links = 0;
+        for (int r = 0; r < N; r++) { inst += st[r].n_instances; solid += st[r].n_solid; links += view[r].n_links; }
+        printf("sequences: %llu   nucleotide stream: %llu bytes   GPUs: %d\n", (unsigned long long)n_records, (unsigned long long)stream.size(), N);
+        printf("kmers: %llu instances, %llu solid\n", (unsigned long long)inst, (unsigned long long)solid);
+        printf("unitigs: %llu, links: %llu\n", (unsigned long long)view[0].n_unitigs_total, (unsigned long long)links);
+        printf("wall s: parse+deal %.3f  gpu (H2D+stages+exchanges+D2H) %.3f  write %.3f  total %.3f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+        printf("output: %s\n", out_path.c_str());
+    }
+    destroy_all();
+    return EXIT_SUCCESS;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && (strcmp(argv[1], "-version") == 0 || strcmp(argv[1], "-v") == 0)) {
         printf("BCALM 2 (B200-native cdbg), version v2.2.3-compatible\nUsing %s\n", cdbg_version());
@@ -409,6 +554,11 @@ int main(int argc, char **argv) {
         if (o.verbose > 1) printf("parse seconds %.3f\n", tp1 - tp0);
         printf("records %llu bytes %llu fnv1a %016llx threads %d\n", (unsigned long long)nrec, (unsigned long long)st0.size(), (unsigned long long)h, g_parse_threads);
         return EXIT_SUCCESS;
+    }
+    if (o.nb_gpus > 1) {
+        ByteBuf st0; uint64_t nrec = 0;
+        load_input(o.in, st0, nrec);
+        return run_sharded(o, st0, nrec, t0);
     }
     cdbg_params prm{};
     prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device;
@@ -457,62 +607,8 @@ int main(int argc, char **argv) {
 
     const std::string prefix = !o.out.empty() ? o.out : base_name(o.in.empty() ? o.solid_in : o.in);
     const std::string out_path = prefix + ".unitigs.fa";
-    const int k = o.k;
-    std::string text;
-    text.reserve(v.total_nt + v.n_unitigs * 64 + v.n_links * 16 + 64);
-    for (uint64_t u = 0; u < v.n_unitigs; u++) {
-        const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
-        const uint32_t *ab = v.abund ? v.abund + (b - u * (uint64_t)(k - 1)) : nullptr;
-        text.push_back('>'); put_u64(text, u);
-        text += " LN:i:"; put_u64(text, len);
-        if (o.all_abund && ab) {
-            text += " ab:Z:";
-            for (uint64_t i = 0; i < nk; i++) { put_u64(text, ab[i]); text.push_back(' '); }
-        } else {
-            text += " KC:i:"; put_u64(text, v.kc[u]);
-            text += " km:f:"; put_km(text, v.kc[u], nk, ab);
-            text.push_back(' ');
-        }
-        for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
-            const cdbg_link_t &l = v.links[i];
-            if (o.edge_km) {   // J:0 = in-link (leaves the BEGIN), J:1 = out-link; last field 1 when the neighbour is entered at its END
-                text += " J:"; text.push_back(l.from_sign == '-' ? '0' : '1'); text.push_back(':'); put_u64(text, l.to);
-                text.push_back(':'); text.push_back(l.to_sign == '-' ? '1' : '0');
-            } else {
-                text += " L:"; text.push_back((char)l.from_sign); text.push_back(':'); put_u64(text, l.to);
-                text.push_back(':'); text.push_back((char)l.to_sign);
-            }
-        }
-        text.push_back('\n');
-        text.append(v.seq + b, len);
-        text.push_back('\n');
-    }
-    FILE *f = fopen(out_path.c_str(), "wb");
-    if (!f) { cdbg_destroy(ctx); die("Unable to open output file '" + out_path + "'"); }
-    fwrite(text.data(), 1, text.size(), f);
-    fclose(f);
-
-    if (!o.out_gfa.empty()) {   // GFA1, same records as scripts/convertToGFA.py:74,97-114
-        std::string g;
-        g.reserve(text.size() + v.n_links * 24);
-        g += "H\tVN:Z:1.0\tks:i:"; put_u64(g, (uint64_t)k); g.push_back('\n');
-        for (uint64_t u = 0; u < v.n_unitigs; u++) {
-            const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
-            g += "S\t"; put_u64(g, u); g.push_back('\t'); g.append(v.seq + b, len);
-            g += "\tLN:i:"; put_u64(g, len); g += "\tKC:i:"; put_u64(g, v.kc[u]); g += "\tkm:f:"; put_km(g, v.kc[u], nk, nullptr);
-            g.push_back('\n');
-        }
-        for (uint64_t u = 0; u < v.n_unitigs; u++)
-            for (uint64_t i = v.link_off[u]; i < v.link_off[u + 1]; i++) {
-                const cdbg_link_t &l = v.links[i];
-                g += "L\t"; put_u64(g, u); g.push_back('\t'); g.push_back((char)l.from_sign); g.push_back('\t'); put_u64(g, l.to);
-                g.push_back('\t'); g.push_back((char)l.to_sign); g.push_back('\t'); put_u64(g, (uint64_t)(k - 1)); g += "M\n";
-            }
-        FILE *gf = fopen(o.out_gfa.c_str(), "wb");
-        if (!gf) { cdbg_destroy(ctx); die("Unable to open output file '" + o.out_gfa + "'"); }
-        fwrite(g.data(), 1, g.size(), gf);
-        fclose(gf);
-    }
+    std::vector<const cdbg_unitig_view *> views{&v};
+    write_outputs(o, views, out_path, ctx);
     const double t3 = now_s();
 
     if (o.verbose) {

@@ -415,7 +415,7 @@ struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
 
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 16; return cudaSuccess; }   // (all ordinals are the same host memory)
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     const char *s = getenv("CDBG_EMU_SMS");

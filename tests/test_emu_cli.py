@@ -83,3 +83,30 @@ def test_counted_kmers_errors_are_reported_like_the_reference(cli, tmp_path):
     assert p.returncode != 0 and "EXCEPTION:" in p.stdout and "k-mer length" in p.stdout
     p = subprocess.run([cli, "-solid-kmers-in", "bad.txt", "-kmer-size", "63"], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode != 0 and "EXCEPTION:" in p.stdout
+
+
+@pytest.mark.parametrize("gpus", [2, 3, 4])
+@pytest.mark.parametrize("name", ["reads_1_k21_a2", "circular_test1", "even_k_dense_k6", "lowcx_11_ACGT_k7_a2"])
+def test_cli_multi_gpu_mode(cli, tmp_path, name, gpus):
+    """-nb-gpus N: one context per (emulated) GPU driven by threads of the CLI process, NCCL stand-in between them; the output
+    file must be the same graph with consecutive ids, whatever the number of shards."""
+    c = CASES[name]
+    fa = tmp_path / "in.fa"
+    write_fasta(fa, c["reads"], width=50)
+    out = run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(c["k"]), "-abundance-min", str(c["abundance_min"]),
+                  "-nb-gpus", str(gpus), "-out-gfa", "g.gfa")
+    assert f"GPUs: {gpus}" in out
+    text = (tmp_path / "in.unitigs.fa").read_text()
+    ids = [int(line[1:].split()[0]) for line in text.split("\n") if line.startswith(">")]
+    assert ids == list(range(len(ids)))
+    d = parity.diff(parity.parse_unitigs_fa(text), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d == "", d
+    gfa = (tmp_path / "g.gfa").read_text().split("\n")
+    assert sum(l.startswith("S\t") for l in gfa) == len(ids)
+
+
+def test_cli_multi_gpu_mode_refuses_what_the_sharded_path_cannot_do(cli, tmp_path):
+    (tmp_path / "x.fa").write_text(">r\nACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT\n")
+    for extra in (["-kmer-size", "41"], ["-kmer-size", "21", "-all-abundance-counts"]):
+        p = subprocess.run([cli, "-in", "x.fa", "-nb-gpus", "2", *extra], cwd=tmp_path, capture_output=True, text=True)
+        assert p.returncode != 0 and "EXCEPTION:" in p.stdout
