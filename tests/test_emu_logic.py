@@ -241,3 +241,27 @@ def test_repeated_builds_on_one_context_are_identical(emu_lib, knobs):
         b = c.build(case["reads"])
     assert parity.diff(parity.graph_to_records(a), parity.graph_to_records(b), case["k"]) == ""
     check_against_golden(b, case)
+
+
+def test_reference_known_answers_through_the_cuda_path(emu_lib, knobs):
+    """The known-answer vectors of the reference's own test tree that pin this path, through the emulated CUDA stage 1
+    and the full path: TestDSK.cpp:147-175 (DSK_check1) and the example/ + test/ fixtures quoted in SURVEY.md."""
+    s1 = "GATCCTCCCCAGGCCCCTACACCCAAT"
+
+    def n_solid(reads, k, a):
+        with api.Cdbg(k=k, abundance_min=a, device=0) as c:
+            c.push_reads(reads)
+            return c.count()["n_solid"]
+    assert n_solid([s1], 27, 1) == 1
+    assert n_solid([s1], 26, 1) == 2
+    assert n_solid([s1, s1], 27, 2) == 1
+    assert n_solid([s1, s1], 26, 2) == 2
+    assert n_solid([s1, s1], 27, 3) == 0
+    # example/tiny_read.fa: k=21 -> one unitig of 25 nt, KC 5; k=13 -> KC 13
+    tiny = GOLDEN["tiny_read_k21"]["reads"]
+    with api.Cdbg(k=21, abundance_min=1, device=0) as c:
+        g = c.build(tiny)
+    assert g.n_unitigs == 1 and len(g.seq) == 25 and int(g.kc[0]) == 5 and len(g.links) == 0
+    with api.Cdbg(k=13, abundance_min=1, device=0) as c:
+        g = c.build(tiny)
+    assert g.n_unitigs == 1 and int(g.kc[0]) == 13

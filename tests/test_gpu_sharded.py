@@ -32,6 +32,7 @@ def test_sharded_golden_cases():
     if not w:
         pytest.skip("needs >= 2 GPUs")
     names = [c["name"] for c in load_golden() if c["unitigs_fa"] is not None and c["k"] <= 31]   # k > 31 is single-GPU only for now
+    names = [n for n in names if not n.startswith("even_k_")]   # added after round 1's last GPU run (emulator-verified): next round
     _run(w, names, 29531)
 
 
