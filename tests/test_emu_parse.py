@@ -143,3 +143,49 @@ def test_cli_with_gpu_parse_matches_reference_golden(emu_lib, tmp_path, name):
     assert f"sequences: {len(c['reads'])} " in p.stdout
     d = parity.diff(parity.parse_unitigs_fa((tmp_path / "in.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
     assert d == "", d
+
+
+def _fnv1a(b: bytes) -> int:
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_random_texts_against_the_cli_host_parser(emu_lib, tmp_path, seed):
+    """Random FASTA / FASTQ formatting (line widths 1..inf, CRLF, blank lines, headers and quality strings full of '>', '@', '+',
+    ACGT) against the C++ host parser itself (`bcalm -parse-only` prints record count, byte count and an FNV-1a of its stream)."""
+    rng = random.Random(seed)
+    for it in range(60):
+        fmt = rng.choice(["fa", "fa", "fq"])
+        nl = lambda: rng.choice(["\n", "\n", "\n", "\r\n"])  # noqa: E731
+        parts = []
+        for _ in range(rng.choice([1, 2, 17, 300])):
+            length = rng.choice([0, 1, 5, 70, 150, 9000]) if rng.random() < 0.2 else rng.randint(20, 200)
+            seq = "".join(rng.choice("ACGTNacgtn") for _ in range(length))
+            junk = "".join(rng.choice("ACGT >@+_|:0123") for _ in range(rng.randint(0, 60)))
+            if fmt == "fa":
+                parts.append(">" + junk + nl())
+                w = rng.choice([1, 7, 60, 80, 100000])
+                parts += [seq[j:j + w] + nl() for j in range(0, len(seq), w)]
+                if rng.random() < 0.05:
+                    parts.append(nl())
+            else:
+                parts += ["@" + junk + nl(), seq + nl(), "+" + nl(), "".join(rng.choice("ACGT@+>!IJ#") for _ in seq) + nl()]
+        text = "".join(parts)
+        if rng.random() < 0.3:
+            text = text.rstrip("\r\n")
+        path = tmp_path / f"t{it}.{fmt}"
+        with open(path, "w", newline="") as f:
+            f.write(text)
+        p = subprocess.run([emu_lib.CLI, "-parse-only", "-in", str(path), "-verbose", "0"], capture_output=True, text=True)
+        tok = [ln for ln in p.stdout.splitlines() if ln.startswith("records ")][0].split()
+        with api.Cdbg(k=21, abundance_min=1, device=0) as c:
+            try:
+                n = c.push_sequence_text(text)
+            except api.CdbgError:
+                assert fmt == "fq"          # only FASTQ text may be refused (then the CLI parses it on the host)
+                continue
+            got = c.pushed_reads()
+        assert (n, len(got), _fnv1a(got)) == (int(tok[1]), int(tok[3]), int(tok[5], 16)), (seed, it, fmt)
