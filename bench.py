@@ -361,6 +361,7 @@ def main():
                     "note": "zero_copy: the pinned host reads are not copied first; the extraction kernel's TMA loads read them in place over PCIe, so the "
                             "h2d bytes cross the bus inside K1" if s2.zero_copy else "host reads copied H2D (cudaMemcpyAsync), then the stages"},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
+            "device_ms_per_step": round(st["ms_count"] + st["ms_compact"] + st["ms_link"], 4),   # CUDA events on the library's stream (rank 0)
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(name) if world == 1 else None, "algorithmic_bytes": int(bytes_k), "kernel_ms": ms_k, "peak_source": peak_src,
                          "stage_ms": groups,
