@@ -1,0 +1,82 @@
+"""bench.py cannot run without a GPU, but the pieces that turn library statistics into the JSON contract can: checked here against
+statistics produced by the emulated library, so that a typo in bench.py is not first discovered on the GPU box."""
+from __future__ import annotations
+
+import json
+import os
+import shutil
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+
+import bench  # noqa: E402
+from bcalm_b200 import api  # noqa: E402
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ to build the CPU emulation of the library")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    path = build_emu.build()
+    saved = (api.LIB_PATH, api._lib)
+    api.LIB_PATH, api._lib = path, None
+    yield build_emu
+    api.LIB_PATH, api._lib = saved
+
+
+def _stats(env=None):
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        case = [c for c in json.load(f) if c["name"] == "reads_0_k15_a2"][0]
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        with api.Cdbg(k=case["k"], abundance_min=case["abundance_min"], device=0) as c:
+            return c.build(case["reads"]).stats
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+
+
+def test_dominant_kernel_groups_for_the_default_path(emu):
+    st = _stats()
+    name, ms, nbytes, groups, k2 = bench.dominant_kernel(st, st["n_bytes"])
+    assert name in groups and ms == max(groups.values()) or abs(ms - max(groups.values())) < 1e-3
+    assert "K1 extract (single pass)" in groups and "K2 count (fine partition + shared-memory tables)" in groups
+    assert set(k2) == {"k2p_hist", "k2p_scatter", "k2c_count"}
+    I, S = st["n_instances"], st["n_solid"]
+    assert k2["k2c_count"][1] == I * 8 + S * 12 and k2["k2p_scatter"][1] == 2 * I * 8
+    # the committed ncu traffic figure is found under the group's name
+    assert bench.load_traffic("K2 count (fine partition + shared-memory tables)") > 0
+
+
+def test_dominant_kernel_groups_for_the_round_start_path(emu):
+    st = _stats({"CDBG_K1": "twopass", "CDBG_K2": "l2", "CDBG_K5": "l2"})
+    name, ms, nbytes, groups, k2 = bench.dominant_kernel(st, st["n_bytes"])
+    assert "K1 extract (hist pass)" in groups and "K2 count (insert+emit, all bins)" in groups and k2 is None
+    assert bench.load_traffic("K2 count (insert+emit, all bins)") > 0
+
+
+def test_file_to_file_sample_runs_the_cli(emu, monkeypatch, tmp_path):
+    g, n_reads = bench.workload(0.001)
+    with api.Cdbg(k=bench.K, abundance_min=bench.AMIN, device=0) as c:
+        ptr, n = c.synth_reads(g, bench.READ_LEN, n_reads, bench.ERR_PPM, bench.SEED)
+        reads = c.copy_to_host(ptr, n)
+    # point the helper at the emulated CLI
+    fake_root = tmp_path / "root"
+    (fake_root / "bcalm_b200").mkdir(parents=True)
+    os.symlink(emu.CLI, fake_root / "bcalm_b200" / "bcalm")
+    monkeypatch.setattr(bench, "ROOT", str(fake_root))
+    out = bench.file_to_file_sample(reads, n_reads * bench.READ_LEN)
+    assert out["value"] > 0 and out["fasta_bytes"] == n_reads * (bench.READ_LEN + 4) and out["cli_split"].startswith("wall s")
+
+
+def test_workload_is_the_configuration_baseline_names():
+    g, n_reads = bench.workload(1.0)
+    assert (g, n_reads, bench.READ_LEN, bench.K, bench.AMIN) == (5_000_000, 1_500_000, 100, 31, 2)
