@@ -336,12 +336,14 @@ K2SmemPlan k2_smem_plan(uint64_t n_bytes) {
 
 // K2 with shared-memory tables: fine histogram -> scan -> fine scatter -> one CTA per fine bin (k2_smem.cuh).  d_kmers holds the
 // I instances in P coarse bins (h_cnt, d_bin_off).  Leaves ctx->d_solid_kmers / d_solid_counts / S like the L2 path.
+// `h_group` (optional): group of every coarse bin (see K2PParams::group), `n_groups` of them; fine bins are then per group.
 int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_kmers, uint64_t I, uint32_t P, const std::vector<uint64_t> &h_cnt,
-                        const std::vector<uint64_t> &h_off) {
+                        const std::vector<uint64_t> &h_off, const std::vector<uint32_t> *h_group = nullptr, uint32_t n_groups = 0) {
     int rc;
     const double per_fine = pl.fill * pl.slots;
-    const uint32_t F = (uint32_t)std::min<uint64_t>(K2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)I / (per_fine * P))));
-    const uint64_t NF = (uint64_t)P * F;
+    const uint32_t G = h_group ? n_groups : P;
+    const uint32_t F = (uint32_t)std::min<uint64_t>(K2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)I / (per_fine * G))));
+    const uint64_t NF = (uint64_t)G * F;
     std::vector<uint32_t> h_tile_first(P + 1);
     uint64_t tiles = 0;
     for (uint32_t b = 0; b < P; b++) { h_tile_first[b] = (uint32_t)tiles; tiles += (h_cnt[b] + K2P_TILE - 1) / K2P_TILE; }
@@ -355,6 +357,11 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     if ((rc = dalloc(ctx, &d_bin_range, 2 * (size_t)P))) return rc;
     CK(cudaMemcpyAsync(d_bin_range, h_range.data(), 2 * (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = dalloc(ctx, &d_tile_first, P + 1))) return rc;
+    uint32_t *d_group = nullptr;
+    if (h_group) {
+        if ((rc = dalloc(ctx, &d_group, P))) return rc;
+        CK(cudaMemcpyAsync(d_group, h_group->data(), (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
     if ((rc = dalloc(ctx, &d_fine_cnt, NF + 1))) return rc;
     if ((rc = dalloc(ctx, &d_fine_cursor, NF + 1))) return rc;
     if ((rc = dalloc(ctx, &d_fine_off, NF + 2))) return rc;
@@ -365,7 +372,7 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
 
     tstart(ctx, T_K2);
     K2PParams pp{};
-    pp.kmers = d_kmers; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first; pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    pp.kmers = d_kmers; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first; pp.group = d_group; pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
     pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out = d_kmers2;
     if (tiles) {
         tstart(ctx, T_K2H);
@@ -427,7 +434,7 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     tstop(ctx, T_K2);
     ctx->st.n_solid = ctx->S;
     if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu): shard over more GPUs", (unsigned long long)ctx->S);
-    dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off); dfree(ctx, d_kmers2);
+    dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_group); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off); dfree(ctx, d_kmers2);
     return CDBG_OK;
 }
 

@@ -29,6 +29,8 @@ struct K2PParams {
     const uint64_t *kmers;          // K1 output, coarse bin b = [bin_beg[b], bin_end[b]) (regions may have gaps)
     const uint64_t *bin_beg, *bin_end;   // [P1] each
     const uint32_t *tile_first;     // [P1 + 1] first tile of each coarse bin (tiles never span coarse bins)
+    const uint32_t *group;          // [P1] or null: fine bins are shared by all coarse "bins" of one group (sharded mode: a bin received
+                                    //      from several GPUs is one run per source; the runs of a bin form a group).  null: group = bin
     uint32_t P1, F;
     uint32_t n_tiles;
     uint32_t *fine_cnt;             // [P1 * F]     hist: out
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(K2P_THREADS) k2p_hist(K2PParams p) {
         // the thread that flushes counter i is the one that zeroes it for the next tile: no barrier needed in between
         for (uint32_t i = t; i < p.F; i += K2P_THREADS) {
             const uint32_t c = s_cnt[i];
-            if (c) atomicAdd(&p.fine_cnt[(size_t)b * p.F + i], c);
+            if (c) atomicAdd(&p.fine_cnt[(size_t)(p.group ? p.group[b] : b) * p.F + i], c);
         }
     }
 }
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
                 const uint32_t cn = s_cnt[b0 + j];
                 s_off[b0 + j] = run;
                 if (cn) {
-                    const size_t g = (size_t)b * p.F + b0 + j;
+                    const size_t g = (size_t)(p.group ? p.group[b] : b) * p.F + b0 + j;
                     s_gbase[b0 + j] = p.fine_off[g] + atomicAdd(&p.fine_cursor[g], cn);
                 }
                 run += cn;

@@ -174,6 +174,31 @@ int shard_stage_count(cdbg_ctx *ctx) {
     TRACE("  free send buffer");
 
     TRACE("X1 kmer exchange");
+    // K2 with shared-memory tables (k2_smem.cuh), opt-in for the sharded path (CDBG_SHARD_K2=smem; its kernels are the single-GPU
+    // default, this wiring has only run under the CPU emulator): every (local bin, source) run is a coarse bin, the runs of one local
+    // bin share their fine bins
+    if (getenv("CDBG_SHARD_K2") && strcmp(getenv("CDBG_SHARD_K2"), "smem") == 0) {
+        K2SmemPlan pl = k2_smem_plan(I_in * 5 / 4);
+        pl.enabled = true;
+        const uint32_t R = P_local * (uint32_t)W;
+        std::vector<uint64_t> r_cnt(R), r_off(R + 1, 0);
+        std::vector<uint32_t> r_group(R);
+        uint64_t worst = 0;
+        for (uint32_t b = 0; b < P_local; b++)
+            for (int s = 0; s < W; s++) {
+                const uint32_t r = b * (uint32_t)W + (uint32_t)s;
+                r_cnt[r] = run_len[(size_t)b * W + s]; r_off[r] = run_off[(size_t)b * W + s]; r_group[r] = b;
+                worst = std::max(worst, r_cnt[r]);
+            }
+        if (worst < (1ULL << 32)) {
+            if ((rc = stage_count_k2_smem(ctx, pl, d_kmers, I_in, R, r_cnt, r_off, &r_group, P_local))) return rc;
+            dfree(ctx, d_kmers);
+            dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+            tstop(ctx, T_COUNT);
+            ctx->stage = ST_COUNTED;
+            return CDBG_OK;
+        }
+    }
     // K2 per local bin; a bin is one run per source rank
     uint64_t max_bin = 0;
     std::vector<uint64_t> bin_tot(P_local, 0);
