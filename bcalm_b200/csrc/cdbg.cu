@@ -372,7 +372,7 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
 
     tstart(ctx, T_K2);
     K2PParams pp{};
-    pp.kmers = d_kmers; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first; pp.group = d_group; pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    pp.kmers = d_kmers; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first; pp.group = d_group; pp.P1 = P; pp.F = F; pp.fine_shift = h_group ? 13u : 32u; pp.n_tiles = (uint32_t)tiles;
     pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out = d_kmers2;
     if (tiles) {
         tstart(ctx, T_K2H);

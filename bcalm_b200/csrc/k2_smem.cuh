@@ -22,8 +22,12 @@ constexpr int K2P_TILE = K2P_THREADS * K2P_PER_THREAD;    // 8192 k-mers per til
 constexpr int K2P_MAX_F = 1024;                            // fine bins per coarse bin (10 bits in the packed rank word)
 #define K2P_NOKEY 0xFFFFFFFFu
 
-// fine bin inside a coarse bin: the HIGH half of mix64 (K1's coarse bin comes from bin_hash32, the table slot from the LOW half)
-__device__ __forceinline__ uint32_t k2p_fine(uint64_t h, uint32_t F) { return (uint32_t)(((h >> 32) * (uint64_t)F) >> 32); }
+// fine bin inside a coarse bin: 32 bits of mix64 starting at `shift`.  Single GPU: shift 32, the HIGH half (K1's coarse bin comes
+// from bin_hash32, the table slot from the LOW half).  Sharded: the local bin already comes from the high half (its top bits), so
+// the fine bin uses bits 13..44 -- its leading bits 44..35 are clear of the local bin's (63..) and of the slot's (12..0).
+__device__ __forceinline__ uint32_t k2p_fine(uint64_t h, uint32_t F, uint32_t shift) {
+    return (uint32_t)((((h >> shift) & 0xFFFFFFFFULL) * (uint64_t)F) >> 32);
+}
 
 struct K2PParams {
     const uint64_t *kmers;          // K1 output, coarse bin b = [bin_beg[b], bin_end[b]) (regions may have gaps)
@@ -32,6 +36,7 @@ struct K2PParams {
     const uint32_t *group;          // [P1] or null: fine bins are shared by all coarse "bins" of one group (sharded mode: a bin received
                                     //      from several GPUs is one run per source; the runs of a bin form a group).  null: group = bin
     uint32_t P1, F;
+    uint32_t fine_shift;            // see k2p_fine
     uint32_t n_tiles;
     uint32_t *fine_cnt;             // [P1 * F]     hist: out
     const uint64_t *fine_off;       // [P1 * F + 1] scatter: exclusive offsets into `out`
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(K2P_THREADS) k2p_hist(K2PParams p) {
         }
 #pragma unroll
         for (int j = 0; j < K2P_PER_THREAD; j++)
-            if (key[j] != EMPTY_KEY) atomicAdd(&s_cnt[k2p_fine(mix64(key[j]), p.F)], 1u);
+            if (key[j] != EMPTY_KEY) atomicAdd(&s_cnt[k2p_fine(mix64(key[j]), p.F, p.fine_shift)], 1u);
         __syncthreads();
         // the thread that flushes counter i is the one that zeroes it for the next tile: no barrier needed in between
         for (uint32_t i = t; i < p.F; i += K2P_THREADS) {
@@ -114,11 +119,11 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
         for (int j = 0; j < K2P_PER_THREAD; j++) {
             if (!MATCH) {
                 if (key[j] == EMPTY_KEY) { fr[j] = K2P_NOKEY; continue; }
-                const uint32_t f = k2p_fine(mix64(key[j]), p.F);
+                const uint32_t f = k2p_fine(mix64(key[j]), p.F, p.fine_shift);
                 fr[j] = (atomicAdd(&s_cnt[f], 1u) << 10) | f;
             } else {   // (every lane takes part: the tile's ragged end is warp-divergent otherwise)
                 const bool ok = key[j] != EMPTY_KEY;
-                const uint32_t f = ok ? k2p_fine(mix64(key[j]), p.F) : K2P_NOKEY;
+                const uint32_t f = ok ? k2p_fine(mix64(key[j]), p.F, p.fine_shift) : K2P_NOKEY;
                 const unsigned m = __match_any_sync(0xFFFFFFFFu, f);
                 const int leader = __ffs(m) - 1;
                 uint32_t base = 0;
