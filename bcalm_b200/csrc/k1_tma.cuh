@@ -562,3 +562,138 @@ __global__ void __launch_bounds__(K1H_THREADS, 2) k1t_single512(K1XParams p) {
         __syncthreads();
     }
 }
+
+// ------------------------------------------------------------------------------------------------ sharded histogram pass, rolling
+//
+// k1t_shard_hist: pass 0 of the SHARDED K1 in the style of k1t_extract<0> (TMA-fed tiles of 8192 positions, 32 consecutive
+// positions per thread, rolling k-mers) instead of k1s_extract<0>'s lane-consecutive, non-rolling 2048-position tiles.  The bin of
+// a k-mer is destination-major: owner(minimizer_k) * P_local + local hash bin, like k1s_extract, so that pass 1 is simply
+// k1t_extract<1> over P = world * P_local bins.  Minimizer = smallest mmer_rank over the w = k-m+1 canonical m-mers inside the
+// k-mer (the same function as k1s_extract / min_rank_of): the ranks of all m-mers of the tile (+ halo) are computed once, rolling,
+// into shared memory, a van Herk / Gil-Werman pass turns them into block prefix / suffix minima, and every k-mer then needs two
+// shared-memory reads.  Rank arrays are padded by one word per 32 (a thread owns 32 consecutive positions).
+// Opt-in (CDBG_SHARD_K1=roll): written after the round's last GPU run, verified under the CPU emulator only.
+constexpr int K1TS_RAW = K1_TILE + 64;                  // m-mers starting in the 32-position halo need 32 more bases
+constexpr int K1TS_RANKS = K1_TILE + 32;                // ranks incl. halo (w - 1 <= 30)
+__device__ __forceinline__ uint32_t k1ts_pad(uint32_t q) { return q + (q >> 5); }
+constexpr int K1TS_RANK_WORDS = K1TS_RANKS + K1TS_RANKS / 32 + 2;
+
+struct K1TSParams {
+    const uint8_t *bytes; uint64_t n_bytes; uint64_t n_tiles;
+    int k, m; uint32_t world, P_local;
+    unsigned long long *bin_count;
+    uint16_t *pos_bin;         // [n_tiles * K1_TILE]
+};
+
+__global__ void __launch_bounds__(K1_THREADS) k1t_shard_hist(K1TSParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t P = p.world * p.P_local;
+    uint8_t *s_raw = smem_raw;                                                              // [2][K1TS_RAW]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * K1TS_RAW);                // [2]
+    uint64_t *s_pk = s_bar + 2;                                                             // [THREADS + 2] (2 halo words)
+    uint32_t *s_vm = reinterpret_cast<uint32_t *>(s_pk + K1_THREADS + 2);                   // [THREADS + 2]
+    uint32_t *s_R = s_vm + K1_THREADS + 2;                                                  // [K1TS_RANK_WORDS] ranks -> block prefix minima
+    uint32_t *s_S = s_R + K1TS_RANK_WORDS;                                                  // [K1TS_RANK_WORDS] block suffix minima
+    uint32_t *s_cnt = s_S + K1TS_RANK_WORDS;                                                // [P]
+
+    const int t = threadIdx.x, k = p.k, m = p.m, w = k - m + 1;
+    const uint64_t first = blockIdx.x, stride = gridDim.x;
+
+    auto issue = [&](uint64_t tile, int stage) {      // thread 0 only
+        const uint64_t start = tile * (uint64_t)K1_TILE;
+        if (start + K1TS_RAW <= p.n_bytes) {
+            mbar_expect_tx(&s_bar[stage], K1TS_RAW);
+            tma_load_1d(s_raw + stage * K1TS_RAW, p.bytes + start, K1TS_RAW, &s_bar[stage]);
+        } else {
+            for (int i = 0; i < K1TS_RAW; i++) { uint64_t q = start + i; s_raw[stage * K1TS_RAW + i] = q < p.n_bytes ? p.bytes[q] : (uint8_t)'\n'; }
+            mbar_expect_tx(&s_bar[stage], 0);
+        }
+    };
+
+    if (t == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    for (uint32_t i = t; i < P; i += K1_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    if (t == 0 && first < p.n_tiles) issue(first, 0);
+
+    uint32_t it = 0;
+    for (uint64_t tile = first; tile < p.n_tiles; tile += stride, it++) {
+        const int stage = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        const uint64_t tile_start = tile * (uint64_t)K1_TILE;
+        if (t == 0 && tile + stride < p.n_tiles) issue(tile + stride, stage ^ 1);
+        mbar_wait(&s_bar[stage], parity);
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(s_raw + stage * K1TS_RAW + t * 32);
+            uint64_t pk; uint32_t vm;
+            pack32(src[0], src[1], pk, vm);
+            s_pk[t] = pk; s_vm[t] = vm;
+            if (t < 2) {                              // the two halo words
+                const uint4 *h = reinterpret_cast<const uint4 *>(s_raw + stage * K1TS_RAW + K1_TILE + t * 32);
+                pack32(h[0], h[1], pk, vm);
+                s_pk[K1_THREADS + t] = pk; s_vm[K1_THREADS + t] = vm;
+            }
+        }
+        __syncthreads();
+        // ---- ranks of the canonical m-mers starting at every position (rolling; thread 0 also does the 32 halo positions)
+        for (int seg = t; seg < K1_THREADS + 1; seg += K1_THREADS) {
+            uint64_t hi = s_pk[seg], lo = s_pk[seg + 1];
+            uint64_t fm = hi >> (64 - 2 * m);
+            uint64_t rm = revcomp64(fm, m);
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fm = hi >> (64 - 2 * m);
+                    rm = (rm >> 2) | (((fm & 3) ^ 2) << (2 * (m - 1)));
+                }
+                s_R[k1ts_pad((uint32_t)(seg * 32 + i))] = mmer_rank((uint32_t)(fm < rm ? fm : rm));
+            }
+        }
+        __syncthreads();
+        // ---- van Herk / Gil-Werman: per block of w ranks, suffix minima into s_S, prefix minima in place
+        for (int b = t; b * w < K1TS_RANKS; b += K1_THREADS) {
+            const int lo_q = b * w, hi_q = min(lo_q + w, K1TS_RANKS);
+            uint32_t run = 0xFFFFFFFFu;
+            for (int q = hi_q - 1; q >= lo_q; q--) { run = min(run, s_R[k1ts_pad((uint32_t)q)]); s_S[k1ts_pad((uint32_t)q)] = run; }
+            run = 0xFFFFFFFFu;
+            for (int q = lo_q; q < hi_q; q++) { run = min(run, s_R[k1ts_pad((uint32_t)q)]); s_R[k1ts_pad((uint32_t)q)] = run; }
+        }
+        __syncthreads();
+        // ---- rolling k-mers, destination-major bin, CTA-private histogram, per-position bins written out
+        {
+            uint64_t hi = s_pk[t], lo = s_pk[t + 1];
+            uint64_t fwd = hi >> (64 - 2 * k);
+            uint64_t rc = revcomp64(fwd, k);
+            const uint64_t V = ((uint64_t)s_vm[t] << 32) | s_vm[t + 1];
+            const uint32_t valid32 = (uint32_t)(kmer_valid_mask(V, k) >> 32);
+            uint32_t packed[K1_PER_THREAD / 2];
+#pragma unroll
+            for (int i = 0; i < K1_PER_THREAD; i++) {
+                if (i > 0) {
+                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                    fwd = hi >> (64 - 2 * k);
+                    rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                }
+                const uint64_t c = fwd < rc ? fwd : rc;
+                const uint32_t q = (uint32_t)(t * 32 + i);
+                const uint32_t mr = min(s_S[k1ts_pad(q)], s_R[k1ts_pad(q + (uint32_t)w - 1)]);
+                uint32_t bin = owner_of_rank(mr, p.world) * p.P_local + hash32_to_bin(bin_hash32(c), p.P_local);
+                const bool ok = (valid32 >> (31 - i)) & 1;
+                if (ok) atomicAdd(&s_cnt[bin], 1u); else bin = K1_NOBIN;
+                if (i & 1) packed[i >> 1] |= bin << 16; else packed[i >> 1] = bin;
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(p.pos_bin + tile_start + (uint64_t)t * K1_PER_THREAD);
+#pragma unroll
+            for (int v = 0; v < K1_PER_THREAD / 8; v++) dst[v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = t; i < P; i += K1_THREADS) { uint32_t c = s_cnt[i]; if (c) atomicAdd(&p.bin_count[i], (unsigned long long)c); }
+}
+
+static inline size_t k1ts_smem_bytes(uint32_t P) {
+    return 2 * (size_t)K1TS_RAW + 16 + (size_t)(K1_THREADS + 2) * 8 + (size_t)(K1_THREADS + 2) * 4 + 2 * (size_t)K1TS_RANK_WORDS * 4 + (size_t)P * 4 + 128;
+}

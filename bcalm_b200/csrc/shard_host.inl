@@ -120,7 +120,11 @@ int shard_stage_count(cdbg_ctx *ctx) {
     uint32_t P_local = (uint32_t)std::min<uint64_t>(K1_MAX_BINS / W, std::max<uint64_t>(1, (total_bytes / W * 4 / 5 + 4999999) / 5000000));
     const uint32_t P = P_local * W;
     ctx->st.n_count_bins = P_local;
-    uint64_t n_tiles = (n + K1S_TILE - 1) / K1S_TILE;
+    // K1 variant of the sharded path (CDBG_SHARD_K1): default = k1s_extract (lane-consecutive 2048-position tiles, non-rolling);
+    // "roll" = k1t_shard_hist + k1t_extract<1> (TMA-fed 8192-position tiles, rolling k-mers; emulator-verified only so far)
+    const bool k1_roll = getenv("CDBG_SHARD_K1") && strcmp(getenv("CDBG_SHARD_K1"), "roll") == 0;
+    const uint64_t tile_sz = k1_roll ? (uint64_t)K1_TILE : (uint64_t)K1S_TILE;
+    uint64_t n_tiles = (n + tile_sz - 1) / tile_sz;
 
     unsigned long long *d_bin_count = nullptr, *d_bin_cursor = nullptr; uint64_t *d_bin_off = nullptr;
     if ((rc = dalloc(ctx, &d_bin_count, P))) return rc;
@@ -129,17 +133,29 @@ int shard_stage_count(cdbg_ctx *ctx) {
     CK(cudaMemsetAsync(d_bin_count, 0, P * 8, ctx->stream));
     CK(cudaMemsetAsync(d_bin_cursor, 0, P * 8, ctx->stream));
     uint16_t *d_pos_bin = nullptr;
-    if ((rc = dalloc(ctx, &d_pos_bin, n_tiles * K1S_TILE + 2))) return rc;
+    if ((rc = dalloc(ctx, &d_pos_bin, n_tiles * tile_sz + 8))) return rc;
     K1SParams kp{};
     kp.pos_bin = d_pos_bin;
     kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = k; kp.m = ctx->m; kp.world = W; kp.P_local = P_local;
     kp.bin_count = d_bin_count; kp.bin_off = d_bin_off; kp.bin_cursor = d_bin_cursor; kp.out_kmers = nullptr;
+    K1TSParams ks{};
+    ks.bytes = ctx->d_bytes; ks.n_bytes = n; ks.n_tiles = n_tiles; ks.k = k; ks.m = ctx->m; ks.world = W; ks.P_local = P_local;
+    ks.bin_count = d_bin_count; ks.pos_bin = d_pos_bin;
+    K1TParams kt{};
+    kt.bytes = ctx->d_bytes; kt.n_bytes = n; kt.n_tiles = n_tiles; kt.k = k; kt.P = P;
+    kt.bin_count = d_bin_count; kt.bin_off = d_bin_off; kt.bin_cursor = d_bin_cursor; kt.out_kmers = nullptr; kt.pos_bin = d_pos_bin;
     std::vector<uint64_t> h_cnt(P, 0), h_off(P + 1, 0);
-    CK(cudaFuncSetAttribute(k1s_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(0, P)));
-    CK(cudaFuncSetAttribute(k1s_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(1, P)));
+    if (k1_roll) {
+        CK(cudaFuncSetAttribute(k1t_shard_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1ts_smem_bytes(P)));
+        CK(cudaFuncSetAttribute(k1t_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1t_smem_bytes(1, P)));
+    } else {
+        CK(cudaFuncSetAttribute(k1s_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(0, P)));
+        CK(cudaFuncSetAttribute(k1s_extract<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1s_smem_bytes(1, P)));
+    }
     if (n_tiles) {
         tstart(ctx, T_K1H);
-        LAUNCH(k1s_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 4), K1S_THREADS, k1s_smem_bytes(0, P), kp);
+        if (k1_roll) LAUNCH(k1t_shard_hist, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1ts_smem_bytes(P), ks);
+        else LAUNCH(k1s_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 4), K1S_THREADS, k1s_smem_bytes(0, P), kp);
         tstop(ctx, T_K1H);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -156,9 +172,10 @@ int shard_stage_count(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &d_send, I_out + 1))) return rc;
     if (I_out) {
         CK(cudaMemcpyAsync(d_bin_off, h_off.data(), (P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        kp.out_kmers = d_send;
+        kp.out_kmers = d_send; kt.out_kmers = d_send;
         tstart(ctx, T_K1S);
-        LAUNCH(k1s_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1S_THREADS, k1s_smem_bytes(1, P), kp);
+        if (k1_roll) LAUNCH(k1t_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1t_smem_bytes(1, P), kt);
+        else LAUNCH(k1s_extract<1>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1S_THREADS, k1s_smem_bytes(1, P), kp);
         tstop(ctx, T_K1S);
     }
     TRACE("k1 scatter + allgather counts");

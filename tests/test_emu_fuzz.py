@@ -27,7 +27,8 @@ CONFIGS = [{}, {"CDBG_K1": "twopass"}, {"CDBG_K1": "classic"}, {"CDBG_K2": "l2"}
            {"CDBG_K6": "list"}, {"CDBG_RANK": "match", "CDBG_K2S_P1": "6"}, {"CDBG_EMU_PINNED": "1", "CDBG_ZEROCOPY_MIN": "0"},
            {"CDBG_K2S_P1": "7", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"CDBG_K5S_P1": "5", "CDBG_K5S_FILL": "0.05"},
            {"CDBG_K2S_FILL": "8", "CDBG_K2S_SLOTS": "4096", "CDBG_K5S_FILL": "8"}, {"shards": 2}, {"shards": 3},
-           {"shards": 3, "CDBG_SHARD_K2": "smem", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"shards": 2, "CDBG_SHARD_K2": "smem"}]
+           {"shards": 3, "CDBG_SHARD_K2": "smem", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"shards": 2, "CDBG_SHARD_K2": "smem"},
+           {"shards": 2, "CDBG_SHARD_K1": "roll"}, {"shards": 4, "CDBG_SHARD_K1": "roll", "CDBG_SHARD_K2": "smem"}]
 KNOBS = sorted({k for c in CONFIGS for k in c if k.startswith("CDBG_")})
 COMP = str.maketrans("ACGTacgt", "TGCAtgca")
 
