@@ -19,10 +19,10 @@ def _world():
     return 8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 0
 
 
-def _run(world, names, port):
+def _run(world, names, port, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "shard_worker.py"), *names]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=dict(os.environ, **(env or {})))
     tail = "\n".join(l for l in (p.stdout + p.stderr).splitlines() if "shard x" in l or "SHARD_RESULT" in l or "rror" in l)
     assert p.returncode == 0 and "SHARD_RESULT PASS" in p.stdout, tail[-4000:]
 
@@ -41,3 +41,23 @@ def test_sharded_c2_like():
     if not w:
         pytest.skip("needs >= 2 GPUs")
     _run(w, ["c2:0.2"], 29532)
+
+
+# Written after round 1's last GPU run and verified under the CPU emulator only (tests/test_emu_*.py): non-gating until they have
+# passed on real GPUs (XPASS = fine).  Each runs in its own torchrun job, so a failure cannot disturb the tests above.
+@pytest.mark.xfail(strict=False, reason="not yet run on GPUs when written; XPASS means it is fine")
+@pytest.mark.parametrize("label,env", [("k1_roll", {"CDBG_SHARD_K1": "roll"}), ("k2_smem", {"CDBG_SHARD_K2": "smem"}),
+                                       ("k1_roll_k2_smem", {"CDBG_SHARD_K1": "roll", "CDBG_SHARD_K2": "smem"})])
+def test_sharded_opt_in_variants(label, env):
+    w = _world()
+    if not w:
+        pytest.skip("needs >= 2 GPUs")
+    _run(w, ["reads_3_k31_a2", "circular_test1", "lowcx_8_ACGT_k8_a1", "pow2_cycle_L256_k21", "c2:0.2"], 29540 + len(label), env)
+
+
+@pytest.mark.xfail(strict=False, reason="even-k golden cases added after round 1's last GPU run; XPASS means fine")
+def test_sharded_even_k_cases():
+    w = _world()
+    if not w:
+        pytest.skip("needs >= 2 GPUs")
+    _run(w, [c["name"] for c in load_golden() if c["name"].startswith("even_k_")], 29539)
