@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE (manual): build the emulated library with ThreadSanitizer and run golden cases on the truly concurrent
+engine (one OS thread per CUDA thread), then list the distinct race locations.
+
+    python tests/emu/run_tsan.py [case ...]            # environment knobs (CDBG_K2C=flat ...) are passed through
+
+Expected, by design (each is a documented lock-free idiom of the kernels, fine under the CUDA memory model used):
+  * ld_volatile_u64 on a table key vs. atomicCAS of the same key  (k2_insert, k2c_count, k5_insert, k5c_join, wide/shard tables)
+  * plain stores of 1 to an overflow / abandon flag vs. volatile reads of it          (s_over, *overflow)
+  * k6_jump / k6_cycle_min: in-place asynchronous pointer jumping on 64-bit words
+Anything else -- in particular two plain accesses to shared memory without a barrier in between -- is a bug.  End of round 1: only
+the expected locations are reported for the default path, the L2-table / two-pass variants, the opt-in variants, forced splits and
+zero-copy input (cases reads_0_k15_a2, lowcx_8_ACGT_k8_a1, circular_test1, even_k_dense_k4)."""
+import glob
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import build_emu  # noqa: E402
+
+
+def main():
+    cases = sys.argv[1:] or ["reads_0_k15_a2", "lowcx_8_ACGT_k8_a1", "circular_test1", "even_k_dense_k4"]
+    build_emu.build()
+    work = tempfile.mkdtemp(prefix="cdbg_tsan_")
+    src = os.path.join(work, "a", "b")
+    os.makedirs(src)
+    os.makedirs(os.path.join(work, "include"))
+    for f in os.listdir(build_emu.OUT):
+        if f.endswith((".cu", ".cuh", ".inl", ".h")):
+            with open(os.path.join(build_emu.OUT, f)) as fi, open(os.path.join(src, f), "w") as fo:
+                fo.write(fi.read())
+    with open(os.path.join(ROOT, "include", "cdbg.h")) as fi, open(os.path.join(work, "include", "cdbg.h"), "w") as fo:
+        fo.write(fi.read())
+    lib = os.path.join(work, "libcdbg_tsan.so")
+    subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-fno-strict-aliasing", "-w",
+                           "-fsanitize=thread", "-I", HERE, "-o", lib, os.path.join(src, "cdbg.cu"), "-ldl"])
+    tsan = subprocess.check_output(["gcc", "-print-file-name=libtsan.so"], text=True).strip()
+    code = (
+        "import sys, json\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from bcalm_b200 import api, parity\n"
+        f"api.LIB_PATH = {lib!r}\n"
+        f"cases = {{c['name']: c for c in json.load(open({os.path.join(ROOT, 'tests', 'golden', 'golden.json')!r}))}}\n"
+        "for n in sys.argv[1:]:\n"
+        "    c = cases[n]\n"
+        "    with api.Cdbg(k=c['k'], abundance_min=c['abundance_min']) as x:\n"
+        "        g = x.build(c['reads'])\n"
+        "    print(n, parity.diff(parity.graph_to_records(g), parity.parse_unitigs_fa(c['unitigs_fa']), c['k']) or 'OK', flush=True)\n")
+    env = dict(os.environ, CDBG_EMU_ENGINE="threads", LD_PRELOAD=tsan,
+               TSAN_OPTIONS=f"halt_on_error=0 log_path={os.path.join(work, 'report')} history_size=3")
+    subprocess.run([sys.executable, "-c", code, *cases], env=env)
+    locs = {}
+    for rep in glob.glob(os.path.join(work, "report.*")):
+        text = open(rep).read()
+        for block in text.split("WARNING: ThreadSanitizer")[1:]:
+            frames = re.findall(r"#\d+ (.+?) \S*a/b/(\S+)", block)
+            if frames:
+                fn, where = frames[0] if "ld_volatile" not in frames[0][0] or len(frames) < 2 else frames[1]
+                key = f"{where}  {fn.split('(')[0]}"
+                locs[key] = locs.get(key, 0) + 1
+    print("distinct race locations:")
+    for k, v in sorted(locs.items()):
+        print(f"  {v:3d}  {k}")
+
+
+if __name__ == "__main__":
+    main()
