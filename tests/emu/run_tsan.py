@@ -7,6 +7,7 @@ Expected, by design (each is a documented lock-free idiom of the kernels, fine u
   * ld_volatile_u64 on a table key vs. atomicCAS of the same key  (k2_insert, k2c_count, k5_insert, k5c_join, wide/shard tables)
   * plain stores of 1 to an overflow / abandon flag vs. volatile reads of it          (s_over, *overflow)
   * k6_jump / k6_cycle_min: in-place asynchronous pointer jumping on 64-bit words
+  * glue_assemble (sharded): neighbouring pieces of a unitig overlap by k-1 characters and both write those (identical) bytes
 Anything else -- in particular two plain accesses to shared memory without a barrier in between -- is a bug.  End of round 1: only
 the expected locations are reported for the default path, the L2-table / two-pass variants, the opt-in variants, forced splits and
 zero-copy input (cases reads_0_k15_a2, lowcx_8_ACGT_k8_a1, circular_test1, even_k_dense_k4)."""
