@@ -1044,7 +1044,7 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     cdbg_ctx *ctx = new cdbg_ctx();
     ctx->prm = *params;
     auto bail = [&](int code) { *out = ctx; return code; };   // caller can still read cdbg_last_error, then destroy
-    // span dispatch of the reference (Integer.hpp:77-85): this build instantiates one 64-bit word, k < 32
+    // span dispatch of the reference (Integer.hpp:77-85: spans 32/64/96/128): one 64-bit word for k <= 31, 2..4 words up to k = 127
     if (params->kmer_size < 4 || params->kmer_size > 127)
         return bail(ctx->fail(CDBG_ERR_PARAM, "unhandled kmer size %d (this build supports 4 <= k <= 127)", params->kmer_size));
     if (params->kmer_size > 31 && params->world_size > 1)
