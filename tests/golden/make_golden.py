@@ -143,6 +143,13 @@ def cases():
         out.append(dict(name=name, k=k, abundance_min=1, minimizer_size=m, reads=[g[: glen // 2 + k], rc(g[glen // 2:])]))
     reads = synth_reads(rng4, 6000, 90, 25, err=0.01)
     out.append(dict(name="even_k_reads_k20_a2", k=20, abundance_min=2, minimizer_size=10, reads=reads))
+    # the literal inputs of the reference's own GraphUnitigs unit tests (TestDebruijnUnitigs.cpp:404-735), with their flags
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_reference_unit_vectors import VECTORS
+    for name, reads, k, _ in VECTORS:
+        out.append(dict(name=f"ut_{name}_k{k}", k=k, abundance_min=1, minimizer_size=3 if k == 5 or name == "test12" else 10, reads=list(reads)))
+    out.append(dict(name="ut_test12_normal_min_k21", k=21, abundance_min=1, minimizer_size=10, reads=list(VECTORS[5][1])))
+    out.append(dict(name="ut_test4_k27", k=27, abundance_min=1, minimizer_size=10, reads=["ACCATGTATAATTATAAGTAGGTACCT"]))
     return out
 
 

@@ -8,10 +8,11 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-# The even_k_* cases were added together with the join fix they exercise, after the round's GPU budget was spent: the fix is
-# verified under the CPU emulator only, so for now these cases report (xfail/xpass) instead of gating `pytest -x`.
+# The even_k_* cases were added together with the join fix they exercise, and the ut_* cases (inputs of the reference's unit tests),
+# after the round's GPU budget was spent: verified under the CPU emulator only, so for now these cases report (xfail/xpass) instead
+# of gating `pytest -x`.
 _NEW = pytest.mark.xfail(strict=False, reason="added after the last GPU run of round 1; XPASS means fine")
-CASES = [pytest.param(c, marks=_NEW) if c["name"].startswith("even_k_") else c for c in load_golden()]
+CASES = [pytest.param(c, marks=_NEW) if c["name"].startswith(("even_k_", "ut_")) else c for c in load_golden()]
 
 
 def _name(c):

@@ -32,7 +32,7 @@ def test_sharded_golden_cases():
     if not w:
         pytest.skip("needs >= 2 GPUs")
     names = [c["name"] for c in load_golden() if c["unitigs_fa"] is not None and c["k"] <= 31]   # k > 31 is single-GPU only for now
-    names = [n for n in names if not n.startswith("even_k_")]   # added after round 1's last GPU run (emulator-verified): next round
+    names = [n for n in names if not n.startswith(("even_k_", "ut_"))]   # added after round 1's last GPU run (emulator-verified): next round
     _run(w, names, 29531)
 
 
@@ -60,4 +60,4 @@ def test_sharded_even_k_cases():
     w = _world()
     if not w:
         pytest.skip("needs >= 2 GPUs")
-    _run(w, [c["name"] for c in load_golden() if c["name"].startswith("even_k_")], 29539)
+    _run(w, [c["name"] for c in load_golden() if c["name"].startswith(("even_k_", "ut_"))], 29539)
