@@ -301,6 +301,36 @@ class Cdbg:
         return out
 
 
+class PinnedBuffer:
+    """Page-locked host memory from cdbg_host_alloc as a numpy uint8 array (`.array`).  Reads placed here are copied at full PCIe
+    speed by push_reads and read IN PLACE by build() (no separate H2D copy, see cdbg_stats.zero_copy)."""
+
+    def __init__(self, n_bytes: int):
+        self.lib = load_library()
+        self.ptr = self.lib.cdbg_host_alloc(max(1, int(n_bytes)))
+        if not self.ptr:
+            raise CdbgError(-3, f"cdbg_host_alloc({n_bytes}) failed")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(int(n_bytes),))
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            self.lib.cdbg_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def owner_of(x: int, n_nt: int, m: int, world: int) -> int:
     """GPU owning the n_nt-mer x in a `world`-way sharded build (host-side, no GPU needed)."""
     return int(load_library().cdbg_owner_of(int(x), n_nt, m, world))

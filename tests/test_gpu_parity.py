@@ -136,3 +136,22 @@ def test_device_resident_input_unaligned_falls_back_to_copy():
             g = c.unitigs()
         d = parity.diff(_records(g), parity.graph_to_records(o), 31)
         assert d == "", d
+
+
+def test_pinned_host_input_is_read_in_place_and_gives_the_same_graph():
+    """cdbg_build with page-locked host reads: K1 reads the buffer over PCIe itself (stats.zero_copy), no separate H2D copy.
+    (This path was timed and compared on the full C2 input in profiles/r01_k2_ab_2.txt / _3.txt.)"""
+    from bcalm_b200.api import PinnedBuffer
+    genome, read_len = 250_000, 100
+    n_reads = genome * 30 // read_len
+    with Cdbg(k=31, abundance_min=2) as c:
+        ptr, n = c.synth_reads(genome, read_len, n_reads, 10000, 5)
+        reads = c.copy_to_host(ptr, n)
+        a = c.build(reads)                                   # pageable numpy memory: copied
+        assert a.stats["zero_copy"] == 0
+        with PinnedBuffer(n) as pb:
+            pb.array[:] = reads
+            b = c.build(pb.array)                            # pinned: read in place
+            assert b.stats["zero_copy"] == 1
+            assert b.stats["n_solid"] == a.stats["n_solid"] and b.stats["n_instances"] == a.stats["n_instances"]
+            assert parity.diff(_records(a), _records(b), 31) == ""
