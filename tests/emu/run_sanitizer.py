@@ -3,7 +3,9 @@ golden cases on the truly concurrent engine (one OS thread per CUDA thread).  TS
 out-of-bounds access to a "device" allocation or a static __shared__ array aborts the run (end of round 1: none, for the same
 configurations as below plus the sharded path with 3 emulated ranks and the FASTA/FASTQ parser).
 
-    python tests/emu/run_sanitizer.py [--asan] [case ...]     # environment knobs (CDBG_K2C=flat ...) are passed through
+    python tests/emu/run_sanitizer.py [--asan | --ubsan] [case ...]     # environment knobs (CDBG_K2C=flat ...) are passed through
+(--ubsan: undefined-behaviour sanitizer on the default fiber engine -- shift counts, misaligned vector accesses, signed overflow;
+end of round 1: no report over all golden cases.)
 
 Expected, by design (each is a documented lock-free idiom of the kernels, fine under the CUDA memory model used):
   * ld_volatile_u64 on a table key vs. atomicCAS of the same key  (k2_insert, k2c_count, k5_insert, k5c_join, wide/shard tables)
@@ -28,7 +30,8 @@ import build_emu  # noqa: E402
 
 def main():
     asan = "--asan" in sys.argv[1:]
-    cases = [a for a in sys.argv[1:] if a != "--asan"] or ["reads_0_k15_a2", "lowcx_8_ACGT_k8_a1", "circular_test1", "even_k_dense_k4"]
+    ubsan = "--ubsan" in sys.argv[1:]
+    cases = [a for a in sys.argv[1:] if a not in ("--asan", "--ubsan")] or ["reads_0_k15_a2", "lowcx_8_ACGT_k8_a1", "circular_test1", "even_k_dense_k4"]
     build_emu.build()
     work = tempfile.mkdtemp(prefix="cdbg_tsan_")
     src = os.path.join(work, "a", "b")
@@ -42,9 +45,9 @@ def main():
         fo.write(fi.read())
     lib = os.path.join(work, "libcdbg_tsan.so")
     subprocess.check_call(["g++", "-x", "c++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-fno-strict-aliasing", "-w",
-                           "-fsanitize=address" if asan else "-fsanitize=thread", "-fno-omit-frame-pointer", "-I", HERE, "-o", lib,
+                           "-fsanitize=address" if asan else "-fsanitize=undefined" if ubsan else "-fsanitize=thread", "-fno-omit-frame-pointer", "-I", HERE, "-o", lib,
                            os.path.join(src, "cdbg.cu"), "-ldl"])
-    tsan = subprocess.check_output(["gcc", "-print-file-name=" + ("libasan.so" if asan else "libtsan.so")], text=True).strip()
+    tsan = subprocess.check_output(["gcc", "-print-file-name=" + ("libasan.so" if asan else "libubsan.so" if ubsan else "libtsan.so")], text=True).strip()
     code = (
         "import sys, json\n"
         f"sys.path.insert(0, {ROOT!r})\n"
@@ -56,12 +59,12 @@ def main():
         "    with api.Cdbg(k=c['k'], abundance_min=c['abundance_min']) as x:\n"
         "        g = x.build(c['reads'])\n"
         "    print(n, parity.diff(parity.graph_to_records(g), parity.parse_unitigs_fa(c['unitigs_fa']), c['k']) or 'OK', flush=True)\n")
-    env = dict(os.environ, CDBG_EMU_ENGINE="threads", LD_PRELOAD=tsan,
+    env = dict(os.environ, CDBG_EMU_ENGINE="fibers" if ubsan else "threads", LD_PRELOAD=tsan,
                TSAN_OPTIONS=f"halt_on_error=0 log_path={os.path.join(work, 'report')} history_size=3",
                ASAN_OPTIONS="detect_leaks=0:halt_on_error=1")
     rc = subprocess.run([sys.executable, "-c", code, *cases], env=env).returncode
-    if asan:
-        print("AddressSanitizer:", "clean" if rc == 0 else f"FAILED (exit {rc})")
+    if asan or ubsan:
+        print("sanitizer run:", "finished" if rc == 0 else f"FAILED (exit {rc})", "(UBSan prints its findings above)" if ubsan else "")
         sys.exit(rc)
     locs = {}
     for rep in glob.glob(os.path.join(work, "report.*")):
