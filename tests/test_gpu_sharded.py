@@ -19,10 +19,10 @@ def _world():
     return 8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 0
 
 
-def _run(world, names, port, env=None):
+def _run(world, names, port, env=None, timeout=1500):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "shard_worker.py"), *names]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, env=dict(os.environ, **(env or {})))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     tail = "\n".join(l for l in (p.stdout + p.stderr).splitlines() if "shard x" in l or "SHARD_RESULT" in l or "rror" in l)
     assert p.returncode == 0 and "SHARD_RESULT PASS" in p.stdout, tail[-4000:]
 
@@ -52,7 +52,7 @@ def test_sharded_opt_in_variants(label, env):
     w = _world()
     if not w:
         pytest.skip("needs >= 2 GPUs")
-    _run(w, ["reads_3_k31_a2", "circular_test1", "lowcx_8_ACGT_k8_a1", "pow2_cycle_L256_k21", "c2:0.2"], 29540 + len(label), env)
+    _run(w, ["reads_3_k31_a2", "circular_test1", "lowcx_8_ACGT_k8_a1", "pow2_cycle_L256_k21", "c2:0.2"], 29540 + len(label), env, timeout=300)
 
 
 @pytest.mark.xfail(strict=False, reason="even-k golden cases added after round 1's last GPU run; XPASS means fine")
@@ -60,4 +60,4 @@ def test_sharded_even_k_cases():
     w = _world()
     if not w:
         pytest.skip("needs >= 2 GPUs")
-    _run(w, [c["name"] for c in load_golden() if c["name"].startswith(("even_k_", "ut_"))], 29539)
+    _run(w, [c["name"] for c in load_golden() if c["name"].startswith(("even_k_", "ut_"))], 29539, timeout=300)
