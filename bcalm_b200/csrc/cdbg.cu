@@ -338,8 +338,10 @@ K2SmemPlan k2_smem_plan(uint64_t n_bytes) {
 // I instances in P coarse bins (h_cnt, d_bin_off).  Leaves ctx->d_solid_kmers / d_solid_counts / S like the L2 path.
 // `h_group` (optional): group of every coarse bin (see K2PParams::group), `n_groups` of them; fine bins are then per group.
 int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_kmers, uint64_t I, uint32_t P, const std::vector<uint64_t> &h_cnt,
-                        const std::vector<uint64_t> &h_off, const std::vector<uint32_t> *h_group = nullptr, uint32_t n_groups = 0) {
+                        const std::vector<uint64_t> &h_off, const std::vector<uint32_t> *h_group = nullptr, uint32_t n_groups = 0, bool allow_regions = true) {
     int rc;
+    // CDBG_K2P=regions (opt-in, not timed yet): no fine histogram pass, fixed-capacity regions per fine bin, exact redo on overflow
+    const bool regions = allow_regions && !h_group && getenv("CDBG_K2P") && strcmp(getenv("CDBG_K2P"), "regions") == 0;
     const double per_fine = pl.fill * pl.slots;
     const uint32_t G = h_group ? n_groups : P;
     const uint32_t F = (uint32_t)std::min<uint64_t>(K2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)I / (per_fine * G))));
@@ -364,8 +366,23 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     }
     if ((rc = dalloc(ctx, &d_fine_cnt, NF + 1))) return rc;
     if ((rc = dalloc(ctx, &d_fine_cursor, NF + 1))) return rc;
-    if ((rc = dalloc(ctx, &d_fine_off, NF + 2))) return rc;
-    if ((rc = dalloc(ctx, &d_kmers2, I + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_off, 2 * NF + 2))) return rc;     // exact: prefix offsets [NF + 1]; regions: begins [NF] then ends [NF]
+    uint64_t *d_region_base = nullptr; uint32_t *d_region_cap = nullptr;
+    uint64_t out_cap = I;
+    if (regions) {
+        std::vector<uint64_t> h_base(P); std::vector<uint32_t> h_cap(P);
+        out_cap = 0;
+        for (uint32_t b = 0; b < P; b++) {
+            const uint64_t mean = (h_cnt[b] + F - 1) / F;
+            h_cap[b] = (uint32_t)std::min<uint64_t>(mean + mean / 16 + 256, 0xFFFFFFFFu);
+            h_base[b] = out_cap; out_cap += (uint64_t)F * h_cap[b];
+        }
+        if ((rc = dalloc(ctx, &d_region_base, P))) return rc;
+        if ((rc = dalloc(ctx, &d_region_cap, P))) return rc;
+        CK(cudaMemcpyAsync(d_region_base, h_base.data(), (size_t)P * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_region_cap, h_cap.data(), (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = dalloc(ctx, &d_kmers2, out_cap + 1))) return rc;
     CK(cudaMemsetAsync(d_fine_cnt, 0, (NF + 1) * 4, ctx->stream));
     CK(cudaMemsetAsync(d_fine_cursor, 0, (NF + 1) * 4, ctx->stream));
     CK(cudaMemcpyAsync(d_tile_first, h_tile_first.data(), (P + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -374,13 +391,21 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     K2PParams pp{};
     pp.kmers = d_kmers; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first; pp.group = d_group; pp.P1 = P; pp.F = F; pp.fine_shift = h_group ? 13u : 32u; pp.n_tiles = (uint32_t)tiles;
     pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out = d_kmers2;
+    pp.region_base = d_region_base; pp.region_cap = d_region_cap; pp.overflow = ctx->d_flag + 2;
+    const uint64_t *d_fine_beg = d_fine_off, *d_fine_end = d_fine_off + 1;
+    if (regions) {
+        if ((rc = ctr_zero(ctx))) return rc;       // the overflow flag must survive until the counters are read after k2c_count
+        d_fine_end = d_fine_off + NF;
+    }
     if (tiles) {
-        tstart(ctx, T_K2H);
-        LAUNCH(k2p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 4), K2P_THREADS, 0, pp);
-        tstop(ctx, T_K2H);
-        uint64_t total = 0;
-        if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;   // entry NF = I
-        if (total != I) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost k-mers (%llu != %llu)", (unsigned long long)total, (unsigned long long)I);
+        if (!regions) {
+            tstart(ctx, T_K2H);
+            LAUNCH(k2p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 4), K2P_THREADS, 0, pp);
+            tstop(ctx, T_K2H);
+            uint64_t total = 0;
+            if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;   // entry NF = I
+            if (total != I) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost k-mers (%llu != %llu)", (unsigned long long)total, (unsigned long long)I);
+        }
         const bool match = rank_by_match() && F <= K2P_MATCH_MAX_F;
         const size_t sm = k2p_scatter_smem_bytes(F, match);
         tstart(ctx, T_K2S);
@@ -392,8 +417,9 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
             LAUNCH(k2p_scatter<false>, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K2P_THREADS, sm, pp);
         }
         tstop(ctx, T_K2S);
+        if (regions) LAUNCH(k2p_region_ranges, grid_for(ctx, NF, 256, 8), 256, 0, d_region_base, d_region_cap, d_fine_cursor, F, NF, d_fine_off, d_fine_off + NF);
     } else {
-        CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
+        CK(cudaMemsetAsync(d_fine_off, 0, (2 * NF + 2) * 8, ctx->stream));
     }
     TRACE("K2 fine partition");
 
@@ -401,9 +427,9 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
         if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
-        if ((rc = ctr_zero(ctx))) return rc;
+        if (!(regions && attempt == 0)) { if ((rc = ctr_zero(ctx))) return rc; }
         K2CParams cp{};
-        cp.kmers = d_kmers2; cp.fine_off = d_fine_off; cp.n_fine = (uint32_t)NF; cp.amin = ctx->amin; cp.amax = ctx->amax;
+        cp.kmers = d_kmers2; cp.fine_beg = d_fine_beg; cp.fine_end = d_fine_end; cp.n_fine = (uint32_t)NF; cp.amin = ctx->amin; cp.amax = ctx->amax;
         cp.solid_kmers = ctx->d_solid_kmers; cp.solid_counts = ctx->d_solid_counts; cp.solid_cap = solid_cap;
         cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
         tstart(ctx, T_K2C);
@@ -422,6 +448,14 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
         }
         tstop(ctx, T_K2C);
         if ((rc = ctr_read(ctx))) return rc;
+        if (regions && attempt == 0 && ((int *)(ctx->h_ctr + 64))[2]) {
+            // a fine bin outgrew its region (repeated k-mers): what was counted is incomplete -- redo with exact offsets
+            dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
+            dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_group); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor);
+            dfree(ctx, d_fine_off); dfree(ctx, d_kmers2); dfree(ctx, d_region_base); dfree(ctx, d_region_cap);
+            ctx->st.k2p_fallback = 1;
+            return stage_count_k2_smem(ctx, pl, d_kmers, I, P, h_cnt, h_off, h_group, n_groups, false);
+        }
         if (((int *)(ctx->h_ctr + 64))[1]) return ctx->fail(CDBG_ERR_INTERNAL, "K2: a fine bin does not fit a shared-memory table after %d splits", K2C_MAX_LEVEL);
         ctx->st.n_k2_splits = ctx->h_ctr[2];
         ctx->S = ctx->h_ctr[0];
@@ -435,6 +469,7 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
     ctx->st.n_solid = ctx->S;
     if (ctx->S >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu): shard over more GPUs", (unsigned long long)ctx->S);
     dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_group); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off); dfree(ctx, d_kmers2);
+    dfree(ctx, d_region_base); dfree(ctx, d_region_cap);
     return CDBG_OK;
 }
 

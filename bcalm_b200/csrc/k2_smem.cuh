@@ -42,7 +42,14 @@ struct K2PParams {
     const uint64_t *fine_off;       // [P1 * F + 1] scatter: exclusive offsets into `out`
     uint32_t *fine_cursor;          // [P1 * F]     scatter: running cursors, zero-initialised
     uint64_t *out;                  // [I] scatter: the stream re-ordered by (coarse, fine) bin
+    // "regions" mode (no histogram pass): fine bin f of coarse bin b owns out[region_base[b] + f * region_cap[b] ...) with room for
+    // region_cap[b] k-mers (mean + slack: fine bins are hash-uniform inside a coarse bin); a bin that outgrows its region raises
+    // *overflow and the host redoes the partition with exact offsets.  fine_cursor ends as the fine counts.
+    const uint64_t *region_base;    // [P1] or null (exact mode: fine_off)
+    const uint32_t *region_cap;     // [P1]
+    int *overflow;
 };
+#define K2P_SKIP 0xFFFFFFFFFFFFFFFFULL
 
 // coarse bin that owns `tile`: largest b with tile_first[b] <= tile (empty coarse bins have tile_first[b] == tile_first[b+1])
 __device__ __forceinline__ uint32_t k2p_bin_of_tile(const uint32_t *__restrict__ tile_first, uint32_t P1, uint32_t tile) {
@@ -166,8 +173,12 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
                 const uint32_t cn = s_cnt[b0 + j];
                 s_off[b0 + j] = run;
                 if (cn) {
-                    const size_t g = (size_t)(p.group ? p.group[b] : b) * p.F + b0 + j;
-                    s_gbase[b0 + j] = p.fine_off[g] + atomicAdd(&p.fine_cursor[g], cn);
+                    const uint32_t gb = p.group ? p.group[b] : b;
+                    const size_t g = (size_t)gb * p.F + b0 + j;
+                    const uint32_t old = atomicAdd(&p.fine_cursor[g], cn);
+                    if (!p.region_base) s_gbase[b0 + j] = p.fine_off[g] + old;
+                    else if ((uint64_t)old + cn > p.region_cap[gb]) { *p.overflow = 1; s_gbase[b0 + j] = K2P_SKIP; }
+                    else s_gbase[b0 + j] = p.region_base[gb] + (uint64_t)(b0 + j) * p.region_cap[gb] + old;
                 }
                 run += cn;
             }
@@ -185,10 +196,22 @@ __global__ void __launch_bounds__(K2P_THREADS, 2) k2p_scatter(K2PParams p) {
         const uint32_t total = (uint32_t)(end - beg);
         for (uint32_t j = t; j < total; j += K2P_THREADS) {
             const uint32_t f = s_sb[j];
-            p.out[s_gbase[f] + (j - s_off[f])] = s_stage[j];
+            const uint64_t gbase = s_gbase[f];
+            if (gbase != K2P_SKIP) p.out[gbase + (j - s_off[f])] = s_stage[j];
         }
         if (MATCH) { for (uint32_t i = t; i < p.F * NW; i += K2P_THREADS) s_wc[i] = 0; }   // (the staging loop is behind the barrier above)
         __syncthreads();     // the staging area and the counters are reused by the next tile
+    }
+}
+
+// regions mode: [begin, end) of every fine bin from the region layout and the final cursors
+__global__ void __launch_bounds__(256) k2p_region_ranges(const uint64_t *__restrict__ region_base, const uint32_t *__restrict__ region_cap,
+                                                         const uint32_t *__restrict__ fine_cursor, uint32_t F, uint64_t NF, uint64_t *fine_beg,
+                                                         uint64_t *fine_end) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < NF; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)(g / F), f = (uint32_t)(g % F);
+        const uint64_t beg = region_base[b] + (uint64_t)f * region_cap[b];
+        fine_beg[g] = beg; fine_end[g] = beg + min(fine_cursor[g], region_cap[b]);
     }
 }
 
@@ -200,7 +223,7 @@ static inline size_t k2p_scatter_smem_bytes(uint32_t F, bool match) {
 
 struct K2CParams {
     const uint64_t *kmers;          // the stream ordered by fine bin
-    const uint64_t *fine_off;       // [n_fine + 1]
+    const uint64_t *fine_beg, *fine_end;   // [n_fine] each (exact offsets: fine_end = fine_beg + 1 of one prefix array)
     uint32_t n_fine;
     uint32_t amin, amax;
     uint64_t *solid_kmers; uint32_t *solid_counts; uint64_t solid_cap;
@@ -245,7 +268,7 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
     unsigned long long my_distinct = 0, my_splits = 0;
 
     for (uint32_t bin = blockIdx.x; bin < p.n_fine; bin += gridDim.x) {
-        const uint64_t beg = p.fine_off[bin], end = p.fine_off[bin + 1];
+        const uint64_t beg = p.fine_beg[bin], end = p.fine_end[bin];
         if (beg == end) continue;                                    // (uniform over the block)
         // work stack of (level << 16 | part): the k-mers of this bin whose hash bits 16.. (level of them) equal `part`.
         // Every thread keeps the same copy: all decisions below are uniform over the block.

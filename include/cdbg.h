@@ -95,6 +95,7 @@ typedef struct {
     uint32_t k1_fallback;   /* 1 when the single-pass K1 overflowed a bin region and stage 1 was redone with the exact two-pass kernels */
     uint32_t zero_copy;     /* 1 when cdbg_build read pinned host memory directly from K1 (no separate H2D copy) */
     uint32_t n_k5_splits;   /* K5 (shared-memory variant): join passes abandoned and redone as two halves */
+    uint32_t k2p_fallback;  /* 1 when the region-based fine partition of K2 (opt-in) overflowed and was redone with exact offsets */
 } cdbg_stats;
 
 typedef struct {

@@ -30,6 +30,8 @@ CONFIGS = [
     ("k2c flat insert loop", {"CDBG_K2C": "flat"}),
     ("k2c flat, fill 1.0", {"CDBG_K2C": "flat", "CDBG_K2S_FILL": "1.0"}),
     ("k2c flat, fill 2.0", {"CDBG_K2C": "flat", "CDBG_K2S_FILL": "2.0"}),
+    ("K2 fine partition by regions (no hist pass)", {"CDBG_K2P": "regions"}),
+    ("K2 regions + k2c flat + K1 512", {"CDBG_K2P": "regions", "CDBG_K2C": "flat", "CDBG_K1_THREADS": "512"}),
     ("K1 512 threads", {"CDBG_K1_THREADS": "512"}),
     ("K1 512 threads + k2c flat", {"CDBG_K1_THREADS": "512", "CDBG_K2C": "flat"}),
     ("ranks by match.any", {"CDBG_RANK": "match"}),
@@ -52,7 +54,7 @@ E2E_CONFIGS = [
     ("e2e + K5 smem + K6 lists + match ranks", {"CDBG_K5": "smem", "CDBG_K6": "list", "CDBG_RANK": "match"}),
     ("e2e round-start (copy, twopass, l2)", {"CDBG_K1": "twopass", "CDBG_K2": "l2", "CDBG_ZEROCOPY": "0"}),
 ]
-TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK", "CDBG_K5", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_K5S_P1", "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS")
+TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK", "CDBG_K5", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_K5S_P1", "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P")
 
 
 def say(*a):

@@ -24,7 +24,7 @@ from test_emu_sharded import sharded_build  # noqa: E402
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ to build the CPU emulation of the library")
 
 CONFIGS = [{}, {"CDBG_K1": "twopass"}, {"CDBG_K1": "classic"}, {"CDBG_K2": "l2"}, {"CDBG_K5": "l2"}, {"CDBG_K2C": "flat"}, {"CDBG_K1_THREADS": "512"},
-           {"CDBG_K6": "list"}, {"CDBG_RANK": "match", "CDBG_K2S_P1": "6"}, {"CDBG_EMU_PINNED": "1", "CDBG_ZEROCOPY_MIN": "0"},
+           {"CDBG_K6": "list"}, {"CDBG_K2P": "regions"}, {"CDBG_K2P": "regions", "CDBG_K2S_FILL": "0.1", "CDBG_K2S_SLOTS": "4096"}, {"CDBG_RANK": "match", "CDBG_K2S_P1": "6"}, {"CDBG_EMU_PINNED": "1", "CDBG_ZEROCOPY_MIN": "0"},
            {"CDBG_K2S_P1": "7", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"CDBG_K5S_P1": "5", "CDBG_K5S_FILL": "0.05"},
            {"CDBG_K2S_FILL": "8", "CDBG_K2S_SLOTS": "4096", "CDBG_K5S_FILL": "8"}, {"shards": 2}, {"shards": 3},
            {"shards": 3, "CDBG_SHARD_K2": "smem", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"shards": 2, "CDBG_SHARD_K2": "smem"},

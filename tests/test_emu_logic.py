@@ -31,7 +31,7 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
 
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
          "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
-         "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS")
+         "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P")
 
 
 @pytest.fixture(scope="module")
@@ -91,6 +91,8 @@ VARIANTS = {
     "k2c_flat_insert_loop": dict(CDBG_K2C="flat"),
     "k2c_flat_forced_splits": dict(CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
     "k1_512_threads": dict(CDBG_K1_THREADS=512, CDBG_K2S_P1=5),
+    "k2p_regions": dict(CDBG_K2P="regions", CDBG_K2S_P1=3),
+    "k2p_regions_tiny_bins": dict(CDBG_K2P="regions", CDBG_K2S_FILL=0.05, CDBG_K2S_SLOTS=4096),
 }
 
 
@@ -181,6 +183,17 @@ def test_k1_single_pass_overflow_falls_back_to_exact_two_pass(emu_lib, knobs):
     with api.Cdbg(k=21, abundance_min=2, device=0) as c:
         g = c.build(reads)
     assert g.stats["k1_fallback"] == 1
+    o = orc.run(reads, 21, 2)
+    d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), 21)
+    assert d == "", d
+
+
+def test_k2_region_partition_overflow_falls_back_to_exact_offsets(emu_lib, knobs):
+    reads = _repeats_input()
+    knobs(CDBG_K2P="regions", CDBG_K2S_FILL=0.05, CDBG_K2S_SLOTS=4096, CDBG_K2S_P1=2)
+    with api.Cdbg(k=21, abundance_min=2, device=0) as c:
+        g = c.build(reads)
+    assert g.stats["k2p_fallback"] == 1
     o = orc.run(reads, 21, 2)
     d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), 21)
     assert d == "", d

@@ -17,6 +17,7 @@ VARIANTS = {
     "k2c_flat_insert_loop": ["CDBG_K2C=flat"],
     "k1_512_threads": ["CDBG_K1_THREADS=512"],
     "k1_512_threads_and_k2c_flat": ["CDBG_K1_THREADS=512", "CDBG_K2C=flat"],
+    "k2p_regions": ["CDBG_K2P=regions"],
 }
 WORKER_TIMEOUT_S = 90      # a healthy worker needs ~10 s; a variant that hangs must not hold up the suite for long
 
