@@ -29,6 +29,7 @@ struct Options {
     std::string in, out, out_gfa;
     std::string solid_in;   // -solid-kmers-in: start from counted k-mers ("KMER count" lines: dsk2ascii / jellyfish dump -c / kmc dump)
     std::string solid_out;  // -solid-kmers-out: also write the solid k-mers of this run in the same format
+    bool kff = false;       // -kff: also write the solid k-mers as <prefix>.kff (KFF 1.0, like the reference's -kff)
     int k = 31, amin = 2, amax = 0, m = 10, verbose = 1, cores = 0, device = 0;
     bool all_abund = false;
     bool parse_only = false; // -parse-only: parse the input, print record/byte counts and a checksum, no GPU (host-side tests)
@@ -47,7 +48,7 @@ const char *IGNORED_1[] = {"-max-memory", "-max-disk", "-out-dir", "-out-tmp", "
                            "-minimizer-type", "-repartition-type", "-bloom", "-debloom", "-debloom-impl", "-branching-nodes",
                            "-topology-stats", "-integer-precision", "-nb-glue-partitions", "-solidity-custom", "-solidity-kind",
                            "-histo-max"};
-const char *IGNORED_0[] = {"-no-mphf", "-kff", "-config-only", "-redo-bcalm", "-skip-bcalm", "-redo-bglue", "-skip-bglue", "-redo-links",
+const char *IGNORED_0[] = {"-no-mphf", "-config-only", "-redo-bcalm", "-skip-bcalm", "-redo-bglue", "-skip-bglue", "-redo-links",
                            "-skip-links"};
 
 void usage() {
@@ -62,6 +63,7 @@ void usage() {
            "       -solid-kmers-in       (1 arg) :    start from counted k-mers instead of reads: text lines 'KMER count' (dsk2ascii,\n"
            "                                          jellyfish dump -c, kmc dump); -abundance-min/-max are applied; -in is then optional\n"
            "       -solid-kmers-out      (1 arg) :    also write the solid k-mers of this run as 'KMER count' lines\n"
+           "       -kff                  (0 arg) :    also write the solid k-mers as <prefix>.kff (KFF 1.0); -solid-kmers-in reads KFF too\n"
            "       -all-abundance-counts (0 arg) :    output all k-mer abundance counts instead of mean\n"
            "       -edge-km              (1 arg) :    edge km representation  [default '0']\n"
            "       -nb-cores             (1 arg) :    number of cores (host parsing threads)  [default '0']\n"
@@ -87,6 +89,7 @@ Options parse(int argc, char **argv) {
         else if (a == "-out-gfa") o.out_gfa = need("-out-gfa");
         else if (a == "-solid-kmers-in") o.solid_in = need("-solid-kmers-in");
         else if (a == "-solid-kmers-out") o.solid_out = need("-solid-kmers-out");
+        else if (a == "-kff") o.kff = true;
         else if (a == "-kmer-size") o.k = atoi(need("-kmer-size").c_str());
         else if (a == "-abundance-min") o.amin = atoi(need("-abundance-min").c_str());
         else if (a == "-abundance-max") { long long v = atoll(need("-abundance-max").c_str()); o.amax = v >= 2147483647LL ? 0 : (int)v; }
@@ -110,7 +113,7 @@ Options parse(int argc, char **argv) {
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
     if (!o.solid_in.empty() && o.k > 31) die("-solid-kmers-in needs -kmer-size <= 31");
     if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
-    if (o.nb_gpus > 1 && (o.k > 31 || o.all_abund || !o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse))
+    if (o.nb_gpus > 1 && (o.k > 31 || o.all_abund || !o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
         die("-nb-gpus > 1 supports -kmer-size <= 31 without -all-abundance-counts / -solid-kmers-in / -solid-kmers-out / -gpu-parse");
     return o;
 }
@@ -334,6 +337,111 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 
 // "KMER count" lines -> packed canonical k-mers (A=0 C=1 T=2 G=3, first nucleotide most significant) + abundances.  A dump made
 // without canonical counting lists both orientations of a k-mer: their counts are added.  The abundance filter is applied here.
+// ---- KFF (k-mer file format) 1.0, the format of the reference's `-kff` dump (G/kmer/impl/CountProcessorDumpKff.hpp through the
+// vendored kff-cpp-api).  Layout, all integers big-endian:
+//   "KFF" major minor encoding uniqueness canonicity free_size(4) free_block
+//   sections:  'v' n(8) { name\0 value(8) }*          global variables: k, max, data_size
+//              'r' n_blocks(8) { [n_kmers (ceil(ceil(log2 max)/8) bytes, absent when max = 1)]
+//                                sequence of n_kmers+k-1 nucleotides, 2 bits each, left-padded to whole bytes
+//                                n_kmers * data_size bytes of data (here: the abundance) }*
+//              'i' n(8) { type(1) relative_position(8) }* next_index(8)      index of the sections before it
+//   footer:    'v' with first_index and footer_size, then "KFF"
+// encoding byte = the 2-bit codes of A, C, G, T from the top; the reference writes 0x1e (A=0 C=1 G=3 T=2), the same as this library.
+// 'm' (minimizer) sections are not read.
+uint64_t kff_be(const uint8_t *p, int n) { uint64_t v = 0; for (int i = 0; i < n; i++) v = (v << 8) | p[i]; return v; }
+
+bool load_kff(const Options &o, const FileBuf &in, std::vector<std::pair<uint64_t, uint64_t>> &rec) {
+    const uint8_t *b = (const uint8_t *)in.p, *e = b + in.n;
+    if (in.n < 12 || memcmp(b, "KFF", 3) != 0) return false;
+    if (b[3] != 1) die("unsupported KFF version in '" + o.solid_in + "'");
+    const uint8_t enc = b[5];
+    uint8_t to_ours[4];                                // file code -> our code (A=0 C=1 T=2 G=3)
+    { const uint8_t a = enc >> 6, c = (enc >> 4) & 3, g = (enc >> 2) & 3, t = enc & 3; to_ours[a] = 0; to_ours[c] = 1; to_ours[t] = 2; to_ours[g] = 3; }
+    const uint8_t *p = b + 12 + kff_be(b + 8, 4);
+    uint64_t kk = 0, maxk = 0, dsz = 0;
+    bool have_k = false;
+    auto need = [&](size_t n) { if ((size_t)(e - p) < n) die("truncated KFF file '" + o.solid_in + "'"); };
+    while (p < e) {
+        if (e - p == 3 && memcmp(p, "KFF", 3) == 0) break;           // end signature
+        need(9);
+        const char type = (char)*p++;
+        const uint64_t n = kff_be(p, 8); p += 8;
+        if (type == 'v') {
+            for (uint64_t i = 0; i < n; i++) {
+                const uint8_t *z = (const uint8_t *)memchr(p, 0, (size_t)(e - p));
+                if (!z) die("bad variable section in KFF file '" + o.solid_in + "'");
+                std::string name((const char *)p, (size_t)(z - p));
+                p = z + 1; need(8);
+                const uint64_t v = kff_be(p, 8); p += 8;
+                if (name == "k") { kk = v; have_k = true; } else if (name == "max") maxk = v; else if (name == "data_size") dsz = v;
+            }
+        } else if (type == 'i') {
+            need(n * 9 + 8); p += n * 9 + 8;
+        } else if (type == 'r') {
+            if (!have_k || maxk == 0) die("KFF raw section before the k / max variables in '" + o.solid_in + "'");
+            if ((int)kk != o.k) die("k of the KFF file (" + std::to_string(kk) + ") differs from -kmer-size");
+            if (dsz > 8) die("KFF data_size > 8 is not supported");
+            int nbits = 0; while ((1ULL << nbits) < maxk) nbits++;      // ceil(log2(max))
+            const int nb_bytes = (nbits + 7) / 8;
+            const uint64_t kmask = o.k >= 32 ? ~0ULL : ((1ULL << (2 * o.k)) - 1);
+            for (uint64_t blk = 0; blk < n; blk++) {
+                uint64_t nk = 1;
+                if (nb_bytes) { need((size_t)nb_bytes); nk = kff_be(p, nb_bytes); p += nb_bytes; }
+                const uint64_t nt = nk + kk - 1, sb = (nt + 3) / 4;
+                need(sb + nk * dsz);
+                const uint8_t *seq = p, *dat = p + sb;
+                const uint64_t pad = sb * 4 - nt;                          // leading padding, in nucleotides
+                uint64_t x = 0, r = 0;
+                for (uint64_t i = 0; i < nt; i++) {
+                    const uint64_t q = pad + i;
+                    const uint64_t code = to_ours[(seq[q >> 2] >> (2 * (3 - (q & 3)))) & 3];
+                    x = ((x << 2) | code) & kmask;
+                    r = (r >> 2) | ((code ^ 2) << (2 * (o.k - 1)));
+                    if (i + 1 >= kk) {
+                        const uint64_t j = i + 1 - kk;
+                        rec.emplace_back(x < r ? x : r, dsz ? kff_be(dat + j * dsz, (int)dsz) : 1);
+                    }
+                }
+                p += sb + nk * dsz;
+            }
+        } else if (type == 'm') {
+            die("KFF minimizer sections are not supported: convert the file to raw sections first");
+        } else die("unknown KFF section type in '" + o.solid_in + "'");
+    }
+    return true;
+}
+
+void write_kff(const std::string &path, cdbg_ctx *ctx, int k) {
+    uint64_t n = 0;
+    if (cdbg_get_solid_kmers(ctx, nullptr, nullptr, 0, &n) != CDBG_OK) die(cdbg_last_error(ctx));
+    std::vector<uint64_t> km(n + 1); std::vector<uint32_t> ct(n + 1);
+    if (cdbg_get_solid_kmers(ctx, km.data(), ct.data(), n, &n) != CDBG_OK) die(cdbg_last_error(ctx));
+    std::string f;
+    auto be = [&](uint64_t v, int bytes) { for (int i = bytes - 1; i >= 0; i--) f.push_back((char)(v >> (8 * i))); };
+    auto var = [&](const char *name, uint64_t v) { f += name; f.push_back('\0'); be(v, 8); };
+    const char *note = "b200-cdbg";
+    f += "KFF"; f.push_back(1); f.push_back(0); f.push_back((char)0x1e); f.push_back(1); f.push_back(1);
+    be(strlen(note), 4); f += note;
+    const uint64_t pos_v = f.size();
+    f.push_back('v'); be(3, 8); var("data_size", 4); var("k", (uint64_t)k); var("max", 1);
+    const uint64_t pos_r = f.size();
+    f.push_back('r'); be(n, 8);
+    const int sb = (k + 3) / 4;
+    f.reserve(f.size() + n * (size_t)(sb + 4) + 128);
+    for (uint64_t i = 0; i < n; i++) { be(km[i], sb); be(ct[i], 4); }
+    const uint64_t pos_i = f.size(), end_i = pos_i + 17 + 9 * 2;
+    f.push_back('i'); be(2, 8);
+    f.push_back('v'); be((uint64_t)((int64_t)pos_v - (int64_t)end_i), 8);
+    f.push_back('r'); be((uint64_t)((int64_t)pos_r - (int64_t)end_i), 8);
+    be(0, 8);
+    f.push_back('v'); be(2, 8); var("first_index", pos_i); var("footer_size", 9 + 2 * (12 + 8));
+    f += "KFF";
+    FILE *fp = fopen(path.c_str(), "wb");
+    if (!fp) die("Unable to open output file '" + path + "'");
+    fwrite(f.data(), 1, f.size(), fp);
+    fclose(fp);
+}
+
 void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vector<uint32_t> &counts) {
     FileBuf in;
     if (!read_whole(o.solid_in, in)) die("Unable to open file '" + o.solid_in + "'");
@@ -341,6 +449,7 @@ void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vec
     std::vector<std::pair<uint64_t, uint64_t>> rec;
     const char *p = in.p, *e = in.p + in.n;
     uint64_t line = 0;
+    if (load_kff(o, in, rec)) p = e;                   // a KFF file: the records are in `rec` already
     while (p < e) {
         line++;
         const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
@@ -604,6 +713,10 @@ int main(int argc, char **argv) {
     if (rc != CDBG_OK) { std::string msg = cdbg_last_error(ctx); cdbg_destroy(ctx); die(msg); }
     const double t2 = now_s();
     if (!o.solid_out.empty()) write_counted_kmers(o.solid_out, ctx, o.k);
+    if (o.kff) {
+        if (o.k > 31) { cdbg_destroy(ctx); die("-kff needs -kmer-size <= 31"); }
+        write_kff((!o.out.empty() ? o.out : base_name(o.in.empty() ? o.solid_in : o.in)) + ".kff", ctx, o.k);
+    }
 
     const std::string prefix = !o.out.empty() ? o.out : base_name(o.in.empty() ? o.solid_in : o.in);
     const std::string out_path = prefix + ".unitigs.fa";

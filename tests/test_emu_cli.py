@@ -110,3 +110,116 @@ def test_cli_multi_gpu_mode_refuses_what_the_sharded_path_cannot_do(cli, tmp_pat
     for extra in (["-kmer-size", "41"], ["-kmer-size", "21", "-all-abundance-counts"]):
         p = subprocess.run([cli, "-in", "x.fa", "-nb-gpus", "2", *extra], cwd=tmp_path, capture_output=True, text=True)
         assert p.returncode != 0 and "EXCEPTION:" in p.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------------- KFF
+def _kff_read(path, k):
+    """Python restatement of the KFF 1.0 layout (kff-cpp-api, vendored by the reference): -> {canonical k-mer string: count}."""
+    b = open(path, "rb").read()
+    assert b[:3] == b"KFF" and b[-3:] == b"KFF" and b[3] == 1
+    enc = b[5]
+    nt = {enc >> 6: "A", (enc >> 4) & 3: "C", (enc >> 2) & 3: "G", enc & 3: "T"}
+    p = 12 + int.from_bytes(b[8:12], "big")
+    var, out = {}, {}
+    while p < len(b) - 3:
+        t = chr(b[p]); n = int.from_bytes(b[p + 1:p + 9], "big"); p += 9
+        if t == "v":
+            for _ in range(n):
+                z = b.index(0, p)
+                var[b[p:z].decode()] = int.from_bytes(b[z + 1:z + 9], "big"); p = z + 9
+        elif t == "i":
+            p += n * 9 + 8
+        elif t == "r":
+            assert var["k"] == k
+            nbits = max(0, (var["max"] - 1).bit_length())
+            nb = (nbits + 7) // 8
+            for _ in range(n):
+                nk = 1
+                if nb:
+                    nk = int.from_bytes(b[p:p + nb], "big"); p += nb
+                ln = nk + k - 1
+                sb = (ln + 3) // 4
+                bits = int.from_bytes(b[p:p + sb], "big")
+                seq = "".join(nt[(bits >> (2 * (ln - 1 - i))) & 3] for i in range(ln)); p += sb
+                for j in range(nk):
+                    km = seq[j:j + k]
+                    c = int.from_bytes(b[p:p + var["data_size"]], "big") if var["data_size"] else 1
+                    p += var["data_size"]
+                    out[km] = out.get(km, 0) + c
+        else:
+            raise AssertionError(f"unexpected section {t!r}")
+    return out, var
+
+
+def _kff_write(path, k, blocks, enc=0x1B, max_kmers=8, data_size=2):
+    """A KFF file the way another tool might write it: several k-mers per block (max > 1), another nucleotide encoding, 2-byte counts.
+    blocks: list of (sequence, [count per k-mer])."""
+    code = {"A": enc >> 6, "C": (enc >> 4) & 3, "G": (enc >> 2) & 3, "T": enc & 3}
+    f = bytearray(b"KFF" + bytes([1, 0, enc, 0, 0]) + (0).to_bytes(4, "big"))
+    f += b"v" + (3).to_bytes(8, "big")
+    for name, v in (("k", k), ("max", max_kmers), ("data_size", data_size)):
+        f += name.encode() + b"\0" + v.to_bytes(8, "big")
+    f += b"r" + len(blocks).to_bytes(8, "big")
+    nb = (max(0, (max_kmers - 1).bit_length()) + 7) // 8
+    for seq, counts in blocks:
+        nk = len(seq) - k + 1
+        assert nk == len(counts) and nk <= max_kmers
+        f += nk.to_bytes(nb, "big")
+        bits = 0
+        for ch in seq:
+            bits = (bits << 2) | code[ch]
+        f += bits.to_bytes((len(seq) + 3) // 4, "big")
+        for c in counts:
+            f += c.to_bytes(data_size, "big")
+    f += b"KFF"
+    open(path, "wb").write(bytes(f))
+
+
+def test_kff_from_the_reference_is_read(cli, tmp_path):
+    """tests/golden/reads_0_k15_a2.ref.kff was written by the reference binary (`bcalm -kff`, see make_golden.py): the graph built
+    from it must be the reference's graph of the same reads."""
+    c = CASES["reads_0_k15_a2"]
+    kff = os.path.join(ROOT, "tests", "golden", "reads_0_k15_a2.ref.kff")
+    run_cli(cli, tmp_path, "-solid-kmers-in", kff, "-kmer-size", str(c["k"]), "-abundance-min", "1", "-out", "fromkff")
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromkff.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d == "", d
+
+
+def test_kff_written_here_has_the_reference_layout_and_round_trips(cli, tmp_path):
+    c = CASES["reads_0_k15_a2"]
+    fa = tmp_path / "in.fa"
+    write_fasta(fa, c["reads"])
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(c["k"]), "-abundance-min", str(c["abundance_min"]), "-kff", "-solid-kmers-out", "solid.txt")
+    ours, var = _kff_read(tmp_path / "in.kff", c["k"])
+    ref, ref_var = _kff_read(os.path.join(ROOT, "tests", "golden", "reads_0_k15_a2.ref.kff"), c["k"])
+    assert {k_: var[k_] for k_ in ("k", "max", "data_size")} == {k_: ref_var[k_] for k_ in ("k", "max", "data_size")}
+    text = dict((l.split()[0], int(l.split()[1])) for l in (tmp_path / "solid.txt").read_text().split("\n")[:-1])
+    assert ours == text                                            # the KFF and the text dump hold the same (k-mer, count) pairs
+    canon = lambda d_: {min(s, _rc(s)): v for s, v in d_.items()}  # noqa: E731  (the two programs choose the strand differently)
+    assert canon(ours) == canon(ref)                               # ... and they are the reference's solid k-mers with its counts
+    run_cli(cli, tmp_path, "-solid-kmers-in", "in.kff", "-kmer-size", str(c["k"]), "-abundance-min", "1", "-out", "again")
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "again.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d == "", d
+
+
+def test_kff_with_several_kmers_per_block_and_another_encoding(cli, tmp_path):
+    c = CASES["reads_1_k21_a2"]
+    k = c["k"]
+    fa = tmp_path / "in.fa"
+    write_fasta(fa, c["reads"])
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(k), "-abundance-min", str(c["abundance_min"]), "-out", "ref")
+    # re-express the unitigs as KFF blocks of up to 8 k-mers with per-k-mer counts from -all-abundance-counts
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(k), "-abundance-min", str(c["abundance_min"]), "-out", "ab", "-all-abundance-counts")
+    blocks = []
+    lines = (tmp_path / "ab.unitigs.fa").read_text().split("\n")
+    for h, s in zip(lines[0::2], lines[1::2]):
+        if not h.startswith(">"):
+            continue
+        ab = [int(x) for x in h.split("ab:Z:")[1].split("L:")[0].split()]
+        assert len(ab) == len(s) - k + 1
+        for j in range(0, len(ab), 8):
+            blocks.append((s[j:j + min(8, len(ab) - j) + k - 1], ab[j:j + 8]))
+    _kff_write(tmp_path / "other.kff", k, blocks)
+    run_cli(cli, tmp_path, "-solid-kmers-in", "other.kff", "-kmer-size", str(k), "-abundance-min", "1", "-out", "fromother")
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromother.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), k)
+    assert d == "", d
