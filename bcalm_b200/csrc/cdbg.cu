@@ -302,6 +302,9 @@ int free_results(cdbg_ctx *ctx) {
 #ifndef K1_512_DEFAULT
 #define K1_512_DEFAULT 0   // k1t_single with 512 threads x 16 positions (twice the resident warps): opt-in (CDBG_K1_THREADS=512) until timed on a GPU
 #endif
+#ifndef K2P_REGIONS_DEFAULT
+#define K2P_REGIONS_DEFAULT 0   // fine partition of K2 into fixed-capacity regions (no histogram pass): opt-in (CDBG_K2P=regions) until timed on a GPU
+#endif
 #ifndef K2C_FLAT_DEFAULT
 #define K2C_FLAT_DEFAULT 0   // flat (one probe step per iteration) insert loop of k2c_count: opt-in (CDBG_K2C=flat) until timed on a GPU
 #endif
@@ -341,7 +344,8 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
                         const std::vector<uint64_t> &h_off, const std::vector<uint32_t> *h_group = nullptr, uint32_t n_groups = 0, bool allow_regions = true) {
     int rc;
     // CDBG_K2P=regions (opt-in, not timed yet): no fine histogram pass, fixed-capacity regions per fine bin, exact redo on overflow
-    const bool regions = allow_regions && !h_group && getenv("CDBG_K2P") && strcmp(getenv("CDBG_K2P"), "regions") == 0;
+    const char *k2p = getenv("CDBG_K2P");
+    const bool regions = allow_regions && !h_group && (K2P_REGIONS_DEFAULT ? !(k2p && strcmp(k2p, "exact") == 0) : (k2p && strcmp(k2p, "regions") == 0));
     const double per_fine = pl.fill * pl.slots;
     const uint32_t G = h_group ? n_groups : P;
     const uint32_t F = (uint32_t)std::min<uint64_t>(K2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)I / (per_fine * G))));
