@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(K5C_THREADS) k5c_join(K5CParams p) {
                 if (s_keys[i] == EMPTY_KEY) continue;
                 const uint32_t c = s_cnt[i];
                 uint32_t nin = c & 0xFF, nout = (c >> 8) & 0xFF; const bool pal = (c >> 31) != 0;
+                if (c == 0x101u) {                      // the common junction: one IN end, one OUT end, no flags -- no id arrays needed
+                    const uint32_t a = s_ids[(size_t)i * 8], b = s_ids[(size_t)i * 8 + 4];
+                    if ((a >> 1) != (b >> 1)) { p.link[a] = b; p.link[b] = a; compact++; continue; }
+                }
                 if (nin > 4) nin = 4;
                 if (nout > 4) nout = 4;
                 uint32_t in[5], out[5];
