@@ -85,6 +85,21 @@ def test_product_does_not_import_oracle():
                 assert "#include \"../../oracle" not in text
 
 
+def test_product_library_contains_no_emulator_code():
+    """The CPU emulation used by the no-GPU tests (tests/emu) is selected by a macro that only its own header defines: the shipped
+    library and CLI must contain none of it, and nothing under bcalm_b200/ may include or load anything from tests/."""
+    from bcalm_b200 import build
+    lib = open(build.build_lib(), "rb").read()
+    for marker in (b"emu_ctx_switch", b"[emu]", b"CPU emulation (tests/emu)", b"emu_ncclAllGather"):
+        assert marker not in lib, marker
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bcalm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inl")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "libcdbg_emu" not in text and "_emu_build" not in text, f
+                assert "#define CDBG_EMU_ACTIVE" not in text, f
+
+
 def test_cli_version_and_errors():
     from bcalm_b200 import build
     build.build_lib()
