@@ -95,3 +95,36 @@ def test_random_inputs_and_configurations_match_the_oracle(emu_lib, monkeypatch,
         assert n_solid == o.stats["n_solid"], (seed, it, k, amin, cfg)
         d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k)
         assert d == "", (seed, it, k, amin, cfg, d[:400])
+
+
+ALL_KNOBS = {"CDBG_K1": ["single", "twopass", "classic"], "CDBG_K1_THREADS": ["256", "512"], "CDBG_K2": ["smem", "l2"], "CDBG_K2P": ["exact", "regions"],
+             "CDBG_K2C": ["nested", "flat"], "CDBG_K5": ["smem", "l2"], "CDBG_K6": ["full", "list"], "CDBG_RANK": ["atomic", "match"],
+             "CDBG_K2S_SLOTS": ["4096", "8192", "16384"], "CDBG_K2S_FILL": ["0.05", "0.7", "1.5", "8"], "CDBG_K2S_P1": ["1", "3", "11"],
+             "CDBG_K5S_FILL": ["0.05", "1.0", "8"], "CDBG_K5S_SLOTS": ["2048", "4096"], "CDBG_K5S_P1": ["1", "4"], "CDBG_K1_SLACK": ["0", "16384"],
+             "CDBG_EMU_PINNED": ["0", "1"], "CDBG_ZEROCOPY_MIN": ["0"], "CDBG_PDL": ["0", "1"], "CDBG_SHARD_K1": ["classic", "roll"],
+             "CDBG_SHARD_K2": ["l2", "smem"], "CDBG_BIN_TARGET": ["3000", "5000000"], "CDBG_JOIN_TARGET": ["700", "500000"]}
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_combinations_of_all_knobs(emu_lib, monkeypatch, seed):
+    """Every knob is meant to be output-neutral on its own AND together with any other: random subsets, single GPU and sharded."""
+    rng = random.Random(5000 + seed)
+    for it in range(40):
+        k, amin, reads, _ = make_case(rng)
+        env = {name: rng.choice(vals) for name, vals in ALL_KNOBS.items() if rng.random() < 0.5}
+        for name in ALL_KNOBS:
+            monkeypatch.delenv(name, raising=False)
+        for name, v in env.items():
+            monkeypatch.setenv(name, v)
+        shards = rng.choice([0, 0, 2, 3])
+        o = orc.run(reads, k, amin)
+        if shards:
+            g, parts = sharded_build(reads, k, amin, shards)
+            n_solid = sum(p.stats["n_solid"] for p in parts)
+        else:
+            with api.Cdbg(k=k, abundance_min=amin, device=0) as c:
+                g = c.build(reads)
+            n_solid = g.stats["n_solid"]
+        assert n_solid == o.stats["n_solid"], (seed, it, k, amin, shards, env)
+        d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k)
+        assert d == "", (seed, it, k, amin, shards, env, d[:400])
