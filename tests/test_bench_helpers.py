@@ -80,3 +80,41 @@ def test_file_to_file_sample_runs_the_cli(emu, monkeypatch, tmp_path):
 def test_workload_is_the_configuration_baseline_names():
     g, n_reads = bench.workload(1.0)
     assert (g, n_reads, bench.READ_LEN, bench.K, bench.AMIN) == (5_000_000, 1_500_000, 100, 31, 2)
+
+
+def _run_bench_main(monkeypatch, capsys, argv):
+    import torch
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **kw: real_empty(*a, **kw))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **kw: None)
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    for v in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(v, raising=False)
+    bench.main()
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    return json.loads(lines[0])
+
+
+def test_main_prints_the_contract_line_against_the_emulated_library(emu, monkeypatch, capsys):
+    """The whole of bench.main() at a tiny scale, torch's CUDA calls stubbed: every key of the JSON contract is there and consistent."""
+    out = _run_bench_main(monkeypatch, capsys, ["--steps", "2", "--warmup", "1", "--scale", "0.002", "--cpu-scale", "0.002", "--no-clocks"])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "e2e", "gpu_launches", "roofline", "clocks", "cpu_baseline", "file_to_file", "device_ms_per_step"):
+        assert key in out, key
+    assert out["value"] > 0 and out["n_gpus"] == 1 and out["steps"] == 2 and out["warmup"] == 1 and out["vs_baseline"] is None
+    assert "workload" in out["config"] and "model" not in out["config"]
+    e = out["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == out["config"]["input_bytes"] and e["d2h_bytes_per_step"] > 0
+    r = out["roofline"]
+    assert r["bound"] == "hbm" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["kernel"] in r["stage_ms"]
+    assert out["gpu_launches"] > 0 and out["gpu_launches"] % 2 == 0
+    cb = out["cpu_baseline"]
+    assert cb["value"] and cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"]
+
+
+def test_reference_arm_prints_its_line(emu, monkeypatch, capsys):
+    out = _run_bench_main(monkeypatch, capsys, ["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-scale", "0.002"])
+    assert out["impl"] == "reference" and out["value"] > 0 and out["e2e"]["value"] == out["value"]
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["cpu_baseline"]["kind"] in ("reference", "port")
+    assert out["metric"] == "input Gbases/sec to unitigs at k=31" and out["unit"] == "Gbases/s"
