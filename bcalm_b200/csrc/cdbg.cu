@@ -134,7 +134,7 @@ namespace {
 
 // CDBG_EMU_ACTIVE is only ever defined by tests/emu/cuda_runtime.h (the CPU emulation build used by the no-GPU logic tests)
 #ifdef CDBG_EMU_ACTIVE
-#define KLAUNCH(kern, grid, block, smem, ...) emu::launch((unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); })
+#define KLAUNCH(kern, grid, block, smem, ...) emu::launch_kernel((const void *)(kern), #kern, (unsigned)(grid), (unsigned)(block), (size_t)(smem), [&] { kern(__VA_ARGS__); })
 #else
 #define KLAUNCH(kern, grid, block, smem, ...) kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__)
 #endif

@@ -20,6 +20,7 @@
 
 #include <condition_variable>
 #include <functional>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <tuple>
@@ -233,7 +234,7 @@ struct Engine {
     void launch(unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) {
         std::lock_guard<std::mutex> one(launch_mutex);
         if (b == 0 || b > MAX_THREADS || smem > DYN_SMEM_BYTES) { fprintf(stderr, "[emu] bad launch geometry %u x %u, %zu B smem\n", g, b, smem); abort(); }
-        if (g == 0) return;
+        if (g == 0) { fprintf(stderr, "[emu] launch with an empty grid (block %u): cudaErrorInvalidConfiguration on a GPU\n", b); abort(); }
         if (!dyn) {
             if (posix_memalign((void **)&dyn, 1024, DYN_SMEM_BYTES)) abort();
             const char *e = getenv("CDBG_EMU_ENGINE");
@@ -280,6 +281,20 @@ inline void Engine::fiber_main() {
 }
 inline unsigned char *dyn_smem() { return engine().dyn; }
 inline void launch(unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) { engine().launch(g, b, smem, fn); }
+// dynamic shared memory above 48 KB needs cudaFuncAttributeMaxDynamicSharedMemorySize on THAT kernel (at most 227 KB on sm_100)
+inline std::map<const void *, size_t> &smem_optin() { static std::map<const void *, size_t> m; return m; }
+inline std::mutex &smem_optin_mutex() { static std::mutex m; return m; }
+inline void launch_kernel(const void *kern, const char *name, unsigned g, unsigned b, size_t smem, const std::function<void()> &fn) {
+    if (smem > 48 * 1024) {
+        std::lock_guard<std::mutex> l(smem_optin_mutex());
+        auto it = smem_optin().find(kern);
+        if (it == smem_optin().end() || it->second < smem) {
+            fprintf(stderr, "[emu] %s launched with %zu B of dynamic shared memory without the opt-in attribute: cudaErrorInvalidValue on a GPU\n", name, smem);
+            abort();
+        }
+    }
+    engine().launch(g, b, smem, fn);
+}
 inline void yield_now() { engine().yield_now(); }
 
 template <class T>
@@ -457,11 +472,16 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, con
     a->device = 0; a->devicePointer = pinned ? const_cast<void *>(p) : nullptr; a->hostPointer = const_cast<void *>(p);
     return cudaSuccess;
 }
-template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute, int v) {
+    if (v < 0 || v > 227 * 1024) { fprintf(stderr, "[emu] cudaFuncSetAttribute: %d B of dynamic shared memory is above the 227 KB limit\n", v); abort(); }
+    std::lock_guard<std::mutex> l(emu::smem_optin_mutex());
+    emu::smem_optin()[(const void *)f] = (size_t)v;
+    return cudaSuccess;
+}
 
 template <class... Params, class... Args>
 static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void (*kern)(Params...), Args &&...args) {
     std::tuple<typename std::decay<Params>::type...> a{static_cast<typename std::decay<Params>::type>(args)...};
-    emu::launch(cfg->gridDim.x, cfg->blockDim.x, cfg->dynamicSmemBytes, [&] { std::apply(kern, a); });
+    emu::launch_kernel((const void *)kern, "cudaLaunchKernelEx", cfg->gridDim.x, cfg->blockDim.x, cfg->dynamicSmemBytes, [&] { std::apply(kern, a); });
     return cudaSuccess;
 }
