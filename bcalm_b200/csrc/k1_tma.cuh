@@ -42,20 +42,37 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 #else
-// CPU emulation build of the tests (tests/emu): an mbarrier is a count of completed phases, a bulk copy is a memcpy that
-// completes the phase it was announced on.  wait(parity) passes once the phase of that parity has completed.
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { __atomic_store_n(bar, 0, __ATOMIC_SEQ_CST); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { if (bytes == 0) __atomic_fetch_add(bar, 1, __ATOMIC_SEQ_CST); }
+// CPU emulation build of the tests (tests/emu): an mbarrier (arrival count 1) is a count of completed phases in the low half and
+// the bytes still expected by the current phase in the high half; a bulk copy is a memcpy that must deliver exactly the bytes
+// announced on its barrier (on a GPU a mismatch is a phase that never completes: a hang) and then completes the phase.
+// wait(parity) passes once the phase of that parity has completed.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    if (count != 1) { fprintf(stderr, "[emu] mbarrier arrival counts other than 1 are not modelled\n"); abort(); }
+    __atomic_store_n(bar, 0, __ATOMIC_SEQ_CST);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    const uint64_t cur = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+    if (cur >> 32) { fprintf(stderr, "[emu] expect_tx on an mbarrier whose phase still waits for %u bytes\n", (uint32_t)(cur >> 32)); abort(); }
+    if (bytes == 0) __atomic_fetch_add(bar, 1, __ATOMIC_SEQ_CST);
+    else __atomic_fetch_add(bar, (uint64_t)bytes << 32, __ATOMIC_SEQ_CST);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (;;) {
-        uint64_t done = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+        const uint32_t done = (uint32_t)__atomic_load_n(bar, __ATOMIC_SEQ_CST);
         if (done > 0 && ((done - 1) & 1) == parity) return;
         emu::yield_now();
     }
 }
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    // cp.async.bulk: source, destination and size must be multiples of 16 bytes (a GPU raises a misaligned-address fault)
+    if ((reinterpret_cast<uintptr_t>(dst_smem) | reinterpret_cast<uintptr_t>(src_gmem) | bytes) & 15) {
+        fprintf(stderr, "[emu] bulk copy not 16-byte aligned: dst %p src %p bytes %u\n", dst_smem, src_gmem, bytes);
+        abort();
+    }
+    const uint64_t cur = __atomic_load_n(bar, __ATOMIC_SEQ_CST);
+    if ((uint32_t)(cur >> 32) != bytes) { fprintf(stderr, "[emu] bulk copy of %u bytes on an mbarrier expecting %u\n", bytes, (uint32_t)(cur >> 32)); abort(); }
     memcpy(dst_smem, src_gmem, bytes);
-    __atomic_fetch_add(bar, 1, __ATOMIC_SEQ_CST);
+    __atomic_fetch_add(bar, 1 - ((uint64_t)bytes << 32), __ATOMIC_SEQ_CST);      // bytes delivered, phase complete
 }
 __device__ __forceinline__ void mbar_fence_init() {}
 #endif
