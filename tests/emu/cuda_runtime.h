@@ -20,6 +20,7 @@
 
 #include <condition_variable>
 #include <functional>
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -415,9 +416,9 @@ template <class T, class A, class B> static inline T atomicCAS(T *p, A cmp, B va
 }
 
 // ------------------------------------------------------------------------------------------------ runtime API
-typedef enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorUnknown = 999 } cudaError_t;
+typedef enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotReady = 600, cudaErrorUnknown = 999 } cudaError_t;
 typedef void *cudaStream_t;
-struct emuEvent { timespec t; };
+struct emuEvent { timespec t; bool pending = false; };
 typedef emuEvent *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1 };
@@ -445,20 +446,53 @@ template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
     *p = (T *)q;
     return cudaSuccess;
 }
-template <class T> static inline cudaError_t cudaFree(T *p) { free((void *)p); return cudaSuccess; }
+// Kernels run synchronously here, so the one thing a missing stream synchronisation can break on a GPU -- the host reading the
+// destination of an asynchronous device -> host copy (or the time of an event) too early -- is modelled explicitly: such a copy
+// snapshots its source in stream order, POISONS the destination, and only delivers at the next synchronising call of the thread.
+namespace emu {
+struct PendingCopy { void *dst; std::vector<unsigned char> data; };
+inline thread_local std::vector<PendingCopy> pending_d2h;
+inline thread_local std::vector<emuEvent *> pending_events;
+inline void stream_sync() {
+    for (auto &c : pending_d2h) memcpy(c.dst, c.data.data(), c.data.size());
+    pending_d2h.clear();
+    for (auto *e : pending_events) e->pending = false;
+    pending_events.clear();
+}
+}  // namespace emu
+template <class T> static inline cudaError_t cudaFree(T *p) { emu::stream_sync(); free((void *)p); return cudaSuccess; }
 template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { return cudaMalloc(p, n); }
-template <class T> static inline cudaError_t cudaFreeHost(T *p) { free((void *)p); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(dst, src, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { memmove(dst, src, n); return cudaSuccess; }
+template <class T> static inline cudaError_t cudaFreeHost(T *p) { emu::stream_sync(); free((void *)p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *dst, const void *src, size_t n, cudaMemcpyKind kind, cudaStream_t) {
+    if (kind == cudaMemcpyDeviceToHost && n) {
+        emu::PendingCopy c; c.dst = dst; c.data.assign((const unsigned char *)src, (const unsigned char *)src + n);
+        memset(dst, 0xEE, n);
+        emu::pending_d2h.push_back(std::move(c));
+        return cudaSuccess;
+    }
+    emu::stream_sync();          // (a later copy in the same stream sees the earlier ones done)
+    memmove(dst, src, n);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpy(void *dst, const void *src, size_t n, cudaMemcpyKind) { emu::stream_sync(); memmove(dst, src, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *dst, int v, size_t n, cudaStream_t) { memset(dst, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (cudaStream_t)(uintptr_t)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { emu::stream_sync(); return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { emu::stream_sync(); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); return cudaSuccess; }
-static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { clock_gettime(CLOCK_MONOTONIC, &e->t); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
+    auto &v = emu::pending_events; v.erase(std::remove(v.begin(), v.end(), e), v.end());
+    delete e; return cudaSuccess;
+}
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+    clock_gettime(CLOCK_MONOTONIC, &e->t);
+    if (!e->pending) { e->pending = true; emu::pending_events.push_back(e); }
+    return cudaSuccess;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { emu::stream_sync(); return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+    if (a->pending || b->pending) { *ms = 0; return cudaErrorNotReady; }      // a GPU answers the same before the events have completed
     *ms = (float)((b->t.tv_sec - a->t.tv_sec) * 1e3 + (b->t.tv_nsec - a->t.tv_nsec) * 1e-6);
     return cudaSuccess;
 }
