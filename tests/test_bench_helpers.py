@@ -118,3 +118,10 @@ def test_reference_arm_prints_its_line(emu, monkeypatch, capsys):
     assert out["impl"] == "reference" and out["value"] > 0 and out["e2e"]["value"] == out["value"]
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["cpu_baseline"]["kind"] in ("reference", "port")
     assert out["metric"] == "input Gbases/sec to unitigs at k=31" and out["unit"] == "Gbases/s"
+
+
+def test_smoke_entry_point_against_the_emulated_library(emu, capsys):
+    """__graft_entry__.smoke() is the first thing the driver runs on the GPU box: its own logic must not be what fails there."""
+    import __graft_entry__ as entry
+    entry.smoke()
+    assert "smoke OK" in capsys.readouterr().out
