@@ -15,7 +15,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 from bcalm_b200 import parity  # noqa: E402
+import bcalm_b200.api as _api  # noqa: E402
 from bcalm_b200.api import Cdbg, MEM_DEVICE  # noqa: E402
+
+if os.environ.get("CDBG_GPU_TEST_LIB"):      # scripts/dry_run_gpu_tests.py: the tests' own logic against the CPU emulation
+    _api.LIB_PATH = os.environ["CDBG_GPU_TEST_LIB"]
 
 with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
     GOLDEN = {c["name"]: c for c in json.load(f)}
