@@ -46,13 +46,13 @@ def test_sharded_c2_like():
 # Written after round 1's last GPU run and verified under the CPU emulator only (tests/test_emu_*.py): non-gating until they have
 # passed on real GPUs (XPASS = fine).  Each runs in its own torchrun job, so a failure cannot disturb the tests above.
 @pytest.mark.xfail(strict=False, reason="not yet run on GPUs when written; XPASS means it is fine")
-@pytest.mark.parametrize("label,env", [("k1_roll", {"CDBG_SHARD_K1": "roll"}), ("k2_smem", {"CDBG_SHARD_K2": "smem"}),
-                                       ("k1_roll_k2_smem", {"CDBG_SHARD_K1": "roll", "CDBG_SHARD_K2": "smem"})])
-def test_sharded_opt_in_variants(label, env):
+@pytest.mark.parametrize("label,port,env", [("k1_roll", 29541, {"CDBG_SHARD_K1": "roll"}), ("k2_smem", 29542, {"CDBG_SHARD_K2": "smem"}),
+                                            ("k1_roll_k2_smem", 29543, {"CDBG_SHARD_K1": "roll", "CDBG_SHARD_K2": "smem"})])
+def test_sharded_opt_in_variants(label, port, env):
     w = _world()
     if not w:
         pytest.skip("needs >= 2 GPUs")
-    _run(w, ["reads_3_k31_a2", "circular_test1", "lowcx_8_ACGT_k8_a1", "pow2_cycle_L256_k21", "c2:0.2"], 29540 + len(label), env, timeout=300)
+    _run(w, ["reads_3_k31_a2", "circular_test1", "lowcx_8_ACGT_k8_a1", "pow2_cycle_L256_k21", "c2:0.2"], port, env, timeout=300)
 
 
 @pytest.mark.xfail(strict=False, reason="even-k golden cases added after round 1's last GPU run; XPASS means fine")
