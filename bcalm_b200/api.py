@@ -364,7 +364,8 @@ def merge_shards(graphs) -> Graph:
     links = links[order]
     link_off = np.zeros(expect + 1, np.uint64)
     np.cumsum(np.bincount(links["from"], minlength=expect), out=link_off[1:])
-    return Graph(k=k, seq=seq, seq_off=np.concatenate(offs), kc=np.concatenate([g.kc for g in gs]), abund=None, links=links,
+    return Graph(k=k, seq=seq, seq_off=np.concatenate(offs), kc=np.concatenate([g.kc for g in gs]),
+                 abund=np.concatenate([g.abund for g in gs]) if gs and all(g.abund is not None for g in gs) else None, links=links,
                  stats={"shards": [g.stats for g in gs]}, link_off=link_off, first_unitig=0, n_unitigs_total=expect)
 
 

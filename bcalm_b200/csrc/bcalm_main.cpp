@@ -113,8 +113,8 @@ Options parse(int argc, char **argv) {
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
     if (!o.solid_in.empty() && o.k > 31) die("-solid-kmers-in needs -kmer-size <= 31");
     if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
-    if (o.nb_gpus > 1 && (o.k > 31 || o.all_abund || !o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
-        die("-nb-gpus > 1 supports -kmer-size <= 31 without -all-abundance-counts / -solid-kmers-in / -solid-kmers-out / -gpu-parse");
+    if (o.nb_gpus > 1 && (o.k > 31 || !o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
+        die("-nb-gpus > 1 supports -kmer-size <= 31 without -solid-kmers-in / -solid-kmers-out / -gpu-parse / -kff");
     return o;
 }
 
@@ -598,7 +598,7 @@ int run_sharded(const Options &o, ByteBuf &stream, uint64_t n_records, double t0
     for (int r = 0; r < N; r++) {
         cdbg_params prm{};
         prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device + r;
-        prm.flags = o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0;
+        prm.flags = (o.all_abund ? CDBG_FLAG_ALL_ABUNDANCE_COUNTS : 0) | (o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0);
         prm.rank = r; prm.world_size = N;
         if (cdbg_create(&ctx[r], &prm) != CDBG_OK) {
             std::string msg = ctx[r] ? cdbg_last_error(ctx[r]) : "cdbg_create failed";

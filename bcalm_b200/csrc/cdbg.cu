@@ -1092,8 +1092,6 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     if (params->abundance_min < 0) return bail(ctx->fail(CDBG_ERR_PARAM, "abundance-min must be >= 0"));
     if (params->world_size > MAX_WORLD || params->world_size < 0 || (params->world_size > 1 && (params->rank < 0 || params->rank >= params->world_size)))
         return bail(ctx->fail(CDBG_ERR_PARAM, "bad rank/world_size %d/%d (at most %d shards)", params->rank, params->world_size, MAX_WORLD));
-    if (params->world_size > 1 && (params->flags & CDBG_FLAG_ALL_ABUNDANCE_COUNTS))
-        return bail(ctx->fail(CDBG_ERR_PARAM, "-all-abundance-counts is not available in sharded mode yet"));
     ctx->world = params->world_size > 1 ? params->world_size : 1;
     ctx->rank = ctx->world > 1 ? params->rank : 0;
     ctx->k = params->kmer_size;
@@ -1314,7 +1312,8 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
     if (ctx->stage < ST_COMPACTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_get_unitigs needs cdbg_compact first");
     CK(cudaSetDevice(ctx->prm.device));
     int rc;
-    const uint64_t U = ctx->U, nt = ctx->total_nt, S = ctx->S;
+    const uint64_t U = ctx->U, nt = ctx->total_nt;
+    const uint64_t S = ctx->world > 1 ? nt - U * (uint64_t)(ctx->k - 1) : ctx->S;     // k-mers of the unitigs in this view
     const uint64_t nl = ctx->stage >= ST_LINKED ? ctx->n_edges : 0;
     if ((rc = hgrow(ctx, &ctx->h_seq, &ctx->h_seq_cap, nt + 1))) return rc;
     if ((rc = hgrow(ctx, &ctx->h_seq_off, &ctx->h_seq_off_cap, U + 1))) return rc;

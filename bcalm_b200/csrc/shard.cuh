@@ -611,6 +611,29 @@ __global__ void __launch_bounds__(256) glue_assemble(uint64_t G, const uint64_t 
     }
 }
 
+// -all-abundance-counts on shards: the per-k-mer abundances of the unitigs this GPU owns, from the all-gathered per-piece lists
+// (piece q of rank r starts at k-mer  seq_off - q * (k-1)  of that rank's list; a reversed piece lists its k-mers backwards).
+// One warp per piece; unitig u (local) starts at k-mer  seq_off[u] - u * (k-1)  of `abund`, as in the single-GPU view.
+__global__ void __launch_bounds__(256) glue_assemble_abund(uint64_t G, const uint64_t *__restrict__ pinfo, const uint32_t *__restrict__ unitig_of_piece,
+                                                           const uint64_t *__restrict__ nt_scan /*by head piece*/, const PieceDesc *__restrict__ gathered,
+                                                           uint64_t max_p, uint32_t world, const uint64_t *__restrict__ piece_base,
+                                                           const uint32_t *__restrict__ all_abund, uint64_t max_s, uint32_t u_first, uint32_t u_last,
+                                                           uint64_t nt_first, int k, uint32_t *abund) {
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = lane_id();
+    for (uint64_t g = warp; g < G; g += n_warps) {
+        const uint32_t u = unitig_of_piece[g];
+        if (u < u_first || u >= u_last) continue;
+        const uint64_t inf = pinfo[g];
+        const uint32_t B = (uint32_t)(inf >> 32), pos = (uint32_t)inf >> 1, rev = (uint32_t)inf & 1u;
+        uint32_t r;
+        const PieceDesc &d = piece_desc(gathered, max_p, world, piece_base, g, r);
+        const uint32_t *src = all_abund + (uint64_t)r * max_s + (d.seq_off - (g - piece_base[r]) * (uint64_t)(k - 1));
+        uint32_t *dst = abund + (nt_scan[B >> 1] - nt_first) - (uint64_t)(u - u_first) * (uint64_t)(k - 1) + pos;
+        for (uint64_t j = lane; j < d.nk; j += 32) dst[j] = rev ? src[d.nk - 1 - j] : src[j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ stage 4 on shards
 
 // An edge (e, f) between k-mer ends that are unitig extremities: both ends are piece termini, found in the replicated table; the

@@ -426,14 +426,18 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     dfree(ctx, d_uid_scan); dfree(ctx, d_nt_scan);
     // the piece-level arrays move aside; ctx->d_seq etc. will hold the unitigs this GPU owns
     char *d_pseq = ctx->d_seq; uint64_t *d_pseq_off = ctx->d_seq_off; unsigned long long *d_pkc = ctx->d_kc;
-    ctx->d_seq = nullptr; ctx->d_seq_off = nullptr; ctx->d_kc = nullptr;
+    uint32_t *d_pabund = ctx->d_abund;            // -all-abundance-counts: per-k-mer abundances in piece order (else null)
+    ctx->d_seq = nullptr; ctx->d_seq_off = nullptr; ctx->d_kc = nullptr; ctx->d_abund = nullptr;
 
     TRACE("local rank + spell pieces");
     // ---- stage 3: glue.  global piece ids, neighbour messages (X4), all-gather, replicated piece ranking
     uint64_t all_P[MAX_WORLD], all_nt[MAX_WORLD], piece_base[MAX_WORLD + 1] = {0}, max_p = 1, max_nt = 16;
-    uint64_t mine[2] = {Pn, piece_nt}, both[2 * MAX_WORLD];
-    if ((rc = allgather_host_u64(ctx, mine, 2, both))) return rc;
-    for (int r = 0; r < W; r++) { all_P[r] = both[2 * r]; all_nt[r] = both[2 * r + 1]; piece_base[r + 1] = piece_base[r] + all_P[r]; max_p = std::max(max_p, all_P[r]); max_nt = std::max(max_nt, all_nt[r]); }
+    uint64_t mine[3] = {Pn, piece_nt, S}, both[3 * MAX_WORLD], max_s = 4;
+    if ((rc = allgather_host_u64(ctx, mine, 3, both))) return rc;
+    for (int r = 0; r < W; r++) {
+        all_P[r] = both[3 * r]; all_nt[r] = both[3 * r + 1]; piece_base[r + 1] = piece_base[r] + all_P[r];
+        max_p = std::max(max_p, all_P[r]); max_nt = std::max(max_nt, all_nt[r]); max_s = std::max(max_s, both[3 * r + 2]);
+    }
     max_nt = (max_nt + 15) & ~15ULL;
     const uint64_t G = piece_base[W];
     if (G >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 pieces");
@@ -453,6 +457,16 @@ int shard_stage_compact(cdbg_ctx *ctx) {
         if ((rc = dalloc(ctx, &d_pad, max_nt))) return rc;
         if (piece_nt) CK(cudaMemcpyAsync(d_pad, d_pseq, piece_nt, cudaMemcpyDeviceToDevice, ctx->stream));
         NK(ncclAllGather(d_pad, d_seq_all, max_nt, ncclChar, ctx->comm, ctx->stream));
+        dfree(ctx, d_pad);
+    }
+    uint32_t *d_abund_all = nullptr;
+    if (d_pabund) {   // the per-k-mer abundance lists travel like the piece strings
+        max_s = (max_s + 3) & ~3ULL;
+        uint32_t *d_pad = nullptr;
+        if ((rc = dalloc(ctx, &d_abund_all, max_s * W))) return rc;
+        if ((rc = dalloc(ctx, &d_pad, max_s))) return rc;
+        if (S) CK(cudaMemcpyAsync(d_pad, d_pabund, S * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        NK(ncclAllGather(d_pad, d_abund_all, max_s * 4, ncclChar, ctx->comm, ctx->stream));
         dfree(ctx, d_pad);
     }
     TRACE("allgather piece strings");
@@ -505,6 +519,11 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &ctx->d_kc, U_mine + 1))) return rc;
     if (G && U_mine) LAUNCH(glue_assemble, grid_for(ctx, G * 32, 256, 8), 256, 0, G, ctx->d_pinfo, ctx->d_unitig_of_piece, d_pnt, d_desc_all, max_p, (uint32_t)W,
                             d_piece_base, d_seq_all, max_nt, (uint32_t)u_first, (uint32_t)u_last, nt_range[0], k, ctx->d_seq, ctx->d_seq_off);
+    if (d_abund_all) {
+        if ((rc = dalloc(ctx, &ctx->d_abund, nt_mine - U_mine * (uint64_t)(k - 1) + 1))) return rc;
+        if (G && U_mine) LAUNCH(glue_assemble_abund, grid_for(ctx, G * 32, 256, 8), 256, 0, G, ctx->d_pinfo, ctx->d_unitig_of_piece, d_pnt, d_desc_all, max_p,
+                                (uint32_t)W, d_piece_base, d_abund_all, max_s, (uint32_t)u_first, (uint32_t)u_last, nt_range[0], k, ctx->d_abund);
+    }
     CK(cudaMemcpyAsync(ctx->d_seq_off + U_mine, &nt_mine, 8, cudaMemcpyHostToDevice, ctx->stream));
     if (U_mine) CK(cudaMemcpyAsync(ctx->d_kc, d_kc_all + u_first, U_mine * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // nt_mine is a stack variable
@@ -528,7 +547,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     }
     dfree(ctx, d_pedges); dfree(ctx, d_desc); dfree(ctx, d_desc_all); dfree(ctx, d_seq_all); dfree(ctx, d_piece_base); dfree(ctx, d_weight);
     dfree(ctx, d_puid); dfree(ctx, d_pnt); dfree(ctx, d_kc_all); dfree(ctx, d_unt_off);
-    dfree(ctx, d_pseq); dfree(ctx, d_pseq_off); dfree(ctx, d_pkc);
+    dfree(ctx, d_pseq); dfree(ctx, d_pseq_off); dfree(ctx, d_pkc); dfree(ctx, d_pabund); dfree(ctx, d_abund_all);
     tstop(ctx, T_K6S);
     TRACE("edges + cleanup");
     ctx->n_pieces = Pn;

@@ -76,6 +76,34 @@ def parse_unitigs_fa(text: str):
     return recs
 
 
+def abundance_lists(recs):
+    """Records with `ab` lists -> ({canonical unitig string: abundance list in that orientation}, sorted multiset of the sorted lists).
+    A circular unitig may be spelled from any cut point, so only the second part is comparable for it; compare the first on the
+    strings two outputs have in common."""
+    by_seq, sorted_lists = {}, []
+    for r in recs:
+        s, a = r["seq"], list(r["ab"])
+        rc = revcomp_str(s)
+        if rc < s:
+            s, a = rc, a[::-1]
+        elif rc == s:
+            a = min(a, a[::-1])
+        by_seq[s] = a
+        sorted_lists.append(tuple(sorted(a)))
+    return by_seq, sorted(sorted_lists)
+
+
+def diff_abundance_lists(mine, theirs) -> str:
+    """'' when two record lists (graph_to_records(..., with_ab=True)) carry the same per-k-mer abundance lists."""
+    a, b = abundance_lists(mine), abundance_lists(theirs)
+    if a[1] != b[1]:
+        return "multisets of abundance lists differ"
+    for s in set(a[0]) & set(b[0]):
+        if a[0][s] != b[0][s]:
+            return f"abundance list of {s[:60]}... differs: {a[0][s][:20]} vs {b[0][s][:20]}"
+    return ""
+
+
 def graph_to_records(g, with_ab: bool = False):
     """Array-form graph (fields k, seq, seq_off, kc, abund, links) -> the same record list as parse_unitigs_fa."""
     k = g.k

@@ -28,6 +28,9 @@ def main():
         golden = {c["name"]: c for c in json.load(f)}
     failures = []
     for name in sys.argv[1:]:
+        want_ab = name.startswith("ab:")             # ab:<case> = the same case with -all-abundance-counts (per-k-mer lists checked too)
+        if want_ab:
+            name = name[3:]
         if name.startswith("c2:"):
             scale = float(name[3:])
             G = int(5_000_000 * scale); L = 100; n_reads = G * 30 // L
@@ -45,7 +48,7 @@ def main():
             mine = np.frombuffer(("\n".join(reads[rank::world]) + "\n").encode(), dtype=np.uint8) if reads[rank::world] else np.zeros(0, np.uint8)
             full = np.frombuffer(("\n".join(reads) + "\n").encode(), dtype=np.uint8)
             ref_text = c["unitigs_fa"]
-        cd = Cdbg(k=k, abundance_min=amin, device=local, rank=rank, world_size=world)
+        cd = Cdbg(k=k, abundance_min=amin, device=local, rank=rank, world_size=world, all_abundance_counts=want_ab)
         cd.shard_init_torch()
         g = cd.build(mine)
         gathered = [None] * world
@@ -58,9 +61,12 @@ def main():
             d = parity.diff(parity.graph_to_records(m), parity.graph_to_records(o), k)
             if not d and ref_text:
                 d = parity.diff(parity.graph_to_records(m), parity.parse_unitigs_fa(ref_text), k)
+            if not d and want_ab:
+                d = "no abundance lists in the merged shards" if m.abund is None else \
+                    parity.diff_abundance_lists(parity.graph_to_records(m, with_ab=True), parity.graph_to_records(o, with_ab=True))
             solid = sum(s["n_solid"] for s in m.stats["shards"])
             ok = (d == "") and solid == o.stats["n_solid"]
-            print(f"[shard x{world}] {name}: {'OK' if ok else 'FAIL'} unitigs={m.n_unitigs} links={len(m.links)} solid={solid}/{o.stats['n_solid']} "
+            print(f"[shard x{world}] {'ab:' if want_ab else ''}{name}: {'OK' if ok else 'FAIL'} unitigs={m.n_unitigs} links={len(m.links)} solid={solid}/{o.stats['n_solid']} "
                   f"per-rank unitigs={[x.n_unitigs for x in gathered]} pieces={[x.stats['n_unitigs'] for x in gathered]}", flush=True)
             if not ok:
                 print(d[:2000], flush=True)

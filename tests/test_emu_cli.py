@@ -105,9 +105,31 @@ def test_cli_multi_gpu_mode(cli, tmp_path, name, gpus):
     assert sum(l.startswith("S\t") for l in gfa) == len(ids)
 
 
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_cli_multi_gpu_all_abundance_counts(cli, tmp_path, gpus):
+    """-nb-gpus N -all-abundance-counts: the ab:Z: lists against the oracle's per-k-mer abundances, like the single-GPU test."""
+    from oracle import oracle as orc
+    c = CASES["reads_0_k15_a2"]
+    fa = tmp_path / "x.fa"
+    write_fasta(fa, c["reads"])
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", "15", "-abundance-min", "2", "-all-abundance-counts", "-nb-gpus", str(gpus))
+    recs = parity.parse_unitigs_fa((tmp_path / "x.unitigs.fa").read_text())
+    o = parity.graph_to_records(orc.run(c["reads"], 15, 2), with_ab=True)
+
+    def canon(recs_):
+        out = []
+        for r in recs_:
+            s, ab = r["seq"], r["ab"]
+            rc = parity.revcomp_str(s)
+            assert ab is not None and len(ab) == len(s) - 15 + 1
+            out.append((s, tuple(ab)) if s <= rc else (rc, tuple(reversed(ab))))
+        return sorted(out)
+    assert canon(recs) == canon(o)
+
+
 def test_cli_multi_gpu_mode_refuses_what_the_sharded_path_cannot_do(cli, tmp_path):
     (tmp_path / "x.fa").write_text(">r\nACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT\n")
-    for extra in (["-kmer-size", "41"], ["-kmer-size", "21", "-all-abundance-counts"]):
+    for extra in (["-kmer-size", "41"], ["-kmer-size", "21", "-gpu-parse", "1"]):
         p = subprocess.run([cli, "-in", "x.fa", "-nb-gpus", "2", *extra], cwd=tmp_path, capture_output=True, text=True)
         assert p.returncode != 0 and "EXCEPTION:" in p.stdout
 

@@ -117,14 +117,18 @@ def test_random_combinations_of_all_knobs(emu_lib, monkeypatch, seed):
         for name, v in env.items():
             monkeypatch.setenv(name, v)
         shards = rng.choice([0, 0, 2, 3])
+        ab = rng.random() < 0.4                      # -all-abundance-counts: per-k-mer lists, also on shards
         o = orc.run(reads, k, amin)
         if shards:
-            g, parts = sharded_build(reads, k, amin, shards)
+            g, parts = sharded_build(reads, k, amin, shards, all_abundance_counts=ab)
             n_solid = sum(p.stats["n_solid"] for p in parts)
         else:
-            with api.Cdbg(k=k, abundance_min=amin, device=0) as c:
+            with api.Cdbg(k=k, abundance_min=amin, device=0, all_abundance_counts=ab) as c:
                 g = c.build(reads)
             n_solid = g.stats["n_solid"]
         assert n_solid == o.stats["n_solid"], (seed, it, k, amin, shards, env)
         d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k)
         assert d == "", (seed, it, k, amin, shards, env, d[:400])
+        if ab:
+            d = parity.diff_abundance_lists(parity.graph_to_records(g, with_ab=True), parity.graph_to_records(o, with_ab=True))
+            assert d == "", (seed, it, k, amin, shards, env, d)
