@@ -3,7 +3,7 @@ golden cases on the truly concurrent engine (one OS thread per CUDA thread).  TS
 out-of-bounds access to a "device" allocation or a static __shared__ array aborts the run (end of round 1: none, for the same
 configurations as below plus the sharded path with 3 emulated ranks and the FASTA/FASTQ parser).
 
-    python tests/emu/run_sanitizer.py [--asan | --ubsan] [case ...]     # environment knobs (CDBG_K2C=flat ...) are passed through
+    python tests/emu/run_sanitizer.py [--asan | --ubsan] [--sharded] [case ...]     # environment knobs (CDBG_K2C=flat ...) are passed through
 (--ubsan: undefined-behaviour sanitizer on the default fiber engine -- shift counts, misaligned vector accesses, signed overflow;
 end of round 1: no report over all golden cases.)
 
@@ -31,7 +31,8 @@ import build_emu  # noqa: E402
 def main():
     asan = "--asan" in sys.argv[1:]
     ubsan = "--ubsan" in sys.argv[1:]
-    cases = [a for a in sys.argv[1:] if a not in ("--asan", "--ubsan")] or ["reads_0_k15_a2", "lowcx_8_ACGT_k8_a1", "circular_test1", "even_k_dense_k4"]
+    sharded = "--sharded" in sys.argv[1:]          # 3 emulated ranks (host threads + the NCCL stand-in), with -all-abundance-counts
+    cases = [a for a in sys.argv[1:] if a not in ("--asan", "--ubsan", "--sharded")] or ["reads_0_k15_a2", "lowcx_8_ACGT_k8_a1", "circular_test1", "even_k_dense_k4"]
     build_emu.build()
     work = tempfile.mkdtemp(prefix="cdbg_tsan_")
     src = os.path.join(work, "a", "b")
@@ -54,10 +55,16 @@ def main():
         "from bcalm_b200 import api, parity\n"
         f"api.LIB_PATH = {lib!r}\n"
         f"cases = {{c['name']: c for c in json.load(open({os.path.join(ROOT, 'tests', 'golden', 'golden.json')!r}))}}\n"
+        f"sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+        f"sharded = {sharded!r}\n"
         "for n in sys.argv[1:]:\n"
         "    c = cases[n]\n"
-        "    with api.Cdbg(k=c['k'], abundance_min=c['abundance_min']) as x:\n"
-        "        g = x.build(c['reads'])\n"
+        "    if sharded:\n"
+        "        import test_emu_sharded as tes\n"
+        "        g, _ = tes.sharded_build(c['reads'], c['k'], c['abundance_min'], 3, all_abundance_counts=True)\n"
+        "    else:\n"
+        "        with api.Cdbg(k=c['k'], abundance_min=c['abundance_min']) as x:\n"
+        "            g = x.build(c['reads'])\n"
         "    print(n, parity.diff(parity.graph_to_records(g), parity.parse_unitigs_fa(c['unitigs_fa']), c['k']) or 'OK', flush=True)\n")
     env = dict(os.environ, CDBG_EMU_ENGINE="fibers" if ubsan else "threads", LD_PRELOAD=tsan,
                TSAN_OPTIONS=f"halt_on_error=0 log_path={os.path.join(work, 'report')} history_size=3",
