@@ -113,8 +113,8 @@ Options parse(int argc, char **argv) {
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
     if (!o.solid_in.empty() && o.k > 31) die("-solid-kmers-in needs -kmer-size <= 31");
     if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
-    if (o.nb_gpus > 1 && (o.k > 31 || !o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
-        die("-nb-gpus > 1 supports -kmer-size <= 31 without -solid-kmers-in / -solid-kmers-out / -gpu-parse / -kff");
+    if (o.nb_gpus > 1 && (!o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
+        die("-nb-gpus > 1 does not support -solid-kmers-in / -solid-kmers-out / -gpu-parse / -kff");
     return o;
 }
 

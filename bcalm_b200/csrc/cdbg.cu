@@ -817,7 +817,12 @@ int spell_units(cdbg_ctx *ctx, const uint64_t *d_uid_scan, const uint64_t *d_nt_
         sp.seq = ctx->d_seq; sp.seq_off = ctx->d_seq_off; sp.kc = ctx->d_kc; sp.abund = ctx->d_abund;
         sp.unitig_of_kmer = ctx->d_unitig_of_kmer;
         sp.link = ctx->d_link; sp.term_begin = want_terms ? ctx->d_term_begin : nullptr; sp.term_end = want_terms ? ctx->d_term_end : nullptr;
-        LAUNCH(k8_spell, grid_for(ctx, S, 256, 8), 256, 0, sp);
+        switch (ctx->W) {      // (multi-word k-mers reach this function only on the sharded path: its pieces are spelled here)
+            case 1: LAUNCH(k8_spell, grid_for(ctx, S, 256, 8), 256, 0, sp); break;
+            case 2: LAUNCH(kw8_spell<2>, grid_for(ctx, S, 256, 8), 256, 0, sp); break;
+            case 3: LAUNCH(kw8_spell<3>, grid_for(ctx, S, 256, 8), 256, 0, sp); break;
+            default: LAUNCH(kw8_spell<4>, grid_for(ctx, S, 256, 8), 256, 0, sp); break;
+        }
     }
     CK(cudaMemcpyAsync(ctx->d_seq_off + U, &ctx->total_nt, 8, cudaMemcpyHostToDevice, ctx->stream));
     return CDBG_OK;
@@ -1055,6 +1060,7 @@ int stage_link(cdbg_ctx *ctx) {
 
 #include "shard_host.inl"
 #include "wide_host.inl"
+#include "shard_wide_host.inl"
 
 void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
     cudaStreamSynchronize(ctx->stream);
@@ -1086,8 +1092,6 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     // span dispatch of the reference (Integer.hpp:77-85: spans 32/64/96/128): one 64-bit word for k <= 31, 2..4 words up to k = 127
     if (params->kmer_size < 4 || params->kmer_size > 127)
         return bail(ctx->fail(CDBG_ERR_PARAM, "unhandled kmer size %d (this build supports 4 <= k <= 127)", params->kmer_size));
-    if (params->kmer_size > 31 && params->world_size > 1)
-        return bail(ctx->fail(CDBG_ERR_PARAM, "k > 31 is not available in sharded mode yet (kmer size %d)", params->kmer_size));
     ctx->W = params->kmer_size <= 31 ? 1 : std::max(2, (2 * params->kmer_size + 63) / 64);   // k = 32 also takes two words (reference: k < span)
     if (params->abundance_min < 0) return bail(ctx->fail(CDBG_ERR_PARAM, "abundance-min must be >= 0"));
     if (params->world_size > MAX_WORLD || params->world_size < 0 || (params->world_size > 1 && (params->rank < 0 || params->rank >= params->world_size)))
@@ -1278,7 +1282,8 @@ int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats) {
     }
     ctx->last_n_bytes = ctx->n_bytes;
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = ctx->W > 1 ? stage_count_wide_dispatch(ctx) : ctx->world > 1 ? shard_stage_count(ctx) : stage_count(ctx);
+    int rc = ctx->world > 1 ? (ctx->W > 1 ? shard_stage_count_wide_dispatch(ctx) : shard_stage_count(ctx))
+                            : (ctx->W > 1 ? stage_count_wide_dispatch(ctx) : stage_count(ctx));
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }
@@ -1287,7 +1292,7 @@ int cdbg_compact(cdbg_ctx *ctx, cdbg_stats *stats) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if (ctx->stage != ST_COUNTED) return ctx->fail(CDBG_ERR_STATE, "cdbg_compact needs cdbg_count first");
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = ctx->W > 1 ? stage_compact_wide_dispatch(ctx) : ctx->world > 1 ? shard_stage_compact(ctx) : stage_compact(ctx);
+    int rc = ctx->world > 1 ? shard_stage_compact(ctx) : ctx->W > 1 ? stage_compact_wide_dispatch(ctx) : stage_compact(ctx);
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }

@@ -277,15 +277,12 @@ int shard_stage_count(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stages 2+3 (sharded)
 
-int shard_stage_compact(cdbg_ctx *ctx) {
+// K3 + X2 + K5 of the sharded path for one-word k-mers: end records to the owner of their junction, the join there; leaves
+// ctx->d_link64 (links whose end is local), the link messages for ends on other GPUs, and the unitig-level edges in ctx->d_sedges.
+int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, uint64_t *out_n_msgs) {
     const int W = ctx->world, me = ctx->rank, k = ctx->k;
     const uint64_t S = ctx->S, n2 = 2 * S;
     int rc;
-    tstart(ctx, T_COMPACT);
-    uint64_t all_S[MAX_WORLD], S_total = 0;
-    if ((rc = allgather_host_u64(ctx, &S, 1, all_S))) return rc;
-    for (int r = 0; r < W; r++) S_total += all_S[r];
-
     // ---- K3: end records, destination-major bins, X2
     uint32_t P_local = (uint32_t)std::min<uint64_t>(2048 / W, std::max<uint64_t>(1, (2 * S_total / W + 499999) / 500000));
     const uint32_t P = P_local * W;
@@ -394,6 +391,23 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     ctx->st.n_compactions = ctx->h_ctr[2];
     dfree(ctx, d_rec_key); dfree(ctx, d_rec_val); dfree(ctx, T.keys); dfree(ctx, T.cnt); dfree(ctx, T.ids);
     dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+    *out_msgs = d_link_msgs; *out_n_msgs = n_link_msgs;
+    return CDBG_OK;
+}
+
+int shard_join_wide_dispatch(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, uint64_t *out_n_msgs);   // shard_wide_host.inl
+
+int shard_stage_compact(cdbg_ctx *ctx) {
+    const int W = ctx->world, me = ctx->rank, k = ctx->k;
+    const uint64_t S = ctx->S, n2 = 2 * S;
+    int rc;
+    tstart(ctx, T_COMPACT);
+    uint64_t all_S[MAX_WORLD], S_total = 0;
+    if ((rc = allgather_host_u64(ctx, &S, 1, all_S))) return rc;
+    for (int r = 0; r < W; r++) S_total += all_S[r];
+
+    ulonglong2 *d_link_msgs = nullptr; uint64_t n_link_msgs = 0;
+    if ((rc = ctx->W > 1 ? shard_join_wide_dispatch(ctx, S_total, &d_link_msgs, &n_link_msgs) : shard_join_narrow(ctx, S_total, &d_link_msgs, &n_link_msgs))) return rc;
 
     TRACE("k5 join");
     // ---- X3: link messages to the owners of the ends; local view of the links

@@ -8,6 +8,7 @@
 // no tile-local sort); the k <= 31 path in kernels.cuh / k1_tma.cuh is the tuned one.
 #pragma once
 #include "kernels.cuh"
+#include "shard.cuh"
 
 template <int W> struct KM { uint64_t w[W]; };
 
@@ -282,6 +283,7 @@ struct KW3Params {
     unsigned long long *bin_count; const uint64_t *bin_off; unsigned long long *bin_cursor;
     uint64_t *rec_key;   // [2S * W]
     uint64_t *rec_val;   // [2S]
+    int sharded; uint32_t rank;   // sharded path: values carry the gid (rank << 32 | end) and the SREC_* flags of shard.cuh
 };
 
 // per-tile shared-memory aggregation like k3_ends: the hot per-bin cursors are hit once per (tile, bin)
@@ -303,6 +305,11 @@ __global__ void __launch_bounds__(K3_THREADS) kw3_ends(KW3Params p) {
 #pragma unroll
             for (int end = 0; end < 2; end++) {
                 kmer_end_record_w<W>(x, p.k, end, (uint32_t)i, key[end], val[end]);
+                if (p.sharded) {
+                    const uint64_t v = val[end];
+                    val[end] = ((uint64_t)p.rank << 32) | (uint32_t)v | ((v & REC_SIDE_OUT) ? SREC_SIDE_OUT : 0) | ((v & REC_PALIN) ? SREC_PALIN : 0) |
+                               ((v & REC_BOTH) ? SREC_BOTH : 0) | ((v & REC_SKIP) ? SREC_SKIP : 0);
+                }
                 bin[end] = hash_to_bin(km_hash<W>(key[end]), p.P);
                 rnk[end] = atomicAdd(&s_cnt[bin[end]], 1u);
             }
@@ -382,6 +389,29 @@ __global__ void __launch_bounds__(256) kw5_resolve(JoinTableW T, uint32_t cap, u
     block_add(n_compact, compact);
 }
 
+// Sharded join on multi-word keys: the slot is found through the tag protocol; the per-slot state lives in a JoinTable64 (64-bit
+// gids, like the k <= 31 sharded join) whose `keys` array only marks occupancy, so that k5s_resolve serves both widths.
+template <int W>
+__global__ void __launch_bounds__(256) kw5s_insert(const uint64_t *__restrict__ rec_key, const uint64_t *__restrict__ rec_val, uint64_t n, uint32_t *tags,
+                                                   uint64_t *wkeys, JoinTable64 T, int *overflow) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const KM<W> key = km_load<W>(rec_key + i * W);
+        const uint64_t val = rec_val[i];
+        if (val & SREC_SKIP) continue;
+        const uint32_t slot = wide_find_or_insert<W>(key, km_hash<W>(key) * 0x9E3779B97F4A7C15ULL + 0x7F4A7C15ULL, tags, wkeys, T.cap);
+        if (slot == 0xFFFFFFFFu) { *overflow = 1; continue; }
+        T.keys[slot] = 0;                              // occupied (anything but EMPTY_KEY; every writer stores the same value)
+        const bool pal = (val & SREC_PALIN) != 0, use_out = (val & SREC_SIDE_OUT) != 0 && !pal;
+        const uint32_t old = atomicAdd(&T.cnt[slot], use_out ? 0x100u : 0x1u);
+        if (pal) atomicOr(&T.cnt[slot], 0x80000000u);
+        const uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
+        if (pos < 4) {
+            T.ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = val & GID_MASK;
+            if (val & SREC_BOTH) atomicOr(&T.cnt[slot], 1u << ((use_out ? JOIN_BOTH_SHIFT_OUT : JOIN_BOTH_SHIFT_IN) + pos));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ spell (wide)
 
 template <int W>
@@ -394,6 +424,11 @@ __global__ void __launch_bounds__(256) kw8_spell(SpellParams p) {
         uint64_t u = p.uid_scan[h], off = p.nt_scan[h];
         KM<W> x = km_load<W>(p.solid_kmers + v * W);
         if (rev) x = km_revcomp<W>(x, p.k);
+        if (p.term_begin) {                          // sharded path: the k-mer ends at which this piece begins and ends (see k8_spell)
+            if (pos == 0) p.term_begin[u] = B;
+            const uint32_t exit_end = 2u * (uint32_t)v + (rev ? 0u : 1u);
+            if (p.link[exit_end] == NOLINK) p.term_end[u] = exit_end;
+        }
         if (pos == 0) {
             p.seq_off[u] = off;
             for (int j = 0; j < p.k; j++) p.seq[off + j] = NT[km_nt<W>(x, p.k - 1 - j)];

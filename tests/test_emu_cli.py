@@ -86,7 +86,7 @@ def test_counted_kmers_errors_are_reported_like_the_reference(cli, tmp_path):
 
 
 @pytest.mark.parametrize("gpus", [2, 3, 4])
-@pytest.mark.parametrize("name", ["reads_1_k21_a2", "circular_test1", "even_k_dense_k6", "lowcx_11_ACGT_k7_a2"])
+@pytest.mark.parametrize("name", ["reads_1_k21_a2", "circular_test1", "even_k_dense_k6", "lowcx_11_ACGT_k7_a2", "wide_2_k47_a2", "wide_9_k127_a1"])
 def test_cli_multi_gpu_mode(cli, tmp_path, name, gpus):
     """-nb-gpus N: one context per (emulated) GPU driven by threads of the CLI process, NCCL stand-in between them; the output
     file must be the same graph with consecutive ids, whatever the number of shards."""
@@ -129,7 +129,7 @@ def test_cli_multi_gpu_all_abundance_counts(cli, tmp_path, gpus):
 
 def test_cli_multi_gpu_mode_refuses_what_the_sharded_path_cannot_do(cli, tmp_path):
     (tmp_path / "x.fa").write_text(">r\nACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGT\n")
-    for extra in (["-kmer-size", "41"], ["-kmer-size", "21", "-gpu-parse", "1"]):
+    for extra in (["-kmer-size", "21", "-kff"], ["-kmer-size", "21", "-gpu-parse", "1"], ["-kmer-size", "21", "-solid-kmers-out", "s.txt"]):
         p = subprocess.run([cli, "-in", "x.fa", "-nb-gpus", "2", *extra], cwd=tmp_path, capture_output=True, text=True)
         assert p.returncode != 0 and "EXCEPTION:" in p.stdout
 

@@ -63,7 +63,7 @@ def sharded_build(reads, k, amin, world, **kw):
     return api.merge_shards(out), out
 
 
-CASES = sorted(n for n, c in GOLDEN.items() if c["k"] <= 31)   # (k > 31 is single-GPU only)
+CASES = sorted(n for n, c in GOLDEN.items() if c["unitigs_fa"] is not None)   # k <= 31 (minimizer-sharded) and k = 32..127 (hash-sharded, shard_wide_host.inl)
 
 
 @pytest.mark.parametrize("world", [2, 3, 4])
@@ -90,7 +90,8 @@ def test_sharded_solid_kmer_count_equals_oracle(emu_lib):
 
 
 # ---------------------------------------------------------------------------------------------------------------- ab:Z: on shards
-AB_CASES = ["reads_0_k15_a2", "reads_3_k31_a2", "reads_5_k25_a1", "circular_test1", "lowcx_8_ACGT_k8_a1", "minitip_k21_a1", "even_k_reads_k20_a2", "circular_test2_polyA", "circular_genome_2_k21", "pow2_cycle_L256_k21", "lowcx_4_AT_k7_a2"]
+AB_CASES = ["reads_0_k15_a2", "reads_3_k31_a2", "reads_5_k25_a1", "circular_test1", "lowcx_8_ACGT_k8_a1", "minitip_k21_a1", "even_k_reads_k20_a2", "circular_test2_polyA", "circular_genome_2_k21", "pow2_cycle_L256_k21", "lowcx_4_AT_k7_a2",
+            "wide_1_k33_a2", "wide_4_k64_a2", "wide_8_k127_a2", "wide_lowcx_0_AT_k33"]
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -69,3 +69,11 @@ def test_sharded_all_abundance_counts():
     if not w:
         pytest.skip("needs >= 2 GPUs")
     _run(w, ["ab:reads_3_k31_a2", "ab:reads_0_k15_a2", "ab:circular_test1", "ab:lowcx_8_ACGT_k8_a1", "ab:c2:0.05"], 29544, timeout=300)
+
+
+@pytest.mark.xfail(strict=False, reason="the sharded path for k > 31 was written after round 1's last GPU run; XPASS means fine")
+def test_sharded_multi_word_kmers():
+    w = _world()
+    if not w:
+        pytest.skip("needs >= 2 GPUs")
+    _run(w, [c["name"] for c in load_golden() if c["unitigs_fa"] is not None and c["k"] > 31], 29545, timeout=300)
