@@ -70,7 +70,7 @@ typedef struct {
     int32_t device;         /* CUDA device ordinal */
     int32_t flags;          /* CDBG_FLAG_* */
     int32_t rank;           /* shard index of this context (0 when world_size == 1) */
-    int32_t world_size;     /* number of shards (GPUs); buckets are owned by hash(minimizer) % world_size */
+    int32_t world_size;     /* number of shards (GPUs); k <= 31: buckets owned by hash(minimizer) % world_size, k >= 32: by hash(k-mer) */
 } cdbg_params;
 
 typedef struct {
