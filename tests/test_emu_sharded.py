@@ -110,3 +110,32 @@ def test_sharded_all_abundance_counts_match_the_single_gpu_lists(emu_lib, name, 
     assert len(common) >= len(r_one) - 2 or name.startswith("circular")         # only circular unitigs may be spelled from another cut point
     d = parity.diff(parity.graph_to_records(m), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
     assert d == "", d
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs the reference binary (oracle/_ref/bcalm)")
+@pytest.mark.parametrize("k,world", [(63, 3), (127, 4), (33, 2)])
+def test_sharded_multi_word_kmers_on_sequencing_like_reads_match_the_reference_binary(emu_lib, tmp_path, k, world):
+    """60 kbp genome, 150 bp reads, 20x, 1 % errors, both strands: the hash-sharded k > 31 path against the reference itself (the C
+    oracle stops at k = 31), per-k-mer abundance lists against the single-GPU path, and the shards must be balanced."""
+    import random
+    rng = random.Random(1000 + k)
+    comp = str.maketrans("ACGT", "TGCA")
+    genome = "".join(rng.choice("ACGT") for _ in range(60000))
+    reads = []
+    for _ in range(len(genome) * 20 // 150):
+        s = rng.randrange(0, len(genome) - 150)
+        r = genome[s:s + 150]
+        if rng.random() < 0.5:
+            r = r[::-1].translate(comp)
+        reads.append("".join(c if rng.random() > 0.01 else rng.choice("ACGT") for c in r))
+    fa = tmp_path / "x.fa"
+    fa.write_text("".join(f">r\n{r}\n" for r in reads))
+    ref = orc.run_ref(str(fa), k, 2, nb_cores=2, extra=["-verbose", "0"])[0]
+    m, shards = sharded_build(reads, k, 2, world, all_abundance_counts=True)
+    d = parity.diff(parity.graph_to_records(m), parity.parse_unitigs_fa(ref), k)
+    assert d == "", d[:500]
+    with api.Cdbg(k=k, abundance_min=2, device=0, all_abundance_counts=True) as c:
+        one = c.build(reads)
+    assert parity.diff_abundance_lists(parity.graph_to_records(m, with_ab=True), parity.graph_to_records(one, with_ab=True)) == ""
+    solid = [s.stats["n_solid"] for s in shards]
+    assert sum(solid) == one.stats["n_solid"] and max(solid) < 1.2 * min(solid) + 100
