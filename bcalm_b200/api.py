@@ -252,12 +252,14 @@ class Cdbg:
         return (km if W == 1 else km.reshape(-1, W)), ct
 
     def set_solid_kmers(self, kmers, counts):
-        """Start from counted k-mers instead of reads (k <= 31): uint64 k-mers in either orientation, uint32 abundances."""
+        """Start from counted k-mers instead of reads: uint64 k-mers in either orientation (k <= 31: shape (n,); k >= 32: shape (n, W),
+        little-endian words, as solid_kmers() returns them), uint32 abundances."""
+        W = 1 if self.k <= 31 else max(2, (2 * self.k + 63) // 64)
         km = np.ascontiguousarray(kmers, dtype=np.uint64)
         ct = np.ascontiguousarray(counts, dtype=np.uint32)
-        if km.shape != ct.shape or km.ndim != 1:
-            raise ValueError("kmers and counts must be 1-D arrays of the same length")
-        self._ck(self.lib.cdbg_set_solid_kmers(self.h, km.ctypes.data, ct.ctypes.data, km.size, MEM_HOST))
+        if ct.ndim != 1 or km.shape != ((ct.size,) if W == 1 else (ct.size, W)):
+            raise ValueError(f"kmers must have shape {'(n,)' if W == 1 else f'(n, {W})'} and counts shape (n,)")
+        self._ck(self.lib.cdbg_set_solid_kmers(self.h, km.ctypes.data, ct.ctypes.data, ct.size, MEM_HOST))
 
     def _view_to_graph(self, v: UnitigView, copy: bool = True) -> Graph:
         def arr(ptr, n, dt):

@@ -111,7 +111,6 @@ Options parse(int argc, char **argv) {
         }
     }
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
-    if (!o.solid_in.empty() && o.k > 31) die("-solid-kmers-in needs -kmer-size <= 31");
     if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
     if (o.nb_gpus > 1 && (!o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
         die("-nb-gpus > 1 does not support -solid-kmers-in / -solid-kmers-out / -gpu-parse / -kff");
@@ -350,7 +349,28 @@ double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock:
 // 'm' (minimizer) sections are not read.
 uint64_t kff_be(const uint8_t *p, int n) { uint64_t v = 0; for (int i = 0; i < n; i++) v = (v << 8) | p[i]; return v; }
 
-bool load_kff(const Options &o, const FileBuf &in, std::vector<std::pair<uint64_t, uint64_t>> &rec) {
+// A k-mer of up to 127 nucleotides on the host: 4 little-endian 64-bit words (the library's layout, W = words_of(k) of them are used),
+// compared most significant word first like the device code.
+struct HostKmer {
+    uint64_t w[4];
+    bool operator<(const HostKmer &o) const { for (int i = 3; i >= 0; i--) if (w[i] != o.w[i]) return w[i] < o.w[i]; return false; }
+    bool operator==(const HostKmer &o) const { return w[0] == o.w[0] && w[1] == o.w[1] && w[2] == o.w[2] && w[3] == o.w[3]; }
+};
+inline int words_of(int k) { return k <= 31 ? 1 : std::max(2, (2 * k + 63) / 64); }
+// roll one nucleotide (our 2-bit code) into the forward k-mer x and its reverse complement r
+inline void kmer_roll(HostKmer &x, HostKmer &r, uint64_t code, int k) {
+    for (int i = 3; i > 0; i--) x.w[i] = (x.w[i] << 2) | (x.w[i - 1] >> 62);
+    x.w[0] = (x.w[0] << 2) | code;
+    const int bits = 2 * k;                                  // keep the low 2k bits
+    for (int i = 0; i < 4; i++) { const int lo = 64 * i; if (bits <= lo) x.w[i] = 0; else if (bits < lo + 64) x.w[i] &= (1ULL << (bits - lo)) - 1ULL; }
+    for (int i = 0; i < 3; i++) r.w[i] = (r.w[i] >> 2) | (r.w[i + 1] << 62);
+    r.w[3] >>= 2;
+    const int top = 2 * (k - 1);
+    r.w[top >> 6] |= (code ^ 2) << (top & 63);
+}
+inline unsigned kmer_nt(const uint64_t *km, int j) { return (unsigned)(km[(2 * j) >> 6] >> ((2 * j) & 63)) & 3u; }   // nucleotide j from the last
+
+bool load_kff(const Options &o, const FileBuf &in, std::vector<std::pair<HostKmer, uint64_t>> &rec) {
     const uint8_t *b = (const uint8_t *)in.p, *e = b + in.n;
     if (in.n < 12 || memcmp(b, "KFF", 3) != 0) return false;
     if (b[3] != 1) die("unsupported KFF version in '" + o.solid_in + "'");
@@ -383,7 +403,6 @@ bool load_kff(const Options &o, const FileBuf &in, std::vector<std::pair<uint64_
             if (dsz > 8) die("KFF data_size > 8 is not supported");
             int nbits = 0; while ((1ULL << nbits) < maxk) nbits++;      // ceil(log2(max))
             const int nb_bytes = (nbits + 7) / 8;
-            const uint64_t kmask = o.k >= 32 ? ~0ULL : ((1ULL << (2 * o.k)) - 1);
             for (uint64_t blk = 0; blk < n; blk++) {
                 uint64_t nk = 1;
                 if (nb_bytes) { need((size_t)nb_bytes); nk = kff_be(p, nb_bytes); p += nb_bytes; }
@@ -391,12 +410,11 @@ bool load_kff(const Options &o, const FileBuf &in, std::vector<std::pair<uint64_
                 need(sb + nk * dsz);
                 const uint8_t *seq = p, *dat = p + sb;
                 const uint64_t pad = sb * 4 - nt;                          // leading padding, in nucleotides
-                uint64_t x = 0, r = 0;
+                HostKmer x{}, r{};
                 for (uint64_t i = 0; i < nt; i++) {
                     const uint64_t q = pad + i;
                     const uint64_t code = to_ours[(seq[q >> 2] >> (2 * (3 - (q & 3)))) & 3];
-                    x = ((x << 2) | code) & kmask;
-                    r = (r >> 2) | ((code ^ 2) << (2 * (o.k - 1)));
+                    kmer_roll(x, r, code, o.k);
                     if (i + 1 >= kk) {
                         const uint64_t j = i + 1 - kk;
                         rec.emplace_back(x < r ? x : r, dsz ? kff_be(dat + j * dsz, (int)dsz) : 1);
@@ -414,7 +432,8 @@ bool load_kff(const Options &o, const FileBuf &in, std::vector<std::pair<uint64_
 void write_kff(const std::string &path, cdbg_ctx *ctx, int k) {
     uint64_t n = 0;
     if (cdbg_get_solid_kmers(ctx, nullptr, nullptr, 0, &n) != CDBG_OK) die(cdbg_last_error(ctx));
-    std::vector<uint64_t> km(n + 1); std::vector<uint32_t> ct(n + 1);
+    const int W = words_of(k);
+    std::vector<uint64_t> km(n * W + 1); std::vector<uint32_t> ct(n + 1);
     if (cdbg_get_solid_kmers(ctx, km.data(), ct.data(), n, &n) != CDBG_OK) die(cdbg_last_error(ctx));
     std::string f;
     auto be = [&](uint64_t v, int bytes) { for (int i = bytes - 1; i >= 0; i--) f.push_back((char)(v >> (8 * i))); };
@@ -428,7 +447,10 @@ void write_kff(const std::string &path, cdbg_ctx *ctx, int k) {
     f.push_back('r'); be(n, 8);
     const int sb = (k + 3) / 4;
     f.reserve(f.size() + n * (size_t)(sb + 4) + 128);
-    for (uint64_t i = 0; i < n; i++) { be(km[i], sb); be(ct[i], 4); }
+    for (uint64_t i = 0; i < n; i++) {
+        for (int b = sb - 1; b >= 0; b--) f.push_back((char)(km[i * W + ((8 * b) >> 6)] >> ((8 * b) & 63)));     // 2k bits, big-endian, left-padded
+        be(ct[i], 4);
+    }
     const uint64_t pos_i = f.size(), end_i = pos_i + 17 + 9 * 2;
     f.push_back('i'); be(2, 8);
     f.push_back('v'); be((uint64_t)((int64_t)pos_v - (int64_t)end_i), 8);
@@ -446,7 +468,8 @@ void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vec
     FileBuf in;
     if (!read_whole(o.solid_in, in)) die("Unable to open file '" + o.solid_in + "'");
     const int k = o.k;
-    std::vector<std::pair<uint64_t, uint64_t>> rec;
+    std::vector<std::pair<HostKmer, uint64_t>> rec;
+    const int W = words_of(k);
     const char *p = in.p, *e = in.p + in.n;
     uint64_t line = 0;
     if (load_kff(o, in, rec)) p = e;                   // a KFF file: the records are in `rec` already
@@ -457,15 +480,13 @@ void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vec
         const char *q = p;
         while (q < le && (*q == ' ' || *q == '\t')) q++;
         if (q < le && *q != '#' && *q != '\r') {
-            uint64_t x = 0, r = 0;
+            HostKmer x{}, r{};
             int len = 0;
             for (; q < le && *q != ' ' && *q != '\t' && *q != '\r'; q++, len++) {
                 const char c = *q & 0xDF;
                 if (len >= k) die("k-mer longer than -kmer-size in '" + o.solid_in + "' line " + std::to_string(line));
                 if (c != 'A' && c != 'C' && c != 'G' && c != 'T') die("bad nucleotide in '" + o.solid_in + "' line " + std::to_string(line));
-                const uint64_t code = ((uint64_t)c >> 1) & 3;
-                x = (x << 2) | code;
-                r = (r >> 2) | ((code ^ 2) << (2 * (k - 1)));
+                kmer_roll(x, r, ((uint64_t)c >> 1) & 3, k);
             }
             if (len != k) die("k-mer length differs from -kmer-size in '" + o.solid_in + "' line " + std::to_string(line));
             while (q < le && (*q == ' ' || *q == '\t')) q++;
@@ -481,7 +502,7 @@ void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vec
     for (size_t i = 0; i < rec.size();) {
         size_t j = i; uint64_t c = 0;
         for (; j < rec.size() && rec[j].first == rec[i].first; j++) c += rec[j].second;
-        if (c >= amin && c <= amax) { kmers.push_back(rec[i].first); counts.push_back((uint32_t)c); }
+        if (c >= amin && c <= amax) { for (int w = 0; w < W; w++) kmers.push_back(rec[i].first.w[w]); counts.push_back((uint32_t)c); }
         i = j;
     }
 }
@@ -489,13 +510,14 @@ void load_counted_kmers(const Options &o, std::vector<uint64_t> &kmers, std::vec
 void write_counted_kmers(const std::string &path, cdbg_ctx *ctx, int k) {
     uint64_t n = 0;
     if (cdbg_get_solid_kmers(ctx, nullptr, nullptr, 0, &n) != CDBG_OK) die(cdbg_last_error(ctx));
-    std::vector<uint64_t> km(n + 1); std::vector<uint32_t> ct(n + 1);
+    const int W = words_of(k);
+    std::vector<uint64_t> km(n * W + 1); std::vector<uint32_t> ct(n + 1);
     if (cdbg_get_solid_kmers(ctx, km.data(), ct.data(), n, &n) != CDBG_OK) die(cdbg_last_error(ctx));
     std::string text;
     text.reserve(n * (size_t)(k + 12));
     const char NT[4] = {'A', 'C', 'T', 'G'};
     for (uint64_t i = 0; i < n; i++) {
-        for (int j = k - 1; j >= 0; j--) text.push_back(NT[(km[i] >> (2 * j)) & 3]);
+        for (int j = k - 1; j >= 0; j--) text.push_back(NT[kmer_nt(&km[i * W], j)]);
         text.push_back(' '); put_u64(text, ct[i]); text.push_back('\n');
     }
     FILE *f = fopen(path.c_str(), "wb");
@@ -690,7 +712,7 @@ int main(int argc, char **argv) {
         std::vector<uint64_t> km; std::vector<uint32_t> ct;
         load_counted_kmers(o, km, ct);
         t1 = now_s();
-        rc = cdbg_set_solid_kmers(ctx, km.data(), ct.data(), km.size(), CDBG_MEM_HOST);
+        rc = cdbg_set_solid_kmers(ctx, km.data(), ct.data(), ct.size(), CDBG_MEM_HOST);
         if (rc == CDBG_OK) rc = cdbg_compact(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_link(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_get_unitigs(ctx, &v);
@@ -714,7 +736,6 @@ int main(int argc, char **argv) {
     const double t2 = now_s();
     if (!o.solid_out.empty()) write_counted_kmers(o.solid_out, ctx, o.k);
     if (o.kff) {
-        if (o.k > 31) { cdbg_destroy(ctx); die("-kff needs -kmer-size <= 31"); }
         write_kff((!o.out.empty() ? o.out : base_name(o.in.empty() ? o.solid_in : o.in)) + ".kff", ctx, o.k);
     }
 

@@ -1393,19 +1393,24 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
 int cdbg_set_solid_kmers(cdbg_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, uint64_t n, int location) {
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     if ((!kmers || !counts) && n) return ctx->fail(CDBG_ERR_PARAM, "null k-mer / count pointer");
-    if (ctx->W != 1 || ctx->world != 1) return ctx->fail(CDBG_ERR_PARAM, "cdbg_set_solid_kmers needs k <= 31 on a single-GPU context");
+    if (ctx->world != 1) return ctx->fail(CDBG_ERR_PARAM, "cdbg_set_solid_kmers needs a single-GPU context");
     if (ctx->stage != ST_EMPTY) return ctx->fail(CDBG_ERR_STATE, "cdbg_set_solid_kmers on a context that already holds reads or results: call cdbg_reset first");
     if (n >= (1ULL << 31)) return ctx->fail(CDBG_ERR_PARAM, "more than 2^31 solid k-mers on one device (%llu)", (unsigned long long)n);
     CK(cudaSetDevice(ctx->prm.device));
     int rc;
     tstart(ctx, T_COUNT);
-    if ((rc = dalloc(ctx, &ctx->d_solid_kmers, n + 1))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_solid_kmers, n * ctx->W + 1))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_solid_counts, n + 1))) return rc;
     const cudaMemcpyKind kind = location == CDBG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (n) {
-        CK(cudaMemcpyAsync(ctx->d_solid_kmers, kmers, n * 8, kind, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_solid_kmers, kmers, n * 8 * ctx->W, kind, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_solid_counts, counts, n * 4, kind, ctx->stream));
-        LAUNCH(k2_canonicalise, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k);
+        switch (ctx->W) {
+            case 1: LAUNCH(k2_canonicalise, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k); break;
+            case 2: LAUNCH(kw2_canonicalise<2>, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k); break;
+            case 3: LAUNCH(kw2_canonicalise<3>, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k); break;
+            default: LAUNCH(kw2_canonicalise<4>, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k); break;
+        }
     }
     CK(cudaStreamSynchronize(ctx->stream));   // the caller may free its arrays when this returns
     tstop(ctx, T_COUNT);

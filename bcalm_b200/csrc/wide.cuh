@@ -262,6 +262,17 @@ __global__ void __launch_bounds__(256) kw2_emit(uint32_t *tags, uint64_t *keys, 
     block_add(n_distinct, (unsigned long long)my_distinct);
 }
 
+// counted k-mers handed in from outside (cdbg_set_solid_kmers, k >= 32): mask to 2k bits and bring to the canonical orientation
+template <int W>
+__global__ void __launch_bounds__(256) kw2_canonicalise(uint64_t *kmers, uint64_t n, int k) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        KM<W> x = km_load<W>(kmers + i * W);
+        km_mask<W>(x, k);
+        const KM<W> r = km_revcomp<W>(x, k);
+        km_store<W>(kmers + i * W, km_less<W>(r, x) ? r : x);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K3 (wide)
 
 template <int W>

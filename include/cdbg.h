@@ -166,7 +166,8 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
  * k-mers of its `.h5`, GraphUnitigs.cpp:884-951): install `n` solid (k-mer, abundance) pairs -- e.g. a DSK / KMC / Jellyfish dump
  * after the caller's abundance filter -- and continue with cdbg_compact / cdbg_link.  K-mers are 2 bits per nucleotide, first
  * nucleotide most significant, A=0 C=1 T=2 G=3, in either orientation (they are canonicalised on the device); every canonical
- * k-mer must occur once.  k <= 31, single GPU, on an empty context (after cdbg_create or cdbg_reset). */
+ * k-mer must occur once (W words per k-mer as for cdbg_get_solid_kmers).  Single GPU, on an empty context (after cdbg_create or
+ * cdbg_reset). */
 int cdbg_set_solid_kmers(cdbg_ctx *ctx, const uint64_t *kmers, const uint32_t *counts, uint64_t n, int location);
 
 /* Device-side synthetic read generator used by bench.py (inputs resident in HBM when the timed region starts):

@@ -42,7 +42,8 @@ def _rc(s):
     return s[::-1].translate(str.maketrans("ACGT", "TGCA"))
 
 
-@pytest.mark.parametrize("name", ["reads_1_k21_a2", "lowcx_11_ACGT_k7_a2", "circular_test1"])
+@pytest.mark.parametrize("name", ["reads_1_k21_a2", "lowcx_11_ACGT_k7_a2", "circular_test1", "wide_0_k32_a2", "wide_2_k47_a2", "wide_4_k64_a2", "wide_5_k65_a2",
+                                  "wide_7_k96_a2", "wide_8_k127_a2", "wide_lowcx_1_AT_k35"])
 def test_counted_kmers_round_trip(cli, tmp_path, name):
     """reads -> unitigs with -solid-kmers-out, then -solid-kmers-in alone must give the same graph."""
     c = CASES[name]
@@ -82,7 +83,7 @@ def test_counted_kmers_errors_are_reported_like_the_reference(cli, tmp_path):
     p = subprocess.run([cli, "-solid-kmers-in", "bad.txt", "-kmer-size", "21"], cwd=tmp_path, capture_output=True, text=True)
     assert p.returncode != 0 and "EXCEPTION:" in p.stdout and "k-mer length" in p.stdout
     p = subprocess.run([cli, "-solid-kmers-in", "bad.txt", "-kmer-size", "63"], cwd=tmp_path, capture_output=True, text=True)
-    assert p.returncode != 0 and "EXCEPTION:" in p.stdout
+    assert p.returncode != 0 and "EXCEPTION:" in p.stdout and "k-mer length" in p.stdout
 
 
 @pytest.mark.parametrize("gpus", [2, 3, 4])
@@ -244,4 +245,32 @@ def test_kff_with_several_kmers_per_block_and_another_encoding(cli, tmp_path):
     _kff_write(tmp_path / "other.kff", k, blocks)
     run_cli(cli, tmp_path, "-solid-kmers-in", "other.kff", "-kmer-size", str(k), "-abundance-min", "1", "-out", "fromother")
     d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromother.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), k)
+    assert d == "", d
+
+
+@pytest.mark.parametrize("name", ["wide_1_k33_a2", "wide_3_k63_a2", "wide_6_k95_a2", "wide_9_k127_a1"])
+def test_kff_and_non_canonical_text_dumps_with_multi_word_kmers(cli, tmp_path, name):
+    """k = 32..127: the KFF written here holds the same (k-mer, count) pairs as the text dump, both read back into the reference's graph;
+    a dump listing the other strand (split counts) is merged like for k <= 31."""
+    c = CASES[name]
+    k = c["k"]
+    fa = tmp_path / "in.fa"
+    write_fasta(fa, c["reads"])
+    run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(k), "-abundance-min", "1", "-kff", "-solid-kmers-out", "all.txt")
+    ours, var = _kff_read(tmp_path / "in.kff", k)
+    text = dict((l.split()[0], int(l.split()[1])) for l in (tmp_path / "all.txt").read_text().split("\n")[:-1])
+    assert var["k"] == k and ours == text and all(len(s_) == k for s_ in text)
+    want = parity.parse_unitigs_fa(c["unitigs_fa"])
+    run_cli(cli, tmp_path, "-solid-kmers-in", "in.kff", "-kmer-size", str(k), "-abundance-min", str(c["abundance_min"]), "-out", "fromkff")
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromkff.unitigs.fa").read_text()), want, k)
+    assert d == "", d
+    out = []
+    for i, (km, n) in enumerate(text.items()):
+        if n >= 2 and i % 2 == 0:
+            out += [f"{km.lower()}\t{n - 1}", f"{_rc(km)} 1"]
+        else:
+            out.append(f"{_rc(km) if i % 3 == 0 else km} {n}")
+    (tmp_path / "dump.txt").write_text("\n".join(out) + "\n")
+    run_cli(cli, tmp_path, "-solid-kmers-in", "dump.txt", "-kmer-size", str(k), "-abundance-min", str(c["abundance_min"]), "-out", "fromdump")
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromdump.unitigs.fa").read_text()), want, k)
     assert d == "", d

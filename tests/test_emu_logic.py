@@ -243,8 +243,34 @@ def test_counted_kmers_hand_off_through_the_abi(emu_lib, knobs):
         with pytest.raises(api.CdbgError):
             b.set_solid_kmers(mixed, ct)          # not on a context that already holds results
     check_against_golden(g, case)
-    with api.Cdbg(k=63, abundance_min=1, device=0) as w, pytest.raises(api.CdbgError):
-        w.set_solid_kmers(km, ct)                 # k <= 31 only
+    with api.Cdbg(k=63, abundance_min=1, device=0) as w, pytest.raises(ValueError):
+        w.set_solid_kmers(km, ct)                 # k = 63 takes (n, 2) words
+
+
+@pytest.mark.parametrize("name", ["wide_0_k32_a2", "wide_3_k63_a2", "wide_5_k65_a2", "wide_8_k127_a2"])
+def test_counted_kmers_hand_off_with_multi_word_kmers(emu_lib, knobs, name):
+    """The same hand-off for k = 32..127: (n, W) little-endian words, half of them handed over as the other strand."""
+    case = GOLDEN[name]
+    k = case["k"]
+    with api.Cdbg(k=k, abundance_min=case["abundance_min"], device=0) as a:
+        a.push_reads(case["reads"])
+        a.count()
+        km, ct = a.solid_kmers()
+    W = km.shape[1]
+    mixed = km.copy()
+    for i in range(0, len(km), 2):
+        x = sum(int(km[i, w]) << (64 * w) for w in range(W))
+        r = 0
+        for j in range(k):
+            r = (r << 2) | (((x >> (2 * j)) & 3) ^ 2)
+        mixed[i] = [(r >> (64 * w)) & 0xFFFFFFFFFFFFFFFF for w in range(W)]
+    assert not np.array_equal(mixed, km)
+    with api.Cdbg(k=k, abundance_min=1, device=0) as b:
+        b.set_solid_kmers(mixed, ct)
+        b.compact()
+        b.link()
+        g = b.unitigs()
+    check_against_golden(g, case)
 
 
 def test_repeated_builds_on_one_context_are_identical(emu_lib, knobs):
