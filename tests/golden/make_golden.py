@@ -171,20 +171,25 @@ def main():
         n = text.count(">") if text else -1
         print(f"{c['name']:32s} k={c['k']:2d} a={c['abundance_min']} reads={len(c['reads']):5d} -> {n} unitigs")
         res.append(c)
-    # the reference's own KFF dump of one case (-kff): fixture for the KFF reader of the CLI (tests/test_emu_cli.py)
-    kc = [c for c in res if c["name"] == "reads_0_k15_a2"][0]
-    with tempfile.TemporaryDirectory() as d:
-        fa = os.path.join(d, "r.fa")
-        orc.write_fasta(fa, kc["reads"])
-        orc.run_ref(fa, kc["k"], kc["abundance_min"], nb_cores=2, extra=["-minimizer-size", str(kc["minimizer_size"]), "-verbose", "0", "-kff"], timeout=300,
-                    keep_dir=d)
-        for fn in os.listdir(d):
-            if fn.endswith(".kff"):
-                with open(os.path.join(d, fn), "rb") as fi, open(os.path.join(ROOT, "tests", "golden", "reads_0_k15_a2.ref.kff"), "wb") as fo:
-                    fo.write(fi.read())
+    # the reference's own KFF dumps (-kff) of two cases, one- and two-word k-mers: fixtures for the KFF reader of the CLI (tests/test_emu_cli.py)
+    write_reference_kff(res)
     with open(os.path.join(ROOT, "tests", "golden", "golden.json"), "w") as f:
         json.dump(res, f, indent=0)
     print("wrote tests/golden/golden.json", os.path.getsize(os.path.join(ROOT, "tests", "golden", "golden.json")), "bytes")
+
+
+def write_reference_kff(cases, names=("reads_0_k15_a2", "wide_2_k47_a2")):
+    for name in names:
+        kc = [c for c in cases if c["name"] == name][0]
+        with tempfile.TemporaryDirectory() as d:
+            fa = os.path.join(d, "r.fa")
+            orc.write_fasta(fa, kc["reads"])
+            extra = ["-minimizer-size", str(kc["minimizer_size"])] if kc.get("minimizer_size") else []
+            orc.run_ref(fa, kc["k"], kc["abundance_min"], nb_cores=2, extra=[*extra, "-verbose", "0", "-kff"], timeout=300, keep_dir=d)
+            for fn in os.listdir(d):
+                if fn.endswith(".kff"):
+                    with open(os.path.join(d, fn), "rb") as fi, open(os.path.join(ROOT, "tests", "golden", name + ".ref.kff"), "wb") as fo:
+                        fo.write(fi.read())
 
 
 if __name__ == "__main__":

@@ -198,11 +198,12 @@ def _kff_write(path, k, blocks, enc=0x1B, max_kmers=8, data_size=2):
     open(path, "wb").write(bytes(f))
 
 
-def test_kff_from_the_reference_is_read(cli, tmp_path):
-    """tests/golden/reads_0_k15_a2.ref.kff was written by the reference binary (`bcalm -kff`, see make_golden.py): the graph built
-    from it must be the reference's graph of the same reads."""
-    c = CASES["reads_0_k15_a2"]
-    kff = os.path.join(ROOT, "tests", "golden", "reads_0_k15_a2.ref.kff")
+@pytest.mark.parametrize("name", ["reads_0_k15_a2", "wide_2_k47_a2"])
+def test_kff_from_the_reference_is_read(cli, tmp_path, name):
+    """tests/golden/<case>.ref.kff were written by the reference binary (`bcalm -kff`, see make_golden.py; one- and two-word k-mers):
+    the graph built from each must be the reference's graph of the same reads."""
+    c = CASES[name]
+    kff = os.path.join(ROOT, "tests", "golden", name + ".ref.kff")
     run_cli(cli, tmp_path, "-solid-kmers-in", kff, "-kmer-size", str(c["k"]), "-abundance-min", "1", "-out", "fromkff")
     d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromkff.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
     assert d == "", d
