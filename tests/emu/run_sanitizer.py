@@ -11,6 +11,8 @@ Expected, by design (each is a documented lock-free idiom of the kernels, fine u
   * ld_volatile_u64 on a table key vs. atomicCAS of the same key  (k2_insert, k2c_count, k5_insert, k5c_join, wide/shard tables)
   * plain stores of 1 to an overflow / abandon flag vs. volatile reads of it          (s_over, *overflow)
   * k6_jump / k6_cycle_min: in-place asynchronous pointer jumping on 64-bit words
+  * wide_find_or_insert (k >= 32): the tag protocol -- volatile tag reads vs. the CAS that locks a slot, key words published by a fence + tag store
+  * kw5s_insert (sharded, k >= 32): every record of a slot stores the same occupancy marker into T.keys[slot]
   * glue_assemble (sharded): neighbouring pieces of a unitig overlap by k-1 characters and both write those (identical) bytes
 Anything else -- in particular two plain accesses to shared memory without a barrier in between -- is a bug.  End of round 1: only
 the expected locations are reported for the default path, the L2-table / two-pass variants, the opt-in variants, forced splits and
