@@ -305,6 +305,9 @@ int free_results(cdbg_ctx *ctx) {
 #ifndef K2P_REGIONS_DEFAULT
 #define K2P_REGIONS_DEFAULT 0   // fine partition of K2 into fixed-capacity regions (no histogram pass): opt-in (CDBG_K2P=regions) until timed on a GPU
 #endif
+#ifndef K2C_HASH_MUL32_DEFAULT
+#define K2C_HASH_MUL32_DEFAULT 0   // cheaper slot hash of k2c_count (k2c_hash_mul32): opt-in (CDBG_K2C_HASH=mul32) until timed on a GPU
+#endif
 #ifndef K2C_FLAT_DEFAULT
 #define K2C_FLAT_DEFAULT 0   // flat (one probe step per iteration) insert loop of k2c_count: opt-in (CDBG_K2C=flat) until timed on a GPU
 #endif
@@ -436,6 +439,7 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
         cp.kmers = d_kmers2; cp.fine_beg = d_fine_beg; cp.fine_end = d_fine_end; cp.n_fine = (uint32_t)NF; cp.amin = ctx->amin; cp.amax = ctx->amax;
         cp.solid_kmers = ctx->d_solid_kmers; cp.solid_counts = ctx->d_solid_counts; cp.solid_cap = solid_cap;
         cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
+        { const char *hm = getenv("CDBG_K2C_HASH"); cp.hash_mode = K2C_HASH_MUL32_DEFAULT ? !(hm && strcmp(hm, "mix64") == 0) : (hm && strcmp(hm, "mul32") == 0); }
         tstart(ctx, T_K2C);
         if (I) {
 #define K2C_LAUNCH(SL, FL, PER_SM)                                                                                                          \

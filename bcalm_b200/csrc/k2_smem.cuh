@@ -230,7 +230,17 @@ struct K2CParams {
     unsigned long long *n_solid, *n_distinct;
     unsigned long long *n_splits;   // statistics: how many times a (part of a) fine bin had to be split
     int *failed;                    // set when a fine bin still does not fit after K2C_MAX_LEVEL splits (host reports an error)
+    uint32_t hash_mode;             // 0: slot and split bits from mix64 (default); 1: from k2c_hash_mul32 (CDBG_K2C_HASH=mul32, see below)
 };
+
+// Slot / split-bit hash of the table kernel.  The fine bin was chosen from the HIGH half of mix64(key), so anything that is not a
+// function of those bits will do inside a bin.  mix64 costs two 64-bit multiplies (~20 instructions of an issue-bound kernel);
+// mul32 is two 32-bit multiplies and a shift-xor.  Placement only: the (k-mer, count) multiset that comes out is the same.
+__device__ __forceinline__ uint32_t k2c_hash_mul32(uint64_t key) {
+    uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
+    return h ^ (h >> 15);
+}
+__device__ __forceinline__ uint32_t k2c_hash(uint64_t key, uint32_t mode) { return mode ? k2c_hash_mul32(key) : (uint32_t)mix64(key); }
 
 constexpr int K2C_MAX_LEVEL = 10;   // a fine bin is split into at most 2^10 parts by further hash bits
 
@@ -293,9 +303,9 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (key[u] == EMPTY_KEY) continue;
-                    const uint64_t h = mix64(key[u]);
-                    if ((((uint32_t)h >> 16) & sel_mask) != part) continue;
-                    uint32_t slot = (uint32_t)h & MASK;
+                    const uint32_t h = k2c_hash(key[u], p.hash_mode);
+                    if (((h >> 16) & sel_mask) != part) continue;
+                    uint32_t slot = h & MASK;
                     for (uint32_t probes = 0;;) {
                         uint64_t cur = ld_volatile_u64(&s_keys[slot]);
                         if (cur == EMPTY_KEY) {
@@ -322,8 +332,8 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
                         cur = q0; q0 = q1; q1 = nxt < end ? p.kmers[nxt] : EMPTY_KEY; nxt += T;
                         if (cur == EMPTY_KEY) drained = true;
                         else {
-                            const uint64_t h = mix64(cur);
-                            if ((((uint32_t)h >> 16) & sel_mask) == part) { slot = (uint32_t)h & MASK; probes = 0; have = true; }
+                            const uint32_t h = k2c_hash(cur, p.hash_mode);
+                            if (((h >> 16) & sel_mask) == part) { slot = h & MASK; probes = 0; have = true; }
                         }
                     }
                     if (have) {                                           // one probe step

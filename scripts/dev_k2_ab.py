@@ -28,6 +28,8 @@ TUNABLES = ("CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_J
 CONFIGS = [
     ("default: K1 single, K2 smem, K5 l2, atomic ranks", {}),
     ("k2c flat insert loop", {"CDBG_K2C": "flat"}),
+    ("k2c mul32 slot hash", {"CDBG_K2C_HASH": "mul32"}),
+    ("k2c mul32 slot hash + flat", {"CDBG_K2C_HASH": "mul32", "CDBG_K2C": "flat"}),
     ("k2c flat, fill 1.0", {"CDBG_K2C": "flat", "CDBG_K2S_FILL": "1.0"}),
     ("k2c flat, fill 2.0", {"CDBG_K2C": "flat", "CDBG_K2S_FILL": "2.0"}),
     ("K2 fine partition by regions (no hist pass)", {"CDBG_K2P": "regions"}),
@@ -54,7 +56,7 @@ E2E_CONFIGS = [
     ("e2e + K5 smem + K6 lists + match ranks", {"CDBG_K5": "smem", "CDBG_K6": "list", "CDBG_RANK": "match"}),
     ("e2e round-start (copy, twopass, l2)", {"CDBG_K1": "twopass", "CDBG_K2": "l2", "CDBG_ZEROCOPY": "0"}),
 ]
-TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK", "CDBG_K5", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_K5S_P1", "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P")
+TUNABLES = TUNABLES + ("CDBG_ZEROCOPY", "CDBG_K1_SLACK", "CDBG_K5", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_K5S_P1", "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH")
 
 
 def say(*a):

@@ -23,7 +23,7 @@ from test_emu_sharded import sharded_build  # noqa: E402
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ to build the CPU emulation of the library")
 
-CONFIGS = [{}, {"CDBG_K1": "twopass"}, {"CDBG_K1": "classic"}, {"CDBG_K2": "l2"}, {"CDBG_K5": "l2"}, {"CDBG_K2C": "flat"}, {"CDBG_K1_THREADS": "512"},
+CONFIGS = [{}, {"CDBG_K1": "twopass"}, {"CDBG_K1": "classic"}, {"CDBG_K2": "l2"}, {"CDBG_K5": "l2"}, {"CDBG_K2C": "flat"}, {"CDBG_K2C_HASH": "mul32"}, {"CDBG_K1_THREADS": "512"},
            {"CDBG_K6": "list"}, {"CDBG_K2P": "regions"}, {"CDBG_K2P": "regions", "CDBG_K2S_FILL": "0.1", "CDBG_K2S_SLOTS": "4096"}, {"CDBG_RANK": "match", "CDBG_K2S_P1": "6"}, {"CDBG_EMU_PINNED": "1", "CDBG_ZEROCOPY_MIN": "0"},
            {"CDBG_K2S_P1": "7", "CDBG_K2S_FILL": "0.05", "CDBG_K2S_SLOTS": "4096"}, {"CDBG_K5S_P1": "5", "CDBG_K5S_FILL": "0.05"},
            {"CDBG_K2S_FILL": "8", "CDBG_K2S_SLOTS": "4096", "CDBG_K5S_FILL": "8"}, {"shards": 2}, {"shards": 3},
@@ -98,7 +98,7 @@ def test_random_inputs_and_configurations_match_the_oracle(emu_lib, monkeypatch,
 
 
 ALL_KNOBS = {"CDBG_K1": ["single", "twopass", "classic"], "CDBG_K1_THREADS": ["256", "512"], "CDBG_K2": ["smem", "l2"], "CDBG_K2P": ["exact", "regions"],
-             "CDBG_K2C": ["nested", "flat"], "CDBG_K5": ["smem", "l2"], "CDBG_K6": ["full", "list"], "CDBG_RANK": ["atomic", "match"],
+             "CDBG_K2C": ["nested", "flat"], "CDBG_K2C_HASH": ["mix64", "mul32"], "CDBG_K5": ["smem", "l2"], "CDBG_K6": ["full", "list"], "CDBG_RANK": ["atomic", "match"],
              "CDBG_K2S_SLOTS": ["4096", "8192", "16384"], "CDBG_K2S_FILL": ["0.05", "0.7", "1.5", "8"], "CDBG_K2S_P1": ["1", "3", "11"],
              "CDBG_K5S_FILL": ["0.05", "1.0", "8"], "CDBG_K5S_SLOTS": ["2048", "4096"], "CDBG_K5S_P1": ["1", "4"], "CDBG_K1_SLACK": ["0", "16384"],
              "CDBG_EMU_PINNED": ["0", "1"], "CDBG_ZEROCOPY_MIN": ["0"], "CDBG_PDL": ["0", "1"], "CDBG_SHARD_K1": ["classic", "roll"],

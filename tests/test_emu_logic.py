@@ -31,7 +31,7 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
 
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
          "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
-         "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P")
+         "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH")
 
 
 @pytest.fixture(scope="module")
@@ -89,6 +89,8 @@ VARIANTS = {
     "ranks_by_match": dict(CDBG_RANK="match", CDBG_K2S_P1=9),
     "k6_over_lists": dict(CDBG_K6="list"),
     "k2c_flat_insert_loop": dict(CDBG_K2C="flat"),
+    "k2c_mul32_slot_hash": dict(CDBG_K2C_HASH="mul32"),
+    "k2c_mul32_flat_forced_splits": dict(CDBG_K2C_HASH="mul32", CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
     "k2c_flat_forced_splits": dict(CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
     "k1_512_threads": dict(CDBG_K1_THREADS=512, CDBG_K2S_P1=5),
     "k2p_regions": dict(CDBG_K2P="regions", CDBG_K2S_P1=3),

@@ -15,6 +15,7 @@ WORKER = os.path.join(ROOT, "tests", "gpu_variant_worker.py")
 
 VARIANTS = {
     "k2c_flat_insert_loop": ["CDBG_K2C=flat"],
+    "k2c_mul32_slot_hash": ["CDBG_K2C_HASH=mul32"],
     "k1_512_threads": ["CDBG_K1_THREADS=512"],
     "k1_512_threads_and_k2c_flat": ["CDBG_K1_THREADS=512", "CDBG_K2C=flat"],
     "k2p_regions": ["CDBG_K2P=regions"],
