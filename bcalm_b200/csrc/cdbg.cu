@@ -439,19 +439,25 @@ int stage_count_k2_smem(cdbg_ctx *ctx, const K2SmemPlan &pl, const uint64_t *d_k
         cp.kmers = d_kmers2; cp.fine_beg = d_fine_beg; cp.fine_end = d_fine_end; cp.n_fine = (uint32_t)NF; cp.amin = ctx->amin; cp.amax = ctx->amax;
         cp.solid_kmers = ctx->d_solid_kmers; cp.solid_counts = ctx->d_solid_counts; cp.solid_cap = solid_cap;
         cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
-        { const char *hm = getenv("CDBG_K2C_HASH"); cp.hash_mode = K2C_HASH_MUL32_DEFAULT ? !(hm && strcmp(hm, "mix64") == 0) : (hm && strcmp(hm, "mul32") == 0); }
         tstart(ctx, T_K2C);
         if (I) {
-#define K2C_LAUNCH(SL, FL, PER_SM)                                                                                                          \
-    do {                                                                                                                                    \
-        CK(cudaFuncSetAttribute(k2c_count<SL, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<SL>()));                 \
-        LAUNCH((k2c_count<SL, FL>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * (PER_SM)), k2c_threads<SL>(), k2c_smem_bytes<SL>(), cp); \
+#define K2C_LAUNCH1(SL, FL, MU, PER_SM)                                                                                                              \
+    do {                                                                                                                                            \
+        CK(cudaFuncSetAttribute(k2c_count<SL, FL, MU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2c_smem_bytes<SL>()));                     \
+        LAUNCH((k2c_count<SL, FL, MU>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * (PER_SM)), k2c_threads<SL>(), k2c_smem_bytes<SL>(), cp); \
     } while (0)
-            const char *k2c = getenv("CDBG_K2C");
+#define K2C_LAUNCH(SL, PER_SM)                                                                                  \
+    do {                                                                                                        \
+        if (flat) { if (mul32) K2C_LAUNCH1(SL, true, true, PER_SM); else K2C_LAUNCH1(SL, true, false, PER_SM); }  \
+        else { if (mul32) K2C_LAUNCH1(SL, false, true, PER_SM); else K2C_LAUNCH1(SL, false, false, PER_SM); }     \
+    } while (0)
+            const char *k2c = getenv("CDBG_K2C"), *hm = getenv("CDBG_K2C_HASH");
             const bool flat = K2C_FLAT_DEFAULT ? !(k2c && strcmp(k2c, "nested") == 0) : (k2c && strcmp(k2c, "flat") == 0);
-            if (pl.slots == 4096) { if (flat) K2C_LAUNCH(4096, true, 4); else K2C_LAUNCH(4096, false, 4); }
-            else if (pl.slots == 8192) { if (flat) K2C_LAUNCH(8192, true, 2); else K2C_LAUNCH(8192, false, 2); }
-            else { if (flat) K2C_LAUNCH(16384, true, 1); else K2C_LAUNCH(16384, false, 1); }
+            const bool mul32 = K2C_HASH_MUL32_DEFAULT ? !(hm && strcmp(hm, "mix64") == 0) : (hm && strcmp(hm, "mul32") == 0);
+            if (pl.slots == 4096) K2C_LAUNCH(4096, 4);
+            else if (pl.slots == 8192) K2C_LAUNCH(8192, 2);
+            else K2C_LAUNCH(16384, 1);
+#undef K2C_LAUNCH1
 #undef K2C_LAUNCH
         }
         tstop(ctx, T_K2C);

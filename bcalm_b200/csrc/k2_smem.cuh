@@ -230,7 +230,6 @@ struct K2CParams {
     unsigned long long *n_solid, *n_distinct;
     unsigned long long *n_splits;   // statistics: how many times a (part of a) fine bin had to be split
     int *failed;                    // set when a fine bin still does not fit after K2C_MAX_LEVEL splits (host reports an error)
-    uint32_t hash_mode;             // 0: slot and split bits from mix64 (default); 1: from k2c_hash_mul32 (CDBG_K2C_HASH=mul32, see below)
 };
 
 // Slot / split-bit hash of the table kernel.  The fine bin was chosen from the HIGH half of mix64(key), so anything that is not a
@@ -240,7 +239,8 @@ __device__ __forceinline__ uint32_t k2c_hash_mul32(uint64_t key) {
     uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
     return h ^ (h >> 15);
 }
-__device__ __forceinline__ uint32_t k2c_hash(uint64_t key, uint32_t mode) { return mode ? k2c_hash_mul32(key) : (uint32_t)mix64(key); }
+// (a template parameter of the kernel, not a run-time switch: a run-time one changed the register allocation of the default kernel)
+template <bool MUL32> __device__ __forceinline__ uint32_t k2c_hash(uint64_t key) { return MUL32 ? k2c_hash_mul32(key) : (uint32_t)mix64(key); }
 
 constexpr int K2C_MAX_LEVEL = 10;   // a fine bin is split into at most 2^10 parts by further hash bits
 
@@ -261,7 +261,7 @@ template <int SLOTS> static inline size_t k2c_smem_bytes() { return (size_t)SLOT
 // ONE probe step per iteration and a lane that has placed its key takes its next one immediately (keys are prefetched two
 // ahead into registers), so lanes drift apart across keys instead of idling: the warp runs for max-over-lanes of the SUM of
 // probe lengths instead of the sum of the per-key maxima.
-template <int SLOTS, bool FLAT>
+template <int SLOTS, bool FLAT, bool MUL32 = false>
 __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
     constexpr int T = SLOTS / 16, NW = T / 32, PER_WARP = SLOTS / NW;   // PER_WARP = 512 slots
     constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     if (key[u] == EMPTY_KEY) continue;
-                    const uint32_t h = k2c_hash(key[u], p.hash_mode);
+                    const uint32_t h = k2c_hash<MUL32>(key[u]);
                     if (((h >> 16) & sel_mask) != part) continue;
                     uint32_t slot = h & MASK;
                     for (uint32_t probes = 0;;) {
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(SLOTS / 16) k2c_count(K2CParams p) {
                         cur = q0; q0 = q1; q1 = nxt < end ? p.kmers[nxt] : EMPTY_KEY; nxt += T;
                         if (cur == EMPTY_KEY) drained = true;
                         else {
-                            const uint32_t h = k2c_hash(cur, p.hash_mode);
+                            const uint32_t h = k2c_hash<MUL32>(cur);
                             if (((h >> 16) & sel_mask) == part) { slot = h & MASK; probes = 0; have = true; }
                         }
                     }
