@@ -139,3 +139,19 @@ def test_sharded_multi_word_kmers_on_sequencing_like_reads_match_the_reference_b
     assert parity.diff_abundance_lists(parity.graph_to_records(m, with_ab=True), parity.graph_to_records(one, with_ab=True)) == ""
     solid = [s.stats["n_solid"] for s in shards]
     assert sum(solid) == one.stats["n_solid"] and max(solid) < 1.2 * min(solid) + 100
+
+
+@pytest.mark.parametrize("k", [33, 64, 127])
+def test_sharded_multi_word_kmers_degenerate_inputs(emu_lib, k):
+    """Ranks without reads, reads without a single k-mer, no reads at all: the sharded k > 31 path must agree with one GPU (and, under the
+    strict emulator, must not launch an empty grid on the way)."""
+    import random
+    rng = random.Random(5)
+    r = "".join(rng.choice("ACGT") for _ in range(300))
+    for reads in ([r], [r, r[10:200]], ["ACGT" * 5], []):
+        with api.Cdbg(k=k, abundance_min=1, device=0) as c:
+            one = c.build(reads if reads else "\n")
+        for world in (2, 4):
+            m, _ = sharded_build(reads, k, 1, world)
+            d = parity.diff(parity.graph_to_records(m), parity.graph_to_records(one), k)
+            assert d == "" and m.n_unitigs == one.n_unitigs, (len(reads), world, d[:300])
