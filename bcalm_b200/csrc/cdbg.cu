@@ -21,6 +21,7 @@
 #include "k1_tma.cuh"
 #include "k2_smem.cuh"
 #include "k5_smem.cuh"
+#include "sk.cuh"
 #include "parse.cuh"
 #include "wide.cuh"
 
@@ -1068,6 +1069,7 @@ int stage_link(cdbg_ctx *ctx) {
     return CDBG_OK;
 }
 
+#include "sk_host.inl"
 #include "shard_host.inl"
 #include "wide_host.inl"
 #include "shard_wide_host.inl"
@@ -1292,8 +1294,8 @@ int cdbg_count(cdbg_ctx *ctx, cdbg_stats *stats) {
     }
     ctx->last_n_bytes = ctx->n_bytes;
     CK(cudaSetDevice(ctx->prm.device));
-    int rc = ctx->world > 1 ? (ctx->W > 1 ? shard_stage_count_wide_dispatch(ctx) : shard_stage_count(ctx))
-                            : (ctx->W > 1 ? stage_count_wide_dispatch(ctx) : stage_count(ctx));
+    int rc = ctx->world > 1 ? (ctx->W > 1 ? shard_stage_count_wide_dispatch(ctx) : sk_enabled(ctx) ? shard_stage_count_sk(ctx) : shard_stage_count(ctx))
+                            : (ctx->W > 1 ? stage_count_wide_dispatch(ctx) : sk_enabled(ctx) ? stage_count_sk(ctx) : stage_count(ctx));
     if (rc == CDBG_OK && stats) fill_stats(ctx, stats);
     return rc;
 }

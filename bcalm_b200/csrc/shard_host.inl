@@ -107,6 +107,73 @@ inline uint32_t table_cap_for(uint64_t n) { return (uint32_t)std::min<uint64_t>(
 
 // ------------------------------------------------------------------------------------------------ stage 1 (sharded)
 
+// Stage 1 on super-k-mers (sk.cuh): K1 cuts this rank's reads into super-k-mer records in destination-major coarse bins
+// (owner = bin / P_local = owner_of_rank(minimizer rank)), the records -- not 8-byte k-mer instances -- cross NVLink (X1), and the
+// owner runs the single-GPU fine partition + shared-memory counting over the received (local bin, source) runs.
+int shard_stage_count_sk(cdbg_ctx *ctx) {
+    const int W = ctx->world, me = ctx->rank;
+    int rc;
+    tstart(ctx, T_COUNT);
+    ctx->trace_t0 = host_now();
+    uint64_t all_n[MAX_WORLD], total_bytes = 0;
+    const uint64_t n = ctx->n_bytes;
+    if ((rc = allgather_host_u64(ctx, &n, 1, all_n))) return rc;
+    for (int r = 0; r < W; r++) total_bytes += all_n[r];
+    const SKPlan pl = sk_plan(ctx, total_bytes, (uint32_t)W);
+    const uint32_t P_local = pl.Pc_local, Pc = P_local * (uint32_t)W;
+    ctx->st.n_count_bins = P_local;
+    ctx->st.sk_m = (uint32_t)pl.m;
+    ctx->m = pl.m;      // junctions are owned through the same minimizer order and length: ~1 - 2/(k-m+1) of a k-mer's end records stay local
+    std::vector<uint64_t> h_cnt, h_base;
+    ulonglong2 *d_recs = nullptr;
+    if ((rc = sk_run_k1(ctx, pl, Pc, &d_recs, h_cnt, h_base))) return rc;
+    TRACE("SK K1");
+    // counts of every rank (+ its number of k-mer instances, which sizes the solid buffers)
+    std::vector<uint64_t> mine(Pc + 1), all((size_t)W * (Pc + 1)), all_cnt((size_t)W * Pc);
+    for (uint32_t b = 0; b < Pc; b++) mine[b] = h_cnt[b];
+    mine[Pc] = ctx->st.n_instances;
+    if ((rc = allgather_host_u64(ctx, mine.data(), Pc + 1, all.data()))) return rc;
+    uint64_t I_total = 0;
+    for (int r = 0; r < W; r++) {
+        for (uint32_t b = 0; b < Pc; b++) all_cnt[(size_t)r * Pc + b] = all[(size_t)r * (Pc + 1) + b];
+        I_total += all[(size_t)r * (Pc + 1) + Pc];
+    }
+    // the bins' regions have gaps: gather them into one contiguous send buffer (destination-major)
+    std::vector<uint64_t> h_out(Pc + 1, 0);
+    for (uint32_t b = 0; b < Pc; b++) h_out[b + 1] = h_out[b] + h_cnt[b];
+    const uint64_t R_out = h_out[Pc];
+    ulonglong2 *d_send = nullptr; uint64_t *d_base = nullptr, *d_out_off = nullptr;
+    if ((rc = dalloc(ctx, &d_send, R_out + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_base, Pc + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_out_off, Pc + 1))) return rc;
+    CK(cudaMemcpyAsync(d_base, h_base.data(), (size_t)(Pc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_out_off, h_out.data(), (size_t)(Pc + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (R_out) LAUNCH(sk_compact, grid_for(ctx, R_out, 256, 8), 256, 0, d_recs, d_base, d_out_off, Pc, d_send);
+    dfree(ctx, d_recs); dfree(ctx, d_base); dfree(ctx, d_out_off);
+    // X1: records to the owner of their minimizer
+    uint64_t send_cnt[MAX_WORLD] = {0}, recv_cnt[MAX_WORLD] = {0};
+    std::vector<uint64_t> run_off((size_t)P_local * W), run_len((size_t)P_local * W);
+    plan_shard_exchange(W, me, P_local, all_cnt.data(), send_cnt, recv_cnt, run_off.data(), run_len.data());
+    void *recv = nullptr; uint64_t R_in = 0;
+    if ((rc = exchange_with_counts(ctx, d_send, send_cnt, recv_cnt, 16, &recv, &R_in))) return rc;
+    dfree(ctx, d_send);
+    TRACE("X1 super-k-mer exchange");
+    const uint32_t R = P_local * (uint32_t)W;
+    std::vector<uint64_t> r_cnt(R), r_off(R + 1, 0);
+    std::vector<uint32_t> r_group(R);
+    for (uint32_t b = 0; b < P_local; b++)
+        for (int s_ = 0; s_ < W; s_++) {
+            const uint32_t r = b * (uint32_t)W + (uint32_t)s_;
+            r_cnt[r] = run_len[(size_t)b * W + s_]; r_off[r] = run_off[(size_t)b * W + s_]; r_group[r] = b;
+        }
+    const uint64_t I_est = I_total / W + I_total / (4 * W) + 1024;
+    if ((rc = sk_partition_count(ctx, pl, (const ulonglong2 *)recv, I_est, R, r_cnt, r_off, &r_group, P_local))) return rc;
+    dfree(ctx, recv);
+    tstop(ctx, T_COUNT);
+    ctx->stage = ST_COUNTED;
+    return CDBG_OK;
+}
+
 int shard_stage_count(cdbg_ctx *ctx) {
     const int W = ctx->world, me = ctx->rank, k = ctx->k;
     const uint64_t n = ctx->n_bytes;

@@ -96,6 +96,8 @@ typedef struct {
     uint32_t zero_copy;     /* 1 when cdbg_build read pinned host memory directly from K1 (no separate H2D copy) */
     uint32_t n_k5_splits;   /* K5 (shared-memory variant): join passes abandoned and redone as two halves */
     uint32_t k2p_fallback;  /* 1 when the region-based fine partition of K2 (opt-in) overflowed and was redone with exact offsets */
+    uint32_t sk_m;          /* minimizer length used to bucket the super-k-mers (stage 1 on super-k-mers, k <= 31; 0 otherwise) */
+    uint64_t n_superkmers;  /* super-k-mer records written by K1 (16 bytes each) */
 } cdbg_stats;
 
 typedef struct {

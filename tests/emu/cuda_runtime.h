@@ -377,7 +377,26 @@ static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
     return r;
 }
 
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+    emu::need_full_mask(mask);
+    emu::Engine &e = emu::engine();
+    const unsigned w = emu::tls.warp;
+    e.warp_slot[w][emu::tls.lane] = v;
+    e.sync_warp();
+    unsigned r = 0;
+    const unsigned lanes = e.block - w * 32 < 32 ? e.block - w * 32 : 32;
+    for (unsigned i = 0; i < lanes; i++) r = (unsigned)e.warp_slot[w][i] > r ? (unsigned)e.warp_slot[w][i] : r;
+    e.sync_warp();
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ intrinsics
+static inline unsigned __brev(unsigned x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+    return __builtin_bswap32(x);
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }

@@ -31,7 +31,8 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
 
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
          "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
-         "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH")
+         "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH",
+         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK")
 
 
 @pytest.fixture(scope="module")
@@ -71,30 +72,45 @@ def test_default_configuration_matches_reference_output(emu_lib, knobs, name):
     check_against_golden(g, GOLDEN[name])
 
 
+KMER = dict(CDBG_S1="kmer")    # stage 1 on k-mer instances (k1_tma.cuh / k2_smem.cuh): the round-1 default, now behind CDBG_S1=kmer
 VARIANTS = {
-    "k1_twopass_tma": dict(CDBG_K1="twopass"),
-    "k1_classic_ldg": dict(CDBG_K1="classic"),
-    "k2_l2_tables": dict(CDBG_K2="l2"),
-    "k2_l2_many_bins": dict(CDBG_K2="l2", CDBG_BIN_TARGET=3000),
-    "k2_smem_many_fine_bins": dict(CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=0.05),
-    "k2_smem_16384": dict(CDBG_K2S_SLOTS=16384, CDBG_K2S_FILL=0.2),
-    "k2_smem_forced_splits": dict(CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
-    "k1_many_coarse_bins": dict(CDBG_K2S_P1=37),
-    "zero_copy_input": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0),
+    # stage 1 on super-k-mers (sk.cuh, the default)
+    "sk_m_4": dict(CDBG_SK_M=4),
+    "sk_m_16": dict(CDBG_SK_M=16),
+    "sk_many_coarse_bins": dict(CDBG_SK_P1=37),
+    "sk_tiny_fine_bins": dict(CDBG_SK_FILL=0.05),
+    "sk_forced_splits": dict(CDBG_SK_FILL=8),
+    "sk_slots_8192": dict(CDBG_SK_SLOTS=8192, CDBG_SK_FILL=0.2),
+    "sk_mul32_slot_hash": dict(CDBG_K2C_HASH="mul32"),
+    "sk_exact_regions_after_overflow": dict(CDBG_SK_DENSITY=0.001, CDBG_SK_SLACK=0, CDBG_SK_P1=5),
+    "sk_zero_copy_input": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0),
+    "sk_zero_copy_overflow": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0, CDBG_SK_DENSITY=0.001, CDBG_SK_SLACK=0),
+    # stage 1 on k-mer instances
+    "k1_single_pass": dict(**KMER),
+    "k1_twopass_tma": dict(CDBG_K1="twopass", **KMER),
+    "k1_classic_ldg": dict(CDBG_K1="classic", **KMER),
+    "k2_l2_tables": dict(CDBG_K2="l2", **KMER),
+    "k2_l2_many_bins": dict(CDBG_K2="l2", CDBG_BIN_TARGET=3000, **KMER),
+    "k2_smem_many_fine_bins": dict(CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=0.05, **KMER),
+    "k2_smem_16384": dict(CDBG_K2S_SLOTS=16384, CDBG_K2S_FILL=0.2, **KMER),
+    "k2_smem_forced_splits": dict(CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8, **KMER),
+    "k1_many_coarse_bins": dict(CDBG_K2S_P1=37, **KMER),
+    "zero_copy_input": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0, **KMER),
+    "ranks_by_match": dict(CDBG_RANK="match", CDBG_K2S_P1=9, **KMER),
+    "k2c_flat_insert_loop": dict(CDBG_K2C="flat", **KMER),
+    "k2c_mul32_slot_hash": dict(CDBG_K2C_HASH="mul32", **KMER),
+    "k2c_mul32_flat_forced_splits": dict(CDBG_K2C_HASH="mul32", CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8, **KMER),
+    "k2c_flat_forced_splits": dict(CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8, **KMER),
+    "k1_512_threads": dict(CDBG_K1_THREADS=512, CDBG_K2S_P1=5, **KMER),
+    "k2p_regions": dict(CDBG_K2P="regions", CDBG_K2S_P1=3, **KMER),
+    "k2p_regions_tiny_bins": dict(CDBG_K2P="regions", CDBG_K2S_FILL=0.05, CDBG_K2S_SLOTS=4096, **KMER),
+    # stages 2-4
     "no_pdl": dict(CDBG_PDL=0),
     "k5_l2_tables": dict(CDBG_K5="l2"),
     "k5_l2_many_bins": dict(CDBG_K5="l2", CDBG_JOIN_TARGET=500),
     "k5_smem_many_fine_bins": dict(CDBG_K5S_FILL=0.05, CDBG_K5S_P1=7),
     "k5_smem_forced_splits": dict(CDBG_K5S_FILL=8, CDBG_K5S_SLOTS=4096),
-    "ranks_by_match": dict(CDBG_RANK="match", CDBG_K2S_P1=9),
     "k6_over_lists": dict(CDBG_K6="list"),
-    "k2c_flat_insert_loop": dict(CDBG_K2C="flat"),
-    "k2c_mul32_slot_hash": dict(CDBG_K2C_HASH="mul32"),
-    "k2c_mul32_flat_forced_splits": dict(CDBG_K2C_HASH="mul32", CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
-    "k2c_flat_forced_splits": dict(CDBG_K2C="flat", CDBG_K2S_SLOTS=4096, CDBG_K2S_FILL=8),
-    "k1_512_threads": dict(CDBG_K1_THREADS=512, CDBG_K2S_P1=5),
-    "k2p_regions": dict(CDBG_K2P="regions", CDBG_K2S_P1=3),
-    "k2p_regions_tiny_bins": dict(CDBG_K2P="regions", CDBG_K2S_FILL=0.05, CDBG_K2S_SLOTS=4096),
 }
 
 
@@ -105,9 +121,15 @@ def test_variants_match_reference_output(emu_lib, knobs, variant, name):
     knobs(**VARIANTS[variant])
     g = run_case(GOLDEN[name])
     check_against_golden(g, GOLDEN[name])
-    if variant == "zero_copy_input":
+    if variant in ("zero_copy_input", "sk_zero_copy_input", "sk_zero_copy_overflow"):
         assert g.stats["zero_copy"] == 1
-    if variant == "k2_smem_forced_splits" and name.startswith("reads_"):
+    if variant.startswith("sk_"):
+        assert g.stats["sk_m"] > 0 and g.stats["n_superkmers"] > 0
+    elif variant.startswith(("k1_", "k2")):
+        assert g.stats["sk_m"] == 0
+    if variant in ("sk_exact_regions_after_overflow", "sk_zero_copy_overflow") and name.startswith("reads_"):
+        assert g.stats["k1_fallback"] == 1
+    if variant in ("k2_smem_forced_splits", "sk_forced_splits") and name.startswith("reads_"):
         assert g.stats["n_k2_splits"] > 0
     if variant == "k5_smem_forced_splits" and name.startswith("reads_"):
         assert g.stats["n_k5_splits"] > 0
@@ -131,8 +153,8 @@ def _synthetic_reads(genome_len, read_len, coverage, err, seed):
     return reads
 
 
-@pytest.mark.parametrize("variant", ["default", "k2c_flat_insert_loop", "k1_512_threads", "k2_l2_tables", "k5_l2_tables", "k1_twopass_tma",
-                                     "k2_smem_forced_splits", "k5_smem_forced_splits"])
+@pytest.mark.parametrize("variant", ["default", "sk_forced_splits", "sk_exact_regions_after_overflow", "sk_m_16", "k1_single_pass", "k1_512_threads", "k2_l2_tables",
+                                     "k5_l2_tables", "k1_twopass_tma", "k2_smem_forced_splits", "k5_smem_forced_splits"])
 def test_larger_synthetic_read_set_matches_oracle(emu_lib, knobs, variant):
     """40 kbp genome, 100 bp reads at 30x with 1 % errors (1.2 Mbases): several tiles, coarse and fine bins, real branching."""
     if variant != "default":
@@ -181,7 +203,7 @@ def _repeats_input():
 
 def test_k1_single_pass_overflow_falls_back_to_exact_two_pass(emu_lib, knobs):
     reads = _repeats_input()
-    knobs(CDBG_K2S_P1=8, CDBG_K1_SLACK=0)
+    knobs(CDBG_K2S_P1=8, CDBG_K1_SLACK=0, CDBG_S1="kmer")
     with api.Cdbg(k=21, abundance_min=2, device=0) as c:
         g = c.build(reads)
     assert g.stats["k1_fallback"] == 1
@@ -192,7 +214,7 @@ def test_k1_single_pass_overflow_falls_back_to_exact_two_pass(emu_lib, knobs):
 
 def test_k2_region_partition_overflow_falls_back_to_exact_offsets(emu_lib, knobs):
     reads = _repeats_input()
-    knobs(CDBG_K2P="regions", CDBG_K2S_FILL=0.05, CDBG_K2S_SLOTS=4096, CDBG_K2S_P1=2)
+    knobs(CDBG_K2P="regions", CDBG_K2S_FILL=0.05, CDBG_K2S_SLOTS=4096, CDBG_K2S_P1=2, CDBG_S1="kmer")
     with api.Cdbg(k=21, abundance_min=2, device=0) as c:
         g = c.build(reads)
     assert g.stats["k2p_fallback"] == 1
@@ -203,13 +225,50 @@ def test_k2_region_partition_overflow_falls_back_to_exact_offsets(emu_lib, knobs
 
 def test_zero_copy_overflow_falls_back_with_a_copy(emu_lib, knobs):
     reads = _repeats_input()
-    knobs(CDBG_K2S_P1=8, CDBG_K1_SLACK=0, CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0)
+    knobs(CDBG_K2S_P1=8, CDBG_K1_SLACK=0, CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0, CDBG_S1="kmer")
     with api.Cdbg(k=21, abundance_min=2, device=0) as c:
         g = c.build(reads)
     assert g.stats["k1_fallback"] == 1 and g.stats["zero_copy"] == 1
     o = orc.run(reads, 21, 2)
     d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), 21)
     assert d == "", d
+
+
+def _many_runs_input(k):
+    """Long reads whose minimizer window is only two m-mers wide (k small, m = k-1 is forced by CDBG_SK_M): a run is ~1.5 k-mers long,
+    so a tile of 8192 positions holds several thousand runs -- more than the tile's shared-memory run list (2048) -- and the poly-A
+    stretches are single runs of thousands of k-mers, cut into many records -- more than the staging area holds."""
+    rng = np.random.default_rng(5)
+    reads = []
+    for _ in range(6):
+        body = "".join("ACGT"[i] for i in rng.integers(0, 4, 7000))
+        reads.append(body + "A" * 3000 + body[:500])
+    return reads
+
+
+@pytest.mark.parametrize("k,m", [(5, 4), (7, 6), (9, 3), (31, 16)])
+def test_superkmer_extraction_beyond_the_per_tile_capacities(emu_lib, knobs, k, m):
+    reads = _many_runs_input(k)
+    knobs(CDBG_SK_M=m)
+    with api.Cdbg(k=k, abundance_min=1, device=0) as c:
+        g = c.build(reads)
+    o = orc.run(reads, k, 1)
+    assert g.stats["n_instances"] == o.stats["n_instances"] and g.stats["n_solid"] == o.stats["n_solid"]
+    if k - m == 1:
+        assert g.stats["n_superkmers"] > 2048 * 6          # (the direct path was taken)
+    d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k)
+    assert d == "", d
+
+
+def test_superkmer_record_layout_is_what_the_header_says(emu_lib, knobs):
+    """Every k-mer instance is in exactly one record: the instance count equals the sum of the records' k-mer counts, and a read
+    with no minimizer change (poly-A) becomes ceil(n / (53 - k)) records."""
+    k = 21
+    with api.Cdbg(k=k, abundance_min=1, device=0) as c:
+        c.push_reads(["A" * 200])
+        st = c.count()
+    n = 200 - k + 1
+    assert st["n_instances"] == n and st["n_superkmers"] == -(-n // (53 - k)) and st["n_solid"] == 1
 
 
 def test_stage_one_in_isolation_matches_oracle_counts(emu_lib, knobs):
