@@ -22,7 +22,7 @@ api.LIB_PATH = build_emu.build()
 api._lib = None
 build.build_cli = lambda force=False: build_emu.CLI            # the unchanged CLI source linked against the emulated library
 os.environ["CDBG_GPU_TEST_LIB"] = api.LIB_PATH                  # for the subprocess worker of the variant tests
-args = sys.argv[1:] or ["tests/test_gpu_parity.py", "tests/test_gpu_cli.py", "tests/test_gpu_zz_not_yet_validated.py"]
+args = sys.argv[1:] or ["tests/test_gpu_parity.py", "tests/test_gpu_cli.py", "tests/test_gpu_variants.py"]
 # two tests need the real thing: a torch CUDA tensor, and pinned memory that is told apart from pageable memory
 SKIP = "not unaligned_falls_back_to_copy and not pinned_host_input_is_read_in_place"
 sys.exit(pytest.main([*args, "-q", "-m", "gpu", "-k", SKIP, "-p", "no:cacheprovider"]))

@@ -1,4 +1,4 @@
-"""Worker of tests/test_gpu_zz_not_yet_validated.py: one process = one CUDA context = one configuration.
+"""Worker of tests/test_gpu_variants.py: one process = one CUDA context = one configuration.
 
     python tests/gpu_variant_worker.py variant  NAME=VALUE ...      build golden cases + a 7.5 Mbase synthetic set under the
                                                                     environment given, compare with the reference's golden output /

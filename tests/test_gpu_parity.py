@@ -8,11 +8,8 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-# The even_k_* cases were added together with the join fix they exercise, and the ut_* cases (inputs of the reference's unit tests),
-# after the round's GPU budget was spent: verified under the CPU emulator only, so for now these cases report (xfail/xpass) instead
-# of gating `pytest -x`.
-_NEW = pytest.mark.xfail(strict=False, reason="added after the last GPU run of round 1; XPASS means fine")
-CASES = [pytest.param(c, marks=_NEW) if c["name"].startswith(("even_k_", "ut_")) else c for c in load_golden()]
+# every golden case gates (the even_k_* and ut_* cases passed on hardware: GPUTEST_r01, profiles/r02_gpu_tests_1gpu_start.txt)
+CASES = load_golden()
 
 
 def _name(c):

@@ -32,7 +32,7 @@ def test_sharded_golden_cases():
     if not w:
         pytest.skip("needs >= 2 GPUs")
     names = [c["name"] for c in load_golden() if c["unitigs_fa"] is not None and c["k"] <= 31]   # k > 31 is single-GPU only for now
-    names = [n for n in names if not n.startswith(("even_k_", "ut_"))]   # added after round 1's last GPU run (emulator-verified): next round
+    names = [n for n in names if not n.startswith(("even_k_", "ut_"))]   # those run in test_sharded_even_k_cases
     _run(w, names, 29531)
 
 
@@ -43,9 +43,7 @@ def test_sharded_c2_like():
     _run(w, ["c2:0.2"], 29532)
 
 
-# Written after round 1's last GPU run and verified under the CPU emulator only (tests/test_emu_*.py): non-gating until they have
-# passed on real GPUs (XPASS = fine).  Each runs in its own torchrun job, so a failure cannot disturb the tests above.
-@pytest.mark.xfail(strict=False, reason="not yet run on GPUs when written; XPASS means it is fine")
+# Each of the following runs in its own torchrun job.
 @pytest.mark.parametrize("label,port,env", [("k1_roll", 29541, {"CDBG_SHARD_K1": "roll"}), ("k2_smem", 29542, {"CDBG_SHARD_K2": "smem"}),
                                             ("k1_roll_k2_smem", 29543, {"CDBG_SHARD_K1": "roll", "CDBG_SHARD_K2": "smem"})])
 def test_sharded_opt_in_variants(label, port, env):
@@ -55,7 +53,6 @@ def test_sharded_opt_in_variants(label, port, env):
     _run(w, ["reads_3_k31_a2", "circular_test1", "lowcx_8_ACGT_k8_a1", "pow2_cycle_L256_k21", "c2:0.2"], port, env, timeout=300)
 
 
-@pytest.mark.xfail(strict=False, reason="even-k golden cases added after round 1's last GPU run; XPASS means fine")
 def test_sharded_even_k_cases():
     w = _world()
     if not w:
@@ -63,7 +60,6 @@ def test_sharded_even_k_cases():
     _run(w, [c["name"] for c in load_golden() if c["name"].startswith(("even_k_", "ut_"))], 29539, timeout=300)
 
 
-@pytest.mark.xfail(strict=False, reason="-all-abundance-counts on shards was written after round 1's last GPU run; XPASS means fine")
 def test_sharded_all_abundance_counts():
     w = _world()
     if not w:
@@ -71,7 +67,6 @@ def test_sharded_all_abundance_counts():
     _run(w, ["ab:reads_3_k31_a2", "ab:reads_0_k15_a2", "ab:circular_test1", "ab:lowcx_8_ACGT_k8_a1", "ab:c2:0.05"], 29544, timeout=300)
 
 
-@pytest.mark.xfail(strict=False, reason="the sharded path for k > 31 was written after round 1's last GPU run; XPASS means fine")
 def test_sharded_multi_word_kmers():
     w = _world()
     if not w:

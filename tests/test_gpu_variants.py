@@ -1,8 +1,6 @@
-"""GPU checks of code that could only be verified under the CPU emulator when it was written (the round's GPU budget was spent):
-the opt-in kernel variants and the entry points added late (counted k-mers in, FASTA/FASTQ text in, the even-k
-join fix's golden cases).  Each check runs in its OWN process, so a misbehaving variant cannot damage the CUDA context of the
-suite, and is marked xfail(strict=False): it reports (XPASS = fine on the GPU, XFAIL = needs attention) without ever stopping
-`pytest -x`.  The file sorts last on purpose.  Promote a check to a normal test once it has passed on a GPU."""
+"""GPU checks of the opt-in kernel variants and of the late entry points (counted k-mers in, FASTA/FASTQ text in).
+Each check runs in its OWN process, so a misbehaving variant cannot damage the CUDA context of the suite.  All of them passed on
+hardware (GPUTEST_r01: xpassed) and gate like any other test since round 2."""
 import os
 import subprocess
 import sys
@@ -30,12 +28,10 @@ def run_worker(*args):
     return p.returncode
 
 
-@pytest.mark.xfail(strict=False, reason="not yet run on a GPU when written; XPASS means it is fine")
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
 def test_variant_gives_identical_output_on_the_gpu(variant):
     assert run_worker("variant", *VARIANTS[variant]) == 0
 
 
-@pytest.mark.xfail(strict=False, reason="not yet run on a GPU when written; XPASS means it is fine")
 def test_late_entry_points_on_the_gpu():
     assert run_worker("features") == 0
