@@ -1182,19 +1182,26 @@ int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int l
         ctx->n_bytes = n_bytes; ctx->bytes_borrowed = true;
     } else {
         // append (a break byte separates pushes)
-        uint64_t need = ctx->n_bytes + n_bytes + 1;
+        uint64_t need = ctx->n_bytes + n_bytes + 1 + (ctx->bytes_borrowed ? 1 : 0);
         if (ctx->bytes_borrowed || need > ctx->cap_bytes) {
             uint64_t cap = std::max<uint64_t>(need, ctx->cap_bytes * 2);
             uint8_t *nb = nullptr;
             if ((rc = dalloc(ctx, &nb, cap + 64))) return rc;
             if (ctx->n_bytes) CK(cudaMemcpyAsync(nb, ctx->d_bytes, ctx->n_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-            if (!ctx->bytes_borrowed) dfree(ctx, ctx->d_bytes);
+            if (ctx->bytes_borrowed) {
+                // a buffer used in place carries no break byte after its last read: add it now that something follows
+                CK(cudaMemsetAsync(nb + ctx->n_bytes, '\n', 1, ctx->stream));
+                ctx->n_bytes += 1;
+            } else dfree(ctx, ctx->d_bytes);
             ctx->d_bytes = nb; ctx->cap_bytes = cap; ctx->bytes_borrowed = false;
         }
         CK(cudaMemcpyAsync(ctx->d_bytes + ctx->n_bytes, bytes, n_bytes,
                            location == CDBG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->d_bytes + ctx->n_bytes + n_bytes, '\n', 1, ctx->stream));
         ctx->n_bytes += n_bytes + 1;
+        // the caller may refill or free `bytes` as soon as this returns (include/cdbg.h: "copied inside the call"): a copy from
+        // pinned or device memory is otherwise still in flight
+        CK(cudaStreamSynchronize(ctx->stream));
     }
     tstop(ctx, T_PUSH);
     ctx->stage = ST_PUSHED;

@@ -365,3 +365,20 @@ def test_reference_known_answers_through_the_cuda_path(emu_lib, knobs):
     with api.Cdbg(k=13, abundance_min=1, device=0) as c:
         g = c.build(tiny)
     assert g.n_unitigs == 1 and int(g.kc[0]) == 13
+
+
+def test_second_push_after_a_buffer_used_in_place_is_separated_by_a_break(emu_lib, knobs):
+    """a first push of an aligned device buffer is borrowed in place; a later push must not glue its first read to the
+    borrowed buffer's last one (the borrowed bytes need not end in a break byte)."""
+    k = 15
+    with api.Cdbg(k=k, abundance_min=1, device=0) as c:
+        ptr, n = c.synth_reads(3000, 60, 40, 10000, 5)
+        a = c.copy_to_host(ptr, n)[: n - 1]                     # drop the final '\n': the buffer now ends in a nucleotide
+        b = np.frombuffer(b"ACGTTGCATGCCGATAGCTAGGATCCGATTTACGCAGT\n", dtype=np.uint8)
+        c.push_device(ptr, n - 1)
+        c.push_reads(b)
+        assert c.pushed_reads() == a.tobytes() + b"\n" + b.tobytes() + b"\n"
+        c.count(); c.compact(); c.link()
+        g = c.unitigs()
+    o = orc.run(np.concatenate([a, np.frombuffer(b"\n", np.uint8), b]), k, 1)
+    assert parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k) == ""

@@ -91,3 +91,51 @@ def test_c2_idempotent_and_deterministic_multiset(c2):
     a = sorted(zip(np.diff(g.seq_off.astype(np.int64)).tolist(), g.kc.tolist()))
     b = sorted(zip(np.diff(g2.seq_off.astype(np.int64)).tolist(), g2.kc.tolist()))
     assert a == b
+
+
+def test_c2_checksum_matches_the_committed_oracle_checksum(c2):
+    """bench.py's N = 1 parity key compares with tests/golden/c2_checksum.json (the oracle's graph, made on CPU by
+    tests/golden/make_c2_checksum.py with the numpy read generator): the device generator gives the same reads and the GPU graph
+    the same checksum."""
+    import json
+    import os
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import bench
+    from bcalm_b200.checksum import graph_checksum
+    c, reads, g = c2
+    n = 50_000 * (READ_LEN + 1)
+    assert (reads[:n] == bench.synth_reads_numpy(GENOME, READ_LEN, 0, 50_000, 10000, 42)).all()
+    with open(os.path.join(ROOT, "tests", "golden", "c2_checksum.json")) as f:
+        gold = json.load(f)["scale_1"]
+    cs = graph_checksum(g, device="cuda:0")
+    assert {k_: cs[k_] for k_ in bench.CHECK_KEYS} == {k_: gold[k_] for k_ in bench.CHECK_KEYS}
+    assert g.stats["n_solid"] == gold["n_solid"]
+
+
+def test_c3_properties_on_one_gpu():
+    """BASELINE.json configs[2] (250 Mbp genome, 50 M x 150 bp reads = 7.5 Gbases) at full size through size-independent properties:
+    every solid k-mer is spelled once, KC sums to the solid abundances, every link overlaps by k-1, and a second build on a fresh
+    context reproduces the checksum."""
+    from bcalm_b200.checksum import graph_checksum
+    G, L = 250_000_000, 150
+    n_reads = G * 30 // L
+    sums = []
+    for _ in range(2):
+        with Cdbg(k=K, abundance_min=AMIN) as c:
+            ptr, n = c.synth_reads(G, L, n_reads, 10000, 43)
+            c.push_device(ptr, n)
+            st = c.count()
+            km, ct = c.solid_kmers()
+            assert len(km) == st["n_solid"]
+            total_ab = int(ct.astype(np.uint64).sum())
+            del km, ct
+            c.compact(); c.link()
+            g = c.unitigs(copy=False)
+            cs = graph_checksum(g, device="cuda:0")
+            assert cs["bad_overlaps"] == 0
+            assert cs["total_nt"] - cs["n_unitigs"] * (K - 1) == st["n_solid"]
+            assert cs["sum_kc"] == total_ab
+            sums.append(cs)
+    assert sums[0] == sums[1]
