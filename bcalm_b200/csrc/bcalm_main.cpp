@@ -18,6 +18,7 @@
 #include <chrono>
 #include <string>
 #include <algorithm>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -34,7 +35,8 @@ struct Options {
     bool all_abund = false;
     bool parse_only = false; // -parse-only: parse the input, print record/byte counts and a checksum, no GPU (host-side tests)
     int nb_gpus = 1;        // -nb-gpus N: one context per GPU (threads of this process), the graph sharded by minimizer over them
-    bool gpu_parse = false; // -gpu-parse 1: ship the file bytes and strip headers / quality lines on the GPU (cdbg_push_sequence_text)
+    int gpu_parse = -1;     // -gpu-parse 1: ship the file bytes and strip headers / quality lines on the GPU (cdbg_push_sequence_text); 0: host parser;
+                            // default (-1): on the GPU for a single-GPU build from reads, on the host otherwise
     bool edge_km = false;   // -edge-km 1: J:<0|1>:<id>:<0|1> tokens instead of L: (G/debruijn/impl/LinkTigs.cpp:380-384,440-444)
 };
 
@@ -100,7 +102,7 @@ Options parse(int argc, char **argv) {
         else if (a == "-nb-gpus") o.nb_gpus = atoi(need("-nb-gpus").c_str());
         else if (a == "-all-abundance-counts") o.all_abund = true;
         else if (a == "-parse-only") o.parse_only = true;
-        else if (a == "-gpu-parse") o.gpu_parse = atoi(need("-gpu-parse").c_str()) != 0;
+        else if (a == "-gpu-parse") o.gpu_parse = atoi(need("-gpu-parse").c_str()) != 0 ? 1 : 0;
         else if (a == "-edge-km") o.edge_km = atoi(need("-edge-km").c_str()) != 0;
         else if (a == "-help" || a == "-h") { usage(); exit(EXIT_SUCCESS); }
         else {
@@ -112,7 +114,7 @@ Options parse(int argc, char **argv) {
     }
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
     if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
-    if (o.nb_gpus > 1 && (!o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse || o.kff))
+    if (o.nb_gpus > 1 && (!o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse == 1 || o.kff))
         die("-nb-gpus > 1 does not support -solid-kmers-in / -solid-kmers-out / -gpu-parse / -kff");
     return o;
 }
@@ -274,6 +276,7 @@ void parse_sequences_mt(const FileBuf &in, ByteBuf &out, uint64_t &n_records, in
 
 static int g_parse_threads = 1;
 static cdbg_ctx *g_gpu_parse_ctx = nullptr;   // -gpu-parse 1: files are pushed as text and parsed on the device
+static std::function<cdbg_ctx *()> g_gpu_parse_wait;   // the context is created on its own thread while the first file is read: join it here
 
 void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, int depth = 0) {
     size_t start = 0;
@@ -289,6 +292,7 @@ void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, i
         if (i == buf.n) continue;
         if (buf.p[i] == '>' || buf.p[i] == '@') {
             bool done = false;
+            if (!g_gpu_parse_ctx && g_gpu_parse_wait) g_gpu_parse_ctx = g_gpu_parse_wait();
             if (g_gpu_parse_ctx) {   // the library refuses text it cannot parse exactly (e.g. multi-line FASTQ): then the host parser takes it
                 uint64_t nrec = 0;
                 done = cdbg_push_sequence_text(g_gpu_parse_ctx, (const uint8_t *)buf.p + i, buf.n - i, CDBG_MEM_HOST, &nrec) == CDBG_OK;
@@ -617,16 +621,24 @@ int run_sharded(const Options &o, ByteBuf &stream, uint64_t n_records, double t0
     const double t1 = now_s();
     std::vector<cdbg_ctx *> ctx(N, nullptr);
     auto destroy_all = [&]() { for (cdbg_ctx *c : ctx) if (c) cdbg_destroy(c); };
-    for (int r = 0; r < N; r++) {
-        cdbg_params prm{};
-        prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device + r;
-        prm.flags = (o.all_abund ? CDBG_FLAG_ALL_ABUNDANCE_COUNTS : 0) | (o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0);
-        prm.rank = r; prm.world_size = N;
-        if (cdbg_create(&ctx[r], &prm) != CDBG_OK) {
-            std::string msg = ctx[r] ? cdbg_last_error(ctx[r]) : "cdbg_create failed";
-            destroy_all();
-            die(msg);
-        }
+    {
+        std::vector<int> crc(N, CDBG_OK);
+        std::vector<std::thread> mk;
+        for (int r = 0; r < N; r++)
+            mk.emplace_back([&, r]() {
+                cdbg_params prm{};
+                prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device + r;
+                prm.flags = (o.all_abund ? CDBG_FLAG_ALL_ABUNDANCE_COUNTS : 0) | (o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0);
+                prm.rank = r; prm.world_size = N;
+                crc[r] = cdbg_create(&ctx[r], &prm);
+            });
+        for (auto &th : mk) th.join();
+        for (int r = 0; r < N; r++)
+            if (crc[r] != CDBG_OK) {
+                std::string msg = ctx[r] ? cdbg_last_error(ctx[r]) : "cdbg_create failed";
+                destroy_all();
+                die(msg);
+            }
     }
     uint8_t id[128];
     if (cdbg_nccl_unique_id(id) != CDBG_OK) { destroy_all(); die("NCCL is not available (cdbg_nccl_unique_id failed)"); }
@@ -695,13 +707,21 @@ int main(int argc, char **argv) {
     prm.kmer_size = o.k; prm.abundance_min = o.amin; prm.abundance_max = o.amax; prm.minimizer_size = o.m; prm.device = o.device;
     prm.flags = (o.all_abund ? CDBG_FLAG_ALL_ABUNDANCE_COUNTS : 0) | (o.verbose > 1 ? CDBG_FLAG_VERBOSE : 0);
     prm.rank = 0; prm.world_size = 1;
+    // the CUDA context takes a few hundred ms to create: do it on its own thread while the input is read (and parsed, on the host path)
     cdbg_ctx *ctx = nullptr;
-    int rc = cdbg_create(&ctx, &prm);
-    if (rc != CDBG_OK) {
-        std::string msg = ctx ? cdbg_last_error(ctx) : "cdbg_create failed";
-        if (ctx) cdbg_destroy(ctx);
-        die(msg);
-    }
+    int rc = CDBG_OK;
+    double t_ctx = 0;
+    std::thread creator([&]() { const double a = now_s(); rc = cdbg_create(&ctx, &prm); t_ctx = now_s() - a; });
+    bool joined = false;
+    auto wait_ctx = [&]() -> cdbg_ctx * {
+        if (!joined) { creator.join(); joined = true; }
+        if (rc != CDBG_OK) {
+            std::string msg = ctx ? cdbg_last_error(ctx) : "cdbg_create failed";
+            if (ctx) cdbg_destroy(ctx);
+            die(msg);
+        }
+        return ctx;
+    };
 
     ByteBuf stream;
     uint64_t n_records = 0;
@@ -711,15 +731,17 @@ int main(int argc, char **argv) {
     if (!o.solid_in.empty()) {   // stages 2-4 only, from counted k-mers
         std::vector<uint64_t> km; std::vector<uint32_t> ct;
         load_counted_kmers(o, km, ct);
+        wait_ctx();
         t1 = now_s();
         rc = cdbg_set_solid_kmers(ctx, km.data(), ct.data(), ct.size(), CDBG_MEM_HOST);
         if (rc == CDBG_OK) rc = cdbg_compact(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_link(ctx, nullptr);
         if (rc == CDBG_OK) rc = cdbg_get_unitigs(ctx, &v);
         if (rc == CDBG_OK) rc = cdbg_get_stats(ctx, &st);
-    } else if (o.gpu_parse) {
-        g_gpu_parse_ctx = ctx;
+    } else if (o.gpu_parse != 0) {
+        g_gpu_parse_wait = wait_ctx;
         load_input(o.in, stream, n_records);           // GPU-parsed files are already on the device; `stream` holds the rest
+        wait_ctx();
         t1 = now_s();
         rc = stream.size() || n_records == 0 ? cdbg_push_reads(ctx, stream.data(), stream.size(), CDBG_MEM_HOST) : CDBG_OK;
         if (rc == CDBG_OK) rc = cdbg_count(ctx, nullptr);
@@ -729,6 +751,7 @@ int main(int argc, char **argv) {
         if (rc == CDBG_OK) rc = cdbg_get_stats(ctx, &st);
     } else {
         load_input(o.in, stream, n_records);
+        wait_ctx();
         t1 = now_s();
         rc = cdbg_build(ctx, stream.data(), stream.size(), CDBG_MEM_HOST, &v, &st);
     }
@@ -754,7 +777,8 @@ int main(int argc, char **argv) {
         printf("device ms: count %.3f (K1 %.3f+%.3f, K2 %.3f)  compact %.3f (K3 %.3f, K5 %.3f, rank %.3f, spell %.3f)  link %.3f  fetch %.3f\n",
                st.ms_count, st.ms_k1_hist, st.ms_k1_scatter, st.ms_k2, st.ms_compact, st.ms_k3, st.ms_k5, st.ms_k6_rank, st.ms_k6_spell, st.ms_link,
                st.ms_fetch);
-        printf("wall s: parse %.3f  gpu (H2D+stages+D2H) %.3f  write %.3f  total %.3f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+        printf("wall s: parse %.3f  gpu (H2D+stages+D2H) %.3f  write %.3f  total %.3f  (CUDA context %.3f, created while the input was read%s)\n", t1 - t0, t2 - t1,
+               t3 - t2, t3 - t0, t_ctx, o.gpu_parse != 0 ? "; text parsed on the GPU" : "");
         printf("output: %s\n", out_path.c_str());
     }
     cdbg_destroy(ctx);

@@ -34,7 +34,7 @@ struct Timer {
 
 enum Stage { ST_EMPTY = 0, ST_PUSHED, ST_COUNTED, ST_COMPACTED, ST_LINKED };
 
-enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3, T_K5, T_K6R, T_K6S, T_K2H, T_K2S, T_K2C, T_N };
+enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3, T_K5, T_K6R, T_K6S, T_K2H, T_K2S, T_K2C, T_X1, T_X2, T_X3, T_GLUE, T_XLINK, T_N };
 
 }  // namespace
 
@@ -748,6 +748,47 @@ int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remainin
     return ctx->fail(CDBG_ERR_INTERNAL, "list ranking did not converge");
 }
 
+#ifndef K6_TWO_LEVEL_DEFAULT
+#define K6_TWO_LEVEL_DEFAULT 0   // window-local ranking in shared memory + global rounds over representatives (CDBG_K6=local)
+#endif
+
+// Two-level ranking of an unweighted list (kernels.cuh: k6_local / k6_jump_list / k6_resolve).  *remaining as rank_rounds.
+int rank_two_level(cdbg_ctx *ctx, const uint32_t *d_link, uint64_t *d_pair, uint64_t n2, uint64_t *remaining) {
+    int rc;
+    *remaining = 0;
+    uint32_t *d_list[2] = {nullptr, nullptr};
+    if ((rc = dalloc(ctx, &d_list[0], n2 + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_list[1], n2 + 1))) return rc;
+    if ((rc = ctr_zero(ctx))) return rc;
+    const uint64_t n_win = (n2 + 2 * K6L_NV - 1) / (2 * K6L_NV);
+    LAUNCH(k6_local, (int)std::min<uint64_t>(n_win, (uint64_t)ctx->n_sm * 4), K6L_THREADS, 0, d_link, d_pair, n2, d_list[0], ctx->d_ctr + 4);
+    if ((rc = ctr_read(ctx))) return rc;
+    uint64_t n_cur = ctx->h_ctr[4], prev = ~0ULL;
+    const uint32_t *in_list = d_list[0];
+    int result = n_cur ? -1 : 0;
+    for (int round = 0, batch = 1; round < 96 && result < 0; round += 4, batch++) {
+        if ((rc = ctr_zero(ctx))) return rc;
+        uint32_t *out_list = d_list[batch & 1];
+        for (int j = 0; j < 4; j++)
+            LAUNCH_PDL(k6_jump_list, grid_for(ctx, n_cur, 256, 8), 256, 0, d_pair, in_list, n_cur, j == 3 ? out_list : (uint32_t *)nullptr, ctx->d_ctr + 4,
+                       ctx->d_ctr + j);
+        ctx->st.rank_rounds += 4;
+        if ((rc = ctr_read(ctx))) return rc;
+        for (int j = 0; j < 4 && result < 0; j++) {
+            const uint64_t c = ctx->h_ctr[j];
+            if (c == 0) { *remaining = 0; result = 0; }
+            else if (c == prev) { *remaining = std::min<uint64_t>(n2, c * 2 * K6L_NV); result = 0; }   // cycles: every moving representative stands for up to a window of elements
+            prev = c;
+        }
+        in_list = out_list; n_cur = ctx->h_ctr[4];
+        if (result < 0 && n_cur == 0) { *remaining = 0; result = 0; }
+    }
+    dfree(ctx, d_list[0]); dfree(ctx, d_list[1]);
+    if (result != 0) return ctx->fail(CDBG_ERR_INTERNAL, "list ranking did not converge");
+    LAUNCH(k6_resolve, grid_for(ctx, n2, 256, 8), 256, 0, d_pair, n2);
+    return CDBG_OK;
+}
+
 // List ranking over `n_nodes` nodes with two ends each (link[2*n_nodes], NOLINK = chain end).  weight == nullptr: every node
 // counts 1 (k-mers); otherwise hop counts are weighted (pieces of several k-mers).  Cycles are cut at their smallest node;
 // the two edges of each cut junction are appended to edges[] (packed end ids) and *n_edges advanced.
@@ -759,10 +800,16 @@ int run_ranking(cdbg_ctx *ctx, uint32_t *d_link, uint64_t n_nodes, const uint32_
     if ((rc = dalloc(ctx, &d_pair, n2 + 1))) return rc;
     *d_pair_out = d_pair;
     if (!n_nodes) return CDBG_OK;
-    if (d_weight) LAUNCH(k6w_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_weight, d_pair, n2);
-    else LAUNCH(k6_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_pair, n2);
     uint64_t remaining = 0;
-    if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+    const char *k6m = getenv("CDBG_K6");
+    const bool two_level = !d_weight && n2 < (1ULL << 32) && (K6_TWO_LEVEL_DEFAULT ? !(k6m && (strcmp(k6m, "full") == 0 || strcmp(k6m, "list") == 0)) : (k6m && strcmp(k6m, "local") == 0));
+    if (two_level) {
+        if ((rc = rank_two_level(ctx, d_link, d_pair, n2, &remaining))) return rc;
+    } else {
+        if (d_weight) LAUNCH(k6w_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_weight, d_pair, n2);
+        else LAUNCH(k6_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_pair, n2);
+        if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+    }
     for (int guard = 0; remaining && guard < 4; guard++) {
         uint8_t *d_cyc = nullptr; uint64_t *d_lab = nullptr;
         if ((rc = dalloc(ctx, &d_cyc, n2 + 1))) return rc;
@@ -878,7 +925,7 @@ int stage_compact_k5_smem(cdbg_ctx *ctx, uint32_t slots, double per_fine, const 
     tstart(ctx, T_K5);
     K5PParams pp{};
     pp.key = d_rec_key; pp.val = d_rec_val; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P; pp.tile_first = d_tile_first;
-    pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    pp.P1 = P; pp.F = F; pp.n_tiles = (uint32_t)tiles; pp.group = nullptr; pp.G = P;
     pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out_key = d_key2; pp.out_val = d_val2;
     if (tiles) {
         LAUNCH(k5p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 8), K5P_THREADS, 0, pp);
@@ -1084,6 +1131,7 @@ void fill_stats(cdbg_ctx *ctx, cdbg_stats *out) {
     s.ms_k1_hist = tread(ctx, T_K1H); s.ms_k1_scatter = tread(ctx, T_K1S); s.ms_k2 = tread(ctx, T_K2);
     s.ms_k3 = tread(ctx, T_K3); s.ms_k5 = tread(ctx, T_K5); s.ms_k6_rank = tread(ctx, T_K6R); s.ms_k6_spell = tread(ctx, T_K6S);
     s.ms_k2_hist = tread(ctx, T_K2H); s.ms_k2_scatter = tread(ctx, T_K2S); s.ms_k2_table = tread(ctx, T_K2C);
+    s.ms_x1 = tread(ctx, T_X1); s.ms_x2 = tread(ctx, T_X2); s.ms_x3 = tread(ctx, T_X3); s.ms_glue = tread(ctx, T_GLUE); s.ms_xlink = tread(ctx, T_XLINK);
     if (out) *out = s;
 }
 

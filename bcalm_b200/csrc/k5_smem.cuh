@@ -26,8 +26,10 @@ struct K5PParams {
     const uint64_t *key, *val;          // K3 output (SoA), coarse bin b = [bin_beg[b], bin_end[b])
     const uint64_t *bin_beg, *bin_end;  // [P1] each
     const uint32_t *tile_first;         // [P1 + 1]
-    uint32_t P1, F, n_tiles;
-    uint32_t *fine_cnt;                 // [P1 * F]
+    const uint32_t *group;              // [P1] or null.  Sharded mode: the coarse "bins" are the received runs (one per local bin and source
+                                        // GPU); group[b] = the run's local bin = hash_to_bin(h, G), whose fine bins its records share
+    uint32_t P1, F, n_tiles, G;         // G = number of groups (= P1 without `group`)
+    uint32_t *fine_cnt;                 // [G * F]
     const uint64_t *fine_off;           // [P1 * F + 1]
     uint32_t *fine_cursor;              // [P1 * F]
     uint64_t *out_key, *out_val;        // records re-ordered by (coarse, fine) bin
@@ -44,9 +46,10 @@ __device__ __forceinline__ uint32_t k5p_bin_of_tile(const uint32_t *__restrict__
 
 __global__ void __launch_bounds__(K5P_THREADS) k5p_hist(K5PParams p) {
     __shared__ uint32_t s_cnt[K5P_MAX_F];
-    const uint32_t t = threadIdx.x, NF = p.P1 * p.F;
+    const uint32_t t = threadIdx.x, NF = p.G * p.F;
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t b = k5p_bin_of_tile(p.tile_first, p.P1, tile);
+        const uint32_t gb = p.group ? p.group[b] : b;
         const uint64_t beg = p.bin_beg[b] + (uint64_t)(tile - p.tile_first[b]) * K5P_TILE;
         const uint64_t end = min(beg + (uint64_t)K5P_TILE, p.bin_end[b]);
         for (uint32_t i = t; i < p.F; i += K5P_THREADS) s_cnt[i] = 0;
@@ -59,11 +62,11 @@ __global__ void __launch_bounds__(K5P_THREADS) k5p_hist(K5PParams p) {
         }
 #pragma unroll
         for (int j = 0; j < K5P_PER_THREAD; j++)
-            if (key[j] != EMPTY_KEY) atomicAdd(&s_cnt[k5p_fine(mix64(key[j]), NF, p.F, b)], 1u);
+            if (key[j] != EMPTY_KEY) atomicAdd(&s_cnt[k5p_fine(mix64(key[j]), NF, p.F, gb)], 1u);
         __syncthreads();
         for (uint32_t i = t; i < p.F; i += K5P_THREADS) {     // (same thread zeroes counter i for the next tile)
             const uint32_t c = s_cnt[i];
-            if (c) atomicAdd(&p.fine_cnt[(size_t)b * p.F + i], c);
+            if (c) atomicAdd(&p.fine_cnt[(size_t)gb * p.F + i], c);
         }
     }
 }
@@ -77,11 +80,12 @@ __global__ void __launch_bounds__(K5P_THREADS, 2) k5p_scatter(K5PParams p) {
     __shared__ uint32_t s_cnt[K5P_MAX_F];
     __shared__ uint32_t s_off[K5P_MAX_F + 1];
     __shared__ uint32_t s_warp[K5P_THREADS / 32];
-    const uint32_t t = threadIdx.x, NF = p.P1 * p.F;
+    const uint32_t t = threadIdx.x, NF = p.G * p.F;
     const uint32_t per = (p.F + K5P_THREADS - 1) / K5P_THREADS;                  // fine bins scanned per thread (1..4)
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t b = k5p_bin_of_tile(p.tile_first, p.P1, tile);
+        const uint32_t gb = p.group ? p.group[b] : b;
         const uint64_t beg = p.bin_beg[b] + (uint64_t)(tile - p.tile_first[b]) * K5P_TILE;
         const uint64_t end = min(beg + (uint64_t)K5P_TILE, p.bin_end[b]);
         for (uint32_t i = t; i < p.F; i += K5P_THREADS) s_cnt[i] = 0;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(K5P_THREADS, 2) k5p_scatter(K5PParams p) {
 #pragma unroll
         for (int j = 0; j < K5P_PER_THREAD; j++) {
             if (key[j] == EMPTY_KEY) { fr[j] = K5P_NOKEY; continue; }
-            const uint32_t f = k5p_fine(mix64(key[j]), NF, p.F, b);
+            const uint32_t f = k5p_fine(mix64(key[j]), NF, p.F, gb);
             fr[j] = (atomicAdd(&s_cnt[f], 1u) << 10) | f;
         }
         __syncthreads();
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(K5P_THREADS, 2) k5p_scatter(K5PParams p) {
                 const uint32_t cn = s_cnt[b0 + j];
                 s_off[b0 + j] = run;
                 if (cn) {
-                    const size_t g = (size_t)b * p.F + b0 + j;
+                    const size_t g = (size_t)gb * p.F + b0 + j;
                     s_gbase[b0 + j] = p.fine_off[g] + atomicAdd(&p.fine_cursor[g], cn);
                 }
                 run += cn;

@@ -576,6 +576,8 @@ __global__ void __launch_bounds__(256) k5_resolve(JoinTable T, uint32_t cap, uin
 #define K6_DONE 0x80000000u                                   // bit 31 of the hop count: nothing left to do for this element
 #define K6_NIL 0xFFFFFFFFu                                    // next of a tail
 #define K6_TAIL (((uint64_t)K6_NIL << 32) | K6_DONE)          // a tail: next = NIL, 0 hops, done
+#define K6_PARKED 0x40000000u                                 // bit 30 (two-level ranking): waits on the representative of its window-local chain
+#define K6_HOPS 0x3FFFFFFFu
 //
 // Directed element x (0 <= x < 2S) = "traverse k-mer x>>1 entering through end x&1 (0 = left, 1 = right)"; it leaves through
 // end x^1, so succ(x) = link[x^1].  pair[x] = (next << 32 | hops to next); a traversal's last element (the tail) has next = NIL.
@@ -601,10 +603,99 @@ __global__ void __launch_bounds__(256) k6_jump(uint64_t *pair, uint64_t n2, unsi
         uint64_t q = ld_volatile_u64(&pair[n]);
         uint32_t n2_ = (uint32_t)(q >> 32);
         if (n2_ == K6_NIL) { *(volatile uint64_t *)&pair[x] = p | K6_DONE; continue; }        // next is the tail: finished
-        *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p + (uint32_t)q) & ~K6_DONE);
+        *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p & K6_HOPS) + ((uint32_t)q & K6_HOPS));
         upd++;
     }
     block_add(n_updated, upd);
+}
+
+// ---- two-level ranking (unweighted lists).  Solid k-mers leave the counting kernel bucket by bucket, so most compaction links join
+// k-mers whose indices are close: consecutive k-mers of a unitig share their minimizer -- and with it their bucket -- for ~(k-m+2)/2
+// positions.  k6_local ranks every window of K6L_NV consecutive k-mers in SHARED memory first: an element whose successor lies
+// outside its window becomes the REPRESENTATIVE of its window-local chain, the chain's other elements PARK on it (pair = (rep,
+// hops to rep) | K6_PARKED) or finish (chains that end inside the window).  Only the representatives (about one element in
+// (k-m+2)/2) take part in the global, HBM-latency-bound rounds (k6_jump_list over a shrinking list); k6_resolve then adds the
+// representative's result to every parked element.  A parked element is a valid jumping target: "hops = distance to next" holds.
+constexpr int K6L_NV = 2048;                  // k-mers per window: 4096 directed elements, 32 KB of pairs
+constexpr int K6L_THREADS = 512;
+constexpr int K6L_MAX_ROUNDS = 14;
+
+__global__ void __launch_bounds__(K6L_THREADS) k6_local(const uint32_t *__restrict__ link, uint64_t *pair, uint64_t n2, uint32_t *rep_list,
+                                                       unsigned long long *n_reps) {
+    __shared__ uint64_t s_pair[2 * K6L_NV];
+    __shared__ int s_changed;
+    __shared__ uint32_t s_wcnt[K6L_THREADS / 32];
+    __shared__ unsigned long long s_obase;
+    const uint32_t t = threadIdx.x, lane = lane_id(), warp = t >> 5;
+    const uint64_t n_win = (n2 + 2 * K6L_NV - 1) / (2 * K6L_NV);
+    for (uint64_t win = blockIdx.x; win < n_win; win += gridDim.x) {
+        const uint64_t base = win * (2ULL * K6L_NV);
+        const uint32_t cnt = (uint32_t)min((uint64_t)(2 * K6L_NV), n2 - base);      // even: n2 and the window size are
+        for (uint32_t i = t; i < cnt; i += K6L_THREADS) {
+            const uint32_t s_ = link[base + (i ^ 1u)];
+            s_pair[i] = s_ == NOLINK ? K6_TAIL : (((uint64_t)s_ << 32) | 1u);
+        }
+        __syncthreads();
+        for (int round = 0; round < K6L_MAX_ROUNDS; round++) {
+            if (t == 0) s_changed = 0;
+            __syncthreads();
+            bool ch = false;
+            for (uint32_t i = t; i < cnt; i += K6L_THREADS) {
+                const uint64_t p = *(volatile uint64_t *)&s_pair[i];
+                if ((uint32_t)p & (K6_DONE | K6_PARKED)) continue;
+                const uint64_t n = (uint32_t)(p >> 32);
+                if (n < base || n >= base + cnt) continue;                            // a representative (or a tail's predecessor outside: same thing)
+                const uint64_t q = *(volatile uint64_t *)&s_pair[n - base];
+                const uint32_t qn = (uint32_t)(q >> 32);
+                if (qn == K6_NIL) { *(volatile uint64_t *)&s_pair[i] = p | K6_DONE; continue; }                 // next is the tail
+                const uint32_t hops = ((uint32_t)p & K6_HOPS) + ((uint32_t)q & K6_HOPS);
+                if ((uint32_t)q & K6_PARKED) { *(volatile uint64_t *)&s_pair[i] = ((uint64_t)qn << 32) | hops | K6_PARKED; continue; }   // park on the same representative
+                if (!((uint32_t)q & K6_DONE) && ((uint64_t)qn < base || (uint64_t)qn >= base + cnt)) {
+                    *(volatile uint64_t *)&s_pair[i] = p | K6_PARKED;                 // next IS a representative: park on it
+                    continue;
+                }
+                *(volatile uint64_t *)&s_pair[i] = ((uint64_t)qn << 32) | hops;
+                ch = true;
+            }
+            if (ch) s_changed = 1;
+            __syncthreads();
+            if (!s_changed) break;
+            __syncthreads();
+        }
+        // write back; the representatives (unfinished, not parked) go on the list
+        for (uint32_t i0 = 0; i0 < cnt; i0 += K6L_THREADS) {                          // block-uniform
+            const uint32_t i = i0 + t;
+            bool rep = false;
+            if (i < cnt) {
+                const uint64_t p = s_pair[i];
+                pair[base + i] = p;
+                rep = !((uint32_t)p & (K6_DONE | K6_PARKED));
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, rep);
+            if (lane == 0) s_wcnt[warp] = __popc(m);
+            __syncthreads();
+            if (t == 0) {
+                uint32_t tot = 0;
+                for (int w = 0; w < K6L_THREADS / 32; w++) { uint32_t v = s_wcnt[w]; s_wcnt[w] = tot; tot += v; }
+                s_obase = tot ? atomicAdd(n_reps, (unsigned long long)tot) : 0ULL;
+            }
+            __syncthreads();
+            if (rep) rep_list[s_obase + s_wcnt[warp] + __popc(m & ((1u << lane) - 1))] = (uint32_t)(base + i);
+            __syncthreads();
+        }
+    }
+}
+
+// every parked element takes over its representative's result (or, on a cycle, becomes a plain moving element again)
+__global__ void __launch_bounds__(256) k6_resolve(uint64_t *pair, uint64_t n2) {
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = pair[x];
+        if (!((uint32_t)p & K6_PARKED)) continue;
+        const uint32_t e = (uint32_t)(p >> 32);
+        const uint64_t q = pair[e];                                                   // representatives are never parked: not written by this kernel
+        if ((uint32_t)q & K6_DONE) pair[x] = (q & 0xFFFFFFFF00000000ULL) | (((uint32_t)p & K6_HOPS) + ((uint32_t)q & K6_HOPS)) | K6_DONE;
+        else pair[x] = p & ~(uint64_t)K6_PARKED;
+    }
 }
 
 // Variant that walks a LIST of still-moving elements instead of the whole array (in_list == nullptr: all x < n), and can emit
@@ -631,7 +722,7 @@ __global__ void __launch_bounds__(256) k6_jump_list(uint64_t *pair, const uint32
                 uint32_t n2_ = (uint32_t)(q >> 32);
                 if (n2_ == K6_NIL) *(volatile uint64_t *)&pair[x] = p | K6_DONE;
                 else {
-                    *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p + (uint32_t)q) & ~K6_DONE);
+                    *(volatile uint64_t *)&pair[x] = ((uint64_t)n2_ << 32) | (uint32_t)(((uint32_t)p & K6_HOPS) + ((uint32_t)q & K6_HOPS));
                     moved = true; upd++;
                 }
             }

@@ -401,6 +401,153 @@ __global__ void __launch_bounds__(256) k5s_resolve(JoinTable64 T, uint32_t cap, 
     block_add(n_compact, my_c);
 }
 
+// ---- the sharded join with the tables in SHARED memory (the sharded counterpart of k5c_join, k5_smem.cuh): the received end records
+// are split into fine bins (k5p_hist / k5p_scatter with `group`), one CTA joins a fine bin.  A table slot remembers the POSITION of
+// up to 4 IN and 4 OUT records inside the bin (32 bits each, as in k5c_join) -- the 40-bit global end ids are read back from the
+// record array when the junction is decided -- and the decisions leave as in k5s_resolve: links whose end is local are written,
+// the others become messages, unitig-level edges are (gid, gid) pairs.  Reservations are warp-aggregated.
+struct K5CSParams {
+    const uint64_t *key, *val;          // records ordered by fine bin
+    const uint64_t *fine_off;           // [n_fine + 1]
+    uint32_t n_fine, rank;
+    uint64_t *link64;                   // [2S] partner gid of every local k-mer end (pre-set to NOGID)
+    ulonglong2 *link_msgs; uint64_t link_cap; unsigned long long *n_link_msgs;
+    ulonglong2 *edges; uint64_t edge_cap; unsigned long long *n_edges;
+    unsigned long long *n_compact, *n_splits;
+    int *failed;
+};
+
+constexpr int K5CS_THREADS = 256;
+constexpr int K5CS_MAX_LEVEL = 10;
+template <int SLOTS> static inline size_t k5cs_smem_bytes() { return (size_t)SLOTS * (8 + 4 + 32) + 128; }
+
+template <int SLOTS>
+__global__ void __launch_bounds__(K5CS_THREADS) k5cs_join(K5CSParams p) {
+    constexpr int T = K5CS_THREADS, NW = T / 32, PER_WARP = SLOTS / NW;
+    constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);                   // [SLOTS]
+    uint32_t *s_ids = reinterpret_cast<uint32_t *>(s_keys + SLOTS);              // [SLOTS * 8]  record positions: 0..3 IN, 4..7 OUT
+    uint32_t *s_cnt = s_ids + (size_t)SLOTS * 8;                                 // [SLOTS] IN count | OUT count << 8 | pair flags | palindrome << 31
+    __shared__ int s_over;
+    __shared__ uint32_t s_fill;
+    const uint32_t t = threadIdx.x, lane = lane_id(), warp = t >> 5;
+    const uint32_t wb = warp * PER_WARP;
+    unsigned long long compact = 0, my_splits = 0;
+
+    for (uint32_t bin = blockIdx.x; bin < p.n_fine; bin += gridDim.x) {
+        const uint64_t beg = p.fine_off[bin], end = p.fine_off[bin + 1];
+        if (beg == end) continue;
+        uint32_t stk[K5CS_MAX_LEVEL + 2];
+        int sp = 0;
+        stk[sp++] = 0;
+        while (sp) {
+            const uint32_t item = stk[--sp], level = item >> 16, part = item & 0xFFFFu, sel_mask = (1u << level) - 1u;
+            for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
+            if (t == 0) { s_over = 0; s_fill = 0; }
+            __syncthreads();
+
+            for (uint64_t base = beg + warp * 32; base < end; base += (uint64_t)T * 2) {     // warp-uniform trip count
+                uint64_t key[2], val[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint64_t i = base + lane + (uint64_t)u * T;
+                    key[u] = i < end ? p.key[i] : EMPTY_KEY;
+                    val[u] = i < end ? p.val[i] : 0;
+                }
+                if (__any_sync(0xFFFFFFFFu, *(volatile int *)&s_over)) break;
+                uint32_t fresh = 0;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (key[u] == EMPTY_KEY || (val[u] & SREC_SKIP)) continue;
+                    const uint64_t h = mix64(key[u]);
+                    if ((((uint32_t)h >> 16) & sel_mask) != part) continue;
+                    const uint32_t pos_in_bin = (uint32_t)(base + lane + (uint64_t)u * T - beg);
+                    uint32_t slot = (uint32_t)h & MASK;
+                    for (uint32_t probes = 0;;) {
+                        uint64_t cur = ld_volatile_u64(&s_keys[slot]);
+                        if (cur == EMPTY_KEY) {
+                            cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key[u]);
+                            if (cur == EMPTY_KEY) { cur = key[u]; fresh++; }
+                        }
+                        if (cur == key[u]) {
+                            const bool pal = (val[u] & SREC_PALIN) != 0, use_out = (val[u] & SREC_SIDE_OUT) != 0 && !pal;
+                            const uint32_t old = atomicAdd(&s_cnt[slot], use_out ? 0x100u : 0x1u);
+                            if (pal) atomicOr(&s_cnt[slot], 0x80000000u);
+                            const uint32_t pos = use_out ? ((old >> 8) & 0xFF) : (old & 0xFF);
+                            if (pos < 4) {
+                                s_ids[(size_t)slot * 8 + (use_out ? 4 : 0) + pos] = pos_in_bin;
+                                if (val[u] & SREC_BOTH) atomicOr(&s_cnt[slot], 1u << ((use_out ? JOIN_BOTH_SHIFT_OUT : JOIN_BOTH_SHIFT_IN) + pos));
+                            }
+                            break;
+                        }
+                        slot = (slot + 1) & MASK;
+                        if (++probes >= (uint32_t)SLOTS) { s_over = 1; break; }
+                    }
+                }
+                fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+                if (lane == 0 && fresh && atomicAdd(&s_fill, fresh) + fresh > FILL_LIMIT) s_over = 1;
+            }
+            __syncthreads();
+            const int over = s_over;
+            __syncthreads();
+            if (over) {
+                my_splits += t == 0;
+                if (level >= (uint32_t)K5CS_MAX_LEVEL) { if (t == 0) *p.failed = 1; break; }
+                stk[sp++] = ((level + 1) << 16) | part;
+                stk[sp++] = ((level + 1) << 16) | part | (1u << level);
+                continue;
+            }
+
+            // ---- resolve: every warp walks its own slots, 32 at a time (uniform trip count: PER_WARP is a multiple of 32)
+            for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
+                uint32_t nin = 0, nout = 0, n_msg = 0, n_edge = 0;
+                bool pal = false, comp = false, occ = s_keys[i] != EMPTY_KEY;
+                uint64_t ein[5], eout[5];
+                if (occ) {
+                    const uint32_t c = s_cnt[i];
+                    const uint32_t sin = min(c & 0xFFu, 4u), sout = min((c >> 8) & 0xFFu, 4u);
+                    pal = (c >> 31) != 0;
+                    uint64_t gin[4], gout[4];
+                    for (uint32_t a = 0; a < sin; a++) gin[a] = p.val[beg + s_ids[(size_t)i * 8 + a]] & GID_MASK;
+                    for (uint32_t a = 0; a < sout; a++) gout[a] = p.val[beg + s_ids[(size_t)i * 8 + 4 + a]] & GID_MASK;
+                    nin = join_expand_side(gin, sin, (c >> JOIN_BOTH_SHIFT_IN) & ((1u << sin) - 1u), ein);
+                    nout = join_expand_side(gout, sout, (c >> JOIN_BOTH_SHIFT_OUT) & ((1u << sout) - 1u), eout);
+                    comp = !pal && nin == 1 && nout == 1 && (ein[0] >> 1) != (eout[0] >> 1);
+                    if (comp) n_msg = (GID_RANK(ein[0]) != p.rank) + (GID_RANK(eout[0]) != p.rank);
+                    else n_edge = pal ? nin * nin : 2 * nin * nout;
+                }
+                // warp-aggregated reservations
+                uint32_t xm = n_msg, xe = n_edge;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(0xFFFFFFFFu, xm, d), b = __shfl_up_sync(0xFFFFFFFFu, xe, d); if ((int)lane >= d) { xm += a; xe += b; } }
+                const uint32_t tm = __shfl_sync(0xFFFFFFFFu, xm, 31), te = __shfl_sync(0xFFFFFFFFu, xe, 31);
+                unsigned long long bm = 0, be = 0;
+                if (lane == 0) { if (tm) bm = atomicAdd(p.n_link_msgs, (unsigned long long)tm); if (te) be = atomicAdd(p.n_edges, (unsigned long long)te); }
+                bm = __shfl_sync(0xFFFFFFFFu, bm, 0); be = __shfl_sync(0xFFFFFFFFu, be, 0);
+                uint64_t ol = bm + xm - n_msg, oe = be + xe - n_edge;
+                if (!occ) continue;
+                if (comp) {
+                    const uint64_t a = ein[0], b = eout[0];
+                    if (GID_RANK(a) == p.rank) p.link64[GID_LOCAL(a)] = b; else { if (ol < p.link_cap) p.link_msgs[ol] = make_ulonglong2(a, b); ol++; }
+                    if (GID_RANK(b) == p.rank) p.link64[GID_LOCAL(b)] = a; else { if (ol < p.link_cap) p.link_msgs[ol] = make_ulonglong2(b, a); ol++; }
+                    compact++;
+                } else if (pal) {
+                    for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nin; b++) { if (oe < p.edge_cap) p.edges[oe] = make_ulonglong2(ein[a], ein[b]); oe++; }
+                } else {
+                    for (uint32_t a = 0; a < nin; a++) for (uint32_t b = 0; b < nout; b++) {
+                        if (oe + 2 <= p.edge_cap) { p.edges[oe] = make_ulonglong2(ein[a], eout[b]); p.edges[oe + 1] = make_ulonglong2(eout[b], ein[a]); }
+                        oe += 2;
+                    }
+                }
+            }
+            // (no barrier: the next pass clears only this warp's own slots; inserts into them start after the next barrier)
+        }
+    }
+    block_add(p.n_compact, compact);
+    block_add(p.n_splits, my_splits);
+}
+
 // ------------------------------------------------------------------------------------------------ generic routing of 16-byte records
 
 // destination = rank field of rec.x (bits 39..32)

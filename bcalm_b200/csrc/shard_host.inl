@@ -139,6 +139,7 @@ int shard_stage_count_sk(cdbg_ctx *ctx) {
         I_total += all[(size_t)r * (Pc + 1) + Pc];
     }
     // the bins' regions have gaps: gather them into one contiguous send buffer (destination-major)
+    tstart(ctx, T_X1);
     std::vector<uint64_t> h_out(Pc + 1, 0);
     for (uint32_t b = 0; b < Pc; b++) h_out[b + 1] = h_out[b] + h_cnt[b];
     const uint64_t R_out = h_out[Pc];
@@ -157,6 +158,7 @@ int shard_stage_count_sk(cdbg_ctx *ctx) {
     void *recv = nullptr; uint64_t R_in = 0;
     if ((rc = exchange_with_counts(ctx, d_send, send_cnt, recv_cnt, 16, &recv, &R_in))) return rc;
     dfree(ctx, d_send);
+    tstop(ctx, T_X1);
     TRACE("X1 super-k-mer exchange");
     const uint32_t R = P_local * (uint32_t)W;
     std::vector<uint64_t> r_cnt(R), r_off(R + 1, 0);
@@ -344,6 +346,105 @@ int shard_stage_count(cdbg_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------------ stages 2+3 (sharded)
 
+// The sharded join with shared-memory tables (k5p_hist / k5p_scatter with groups, k5cs_join): the received end records (runs: one
+// per local bin and source GPU) are split into fine bins of ~one table each; leaves ctx->d_link64, ctx->d_sedges / n_sedges and the
+// link messages for ends on other GPUs.  Buffers that overflow are re-allocated with the exact size and the join is repeated.
+int shard_join_smem(cdbg_ctx *ctx, const uint64_t *d_rec_key, const uint64_t *d_rec_val, uint64_t T_in, uint32_t P_local,
+                    const std::vector<uint64_t> &run_off, const std::vector<uint64_t> &run_len, ulonglong2 **out_msgs, uint64_t *out_n_msgs) {
+    const int W = ctx->world;
+    const uint64_t n2 = 2 * ctx->S;
+    int rc;
+    const uint32_t slots = getenv("CDBG_K5S_SLOTS") && atoi(getenv("CDBG_K5S_SLOTS")) == 4096 ? 4096u : 2048u;
+    double fill = getenv("CDBG_K5S_FILL") ? atof(getenv("CDBG_K5S_FILL")) : 1.0;
+    if (!(fill >= 0.05 && fill <= 8.0)) fill = 1.0;
+    const uint32_t R = P_local * (uint32_t)W;
+    const uint32_t F = (uint32_t)std::min<uint64_t>(K5P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)T_in / (fill * slots * P_local))));
+    const uint64_t NF = (uint64_t)P_local * F;
+    std::vector<uint32_t> h_tile_first(R + 1), h_group(R);
+    std::vector<uint64_t> h_range(2 * (size_t)R);
+    uint64_t tiles = 0;
+    for (uint32_t b = 0; b < P_local; b++)
+        for (int s_ = 0; s_ < W; s_++) {
+            const uint32_t r = b * (uint32_t)W + (uint32_t)s_;
+            h_tile_first[r] = (uint32_t)tiles; tiles += (run_len[r] + K5P_TILE - 1) / K5P_TILE;
+            h_range[r] = run_off[r]; h_range[R + r] = run_off[r] + run_len[r]; h_group[r] = b;
+        }
+    h_tile_first[R] = (uint32_t)tiles;
+    if (tiles >= (1ULL << 32)) return ctx->fail(CDBG_ERR_PARAM, "too many end-record tiles for one device");
+    uint32_t *d_tile_first = nullptr, *d_fine_cnt = nullptr, *d_fine_cursor = nullptr, *d_group = nullptr;
+    uint64_t *d_fine_off = nullptr, *d_key2 = nullptr, *d_val2 = nullptr, *d_bin_range = nullptr;
+    if ((rc = dalloc(ctx, &d_bin_range, 2 * (size_t)R))) return rc;
+    if ((rc = dalloc(ctx, &d_tile_first, R + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_group, R))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_cnt, NF + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_cursor, NF + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_fine_off, NF + 2))) return rc;
+    if ((rc = dalloc(ctx, &d_key2, T_in + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_val2, T_in + 1))) return rc;
+    CK(cudaMemsetAsync(d_fine_cnt, 0, (NF + 1) * 4, ctx->stream));
+    CK(cudaMemsetAsync(d_fine_cursor, 0, (NF + 1) * 4, ctx->stream));
+    CK(cudaMemcpyAsync(d_bin_range, h_range.data(), 2 * (size_t)R * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tile_first, h_tile_first.data(), (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_group, h_group.data(), (size_t)R * 4, cudaMemcpyHostToDevice, ctx->stream));
+    tstart(ctx, T_K5);
+    K5PParams pp{};
+    pp.key = d_rec_key; pp.val = d_rec_val; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + R; pp.tile_first = d_tile_first; pp.group = d_group;
+    pp.P1 = R; pp.F = F; pp.n_tiles = (uint32_t)tiles; pp.G = P_local;
+    pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out_key = d_key2; pp.out_val = d_val2;
+    if (tiles) {
+        LAUNCH(k5p_hist, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 8), K5P_THREADS, 0, pp);
+        uint64_t total = 0;
+        if ((rc = exclusive_scan(ctx, d_fine_cnt, NF + 1, d_fine_off, &total))) return rc;
+        if (total != T_in) return ctx->fail(CDBG_ERR_INTERNAL, "fine histogram lost end records (%llu != %llu)", (unsigned long long)total, (unsigned long long)T_in);
+        CK(cudaFuncSetAttribute(k5p_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5p_scatter_smem_bytes()));
+        LAUNCH(k5p_scatter, (int)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * 2), K5P_THREADS, k5p_scatter_smem_bytes(), pp);
+    } else {
+        CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
+    }
+    ulonglong2 *d_link_msgs = nullptr;
+    uint64_t link_cap = T_in / 4 + 4096;
+    ctx->sedge_cap = std::max<uint64_t>(T_in / 4, 1 << 16) + 4096;
+    if ((rc = dalloc(ctx, &ctx->d_link64, n2 + 1))) return rc;
+    uint64_t n_link_msgs = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = dalloc(ctx, &d_link_msgs, link_cap))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_sedges, ctx->sedge_cap))) return rc;
+        CK(cudaMemsetAsync(ctx->d_link64, 0xFF, (n2 + 1) * 8, ctx->stream));
+        if ((rc = ctr_zero(ctx))) return rc;
+        K5CSParams cp{};
+        cp.key = d_key2; cp.val = d_val2; cp.fine_off = d_fine_off; cp.n_fine = (uint32_t)NF; cp.rank = (uint32_t)ctx->rank;
+        cp.link64 = ctx->d_link64; cp.link_msgs = d_link_msgs; cp.link_cap = link_cap; cp.n_link_msgs = ctx->d_ctr + 0;
+        cp.edges = ctx->d_sedges; cp.edge_cap = ctx->sedge_cap; cp.n_edges = ctx->d_ctr + 1;
+        cp.n_compact = ctx->d_ctr + 2; cp.n_splits = ctx->d_ctr + 3; cp.failed = ctx->d_flag + 1;
+        if (T_in) {
+            if (slots == 4096) {
+                CK(cudaFuncSetAttribute(k5cs_join<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5cs_smem_bytes<4096>()));
+                LAUNCH(k5cs_join<4096>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm), K5CS_THREADS, k5cs_smem_bytes<4096>(), cp);
+            } else {
+                CK(cudaFuncSetAttribute(k5cs_join<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5cs_smem_bytes<2048>()));
+                LAUNCH(k5cs_join<2048>, (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * 2), K5CS_THREADS, k5cs_smem_bytes<2048>(), cp);
+            }
+        }
+        if (attempt == 0) tstop(ctx, T_K5);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (((int *)(ctx->h_ctr + 64))[1]) return ctx->fail(CDBG_ERR_INTERNAL, "K5: a fine bin does not fit a shared-memory table after %d splits", K5CS_MAX_LEVEL);
+        n_link_msgs = ctx->h_ctr[0];
+        ctx->n_sedges = ctx->h_ctr[1];
+        ctx->st.n_compactions = ctx->h_ctr[2];
+        ctx->st.n_k5_splits = (uint32_t)ctx->h_ctr[3];
+        // room is kept for the edges of locally cut cycles and of piece-level cycle cuts, which are appended later
+        if (n_link_msgs <= link_cap && ctx->n_sedges + 65536 + 4096 <= ctx->sedge_cap) break;
+        if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "join output buffers overflow after resizing");
+        dfree(ctx, d_link_msgs); dfree(ctx, ctx->d_sedges);
+        link_cap = n_link_msgs + 4096;
+        ctx->sedge_cap = ctx->n_sedges + std::max<uint64_t>(ctx->n_sedges / 8, 1 << 17) + 4096;
+    }
+    dfree(ctx, d_bin_range); dfree(ctx, d_tile_first); dfree(ctx, d_group); dfree(ctx, d_fine_cnt); dfree(ctx, d_fine_cursor); dfree(ctx, d_fine_off);
+    dfree(ctx, d_key2); dfree(ctx, d_val2);
+    *out_msgs = d_link_msgs; *out_n_msgs = n_link_msgs;
+    return CDBG_OK;
+}
+
 // K3 + X2 + K5 of the sharded path for one-word k-mers: end records to the owner of their junction, the join there; leaves
 // ctx->d_link64 (links whose end is local), the link messages for ends on other GPUs, and the unitig-level edges in ctx->d_sedges.
 int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, uint64_t *out_n_msgs) {
@@ -393,6 +494,7 @@ int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, ui
     // keys and values travel as two segments of ONE exchange: [keys of all bins for peer d | values ...] would need a repack, so
     // instead both arrays are sent in the same NCCL group (one launch, one synchronisation point)
     uint64_t *d_rec_key = nullptr, *d_rec_val = nullptr; uint64_t T_in = 0;
+    tstart(ctx, T_X2);
     {
         for (int sidx = 0; sidx < W; sidx++) T_in += recv_cnt[sidx];
         if ((rc = dalloc(ctx, &d_rec_key, T_in + 2))) return rc;
@@ -412,10 +514,22 @@ int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, ui
         }
         NK(ncclGroupEnd());
     }
+    tstop(ctx, T_X2);
     dfree(ctx, d_key_s); dfree(ctx, d_val_s); dfree(ctx, d_bins3);
     ctx->st.n_junction_records = T_in;
 
     TRACE("k3 + X2 record exchange");
+    // ---- K5 with shared-memory tables (default; CDBG_SHARD_K5=l2 keeps one L2-resident table per local bin)
+    if (!(getenv("CDBG_SHARD_K5") && strcmp(getenv("CDBG_SHARD_K5"), "l2") == 0)) {
+        uint64_t worst = 0;
+        for (size_t i = 0; i < run_len.size(); i++) worst = std::max(worst, run_len[i]);
+        if (worst < (1ULL << 32)) {
+            if ((rc = shard_join_smem(ctx, d_rec_key, d_rec_val, T_in, P_local, run_off, run_len, out_msgs, out_n_msgs))) return rc;
+            dfree(ctx, d_rec_key); dfree(ctx, d_rec_val);
+            dfree(ctx, d_bin_count); dfree(ctx, d_bin_cursor); dfree(ctx, d_bin_off);
+            return CDBG_OK;
+        }
+    }
     // ---- K5: per-bin join -> link messages + edges (gids)
     uint64_t max_bin = 0;
     std::vector<uint64_t> bin_tot(P_local, 0);
@@ -479,7 +593,9 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     TRACE("k5 join");
     // ---- X3: link messages to the owners of the ends; local view of the links
     ulonglong2 *d_msgs_in = nullptr; uint64_t n_msgs_in = 0;
+    tstart(ctx, T_X3);
     if ((rc = route16(ctx, d_link_msgs, n_link_msgs, &d_msgs_in, &n_msgs_in))) return rc;
+    tstop(ctx, T_X3);
     dfree(ctx, d_link_msgs);
     if ((rc = dalloc(ctx, &ctx->d_link, n2 + 1))) return rc;
     if (n_msgs_in) LAUNCH(shard_apply_links, grid_for(ctx, n_msgs_in, 256, 8), 256, 0, d_msgs_in, n_msgs_in, ctx->d_link64);
@@ -512,6 +628,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
 
     TRACE("local rank + spell pieces");
     // ---- stage 3: glue.  global piece ids, neighbour messages (X4), all-gather, replicated piece ranking
+    tstart(ctx, T_GLUE);
     uint64_t all_P[MAX_WORLD], all_nt[MAX_WORLD], piece_base[MAX_WORLD + 1] = {0}, max_p = 1, max_nt = 16;
     uint64_t mine[3] = {Pn, piece_nt, S}, both[3 * MAX_WORLD], max_s = 4;
     if ((rc = allgather_host_u64(ctx, mine, 3, both))) return rc;
@@ -629,9 +746,10 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     dfree(ctx, d_pedges); dfree(ctx, d_desc); dfree(ctx, d_desc_all); dfree(ctx, d_seq_all); dfree(ctx, d_piece_base); dfree(ctx, d_weight);
     dfree(ctx, d_puid); dfree(ctx, d_pnt); dfree(ctx, d_kc_all); dfree(ctx, d_unt_off);
     dfree(ctx, d_pseq); dfree(ctx, d_pseq_off); dfree(ctx, d_pkc); dfree(ctx, d_pabund); dfree(ctx, d_abund_all);
+    tstop(ctx, T_GLUE);
     tstop(ctx, T_K6S);
     TRACE("edges + cleanup");
-    ctx->n_pieces = Pn;
+    ctx->n_pieces = Pn; ctx->st.n_pieces = (uint32_t)Pn;
     ctx->U = U_mine; ctx->total_nt = nt_mine;
     ctx->st.n_unitigs = U_mine; ctx->st.total_nt = nt_mine;
     tstop(ctx, T_COMPACT);
@@ -650,7 +768,9 @@ int shard_stage_link(cdbg_ctx *ctx) {
     if ((rc = ctr_zero(ctx))) return rc;
     if (ctx->n_sedges) LAUNCH(links_resolve, grid_for(ctx, ctx->n_sedges, 256, 8), 256, 0, ctx->d_sedges, ctx->n_sedges, ctx->gid_table, ctx->d_pinfo,
                               ctx->d_unitig_of_piece, std::max<uint64_t>(ctx->U_total, 1), (uint32_t)W, ctx->d_flag);
+    tstart(ctx, T_XLINK);
     if ((rc = route16(ctx, ctx->d_sedges, ctx->n_sedges, &c, &nc))) return rc;
+    tstop(ctx, T_XLINK);
     {
         int bad = 0;
         CK(cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -42,6 +42,20 @@ __device__ __forceinline__ uint32_t sk_rec_n(const ulonglong2 &r) { return ((uin
 __device__ __forceinline__ uint32_t sk_rec_sub(const ulonglong2 &r) { return ((uint32_t)r.y >> 6) & ((1u << SK_SUB_BITS) - 1u); }
 __device__ __forceinline__ uint32_t sk_fine(uint32_t sub, uint32_t F) { return (sub * F) >> SK_SUB_BITS; }   // F <= 1024: no overflow
 
+// the record read in the other direction: reverse complement of its nt = n + k - 1 nucleotides, left-aligned again
+__device__ __forceinline__ ulonglong2 sk_canon_rec(const ulonglong2 r, int k) {
+    const uint32_t nt = sk_rec_n(r) + (uint32_t)k - 1u;
+    const uint64_t x = r.x, y = r.y & ~0xFFFFFFULL;
+    const uint64_t rx = revcomp64(y, 32), ry = revcomp64(x, 32);      // (rx:ry) = the reversed string right-aligned in 128 bits
+    const uint32_t s = 128u - 2u * nt;                                // nt <= 52: s >= 24
+    uint64_t cx, cy;
+    if (s >= 64) { cx = ry << (s - 64); cy = 0; }
+    else { cx = (rx << s) | (ry >> (64 - s)); cy = ry << s; }
+    const bool flip = cx < x || (cx == x && cy < y);
+    return flip ? make_ulonglong2(cx, cy | (r.y & 0xFFFFFFULL)) : r;
+}
+
+
 // ------------------------------------------------------------------------------------------------ K1: reads -> super-k-mers
 
 constexpr int SK1_LIST_CAP = 2048;        // run descriptors per tile handled through shared memory (more: written directly)
@@ -381,6 +395,7 @@ struct SK2PParams {
     const uint32_t *tile_first;     // [P1 + 1] first tile of each coarse bin (tiles never span coarse bins)
     const uint32_t *group;          // [P1] or null: sharded mode, the runs (one per source GPU) of one local bin share their fine bins
     uint32_t P1, F, n_tiles;
+    int canon, k;                   // canon: write every record in its strand-canonical form (sk_canon_rec), what sk2d_count's dedup needs
     uint32_t *fine_cnt;             // [G * F]     hist: out
     const uint64_t *fine_off;       // [G * F + 1] scatter: exclusive offsets into `out`
     uint32_t *fine_cursor;          // [G * F]     scatter: running cursors, zero-initialised
@@ -432,7 +447,7 @@ __global__ void __launch_bounds__(SK2P_THREADS) sk2p_scatter(SK2PParams p) {
         for (int j = 0; j < SK2P_PER_THREAD; j++) {
             const uint64_t i = beg + (uint64_t)j * SK2P_THREADS + t;
             fr[j] = 0xFFFFFFFFu;
-            if (i < end) rec[j] = p.recs[i];
+            if (i < end) { rec[j] = p.recs[i]; if (p.canon) rec[j] = sk_canon_rec(rec[j], p.k); }
             else rec[j] = make_ulonglong2(0, 0);
         }
 #pragma unroll
@@ -642,6 +657,233 @@ __global__ void __launch_bounds__(T) sk2c_count(SK2CParams p) {
                 }
             }
             __syncthreads();     // the next pass clears the table and thread 0 resets s_over / s_fill
+        }
+    }
+    block_add(p.n_distinct, my_distinct);
+    block_add(p.n_splits, my_splits);
+}
+
+// ------------------------------------------------------------------------------------------------ K2b': counting with record dedup
+//
+// Sequencing reads cover every genome position many times, so most super-k-mers of a bucket are exact copies of one another (at 30x
+// about two thirds of the records: the ones without a sequencing error that are not cut by a read end).  sk2d_count therefore counts
+// the distinct RECORDS of a fine bin first and expands each distinct record once, adding its multiplicity to its k-mers' counts:
+//   B  records -> record table (RS slots: 64-bit fingerprint of the 16 record bytes, multiplicity, index of the first such record);
+//      after a barrier every record compares its 16 bytes with the table's representative -- a record whose fingerprint collides with
+//      a different record, or that finds the record table full, is expanded directly with weight 1 (exactness never rests on the hash);
+//   C  distinct records -> k-mer table: a warp takes 32 record slots, prefix-sums their k-mer counts and expands ONE K-MER PER LANE
+//      (record found by a 5-step search of the prefix sums), so expansion, hashing and the first probe run with full warps;
+//   D  emit (as sk2c_count).
+// Records must be strand-canonical for copies read from opposite strands to be equal: sk2p_scatter does that (sk_canon_rec) when
+// its `canon` flag is set.  Same table overflow handling as sk2c_count (abandon at 3/4 full, redo as two halves by one more hash bit).
+
+__device__ __forceinline__ uint64_t sk_rec_fp(const ulonglong2 r) {
+    uint64_t h = mix64(r.x ^ (r.y * 0x9E3779B97F4A7C15ULL)) ^ r.y;
+    return h == EMPTY_KEY ? 0 : h;
+}
+
+template <int SLOTS, int RS, int T> static inline size_t sk2d_smem_bytes() { return (size_t)SLOTS * 12 + (size_t)RS * 16 + (size_t)(T / 32) * (32 * 16 + 32 * 8) + 128; }
+
+template <int SLOTS, int RS, int T, bool MUL32, int KC>
+__global__ void __launch_bounds__(T) sk2d_count(SK2CParams p) {
+    constexpr int NW = T / 32, PER_WARP = SLOTS / NW, R_PER = 4;
+    constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3, RMASK = RS - 1, RFILL_LIMIT = RS / 4 * 3, NONE = 0xFFFFFFFFu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);                   // [SLOTS] k-mer table
+    uint64_t *r_fp = s_keys + SLOTS;                                             // [RS]    record table: fingerprints
+    ulonglong2 *w_rec = reinterpret_cast<ulonglong2 *>(r_fp + RS);               // [NW][32] the records a warp is expanding
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(w_rec + NW * 32);             // [SLOTS]
+    uint32_t *r_cnt = s_cnt + SLOTS;                                             // [RS]    multiplicities
+    uint32_t *r_idx = r_cnt + RS;                                                // [RS]    representative (index from the bin's first record)
+    uint32_t *w_incl = r_idx + RS;                                               // [NW][32] inclusive prefix sums of k-mer counts
+    uint32_t *w_wt = w_incl + NW * 32;                                           // [NW][32] weights
+    __shared__ uint32_t s_wsolid[32];
+    __shared__ unsigned long long s_base;
+    __shared__ int s_over, s_rfull;
+    __shared__ uint32_t s_fill, s_rfresh;
+    const uint32_t t = threadIdx.x, lane = lane_id(), warp = t >> 5;
+    const uint32_t wb = warp * PER_WARP;
+    ulonglong2 *my_rec = w_rec + warp * 32;
+    uint32_t *my_incl = w_incl + warp * 32, *my_wt = w_wt + warp * 32;
+    const int k = KC ? KC : p.k;
+    unsigned long long my_distinct = 0, my_splits = 0;
+
+    for (uint32_t bin = blockIdx.x; bin < p.n_fine; bin += gridDim.x) {
+        const uint64_t beg = p.fine_off[bin], end = p.fine_off[bin + 1];
+        if (beg == end) continue;                                    // (uniform over the block)
+        uint32_t stk[K2C_MAX_LEVEL + 2];
+        int sp = 0;
+        stk[sp++] = 0;
+        while (sp) {
+            const uint32_t item = stk[--sp], level = item >> 16, part = item & 0xFFFFu, sel_mask = (1u << level) - 1u;
+#pragma unroll 4
+            for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) { s_keys[i] = EMPTY_KEY; s_cnt[i] = 0; }
+            for (uint32_t i = t; i < (uint32_t)RS; i += T) { r_fp[i] = EMPTY_KEY; r_cnt[i] = 0; }
+            if (t == 0) { s_over = 0; s_fill = 0; s_rfull = 0; s_rfresh = 0; }
+            __syncthreads();
+            uint32_t fresh = 0;
+
+            // insert one k-mer with weight w (probe until placed; the caller has applied the part selection)
+            auto insert = [&](uint64_t key, uint32_t h, uint32_t w) {
+                uint32_t slot = h & MASK;
+                for (uint32_t probes = 0;;) {
+                    uint64_t cur = ld_volatile_u64(&s_keys[slot]);
+                    if (cur == EMPTY_KEY) {
+                        cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                        if (cur == EMPTY_KEY) { cur = key; fresh++; }
+                    }
+                    if (cur == key) { atomicAdd(&s_cnt[slot], w); break; }
+                    slot = (slot + 1) & MASK;
+                    if (++probes >= (uint32_t)SLOTS) { s_over = 1; break; }
+                }
+            };
+
+            // ---- B: records -> record table, T * R_PER records at a time
+            for (uint64_t c0 = beg; c0 < end; c0 += (uint64_t)T * R_PER) {
+                ulonglong2 rec[R_PER];
+                uint32_t mys[R_PER];
+#pragma unroll
+                for (int r = 0; r < R_PER; r++) {
+                    const uint64_t i = c0 + (uint64_t)r * T + t;
+                    mys[r] = NONE;
+                    rec[r] = make_ulonglong2(0, 0);
+                    if (i < end) {
+                        rec[r] = p.recs[i];
+                        const uint64_t fp = sk_rec_fp(rec[r]);
+                        uint32_t slot = (uint32_t)(fp >> 32) & RMASK;
+                        for (uint32_t probes = 0; probes < (uint32_t)RS; probes++) {
+                            uint64_t cur = ld_volatile_u64(&r_fp[slot]);
+                            if (cur == EMPTY_KEY) {
+                                if (*(volatile int *)&s_rfull) break;                    // no new entries: this record is expanded directly
+                                cur = atomicCAS((unsigned long long *)&r_fp[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)fp);
+                                if (cur == EMPTY_KEY) {
+                                    cur = fp;
+                                    r_idx[slot] = (uint32_t)(i - beg);
+                                    if (atomicAdd(&s_rfresh, 1u) + 1u >= RFILL_LIMIT) s_rfull = 1;
+                                }
+                            }
+                            if (cur == fp) { atomicAdd(&r_cnt[slot], 1u); mys[r] = slot; break; }
+                            slot = (slot + 1) & RMASK;
+                        }
+                    }
+                }
+                __syncthreads();                                     // the representatives' indices are published
+#pragma unroll
+                for (int r = 0; r < R_PER; r++) {
+                    const uint64_t i = c0 + (uint64_t)r * T + t;
+                    if (i >= end) continue;
+                    if (mys[r] != NONE) {
+                        const ulonglong2 rep = p.recs[beg + r_idx[mys[r]]];
+                        if (rep.x == rec[r].x && rep.y == rec[r].y) continue;
+                        atomicSub(&r_cnt[mys[r]], 1u);               // a different record with the same fingerprint
+                    }
+                    // direct expansion, weight 1 (rare: fingerprint collision or record table full)
+                    if (*(volatile int *)&s_over) continue;
+                    const uint32_t n = sk_rec_n(rec[r]);
+                    uint64_t hi = rec[r].x, lo = rec[r].y & ~0xFFFFFFULL;
+                    uint64_t fwd = hi >> (64 - 2 * k);
+                    uint64_t rc = revcomp64(fwd, k);
+                    for (uint32_t j = 0; j < n; j++) {
+                        if (j) {
+                            hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                            fwd = hi >> (64 - 2 * k);
+                            rc = (rc >> 2) | (((fwd & 3) ^ 2) << (2 * (k - 1)));
+                        }
+                        const uint64_t key = fwd < rc ? fwd : rc;
+                        const uint32_t h = k2c_hash<MUL32>(key);
+                        if (((h >> 16) & sel_mask) == part) insert(key, h, 1u);
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- C: distinct records -> k-mer table, one k-mer per lane
+            for (uint32_t s0 = warp * 32; s0 < (uint32_t)RS; s0 += NW * 32) {
+                if (__any_sync(0xFFFFFFFFu, *(volatile int *)&s_over)) break;
+                const uint32_t s = s0 + lane;
+                const uint32_t wgt = r_fp[s] != EMPTY_KEY ? r_cnt[s] : 0u;
+                ulonglong2 rec = make_ulonglong2(0, 0);
+                uint32_t n = 0;
+                if (wgt) { rec = p.recs[beg + r_idx[s]]; n = sk_rec_n(rec); }
+                uint32_t incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (!total) continue;
+                my_rec[lane] = rec; my_incl[lane] = incl; my_wt[lane] = wgt;
+                __syncwarp();
+                for (uint32_t g0 = 0; g0 < total; g0 += 32) {
+                    const uint32_t g = g0 + lane;
+                    if (g < total) {
+                        uint32_t r = 0;
+                        if (my_incl[r + 15] <= g) r += 16;
+                        if (my_incl[r + 7] <= g) r += 8;
+                        if (my_incl[r + 3] <= g) r += 4;
+                        if (my_incl[r + 1] <= g) r += 2;
+                        if (my_incl[r] <= g) r += 1;
+                        const ulonglong2 rr = my_rec[r];
+                        const uint32_t j = g - (my_incl[r] - sk_rec_n(rr));
+                        const uint64_t ylo = rr.y & ~0xFFFFFFULL;
+                        const uint64_t hi = j ? (rr.x << (2 * j)) | (ylo >> (64 - 2 * j)) : rr.x;
+                        const uint64_t fwd = hi >> (64 - 2 * k);
+                        const uint64_t rc = revcomp64(fwd, k);
+                        const uint64_t key = fwd < rc ? fwd : rc;
+                        const uint32_t h = k2c_hash<MUL32>(key);
+                        if (((h >> 16) & sel_mask) == part) insert(key, h, my_wt[r]);
+                    }
+                }
+                __syncwarp();
+                fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);
+                if (lane == 0 && fresh && atomicAdd(&s_fill, fresh) + fresh > FILL_LIMIT) s_over = 1;
+                fresh = 0;
+            }
+            fresh = __reduce_add_sync(0xFFFFFFFFu, fresh);           // (keys placed by direct expansion in B)
+            if (lane == 0 && fresh && atomicAdd(&s_fill, fresh) + fresh > FILL_LIMIT) s_over = 1;
+            __syncthreads();
+            const int over = s_over;
+            __syncthreads();                                         // everyone has read s_over before thread 0 may reset it
+            if (over) {
+                my_splits += t == 0;
+                if (level >= (uint32_t)K2C_MAX_LEVEL) { if (t == 0) *p.failed = 1; break; }
+                stk[sp++] = ((level + 1) << 16) | part;
+                stk[sp++] = ((level + 1) << 16) | part | (1u << level);
+                continue;
+            }
+
+            // ---- D: emit: count the solid entries, reserve the output range with ONE global atomic, write ballot-ranked
+            uint32_t my_solid = 0;
+#pragma unroll 4
+            for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
+                const bool occ = s_keys[i] != EMPTY_KEY;
+                const uint32_t c = s_cnt[i];
+                my_distinct += occ;
+                my_solid += occ && c >= p.amin && c <= p.amax;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) my_solid += __shfl_xor_sync(0xFFFFFFFFu, my_solid, d);
+            if (lane == 0) s_wsolid[warp] = my_solid;
+            __syncthreads();
+            if (t == 0) {
+                uint32_t tot = 0;
+                for (int x = 0; x < NW; x++) { uint32_t v = s_wsolid[x]; s_wsolid[x] = tot; tot += v; }
+                s_base = tot ? atomicAdd(p.n_solid, (unsigned long long)tot) : 0ULL;
+            }
+            __syncthreads();
+            uint64_t out = s_base + s_wsolid[warp];
+            if (my_solid) {                                          // (uniform over the warp after the reduction)
+                for (uint32_t i = wb + lane; i < wb + PER_WARP; i += 32) {
+                    const uint64_t key = s_keys[i];
+                    const uint32_t c = s_cnt[i];
+                    const bool solid = key != EMPTY_KEY && c >= p.amin && c <= p.amax;
+                    const unsigned mk = __ballot_sync(0xFFFFFFFFu, solid);
+                    if (solid) {
+                        const uint64_t pos = out + __popc(mk & ((1u << lane) - 1));
+                        if (pos < p.solid_cap) { p.solid_kmers[pos] = key; p.solid_counts[pos] = c; }
+                    }
+                    out += __popc(mk);
+                }
+            }
+            __syncthreads();     // the next pass clears the tables and thread 0 resets the flags
         }
     }
     block_add(p.n_distinct, my_distinct);

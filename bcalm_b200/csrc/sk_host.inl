@@ -26,6 +26,15 @@ bool sk_enabled(const cdbg_ctx *ctx) {
     return SK_DEFAULT ? !(s && strcmp(s, "kmer") == 0) : (s && strcmp(s, "sk") == 0);
 }
 
+// Counting kernel: sk2d_count (distinct records first, CDBG_SK2C=dedup) or sk2c_count (every record expanded, CDBG_SK2C=direct).
+#ifndef SK_DEDUP_DEFAULT
+#define SK_DEDUP_DEFAULT 0
+#endif
+bool sk_dedup_enabled() {
+    const char *s = getenv("CDBG_SK2C");
+    return SK_DEDUP_DEFAULT ? !(s && strcmp(s, "direct") == 0) : (s && strcmp(s, "dedup") == 0);
+}
+
 // Minimizer length.  A bucket is counted in a shared-memory table, so the k-mers of one minimizer must stay a small part of a
 // bucket, or buckets overflow their table and are split (each split re-expands the whole bucket).  Measured on a B200
 // (profiles/r02_sk_ab_*): C2 (1e8 instances) m = 11 -> 346 splits, 12 -> 10, 14 -> 0; 1.2e9 instances m = 12 -> 21 835 splits.
@@ -181,6 +190,8 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
     SK2PParams pp{};
     pp.recs = d_recs; pp.bin_beg = d_bin_range; pp.bin_end = d_bin_range + P1; pp.tile_first = d_tile_first; pp.group = d_group;
     pp.P1 = P1; pp.F = F; pp.n_tiles = (uint32_t)tiles;
+    const bool dedup = sk_dedup_enabled();
+    pp.canon = dedup ? 1 : 0; pp.k = ctx->k;
     pp.fine_cnt = d_fine_cnt; pp.fine_off = d_fine_off; pp.fine_cursor = d_fine_cursor; pp.out = d_recs2;
     if (tiles) {
         tstart(ctx, T_K2H);
@@ -221,15 +232,32 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
         if (k31) { if (mul32) SK2C_LAUNCH1(SL, TH, true, 31); else SK2C_LAUNCH1(SL, TH, false, 31); }                 \
         else { if (mul32) SK2C_LAUNCH1(SL, TH, true, 0); else SK2C_LAUNCH1(SL, TH, false, 0); }                       \
     } while (0)
+#define SK2D_LAUNCH1(SL, RS_, TH, MU, KC)                                                                                                    \
+    do {                                                                                                                                    \
+        const size_t sm_ = sk2d_smem_bytes<SL, RS_, TH>();                                                                                  \
+        CK(cudaFuncSetAttribute(sk2d_count<SL, RS_, TH, MU, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));                    \
+        const uint64_t per_sm_ = std::max<uint64_t>(1, std::min<uint64_t>(2048 / (TH), (227 * 1024) / (sm_ + 1024)));                       \
+        LAUNCH((sk2d_count<SL, RS_, TH, MU, KC>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * per_sm_), (TH), sm_, cp);               \
+    } while (0)
+#define SK2D_LAUNCH(SL, RS_, TH)                                                                                      \
+    do {                                                                                                              \
+        if (k31) { if (mul32) SK2D_LAUNCH1(SL, RS_, TH, true, 31); else SK2D_LAUNCH1(SL, RS_, TH, false, 31); }       \
+        else { if (mul32) SK2D_LAUNCH1(SL, RS_, TH, true, 0); else SK2D_LAUNCH1(SL, RS_, TH, false, 0); }             \
+    } while (0)
             const char *hm = getenv("CDBG_K2C_HASH");
             const bool mul32 = K2C_HASH_MUL32_DEFAULT ? !(hm && strcmp(hm, "mix64") == 0) : (hm && strcmp(hm, "mul32") == 0);
             const bool k31 = ctx->k == 31 && !(getenv("CDBG_SK_KC") && atoi(getenv("CDBG_SK_KC")) == 0);   // k = 31 has its own instantiation
             const int th = getenv("CDBG_SK_THREADS") ? atoi(getenv("CDBG_SK_THREADS")) : 256;
-            if (pl.slots == 8192) { if (th == 512) SK2C_LAUNCH(8192, 512); else SK2C_LAUNCH(8192, 256); }
+            if (dedup) {
+                const int rs = getenv("CDBG_SK_RS") ? atoi(getenv("CDBG_SK_RS")) : 1024;
+                if (pl.slots == 8192) { if (rs == 2048) SK2D_LAUNCH(8192, 2048, 256); else SK2D_LAUNCH(8192, 1024, 256); }
+                else { if (rs == 2048) SK2D_LAUNCH(4096, 2048, 256); else if (rs == 512) SK2D_LAUNCH(4096, 512, 256); else SK2D_LAUNCH(4096, 1024, 256); }
+            } else if (pl.slots == 8192) { if (th == 512) SK2C_LAUNCH(8192, 512); else SK2C_LAUNCH(8192, 256); }
             else { if (th == 128) SK2C_LAUNCH(4096, 128); else SK2C_LAUNCH(4096, 256); }
 #undef SK2C_LAUNCH
 #undef SK2C_LAUNCH1
-#undef SK2C_LAUNCH
+#undef SK2D_LAUNCH
+#undef SK2D_LAUNCH1
         }
         tstop(ctx, T_K2C);
         if ((rc = ctr_read(ctx))) return rc;

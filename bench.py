@@ -284,9 +284,16 @@ def roofline_block(st: dict, n_bytes: int, with_traffic: bool):
     return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": load_traffic(name) if with_traffic else None, "algorithmic_bytes": int(bytes_k), "kernel_ms": ms_k, "peak_source": peak_src,
             "stage_ms": groups,
+            "shard_ms": None if not st.get("ms_x1") and not st.get("ms_glue") else {
+                "X1 super-k-mer exchange (pack + all-to-all)": round(st["ms_x1"], 4), "X2 end-record exchange": round(st["ms_x2"], 4),
+                "X3 link-message routing": round(st["ms_x3"], 4), "glue (inside K6/K8 numbering + spelling)": round(st["ms_glue"], 4),
+                "link-record routing": round(st["ms_xlink"], 4), "count stage": round(st["ms_count"], 4), "compact stage": round(st["ms_compact"], 4),
+                "link stage": round(st["ms_link"], 4), "pieces_rank0": int(st.get("n_pieces", 0))},
+            # per kernel: `achieved` / `frac` on the bytes the kernel's data format really moves (super-k-mer records are ~4x smaller than
+            # the 8-byte k-mer instances of SURVEY 8d's accounting, which `algorithmic_bytes` keeps for comparison with round 1)
             "kernels": None if not kernels else {k_: {"ms": round(m_, 4), "algorithmic_bytes": int(b_), "format_bytes": int(f_),
-                                                      "achieved": round(b_ / (m_ / 1e3) / 1e9, 1) if m_ > 0 else None,
-                                                      "frac": round(b_ / (m_ / 1e3) / 1e9 / peak, 4) if m_ > 0 else None} for k_, (m_, b_, f_) in kernels.items()}}
+                                                      "achieved": round(f_ / (m_ / 1e3) / 1e9, 1) if m_ > 0 else None,
+                                                      "frac": round(f_ / (m_ / 1e3) / 1e9 / peak, 4) if m_ > 0 else None} for k_, (m_, b_, f_) in kernels.items()}}
 
 
 # ---------------------------------------------------------------------------------------------- parity (untimed)

@@ -98,6 +98,9 @@ typedef struct {
     uint32_t k2p_fallback;  /* 1 when the region-based fine partition of K2 (opt-in) overflowed and was redone with exact offsets */
     uint32_t sk_m;          /* minimizer length used to bucket the super-k-mers (stage 1 on super-k-mers, k <= 31; 0 otherwise) */
     uint64_t n_superkmers;  /* super-k-mer records written by K1 (16 bytes each) */
+    float ms_x1, ms_x2, ms_x3, ms_glue, ms_xlink; /* sharded mode, device time: super-k-mer exchange (incl. packing), end-record exchange, link-message
+                               routing, glue (piece exchange + piece-level ranking + assembly), link-record routing */
+    uint32_t n_pieces;      /* sharded mode: shard-local unitigs before the glue */
 } cdbg_stats;
 
 typedef struct {

@@ -18,10 +18,18 @@ K = 31
 n_reads = G * 30 // L
 T0 = time.time()
 BUDGET_S = float(os.environ.get("AB_BUDGET_S", "90"))
-TUN = ("CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_K2C_HASH", "CDBG_K1_THREADS", "CDBG_SK_DENSITY", "CDBG_K6", "CDBG_ZEROCOPY", "CDBG_SK_KC")
+TUN = ("CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_K2C_HASH", "CDBG_K1_THREADS", "CDBG_SK_DENSITY", "CDBG_K6", "CDBG_ZEROCOPY", "CDBG_SK_KC", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_MMER_RANK", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS")
 CONFIGS = [
     ("k-mer instances (round-1 default)", {"CDBG_S1": "kmer"}),
     ("super-k-mers default", {}),
+    ("super-k-mers direct count", {"CDBG_SK2C": "direct"}),
+    ("super-k-mers dedup RS 1024", {"CDBG_SK2C": "dedup"}),
+    ("super-k-mers dedup RS 2048", {"CDBG_SK2C": "dedup", "CDBG_SK_RS": "2048"}),
+    ("super-k-mers dedup RS 512", {"CDBG_SK2C": "dedup", "CDBG_SK_RS": "512"}),
+    ("super-k-mers dedup mul32", {"CDBG_SK2C": "dedup", "CDBG_K2C_HASH": "mul32"}),
+    ("super-k-mers dedup fill 2.0", {"CDBG_SK2C": "dedup", "CDBG_SK_FILL": "2.0"}),
+    ("super-k-mers dedup fill 3.0 RS 2048", {"CDBG_SK2C": "dedup", "CDBG_SK_FILL": "3.0", "CDBG_SK_RS": "2048"}),
+    ("super-k-mers dedup 8192 fill 2 RS 2048", {"CDBG_SK2C": "dedup", "CDBG_SK_SLOTS": "8192", "CDBG_SK_FILL": "2.0", "CDBG_SK_RS": "2048"}),
     ("super-k-mers runtime k", {"CDBG_SK_KC": "0"}),
     ("super-k-mers mul32", {"CDBG_K2C_HASH": "mul32"}),
     ("super-k-mers fill 1.0", {"CDBG_SK_FILL": "1.0"}),

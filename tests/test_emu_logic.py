@@ -32,7 +32,7 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
          "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
          "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH",
-         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK")
+         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_SK_KC")
 
 
 @pytest.fixture(scope="module")
@@ -82,6 +82,11 @@ VARIANTS = {
     "sk_forced_splits": dict(CDBG_SK_FILL=8),
     "sk_slots_8192": dict(CDBG_SK_SLOTS=8192, CDBG_SK_FILL=0.2),
     "sk_mul32_slot_hash": dict(CDBG_K2C_HASH="mul32"),
+    "sk_direct_count": dict(CDBG_SK2C="direct"),
+    "sk_dedup_count": dict(CDBG_SK2C="dedup"),
+    "sk_dedup_small_record_table": dict(CDBG_SK2C="dedup", CDBG_SK_RS=512, CDBG_SK_FILL=3),
+    "sk_dedup_forced_splits": dict(CDBG_SK2C="dedup", CDBG_SK_FILL=8),
+    "sk_dedup_runtime_k_8192": dict(CDBG_SK2C="dedup", CDBG_SK_SLOTS=8192, CDBG_SK_KC=0, CDBG_SK_RS=2048),
     "sk_exact_regions_after_overflow": dict(CDBG_SK_DENSITY=0.001, CDBG_SK_SLACK=0, CDBG_SK_P1=5),
     "sk_zero_copy_input": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0),
     "sk_zero_copy_overflow": dict(CDBG_EMU_PINNED=1, CDBG_ZEROCOPY_MIN=0, CDBG_SK_DENSITY=0.001, CDBG_SK_SLACK=0),
@@ -111,6 +116,7 @@ VARIANTS = {
     "k5_smem_many_fine_bins": dict(CDBG_K5S_FILL=0.05, CDBG_K5S_P1=7),
     "k5_smem_forced_splits": dict(CDBG_K5S_FILL=8, CDBG_K5S_SLOTS=4096),
     "k6_over_lists": dict(CDBG_K6="list"),
+    "k6_two_level": dict(CDBG_K6="local"),
 }
 
 
@@ -129,7 +135,7 @@ def test_variants_match_reference_output(emu_lib, knobs, variant, name):
         assert g.stats["sk_m"] == 0
     if variant in ("sk_exact_regions_after_overflow", "sk_zero_copy_overflow") and name.startswith("reads_"):
         assert g.stats["k1_fallback"] == 1
-    if variant in ("k2_smem_forced_splits", "sk_forced_splits") and name.startswith("reads_"):
+    if variant in ("k2_smem_forced_splits", "sk_forced_splits", "sk_dedup_forced_splits") and name.startswith("reads_"):
         assert g.stats["n_k2_splits"] > 0
     if variant == "k5_smem_forced_splits" and name.startswith("reads_"):
         assert g.stats["n_k5_splits"] > 0
@@ -153,7 +159,8 @@ def _synthetic_reads(genome_len, read_len, coverage, err, seed):
     return reads
 
 
-@pytest.mark.parametrize("variant", ["default", "sk_forced_splits", "sk_exact_regions_after_overflow", "sk_m_16", "k1_single_pass", "k1_512_threads", "k2_l2_tables",
+@pytest.mark.parametrize("variant", ["default", "sk_forced_splits", "sk_exact_regions_after_overflow", "sk_m_16", "sk_direct_count", "sk_dedup_count",
+                                     "sk_dedup_small_record_table", "sk_dedup_forced_splits", "k6_two_level", "k1_single_pass", "k1_512_threads", "k2_l2_tables",
                                      "k5_l2_tables", "k1_twopass_tma", "k2_smem_forced_splits", "k5_smem_forced_splits"])
 def test_larger_synthetic_read_set_matches_oracle(emu_lib, knobs, variant):
     """40 kbp genome, 100 bp reads at 30x with 1 % errors (1.2 Mbases): several tiles, coarse and fine bins, real branching."""

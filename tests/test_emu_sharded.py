@@ -155,3 +155,20 @@ def test_sharded_multi_word_kmers_degenerate_inputs(emu_lib, k):
             m, _ = sharded_build(reads, k, 1, world)
             d = parity.diff(parity.graph_to_records(m), parity.graph_to_records(one), k)
             assert d == "" and m.n_unitigs == one.n_unitigs, (len(reads), world, d[:300])
+
+
+# ---------------------------------------------------------------------------------------------------------------- join variants on shards
+@pytest.mark.parametrize("env", [{"CDBG_SHARD_K5": "l2"}, {"CDBG_K5S_FILL": "8"}, {"CDBG_K5S_FILL": "0.05"}],
+                         ids=["l2_tables", "smem_forced_splits", "smem_tiny_fine_bins"])
+@pytest.mark.parametrize("name", ["reads_3_k31_a2", "reads_0_k15_a2", "even_k_dense_k6", "lowcx_8_ACGT_k8_a1", "circular_test1", "pow2_cycle_L256_k21"])
+def test_sharded_join_variants(emu_lib, monkeypatch, name, env):
+    """The sharded join runs in shared-memory tables by default (k5cs_join); the L2-table kernels stay selectable, and table overflow
+    (in-kernel splits) and many tiny fine bins give the same graph."""
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    c = GOLDEN[name]
+    m, shards = sharded_build(c["reads"], c["k"], c["abundance_min"], 3)
+    d = parity.diff(parity.graph_to_records(m), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d == "", d
+    if env.get("CDBG_K5S_FILL") == "8" and name == "reads_3_k31_a2":
+        assert sum(g.stats["n_k5_splits"] for g in shards) > 0
