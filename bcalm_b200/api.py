@@ -40,7 +40,7 @@ class Stats(C.Structure):
                                          "ms_k1_scatter", "ms_k2", "ms_k3", "ms_k5", "ms_k6_rank", "ms_k6_spell",
                                          "ms_k2_hist", "ms_k2_scatter", "ms_k2_table")] + \
                [(n, C.c_uint32) for n in ("n_k2_splits", "k1_fallback", "zero_copy", "n_k5_splits", "k2p_fallback", "sk_m")] + \
-               [("n_superkmers", C.c_uint64)] + [(n, C.c_float) for n in ("ms_x1", "ms_x2", "ms_x3", "ms_glue", "ms_xlink")] + [("n_pieces", C.c_uint32)]
+               [("n_superkmers", C.c_uint64)] + [(n, C.c_float) for n in ("ms_x1", "ms_x2", "ms_x3", "ms_glue", "ms_xlink")] + [("n_pieces", C.c_uint32), ("sk_waves", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

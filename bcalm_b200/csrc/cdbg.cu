@@ -65,6 +65,7 @@ struct cdbg_ctx {
     bool bytes_borrowed = false;
     bool bytes_hostmapped = false;        // d_bytes is pinned HOST memory (cdbg_build zero-copy): only k1t_single may read it
     const uint8_t *h_bytes_src = nullptr; // the caller's host pointer behind it
+    uint64_t sk_solid_cap = 0;    // capacity of d_solid_kmers / d_solid_counts while the waves of stage 1 append to them
     uint8_t *d_synth = nullptr;   // owned by the context across resets (bench input)
     uint64_t synth_cap = 0;
 
@@ -307,7 +308,8 @@ int free_results(cdbg_ctx *ctx) {
 #define K2P_REGIONS_DEFAULT 0   // fine partition of K2 into fixed-capacity regions (no histogram pass): opt-in (CDBG_K2P=regions) until timed on a GPU
 #endif
 #ifndef K2C_HASH_MUL32_DEFAULT
-#define K2C_HASH_MUL32_DEFAULT 0   // cheaper slot hash of k2c_count (k2c_hash_mul32): opt-in (CDBG_K2C_HASH=mul32) until timed on a GPU
+#define K2C_HASH_MUL32_DEFAULT 1   // cheaper slot hash of the counting kernels (k2c_hash_mul32; C2: table pass 1.246 -> 1.229 ms, k-mer path 0.846 -> 0.814 ms);
+                                   // CDBG_K2C_HASH=mix64 selects the murmur finaliser
 #endif
 #ifndef K2C_FLAT_DEFAULT
 #define K2C_FLAT_DEFAULT 0   // flat (one probe step per iteration) insert loop of k2c_count: opt-in (CDBG_K2C=flat) until timed on a GPU
@@ -749,7 +751,8 @@ int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remainin
 }
 
 #ifndef K6_TWO_LEVEL_DEFAULT
-#define K6_TWO_LEVEL_DEFAULT 0   // window-local ranking in shared memory + global rounds over representatives (CDBG_K6=local)
+#define K6_TWO_LEVEL_DEFAULT 1   // window-local ranking in shared memory + global rounds over representatives (C2 on a B200: K6 0.618 -> 0.407 ms,
+                                 // profiles/r02_sk_ab3_c2.txt); CDBG_K6=full / list select the one-level variants
 #endif
 
 // Two-level ranking of an unweighted list (kernels.cuh: k6_local / k6_jump_list / k6_resolve).  *remaining as rank_rounds.

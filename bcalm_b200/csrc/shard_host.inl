@@ -124,9 +124,11 @@ int shard_stage_count_sk(cdbg_ctx *ctx) {
     ctx->st.n_count_bins = P_local;
     ctx->st.sk_m = (uint32_t)pl.m;
     ctx->m = pl.m;      // junctions are owned through the same minimizer order and length: ~1 - 2/(k-m+1) of a k-mer's end records stay local
+    ctx->st.sk_waves = pl.V;
+    for (uint32_t wave = 0; wave < pl.V; wave++) {
     std::vector<uint64_t> h_cnt, h_base;
     ulonglong2 *d_recs = nullptr;
-    if ((rc = sk_run_k1(ctx, pl, Pc, &d_recs, h_cnt, h_base))) return rc;
+    if ((rc = sk_run_k1(ctx, pl, Pc, wave, &d_recs, h_cnt, h_base))) return rc;
     TRACE("SK K1");
     // counts of every rank (+ its number of k-mer instances, which sizes the solid buffers)
     std::vector<uint64_t> mine(Pc + 1), all((size_t)W * (Pc + 1)), all_cnt((size_t)W * Pc);
@@ -169,8 +171,9 @@ int shard_stage_count_sk(cdbg_ctx *ctx) {
             r_cnt[r] = run_len[(size_t)b * W + s_]; r_off[r] = run_off[(size_t)b * W + s_]; r_group[r] = b;
         }
     const uint64_t I_est = I_total / W + I_total / (4 * W) + 1024;
-    if ((rc = sk_partition_count(ctx, pl, (const ulonglong2 *)recv, I_est, R, r_cnt, r_off, &r_group, P_local))) return rc;
+    if ((rc = sk_partition_count(ctx, pl, (const ulonglong2 *)recv, I_est, R, r_cnt, r_off, &r_group, P_local, wave))) return rc;
     dfree(ctx, recv);
+    }
     tstop(ctx, T_COUNT);
     ctx->stage = ST_COUNTED;
     return CDBG_OK;

@@ -33,10 +33,16 @@ static CDBG_HD uint32_t sk_hash(uint32_t minrank) {
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
     return h;
 }
-static CDBG_HD void sk_bins(uint32_t minrank, uint32_t Pc, uint32_t &coarse, uint32_t &sub) {
-    const uint64_t x = (uint64_t)sk_hash(minrank) * Pc;
-    coarse = (uint32_t)(x >> 32);
+// With V > 1 waves (stage 1 repeated over the input, one slice of the buckets per pass: the analogue of the reference's nb_passes,
+// ConfigurationAlgorithm.cpp:350) the hash is cut into Pc * V virtual bins: virtual bin v belongs to wave v % V and is coarse bin
+// v / V of that wave -- so the owner GPU (coarse / P_local) of a minimizer does not depend on V.  Returns the wave.
+static CDBG_HD uint32_t sk_bins(uint32_t minrank, uint32_t Pc, uint32_t V, uint32_t &coarse, uint32_t &sub) {
+    const uint64_t x = (uint64_t)sk_hash(minrank) * ((uint64_t)Pc * V);      // Pc * V < 2^32 (host)
+    const uint32_t v = (uint32_t)(x >> 32);
     sub = (uint32_t)x >> (32 - SK_SUB_BITS);
+    if (V == 1) { coarse = v; return 0; }
+    coarse = v / V;
+    return v - coarse * V;
 }
 __device__ __forceinline__ uint32_t sk_rec_n(const ulonglong2 &r) { return ((uint32_t)r.y & 63u) + 1u; }
 __device__ __forceinline__ uint32_t sk_rec_sub(const ulonglong2 &r) { return ((uint32_t)r.y >> 6) & ((1u << SK_SUB_BITS) - 1u); }
@@ -74,6 +80,7 @@ struct SK1Params {
     uint64_t n_bytes, n_tiles;
     int k, m;
     uint32_t Pc;                     // coarse bins (<= K1_MAX_BINS); sharded: world * P_local, destination-major
+    uint32_t V, wave;                // waves: only the runs whose virtual bin belongs to `wave` are kept (V = 1: all)
     const uint64_t *bin_base;        // [Pc] first record of each coarse bin's region in `out`
     const uint64_t *bin_cap;         // [Pc] capacity of the region (records)
     unsigned long long *bin_cursor;  // [Pc] zero-initialised; ends as the number of records per bin (MODE 0: the histogram)
@@ -104,7 +111,7 @@ __device__ __forceinline__ ulonglong2 sk_make_record(const uint64_t *s_pk, uint3
 template <int MODE>
 __device__ SK_NOINLINE void sk1_direct(const SK1Params &p, const uint64_t *s_pk, uint32_t minrank, uint32_t start, uint32_t len) {
     uint32_t c, sub;
-    sk_bins(minrank, p.Pc, c, sub);
+    if (sk_bins(minrank, p.Pc, p.V, c, sub) != p.wave) return;
     const uint32_t nmax = (uint32_t)sk_nmax(p.k), pieces = (len + nmax - 1) / nmax;
     const unsigned long long old = atomicAdd(&p.bin_cursor[c], (unsigned long long)pieces);
     atomicAdd(p.n_runs, (unsigned long long)pieces);
@@ -294,10 +301,11 @@ __global__ void __launch_bounds__(K1_THREADS, 2) sk1_extract(SK1Params p) {
             if (j < nrec) {
                 const uint64_t d = s_list[j];
                 uint32_t c, sub;
-                sk_bins((uint32_t)(d >> 32), p.Pc, c, sub);
-                const uint32_t len = (uint32_t)d & 0x3FFFu, pieces = (len + nmax - 1) / nmax;
-                cr[r] = (atomicAdd(&s_cnt[c], pieces) << 11) | c;
-                my_runs += pieces;
+                if (sk_bins((uint32_t)(d >> 32), p.Pc, p.V, c, sub) == p.wave) {
+                    const uint32_t len = (uint32_t)d & 0x3FFFu, pieces = (len + nmax - 1) / nmax;
+                    cr[r] = (atomicAdd(&s_cnt[c], pieces) << 11) | c;
+                    my_runs += pieces;
+                }
             }
         }
         __syncthreads();
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) sk1_extract(SK1Params p) {
             const uint64_t d = s_list[(uint32_t)t + (uint32_t)r * K1_THREADS];
             const uint32_t c = cr[r] & 2047u, rank = cr[r] >> 11;
             uint32_t c2, sub;
-            sk_bins((uint32_t)(d >> 32), p.Pc, c2, sub);
+            sk_bins((uint32_t)(d >> 32), p.Pc, p.V, c2, sub);
             const uint32_t start = ((uint32_t)d >> 14) & 0x3FFFu, len = (uint32_t)d & 0x3FFFu;
             const uint64_t g = s_gbase[c];
             uint32_t pos = s_off[c] + rank;

@@ -18,6 +18,8 @@ struct SKPlan {
     uint32_t Pc_local;  // coarse bins per GPU
     uint32_t F;         // fine bins per coarse bin
     double rec_per_byte;  // estimated super-k-mer records per input byte (sizes the single-pass regions)
+    uint32_t V;         // waves: stage 1 runs V times over the input, each time keeping 1/V of the buckets (1 unless the fine bins do not
+                        // fit K1_MAX_BINS x SK2P_MAX_F or the records of the whole input do not fit the device memory)
 };
 
 bool sk_enabled(const cdbg_ctx *ctx) {
@@ -60,17 +62,34 @@ SKPlan sk_plan(const cdbg_ctx *ctx, uint64_t total_bytes, uint32_t world) {
     const double n_fine = std::max(1.0, (double)total_bytes * 0.8 / pl.per_fine);     // over all GPUs
     uint64_t pc = (uint64_t)ceil(sqrt(n_fine / world));                                // per GPU: coarse and fine fan-out about equal
     if (getenv("CDBG_SK_P1")) pc = strtoull(getenv("CDBG_SK_P1"), nullptr, 10);
-    pl.Pc_local = (uint32_t)std::min<uint64_t>(K1_MAX_BINS / world, std::max<uint64_t>(1, pc));
-    pl.F = (uint32_t)std::min<uint64_t>(SK2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil(n_fine / ((double)pl.Pc_local * world))));
     const int w = ctx->k - pl.m + 1;
     pl.rec_per_byte = std::min(0.6, 1.6 / (w + 1) + 0.012) * 1.15;
     if (getenv("CDBG_SK_DENSITY")) pl.rec_per_byte = atof(getenv("CDBG_SK_DENSITY"));   // (tests shrink it to force the exact fallback)
+    // waves (the reference's passes, ConfigurationAlgorithm.cpp:350,399-418: nb_passes from the volume and the memory budget):
+    //   capacity: one wave addresses K1_MAX_BINS / world coarse x SK2P_MAX_F fine bins per GPU (beyond that bins overflow their table and
+    //             are split again and again inside the counting kernel);
+    //   memory:   the records of one wave exist three times at the peak (K1 regions, send / receive or fine-partitioned copy).
+    const double fine_cap = (double)(K1_MAX_BINS / world) * SK2P_MAX_F * world;
+    uint64_t V = (uint64_t)ceil(n_fine / (fine_cap * 1.5));       // (a fine bin may hold 1.5x its nominal share before it splits often)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+        const double rec_bytes = (double)total_bytes / world * pl.rec_per_byte * 16.0 * 3.2;
+        const double budget = 0.55 * (double)total_b;
+        V = std::max<uint64_t>(V, (uint64_t)ceil(rec_bytes / budget));
+    }
+    if (getenv("CDBG_SK_WAVES")) V = strtoull(getenv("CDBG_SK_WAVES"), nullptr, 10);
+    pl.V = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, V));
+    const double n_fine_wave = std::max(1.0, n_fine / pl.V);
+    pc = (uint64_t)ceil(sqrt(n_fine_wave / world));
+    if (getenv("CDBG_SK_P1")) pc = strtoull(getenv("CDBG_SK_P1"), nullptr, 10);
+    pl.Pc_local = (uint32_t)std::min<uint64_t>(K1_MAX_BINS / world, std::max<uint64_t>(1, pc));
+    pl.F = (uint32_t)std::min<uint64_t>(SK2P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil(n_fine_wave / ((double)pl.Pc_local * world))));
     return pl;
 }
 
 // K1 on super-k-mers over this context's reads.  Pc coarse bins; on return d_recs holds the records, bin b in
 // [h_base[b], h_base[b] + h_cnt[b]).  Reads pinned host memory in place when ctx->bytes_hostmapped (single pass only).
-int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, ulonglong2 **d_recs_out, std::vector<uint64_t> &h_cnt, std::vector<uint64_t> &h_base) {
+int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, uint32_t wave, ulonglong2 **d_recs_out, std::vector<uint64_t> &h_cnt, std::vector<uint64_t> &h_base) {
     const uint64_t n = ctx->n_bytes;
     const uint64_t n_tiles = (n + K1_TILE - 1) / K1_TILE;
     int rc;
@@ -84,11 +103,18 @@ int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, ulonglong2 **d_recs_
     if (!n_tiles) { if ((rc = dalloc(ctx, &d_recs, 1))) return rc; *d_recs_out = d_recs; dfree(ctx, d_cursor); dfree(ctx, d_base); dfree(ctx, d_cap); return CDBG_OK; }
 
     SK1Params kp{};
-    kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = ctx->k; kp.m = pl.m; kp.Pc = Pc;
+    kp.bytes = ctx->d_bytes; kp.n_bytes = n; kp.n_tiles = n_tiles; kp.k = ctx->k; kp.m = pl.m; kp.Pc = Pc; kp.V = pl.V; kp.wave = wave;
     kp.bin_base = d_base; kp.bin_cap = d_cap; kp.bin_cursor = d_cursor; kp.overflow = ctx->d_flag + 2;
     kp.n_kmers = ctx->d_ctr + 8; kp.n_runs = ctx->d_ctr + 9;
     kp.tail_start = n > 2 * (uint64_t)K1T_RAW ? ((n - 2 * (uint64_t)K1T_RAW) & ~15ULL) : 0;
     uint8_t *d_tail = nullptr;
+    if (ctx->bytes_hostmapped && pl.V > 1) {          // every wave reads the input again: bring it into HBM once
+        uint8_t *nb = nullptr;
+        if ((rc = dalloc(ctx, &nb, n + 64))) return rc;
+        CK(cudaMemcpyAsync(nb, ctx->h_bytes_src, n, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->d_bytes = nb; ctx->cap_bytes = n; ctx->bytes_borrowed = false; ctx->bytes_hostmapped = false;
+        kp.bytes = nb;
+    }
     if (ctx->bytes_hostmapped) {
         if ((rc = dalloc(ctx, &d_tail, n - kp.tail_start + 16))) return rc;
         CK(cudaMemcpyAsync(d_tail, ctx->h_bytes_src + kp.tail_start, n - kp.tail_start, cudaMemcpyHostToDevice, ctx->stream));
@@ -100,7 +126,7 @@ int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, ulonglong2 **d_recs_
 
     // single pass into regions of the estimated size
     const uint64_t slack = getenv("CDBG_SK_SLACK") ? strtoull(getenv("CDBG_SK_SLACK"), nullptr, 10) : 512;   // (tests use 0 to force the exact fallback)
-    const uint64_t cap = (((uint64_t)((double)n * pl.rec_per_byte / Pc) + slack) + 7) & ~7ULL;
+    const uint64_t cap = (((uint64_t)((double)n * pl.rec_per_byte / Pc / pl.V) + slack) + 7) & ~7ULL;
     std::vector<uint64_t> h_cap(Pc + 1, cap);
     for (uint32_t b = 0; b <= Pc; b++) h_base[b] = (uint64_t)b * cap;
     if ((rc = dalloc(ctx, &d_recs, (uint64_t)Pc * cap + 1))) return rc;
@@ -143,8 +169,8 @@ int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, ulonglong2 **d_recs_
         if ((rc = ctr_read(ctx))) return rc;
         if (((int *)(ctx->h_ctr + 64))[2] || again != h_cnt) return ctx->fail(CDBG_ERR_INTERNAL, "super-k-mer extraction is not reproducible (exact pass overflowed)");
     }
-    ctx->st.n_instances = ctx->h_ctr[8];
-    ctx->st.n_superkmers = ctx->h_ctr[9];
+    if (wave == 0) { ctx->st.n_instances = ctx->h_ctr[8]; ctx->st.n_superkmers = 0; }   // (every wave sees all k-mer positions)
+    ctx->st.n_superkmers += ctx->h_ctr[9];
     dfree(ctx, d_tail); dfree(ctx, d_cursor); dfree(ctx, d_base); dfree(ctx, d_cap);
     *d_recs_out = d_recs;
     return CDBG_OK;
@@ -154,7 +180,7 @@ int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, ulonglong2 **d_recs_
 // local bin (sharded mode: one per source GPU) share their fine bins.  I = k-mer instances (sizes the solid buffers).
 // Leaves ctx->d_solid_kmers / d_solid_counts / S.
 int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs, uint64_t I, uint32_t P1, const std::vector<uint64_t> &h_cnt,
-                       const std::vector<uint64_t> &h_off, const std::vector<uint32_t> *h_group = nullptr, uint32_t n_groups = 0) {
+                       const std::vector<uint64_t> &h_off, const std::vector<uint32_t> *h_group = nullptr, uint32_t n_groups = 0, uint32_t wave = 0) {
     int rc;
     const uint32_t G = h_group ? n_groups : P1, F = pl.F;
     const uint64_t NF = (uint64_t)G * F;
@@ -209,11 +235,21 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
     }
     TRACE("SK fine partition");
 
-    uint64_t solid_cap = std::max<uint64_t>(I <= (1ULL << 28) ? I : std::max<uint64_t>(I / 4, 1ULL << 28), 1);
+    // the solid k-mers of all waves are appended to one pair of arrays: wave 0 sizes them for the whole input
+    uint64_t solid_cap = wave == 0 ? std::max<uint64_t>(I <= (1ULL << 28) ? I : std::max<uint64_t>(I / 4, 1ULL << 28), 1) : ctx->sk_solid_cap;
+    const uint64_t S_prev = wave == 0 ? 0 : ctx->S, D_prev = wave == 0 ? 0 : ctx->st.n_distinct;
+    const uint32_t splits_prev = wave == 0 ? 0 : ctx->st.n_k2_splits;
     for (int attempt = 0; attempt < 2; attempt++) {
-        if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
-        if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
+        if (attempt == 0 && wave == 0) {
+            if ((rc = dalloc(ctx, &ctx->d_solid_kmers, solid_cap))) return rc;
+            if ((rc = dalloc(ctx, &ctx->d_solid_counts, solid_cap))) return rc;
+        }
+        ctx->sk_solid_cap = solid_cap;
         if ((rc = ctr_zero(ctx))) return rc;
+        if (S_prev || D_prev) {
+            CK(cudaMemcpyAsync(ctx->d_ctr + 0, &S_prev, 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_ctr + 1, &D_prev, 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
         SK2CParams cp{};
         cp.recs = d_recs2; cp.fine_off = d_fine_off; cp.n_fine = (uint32_t)NF; cp.k = ctx->k; cp.amin = ctx->amin; cp.amax = ctx->amax;
         cp.solid_kmers = ctx->d_solid_kmers; cp.solid_counts = ctx->d_solid_counts; cp.solid_cap = solid_cap;
@@ -262,13 +298,23 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
         tstop(ctx, T_K2C);
         if ((rc = ctr_read(ctx))) return rc;
         if (((int *)(ctx->h_ctr + 64))[1]) return ctx->fail(CDBG_ERR_INTERNAL, "K2: a fine bin does not fit a shared-memory table after %d splits", K2C_MAX_LEVEL);
-        ctx->st.n_k2_splits = ctx->h_ctr[2];
-        ctx->S = ctx->h_ctr[0];
+        ctx->st.n_k2_splits = splits_prev + (uint32_t)ctx->h_ctr[2];
+        const uint64_t S_now = ctx->h_ctr[0];
         ctx->st.n_distinct = ctx->h_ctr[1];
-        if (ctx->S <= solid_cap) break;
+        if (S_now <= solid_cap) { ctx->S = S_now; break; }
         if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "solid buffer overflow");
+        // grow: exact for this wave plus the same rate for the waves to come; the solid k-mers of earlier waves move over
+        const uint64_t new_cap = S_now + (uint64_t)((double)(S_now - S_prev) * 1.1 * (pl.V - 1 - wave)) + 1024;
+        uint64_t *nk = nullptr; uint32_t *nc = nullptr;
+        if ((rc = dalloc(ctx, &nk, new_cap))) return rc;
+        if ((rc = dalloc(ctx, &nc, new_cap))) return rc;
+        if (S_prev) {
+            CK(cudaMemcpyAsync(nk, ctx->d_solid_kmers, S_prev * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(nc, ctx->d_solid_counts, S_prev * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         dfree(ctx, ctx->d_solid_kmers); dfree(ctx, ctx->d_solid_counts);
-        solid_cap = ctx->S;
+        ctx->d_solid_kmers = nk; ctx->d_solid_counts = nc;
+        solid_cap = new_cap;
     }
     tstop(ctx, T_K2);
     ctx->st.n_solid = ctx->S;
@@ -286,12 +332,15 @@ int stage_count_sk(cdbg_ctx *ctx) {
     const uint32_t Pc = pl.Pc_local;
     ctx->st.n_count_bins = Pc;
     ctx->st.sk_m = (uint32_t)pl.m;
-    std::vector<uint64_t> h_cnt, h_base;
-    ulonglong2 *d_recs = nullptr;
-    if ((rc = sk_run_k1(ctx, pl, Pc, &d_recs, h_cnt, h_base))) return rc;
-    TRACE("SK K1");
-    if ((rc = sk_partition_count(ctx, pl, d_recs, ctx->st.n_instances, Pc, h_cnt, h_base))) return rc;
-    dfree(ctx, d_recs);
+    ctx->st.sk_waves = pl.V;
+    for (uint32_t wave = 0; wave < pl.V; wave++) {
+        std::vector<uint64_t> h_cnt, h_base;
+        ulonglong2 *d_recs = nullptr;
+        if ((rc = sk_run_k1(ctx, pl, Pc, wave, &d_recs, h_cnt, h_base))) return rc;
+        TRACE("SK K1");
+        if ((rc = sk_partition_count(ctx, pl, d_recs, ctx->st.n_instances, Pc, h_cnt, h_base, nullptr, 0, wave))) return rc;
+        dfree(ctx, d_recs);
+    }
     tstop(ctx, T_COUNT);
     ctx->stage = ST_COUNTED;
     return CDBG_OK;

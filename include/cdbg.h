@@ -101,6 +101,7 @@ typedef struct {
     float ms_x1, ms_x2, ms_x3, ms_glue, ms_xlink; /* sharded mode, device time: super-k-mer exchange (incl. packing), end-record exchange, link-message
                                routing, glue (piece exchange + piece-level ranking + assembly), link-record routing */
     uint32_t n_pieces;      /* sharded mode: shard-local unitigs before the glue */
+    uint32_t sk_waves;      /* passes of stage 1 over the input (1 unless the buckets or their records do not fit in one pass) */
 } cdbg_stats;
 
 typedef struct {

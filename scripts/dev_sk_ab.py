@@ -30,6 +30,9 @@ CONFIGS = [
     ("super-k-mers dedup fill 2.0", {"CDBG_SK2C": "dedup", "CDBG_SK_FILL": "2.0"}),
     ("super-k-mers dedup fill 3.0 RS 2048", {"CDBG_SK2C": "dedup", "CDBG_SK_FILL": "3.0", "CDBG_SK_RS": "2048"}),
     ("super-k-mers dedup 8192 fill 2 RS 2048", {"CDBG_SK2C": "dedup", "CDBG_SK_SLOTS": "8192", "CDBG_SK_FILL": "2.0", "CDBG_SK_RS": "2048"}),
+    ("sk + K6 two-level", {"CDBG_K6": "local"}),
+    ("sk dedup + K6 two-level", {"CDBG_SK2C": "dedup", "CDBG_K6": "local"}),
+    ("sk dedup fill 2 + K6 two-level", {"CDBG_SK2C": "dedup", "CDBG_K6": "local", "CDBG_SK_FILL": "2.0"}),
     ("super-k-mers runtime k", {"CDBG_SK_KC": "0"}),
     ("super-k-mers mul32", {"CDBG_K2C_HASH": "mul32"}),
     ("super-k-mers fill 1.0", {"CDBG_SK_FILL": "1.0"}),
@@ -84,7 +87,7 @@ for name, env in CONFIGS:
         say(f"{name:40s} {same:9s} total {tot:7.3f} ms count {st['ms_count']:7.3f} | K1 {st['ms_k1_hist']:.3f}+{st['ms_k1_scatter']:.3f} K2 {st['ms_k2']:.3f} "
             f"(hist {st['ms_k2_hist']:.3f} scatter {st['ms_k2_scatter']:.3f} table {st['ms_k2_table']:.3f}) K3 {st['ms_k3']:.3f} K5 {st['ms_k5']:.3f} "
             f"K6 {st['ms_k6_rank']:.3f}+{st['ms_k6_spell']:.3f} link {st['ms_link']:.3f} | bins {st['n_count_bins']} m {st['sk_m']} sk {st['n_superkmers']} "
-            f"I {st['n_instances']} splits {st['n_k2_splits']} k1fb {st['k1_fallback']} launches {st['kernel_launches']} | {summary}")
+            f"I {st['n_instances']} splits {st['n_k2_splits']} k1fb {st['k1_fallback']} rounds {st['rank_rounds']} launches {st['kernel_launches']} | {summary}")
     except Exception as e:
         say(f"{name:40s} FAILED: {e}")
         try:

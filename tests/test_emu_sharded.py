@@ -158,8 +158,8 @@ def test_sharded_multi_word_kmers_degenerate_inputs(emu_lib, k):
 
 
 # ---------------------------------------------------------------------------------------------------------------- join variants on shards
-@pytest.mark.parametrize("env", [{"CDBG_SHARD_K5": "l2"}, {"CDBG_K5S_FILL": "8"}, {"CDBG_K5S_FILL": "0.05"}],
-                         ids=["l2_tables", "smem_forced_splits", "smem_tiny_fine_bins"])
+@pytest.mark.parametrize("env", [{"CDBG_SHARD_K5": "l2"}, {"CDBG_K5S_FILL": "8"}, {"CDBG_K5S_FILL": "0.05"}, {"CDBG_SK_WAVES": "3"}],
+                         ids=["l2_tables", "smem_forced_splits", "smem_tiny_fine_bins", "stage1_in_three_waves"])
 @pytest.mark.parametrize("name", ["reads_3_k31_a2", "reads_0_k15_a2", "even_k_dense_k6", "lowcx_8_ACGT_k8_a1", "circular_test1", "pow2_cycle_L256_k21"])
 def test_sharded_join_variants(emu_lib, monkeypatch, name, env):
     """The sharded join runs in shared-memory tables by default (k5cs_join); the L2-table kernels stay selectable, and table overflow
