@@ -357,9 +357,11 @@ int shard_join_smem(cdbg_ctx *ctx, const uint64_t *d_rec_key, const uint64_t *d_
     const int W = ctx->world;
     const uint64_t n2 = 2 * ctx->S;
     int rc;
-    const uint32_t slots = getenv("CDBG_K5S_SLOTS") && atoi(getenv("CDBG_K5S_SLOTS")) == 4096 ? 4096u : 2048u;
+    uint32_t slots = getenv("CDBG_K5S_SLOTS") && atoi(getenv("CDBG_K5S_SLOTS")) == 4096 ? 4096u : 2048u;
     double fill = getenv("CDBG_K5S_FILL") ? atof(getenv("CDBG_K5S_FILL")) : 1.0;
     if (!(fill >= 0.05 && fill <= 8.0)) fill = 1.0;
+    // more records than P_local x K5P_MAX_F small tables take: the larger table, before relying on in-kernel splits
+    if (slots == 2048 && !getenv("CDBG_K5S_SLOTS") && (double)T_in / (fill * slots * P_local) > (double)K5P_MAX_F) slots = 4096;
     const uint32_t R = P_local * (uint32_t)W;
     const uint32_t F = (uint32_t)std::min<uint64_t>(K5P_MAX_F, std::max<uint64_t>(1, (uint64_t)ceil((double)T_in / (fill * slots * P_local))));
     const uint64_t NF = (uint64_t)P_local * F;

@@ -532,7 +532,11 @@ template <int SLOTS, int T> static inline size_t sk2c_smem_bytes() { return (siz
 // KC: the k-mer size as a compile-time constant (0 = take it from the parameters): the rolling k-mers are all shifts by k.
 // T threads per CTA.  The warps of a CTA take batches of 32 records from a shared cursor, so a warp that drew expensive batches
 // (long probe sequences, many k-mers per record) is not waited for by warps that would otherwise hold a fixed share.
-template <int SLOTS, int T, bool MUL32, int KC>
+// TWO: two-phase insert.  In the plain loop every lane probes until ITS key is placed, so a warp runs as many iterations as its
+// unluckiest lane (ncu: ~11 of 32 lanes active in the probe loop).  With TWO every staged k-mer gets exactly ONE probe with the whole
+// warp converged; the few keys that met a different key there (~the load factor) are written back to the front of the staging
+// area -- already consumed -- and finish in a second, short pass.
+template <int SLOTS, int T, bool MUL32, int KC, bool TWO = false>
 __global__ void __launch_bounds__(T) sk2c_count(SK2CParams p) {
     constexpr int NW = T / 32, PER_WARP = SLOTS / NW;
     constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
@@ -595,6 +599,46 @@ __global__ void __launch_bounds__(T) sk2c_count(SK2CParams p) {
                     }
                     __syncwarp();
                     const uint32_t cnt = round_end - done;
+                    if (TWO) {
+                        uint32_t n_def = 0;                          // deferred keys so far (warp-uniform), stored at my_stage[0 .. n_def)
+                        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {  // warp-uniform trip count
+                            const uint32_t j = j0 + lane;
+                            bool defer = false;
+                            uint64_t key = 0;
+                            if (j < cnt) {
+                                key = my_stage[j];
+                                const uint32_t h = k2c_hash<MUL32>(key);
+                                if (((h >> 16) & sel_mask) == part) {
+                                    const uint32_t slot = h & MASK;
+                                    uint64_t cur = ld_volatile_u64(&s_keys[slot]);
+                                    if (cur == EMPTY_KEY) {
+                                        cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                                        if (cur == EMPTY_KEY) { cur = key; fresh++; }
+                                    }
+                                    if (cur == key) atomicAdd(&s_cnt[slot], 1u);
+                                    else defer = true;
+                                }
+                            }
+                            const unsigned dm = __ballot_sync(0xFFFFFFFFu, defer);   // (also orders this round's reads before its writes)
+                            if (defer) my_stage[n_def + __popc(dm & ((1u << lane) - 1u))] = key;   // n_def + 32 <= j0 + 32: never past this round's keys
+                            n_def += __popc(dm);
+                            __syncwarp();
+                        }
+                        for (uint32_t j = lane; j < n_def; j += 32) {
+                            const uint64_t key = my_stage[j];
+                            uint32_t slot = (k2c_hash<MUL32>(key) + 1u) & MASK;
+                            for (uint32_t probes = 1;;) {
+                                uint64_t cur = ld_volatile_u64(&s_keys[slot]);
+                                if (cur == EMPTY_KEY) {
+                                    cur = atomicCAS((unsigned long long *)&s_keys[slot], (unsigned long long)EMPTY_KEY, (unsigned long long)key);
+                                    if (cur == EMPTY_KEY) { cur = key; fresh++; }
+                                }
+                                if (cur == key) { atomicAdd(&s_cnt[slot], 1u); break; }
+                                slot = (slot + 1) & MASK;
+                                if (++probes >= (uint32_t)SLOTS) { s_over = 1; break; }
+                            }
+                        }
+                    } else {
                     for (uint32_t j = lane; j < cnt; j += 32) {
                         const uint64_t key = my_stage[j];
                         const uint32_t h = k2c_hash<MUL32>(key);
@@ -610,6 +654,7 @@ __global__ void __launch_bounds__(T) sk2c_count(SK2CParams p) {
                             slot = (slot + 1) & MASK;
                             if (++probes >= (uint32_t)SLOTS) { s_over = 1; break; }
                         }
+                    }
                     }
                     __syncwarp();
                     done = round_end;

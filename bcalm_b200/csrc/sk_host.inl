@@ -32,6 +32,9 @@ bool sk_enabled(const cdbg_ctx *ctx) {
 #ifndef SK_DEDUP_DEFAULT
 #define SK_DEDUP_DEFAULT 0
 #endif
+#ifndef SK_TWO_PHASE_DEFAULT
+#define SK_TWO_PHASE_DEFAULT 0   // sk2c_count's two-phase insert (CDBG_SK_INSERT=two): opt-in until timed on a GPU
+#endif
 bool sk_dedup_enabled() {
     const char *s = getenv("CDBG_SK2C");
     return SK_DEDUP_DEFAULT ? !(s && strcmp(s, "direct") == 0) : (s && strcmp(s, "dedup") == 0);
@@ -256,13 +259,15 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
         cp.n_solid = ctx->d_ctr + 0; cp.n_distinct = ctx->d_ctr + 1; cp.n_splits = ctx->d_ctr + 2; cp.failed = ctx->d_flag + 1;
         tstart(ctx, T_K2C);
         if (R) {
-#define SK2C_LAUNCH1(SL, TH, MU, KC)                                                                                                         \
+#define SK2C_LAUNCH2(SL, TH, MU, KC, TW)                                                                                                     \
     do {                                                                                                                                    \
         const size_t sm_ = sk2c_smem_bytes<SL, TH>();                                                                                       \
-        CK(cudaFuncSetAttribute(sk2c_count<SL, TH, MU, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));                         \
+        CK(cudaFuncSetAttribute(sk2c_count<SL, TH, MU, KC, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));                     \
         const uint64_t per_sm_ = std::max<uint64_t>(1, std::min<uint64_t>(2048 / (TH), (227 * 1024) / (sm_ + 1024)));                       \
-        LAUNCH((sk2c_count<SL, TH, MU, KC>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * per_sm_), (TH), sm_, cp);                    \
+        LAUNCH((sk2c_count<SL, TH, MU, KC, TW>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * per_sm_), (TH), sm_, cp);                \
     } while (0)
+#define SK2C_LAUNCH1(SL, TH, MU, KC)                                                                                  \
+    do { if (two_phase) SK2C_LAUNCH2(SL, TH, MU, KC, true); else SK2C_LAUNCH2(SL, TH, MU, KC, false); } while (0)
 #define SK2C_LAUNCH(SL, TH)                                                                                           \
     do {                                                                                                              \
         if (k31) { if (mul32) SK2C_LAUNCH1(SL, TH, true, 31); else SK2C_LAUNCH1(SL, TH, false, 31); }                 \
@@ -284,6 +289,8 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
             const bool mul32 = K2C_HASH_MUL32_DEFAULT ? !(hm && strcmp(hm, "mix64") == 0) : (hm && strcmp(hm, "mul32") == 0);
             const bool k31 = ctx->k == 31 && !(getenv("CDBG_SK_KC") && atoi(getenv("CDBG_SK_KC")) == 0);   // k = 31 has its own instantiation
             const int th = getenv("CDBG_SK_THREADS") ? atoi(getenv("CDBG_SK_THREADS")) : 256;
+            const char *ins = getenv("CDBG_SK_INSERT");
+            const bool two_phase = SK_TWO_PHASE_DEFAULT ? !(ins && strcmp(ins, "loop") == 0) : (ins && strcmp(ins, "two") == 0);
             if (dedup) {
                 const int rs = getenv("CDBG_SK_RS") ? atoi(getenv("CDBG_SK_RS")) : 1024;
                 if (pl.slots == 8192) { if (rs == 2048) SK2D_LAUNCH(8192, 2048, 256); else SK2D_LAUNCH(8192, 1024, 256); }
@@ -292,6 +299,7 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
             else { if (th == 128) SK2C_LAUNCH(4096, 128); else SK2C_LAUNCH(4096, 256); }
 #undef SK2C_LAUNCH
 #undef SK2C_LAUNCH1
+#undef SK2C_LAUNCH2
 #undef SK2D_LAUNCH
 #undef SK2D_LAUNCH1
         }

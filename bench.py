@@ -319,6 +319,11 @@ def sharded_parity(c, world, rank, local_rank, all_reads_fn, k, amin, dist):
         ok = merged == ref and merged["bad_overlaps"] == 0
         out = {"ok": bool(ok), "check": f"checksum of the merged shards of {world} GPUs == checksum of a single-GPU build of all reads (rank 0)",
                "checksum": merged, **({} if ok else {"single_gpu": ref})}
+        try:
+            import torch
+            torch.cuda.empty_cache()        # the checker's tensors must not stay in the way of the next workload
+        except Exception:
+            pass
     dist.barrier()
     return out
 
@@ -438,6 +443,118 @@ def run_c3(args, rank, local_rank, world, barrier, dist, torch):
             "parity": "ok" if par["ok"] else "FAIL", "parity_detail": par}
 
 
+def run_c4(args, rank, local_rank, world, barrier, dist, torch):
+    """BASELINE.json configs[3]: 3 Gbp genome, 6e8 x 150 bp reads (90 Gbases), k=31, sharded over the GPUs of the box.  The input does
+    not fit one GPU, so parity is by size-independent properties summed over the ranks."""
+    from bcalm_b200.api import Cdbg, MEM_DEVICE
+    G, L = int(3_000_000_000 * args.c4_scale), 150
+    n_total = G * 30 // L
+    n_reads = n_total // world
+    first = rank * n_reads
+    if rank == world - 1:
+        n_reads = n_total - first
+    c = Cdbg(k=K, abundance_min=AMIN, device=local_rank, rank=rank, world_size=world)
+    if world > 1:
+        c.shard_init_torch()
+    ptr, n_bytes = c.synth_reads(G, L, n_reads, ERR_PPM, 44, first_read=first)
+    c.build_raw(ptr, n_bytes, MEM_DEVICE, fetch=False)          # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.c4_steps):
+        v, s = c.build_raw(ptr, n_bytes, MEM_DEVICE, fetch=False)
+    barrier()
+    dt = (time.perf_counter() - t0) / args.c4_steps
+    st = s.as_dict()
+    tt = torch.tensor([float(st["n_solid"]), float(st["total_nt"] - st["n_unitigs"] * (K - 1)), float(st["n_unitigs"]), float(st["n_links"]), float(st["n_pieces"])],
+                      device=_dev(local_rank), dtype=torch.float64)
+    tmax = torch.tensor([dt], device=_dev(local_rank), dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dt = float(tmax.item())
+    solid, spelled, U, links, pieces = [int(x) for x in tt.tolist()]
+    c.close()
+    if rank != 0:
+        return None
+    n_bases = n_total * L
+    ok = solid == spelled and solid > 0
+    return {"workload": f"C4: synthetic {G} bp genome, {n_total} x {L} bp reads ({n_bases / 1e9:.1f} Gbases), 30x, 1% substitutions, k={K}, abundance-min {AMIN}; "
+                        f"sharded over {world} GPUs, reads resident in HBM",
+            "n_gpus": world, "steps": args.c4_steps, "value": n_bases / dt / 1e9, "unit": "Gbases/s", "ms_per_step": dt * 1e3,
+            "solid_kmers": solid, "unitigs": U, "links": links, "pieces_before_glue": pieces, "stage1_waves": int(st.get("sk_waves", 0)),
+            "roofline": roofline_block(st, n_bytes, False),
+            "parity": "ok" if ok else "FAIL",
+            "parity_detail": {"ok": bool(ok), "check": "properties only (no single GPU holds this input): the unitigs of all ranks spell every solid k-mer exactly once "
+                                                      "(sum(LN-k+1) == solid k-mers, summed over the ranks)", "solid": solid, "spelled": spelled}}
+
+
+def run_c5(args, rank, local_rank, world, barrier, dist, torch):
+    """BASELINE.json configs[4] scaled to what the multi-word path holds in HBM: k=127 (4-word k-mers), 250 bp reads, 30x, sharded by
+    k-mer hash.  Parity: the merged shards against a single-GPU build of all reads on rank 0 -- (unitigs, nt, KC sum, links) and the
+    multiset of (LN, KC) pairs (graph_checksum handles one-word k-mers only)."""
+    from bcalm_b200.api import Cdbg, MEM_DEVICE, merge_shards
+    k5 = 127
+    G, L = int(args.c5_genome), 250
+    n_total = G * 30 // L
+    n_reads = n_total // world
+    first = rank * n_reads
+    if rank == world - 1:
+        n_reads = n_total - first
+    c = Cdbg(k=k5, abundance_min=AMIN, device=local_rank, rank=rank, world_size=world)
+    if world > 1:
+        c.shard_init_torch()
+    ptr, n_bytes = c.synth_reads(G, L, n_reads, ERR_PPM, 45, first_read=first)
+    c.build_raw(ptr, n_bytes, MEM_DEVICE, fetch=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.c5_steps):
+        v, s = c.build_raw(ptr, n_bytes, MEM_DEVICE, fetch=True)
+    barrier()
+    dt = (time.perf_counter() - t0) / args.c5_steps
+
+    def lite(g):
+        ln = np.diff(np.asarray(g.seq_off, dtype=np.int64))
+        kc = np.asarray(g.kc, dtype=np.uint64)
+        order = np.lexsort((kc, ln))
+        h = np.uint64(1469598103934665603)
+        with np.errstate(over="ignore"):
+            mixed = (ln[order].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ (kc[order] * np.uint64(0xC2B2AE3D27D4EB4F))
+            acc = np.bitwise_xor.reduce(mixed * (np.arange(1, len(mixed) + 1, dtype=np.uint64) | np.uint64(1))) if len(mixed) else np.uint64(0)
+        return {"n_unitigs": int(len(ln)), "total_nt": int(ln.sum()), "sum_kc": int(kc.sum()), "n_links": int(len(g.links)), "ln_kc_multiset": int(acc ^ h)}
+
+    par = None
+    g = c.unitigs()
+    if world > 1:
+        tmax = torch.tensor([dt], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax.item())
+        gathered = [None] * world
+        dist.gather_object(g, gathered if rank == 0 else None, dst=0)
+        if rank == 0:
+            merged = lite(merge_shards(gathered))
+            with Cdbg(k=k5, abundance_min=AMIN, device=local_rank) as single:
+                p1, n1 = single.synth_reads(G, L, n_total, ERR_PPM, 45)
+                single.build_raw(p1, n1, MEM_DEVICE, fetch=True)
+                ref = lite(single.unitigs(copy=False))
+            par = {"ok": merged == ref, "check": f"(unitigs, nt, KC sum, links, multiset of (LN, KC)) of the merged shards of {world} GPUs == single-GPU build of all reads",
+                   "summary": merged, **({} if merged == ref else {"single_gpu": ref})}
+        dist.barrier()
+    else:
+        cs = lite(g)
+        st1 = s.as_dict()
+        ok = cs["total_nt"] - cs["n_unitigs"] * (k5 - 1) == int(st1["n_solid"])
+        par = {"ok": bool(ok), "check": "the unitigs spell every solid k-mer once; the summary is what the N > 1 runs must reproduce", "summary": cs}
+    st = s.as_dict()
+    c.close()
+    if rank != 0:
+        return None
+    n_bases = n_total * L
+    return {"workload": f"C5 (scaled): synthetic {G} bp genome, {n_total} x {L} bp reads ({n_bases / 1e9:.2f} Gbases), 30x, 1% substitutions, k={k5} (4-word k-mers), "
+                        f"abundance-min {AMIN}; " + ("one GPU" if world == 1 else f"sharded by k-mer hash over {world} GPUs"),
+            "n_gpus": world, "steps": args.c5_steps, "value": n_bases / dt / 1e9, "unit": "Gbases/s", "ms_per_step": dt * 1e3,
+            "note": "timed through the C ABI with the reads resident in HBM and the unitigs fetched to the host",
+            "solid_kmers_rank0": int(st["n_solid"]), "parity": "ok" if par["ok"] else "FAIL", "parity_detail": par}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -453,6 +570,12 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the extra C3 block")
     ap.add_argument("--c3-scale", type=float, default=1.0)
     ap.add_argument("--c3-steps", type=int, default=3)
+    ap.add_argument("--c4", action="store_true", help="also run C4 (3 Gbp genome, 90 Gbases; needs the HBM of 8 GPUs)")
+    ap.add_argument("--c4-scale", type=float, default=1.0)
+    ap.add_argument("--c4-steps", type=int, default=1)
+    ap.add_argument("--c5", action="store_true", help="also run a scaled C5 (k=127, 250 bp reads)")
+    ap.add_argument("--c5-genome", type=float, default=50_000_000)
+    ap.add_argument("--c5-steps", type=int, default=2)
     ap.add_argument("--c3-timeout", type=float, default=420.0, help="seconds after which a hung C3 block is abandoned (the main line is still printed)")
     args = ap.parse_args()
 
@@ -622,10 +745,32 @@ def main():
         if rank == 0:
             out["extra"]["c3"] = c3
 
+    # ---- extra (opt-in): C4 at full size and a scaled C5, each under its own watchdog
+    for name, flag, fn in (("c4", args.c4, run_c4), ("c5", args.c5, run_c5)):
+        if not flag:
+            continue
+        def partial(name=name):
+            if out is not None:
+                out["extra"][name] = {"value": None, "parity": None, "note": f"abandoned after {args.c3_timeout:.0f} s (a rank failed or hung)"}
+            return out
+        with Watchdog(args.c3_timeout, rank, partial):
+            try:
+                res = fn(args, rank, local_rank, world, barrier, dist, torch)
+            except Exception as e:
+                res = {"value": None, "parity": None, "note": f"failed: {e}"}
+                if world > 1:
+                    if rank == 0:
+                        out["extra"][name] = res
+                        print(json.dumps(out), flush=True)
+                    time.sleep(5 if rank == 0 else 30)
+                    os._exit(0)
+        if rank == 0:
+            out["extra"][name] = res
+
     fail = False
     if rank == 0:
         print(json.dumps(out))
-        fail = out["parity"] == "FAIL" or (isinstance(out["extra"].get("c3"), dict) and out["extra"]["c3"].get("parity") == "FAIL")
+        fail = out["parity"] == "FAIL" or any(isinstance(out["extra"].get(n_), dict) and out["extra"][n_].get("parity") == "FAIL" for n_ in ("c3", "c4", "c5"))
     if world > 1:
         dist.destroy_process_group()
     if fail:
