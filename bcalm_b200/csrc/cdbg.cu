@@ -12,6 +12,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -38,12 +39,15 @@ enum { T_PUSH = 0, T_COUNT, T_COMPACT, T_LINK, T_FETCH, T_K1H, T_K1S, T_K2, T_K3
 
 }  // namespace
 
+static std::atomic<int> g_shard_abort{0};   // a sharded context of this process failed: its sibling ranks stop waiting for it (stream_sync)
+
 struct cdbg_ctx {
     cdbg_params prm{};
     int k = 0, m = 0;
     int W = 1;                     // 64-bit words per k-mer: 1 for k <= 31, ceil(2k/64) rounded like the reference spans above
     uint32_t amin = 1, amax = 0x7FFFFFFFu;
     int n_sm = 148;
+    uint64_t total_mem = 0;       // device memory (cudaDeviceProp::totalGlobalMem), for the wave planning of stage 1
     cudaStream_t stream = nullptr;
     std::string err;
     Stage stage = ST_EMPTY;
@@ -65,6 +69,7 @@ struct cdbg_ctx {
     bool bytes_borrowed = false;
     bool bytes_hostmapped = false;        // d_bytes is pinned HOST memory (cdbg_build zero-copy): only k1t_single may read it
     const uint8_t *h_bytes_src = nullptr; // the caller's host pointer behind it
+    bool shard_failed = false;    // a collective was given up: the communicator is aborted, not destroyed
     uint64_t sk_solid_cap = 0;    // capacity of d_solid_kmers / d_solid_counts while the waves of stage 1 append to them
     uint8_t *d_synth = nullptr;   // owned by the context across resets (bench input)
     uint64_t synth_cap = 0;
@@ -120,6 +125,7 @@ struct cdbg_ctx {
         va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
         err = buf;
         if (prm.flags & CDBG_FLAG_VERBOSE) fprintf(stderr, "[cdbg] error: %s\n", buf);
+        if (world > 1) { shard_failed = true; g_shard_abort.store(1, std::memory_order_relaxed); }   // sibling ranks in this process stop waiting (stream_sync)
         return code;
     }
 };
@@ -132,6 +138,33 @@ namespace {
         if (e_ != cudaSuccess)                                                                                     \
             return ctx->fail(e_ == cudaErrorMemoryAllocation ? CDBG_ERR_OOM : CDBG_ERR_CUDA, "%s:%d %s -> %s", __FILE__, \
                              __LINE__, #call, cudaGetErrorString(e_));                                             \
+    } while (0)
+
+inline double host_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }   // milliseconds
+
+// Waiting for the stream.  A sharded context waits by polling: a rank that failed earlier never enters the next collective, and the
+// NCCL kernels of the other ranks would spin for ever inside cudaStreamSynchronize.  Polling lets them give up -- at once when the
+// failed rank lives in this process (g_shard_abort, set by cdbg_ctx::fail), after CDBG_SHARD_TIMEOUT_S (default 120) otherwise --
+// so that every rank returns an error instead of hanging (the context is then only good for cdbg_destroy, which aborts the communicator).
+int stream_sync(cdbg_ctx *ctx) {
+    if (ctx->world <= 1) { CK(cudaStreamSynchronize(ctx->stream)); return CDBG_OK; }
+    static const double limit_s = getenv("CDBG_SHARD_TIMEOUT_S") ? atof(getenv("CDBG_SHARD_TIMEOUT_S")) : 120.0;
+    const double t0 = host_now();
+    for (uint64_t spins = 0;; spins++) {
+        const cudaError_t e = cudaStreamQuery(ctx->stream);
+        if (e == cudaSuccess) return CDBG_OK;
+        if (e != cudaErrorNotReady) return ctx->fail(CDBG_ERR_CUDA, "cudaStreamQuery -> %s", cudaGetErrorString(e));
+        if ((spins & 1023) == 1023) {
+            if (g_shard_abort.load(std::memory_order_relaxed)) { ctx->shard_failed = true; return ctx->fail(CDBG_ERR_NCCL, "another rank of this process failed: giving up the collective"); }
+            if (host_now() - t0 > limit_s * 1e3) { ctx->shard_failed = true; return ctx->fail(CDBG_ERR_NCCL, "a peer GPU did not reach the collective within %.0f s (it failed earlier?): giving up", limit_s); }
+            if (spins > (1u << 16)) { struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr); }
+        }
+    }
+}
+#define SYNC_STREAM(ctx)                          \
+    do {                                          \
+        int s_ = stream_sync(ctx);                \
+        if (s_) return s_;                        \
     } while (0)
 
 // CDBG_EMU_ACTIVE is only ever defined by tests/emu/cuda_runtime.h (the CPU emulation build used by the no-GPU logic tests)
@@ -147,7 +180,6 @@ namespace {
         CK(cudaGetLastError());                                                \
     } while (0)
 
-inline double host_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 inline void trace_point(cdbg_ctx *ctx, const char *label) {
     if (!ctx->trace) return;
     cudaStreamSynchronize(ctx->stream);
@@ -263,7 +295,7 @@ int ctr_zero(cdbg_ctx *ctx) {
 int ctr_read(cdbg_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_ctr + 64, ctx->d_flag, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     return CDBG_OK;
 }
 
@@ -278,7 +310,7 @@ int exclusive_scan(cdbg_ctx *ctx, const uint32_t *d_in, uint64_t n, uint64_t *d_
     LAUNCH(scan_sums_inplace, 1, SCAN_THREADS, 0, d_sums, n_tiles, d_sums + n_tiles);
     LAUNCH(scan_apply, (unsigned)n_tiles, SCAN_THREADS, 0, d_in, n, d_sums, d_out);
     CK(cudaMemcpyAsync(ctx->h_ctr + 32, d_sums + n_tiles, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     *h_total = ctx->h_ctr[32];
     return dfree(ctx, d_sums);
 }
@@ -606,7 +638,7 @@ int stage_count(cdbg_ctx *ctx) {
             }
             tstop(ctx, T_K1H);
             CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
+            SYNC_STREAM(ctx);
         } else std::fill(h_cnt.begin(), h_cnt.end(), 0);
         I = 0; max_bin = 0;
         for (uint32_t b = 0; b < P; b++) { h_off[b] = I; I += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
@@ -699,12 +731,14 @@ int stage_count(cdbg_ctx *ctx) {
 #define K6_LIST_DEFAULT 0   // pointer jumping over shrinking lists of moving elements: opt-in (CDBG_K6=list) until timed on a GPU
 #endif
 
-int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remaining) {
+int rank_rounds(cdbg_ctx *ctx, uint64_t *d_pair, uint64_t n2, uint64_t *remaining, bool prefer_list = false) {
     // pointer jumping until no element moves (paths done) or the number of moving elements stops shrinking (cycles)
     uint64_t prev = ~0ULL;
     *remaining = 0;
     const char *mode = getenv("CDBG_K6");
-    const bool use_list = (K6_LIST_DEFAULT ? !(mode && strcmp(mode, "full") == 0) : (mode && strcmp(mode, "list") == 0)) && n2 < (1ULL << 32);
+    // prefer_list: the piece-level ranking of the sharded glue -- chains of a handful of pieces, so after the first batch of rounds only a
+    // small fraction of the elements still moves (8 GPUs, C3: 69 M elements, the full-array rounds were most of the 29 ms glue)
+    const bool use_list = ((K6_LIST_DEFAULT || prefer_list) ? !(mode && strcmp(mode, "full") == 0) : (mode && strcmp(mode, "list") == 0)) && n2 < (1ULL << 32);
     int rc;
     if (use_list) {
         // rounds come in batches of 4; the last round of a batch writes the list of elements that moved, the next batch walks it
@@ -811,7 +845,7 @@ int run_ranking(cdbg_ctx *ctx, uint32_t *d_link, uint64_t n_nodes, const uint32_
     } else {
         if (d_weight) LAUNCH(k6w_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_weight, d_pair, n2);
         else LAUNCH(k6_init, grid_for(ctx, n2, 256, 8), 256, 0, d_link, d_pair, n2);
-        if ((rc = rank_rounds(ctx, d_pair, n2, &remaining))) return rc;
+        if ((rc = rank_rounds(ctx, d_pair, n2, &remaining, d_weight != nullptr))) return rc;
     }
     for (int guard = 0; remaining && guard < 4; guard++) {
         uint8_t *d_cyc = nullptr; uint64_t *d_lab = nullptr;
@@ -1019,7 +1053,7 @@ int stage_compact(cdbg_ctx *ctx) {
         const int g3 = (int)std::min<uint64_t>((S + K3_TILE - 1) / K3_TILE, (uint64_t)ctx->n_sm * 4);
         LAUNCH(k3_ends<0>, g3, K3_THREADS, k3_smem_bytes(0, P), p3);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
         uint64_t acc = 0;
         for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
         h_off[P] = acc;
@@ -1181,6 +1215,7 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, params->device));
     ctx->n_sm = prop.multiProcessorCount;
+    ctx->total_mem = (uint64_t)prop.totalGlobalMem;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&ctx->d_ctr, 64 * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->d_flag, 4 * sizeof(int)));
@@ -1194,7 +1229,7 @@ void cdbg_destroy(cdbg_ctx *ctx) {
         cudaSetDevice(ctx->prm.device);
         free_results(ctx);
         cudaStreamSynchronize(ctx->stream);
-        if (ctx->comm) ncclCommDestroy(ctx->comm);
+        if (ctx->comm) { if (ctx->shard_failed && g_nccl.CommAbort) g_nccl.CommAbort(ctx->comm); else ncclCommDestroy(ctx->comm); }
         for (auto &b : ctx->blocks) cudaFree(b.p);
         ctx->blocks.clear();
         if (ctx->d_synth) cudaFree(ctx->d_synth);
@@ -1252,7 +1287,7 @@ int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int l
         ctx->n_bytes += n_bytes + 1;
         // the caller may refill or free `bytes` as soon as this returns (include/cdbg.h: "copied inside the call"): a copy from
         // pinned or device memory is otherwise still in flight
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     }
     tstop(ctx, T_PUSH);
     ctx->stage = ST_PUSHED;
@@ -1272,7 +1307,7 @@ int cdbg_push_sequence_text(cdbg_ctx *ctx, const uint8_t *text, uint64_t n_bytes
     uint8_t first = 0;
     if (location == CDBG_MEM_DEVICE) {
         CK(cudaMemcpyAsync(&first, text, 1, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     } else first = text[0];
     if (first != '>' && first != '@') return ctx->fail(CDBG_ERR_PARAM, "text does not start with a FASTA ('>') or FASTQ ('@') record");
     const int fmt = first == '>' ? PARSE_FASTA : PARSE_FASTQ;
@@ -1336,7 +1371,7 @@ int cdbg_get_pushed_reads(cdbg_ctx *ctx, uint8_t *dst, uint64_t cap, uint64_t *n
     *n = ctx->n_bytes;
     const uint64_t c = std::min<uint64_t>(cap, ctx->n_bytes);
     if (c && dst) CK(cudaMemcpyAsync(dst, ctx->d_bytes, c, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     return CDBG_OK;
 }
 
@@ -1406,7 +1441,7 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
     else memset(ctx->h_link_off, 0, (U + 1) * 8);
     if (ab && S) CK(cudaMemcpyAsync(ctx->h_abund, ctx->d_abund, S * 4, cudaMemcpyDeviceToHost, ctx->stream));
     tstop(ctx, T_FETCH);
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     view->kmer_size = ctx->k;
     view->n_unitigs = U; view->total_nt = nt;
     view->seq = ctx->h_seq; view->seq_off = ctx->h_seq_off; view->kc = ctx->h_kc;
@@ -1456,7 +1491,7 @@ int cdbg_get_solid_kmers(cdbg_ctx *ctx, uint64_t *kmers, uint32_t *counts, uint6
     uint64_t c = std::min<uint64_t>(cap, ctx->S);
     if (c && kmers) CK(cudaMemcpyAsync(kmers, ctx->d_solid_kmers, c * 8 * ctx->W, cudaMemcpyDeviceToHost, ctx->stream));
     if (c && counts) CK(cudaMemcpyAsync(counts, ctx->d_solid_counts, c * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     return CDBG_OK;
 }
 
@@ -1482,7 +1517,7 @@ int cdbg_set_solid_kmers(cdbg_ctx *ctx, const uint64_t *kmers, const uint32_t *c
             default: LAUNCH(kw2_canonicalise<4>, grid_for(ctx, n, 256, 8), 256, 0, ctx->d_solid_kmers, n, ctx->k); break;
         }
     }
-    CK(cudaStreamSynchronize(ctx->stream));   // the caller may free its arrays when this returns
+    SYNC_STREAM(ctx);   // the caller may free its arrays when this returns
     tstop(ctx, T_COUNT);
     ctx->S = n;
     ctx->st.n_solid = n; ctx->st.n_distinct = n;
@@ -1508,7 +1543,7 @@ int cdbg_synth_reads_range(cdbg_ctx *ctx, uint64_t genome_len, uint32_t read_len
         ctx->synth_cap = total + 64;
     }
     if (total) LAUNCH(synth_reads_kernel, grid_for(ctx, total, 256, 16), 256, 0, ctx->d_synth, genome_len, read_len, first_read, n_reads, err_ppm, seed);
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     *d_bytes = ctx->d_synth; *n_bytes = total;
     return CDBG_OK;
 }
@@ -1527,6 +1562,8 @@ int cdbg_shard_init(cdbg_ctx *ctx, const uint8_t *id128) {
     if (!ctx || !ctx->stream || !id128) return CDBG_ERR_PARAM;
     if (ctx->world <= 1) return ctx->fail(CDBG_ERR_STATE, "cdbg_shard_init on a context created with world_size <= 1");
     if (ctx->comm) return CDBG_OK;
+    g_shard_abort.store(0, std::memory_order_relaxed);          // a new generation of ranks
+    ctx->shard_failed = false;
     if (!g_nccl.load()) return ctx->fail(CDBG_ERR_NCCL, "%s", g_nccl.error);
     CK(cudaSetDevice(ctx->prm.device));
     ncclUniqueId id;
@@ -1559,7 +1596,7 @@ int cdbg_copy_to_host(cdbg_ctx *ctx, void *dst, const void *d_src, uint64_t n_by
     if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
     CK(cudaSetDevice(ctx->prm.device));
     CK(cudaMemcpyAsync(dst, d_src, n_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     return CDBG_OK;
 }
 

@@ -12,6 +12,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;   // optional
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -24,7 +25,7 @@ struct NcclApi {
         if (handle) return true;
 #ifdef CDBG_EMU_ACTIVE   // CPU emulation build of the tests: ranks are threads of one process, see tests/emu/nccl.h
         handle = this;
-        GetUniqueId = emu_ncclGetUniqueId; CommInitRank = emu_ncclCommInitRank; CommDestroy = emu_ncclCommDestroy;
+        GetUniqueId = emu_ncclGetUniqueId; CommInitRank = emu_ncclCommInitRank; CommDestroy = emu_ncclCommDestroy; CommAbort = emu_ncclCommDestroy;
         AllGather = emu_ncclAllGather; Send = emu_ncclSend; Recv = emu_ncclRecv; GroupStart = emu_ncclGroupStart; GroupEnd = emu_ncclGroupEnd;
         GetErrorString = emu_ncclGetErrorString;
         return true;
@@ -37,6 +38,7 @@ struct NcclApi {
         NCCL_SYM(AllGather, "ncclAllGather") NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv") NCCL_SYM(GroupStart, "ncclGroupStart")
         NCCL_SYM(GroupEnd, "ncclGroupEnd") NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef NCCL_SYM
+        CommAbort = reinterpret_cast<decltype(CommAbort)>(dlsym(handle, "ncclCommAbort"));
         return true;
     }
 };

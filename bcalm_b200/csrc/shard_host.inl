@@ -24,7 +24,7 @@ int allgather_host_u64(cdbg_ctx *ctx, const uint64_t *h_in, size_t count, uint64
     CK(cudaMemcpyAsync(d_in, h_in, count * 8, cudaMemcpyHostToDevice, ctx->stream));
     NK(ncclAllGather(d_in, d_out, count, ncclUint64, ctx->comm, ctx->stream));
     CK(cudaMemcpyAsync(h_out, d_out, count * 8 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     dfree(ctx, d_in); dfree(ctx, d_out);
     return CDBG_OK;
 }
@@ -53,33 +53,34 @@ int exchange_with_counts(cdbg_ctx *ctx, const void *d_send, const uint64_t *send
 int route16(cdbg_ctx *ctx, const ulonglong2 *d_recs, uint64_t n, ulonglong2 **d_out, uint64_t *n_out) {
     int rc;
     const int W = ctx->world;
-    unsigned long long *d_cnt = nullptr, *d_cur = nullptr; uint64_t *d_off = nullptr; ulonglong2 *d_sorted = nullptr;
+    unsigned long long *d_cnt = nullptr, *d_cur = nullptr; uint64_t *d_off = nullptr, *d_all = nullptr; ulonglong2 *d_sorted = nullptr;
     if ((rc = dalloc(ctx, &d_cnt, MAX_WORLD))) return rc;
     if ((rc = dalloc(ctx, &d_cur, MAX_WORLD))) return rc;
     if ((rc = dalloc(ctx, &d_off, MAX_WORLD + 1))) return rc;
+    if ((rc = dalloc(ctx, &d_all, (size_t)MAX_WORLD * MAX_WORLD))) return rc;
     if ((rc = dalloc(ctx, &d_sorted, n + 1))) return rc;
     CK(cudaMemsetAsync(d_cnt, 0, MAX_WORLD * 8, ctx->stream));
     CK(cudaMemsetAsync(d_cur, 0, MAX_WORLD * 8, ctx->stream));
+    // the per-destination counts never visit the host on their own: histogram -> all-gather of the device counters -> ONE read of
+    // the whole world x world matrix (this rank's row included)
+    if (n) LAUNCH(route_hist, grid_for(ctx, n, 256, 4), 256, 0, d_recs, n, (uint32_t)W, d_cnt);
+    NK(ncclAllGather(d_cnt, d_all, W, ncclUint64, ctx->comm, ctx->stream));
+    std::vector<uint64_t> M((size_t)W * W);
+    CK(cudaMemcpyAsync(M.data(), d_all, (size_t)W * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SYNC_STREAM(ctx);
     uint64_t h_cnt[MAX_WORLD] = {0}, h_off[MAX_WORLD + 1] = {0};
-    if (n) {
-        LAUNCH(route_hist, grid_for(ctx, n, 256, 4), 256, 0, d_recs, n, (uint32_t)W, d_cnt);
-        CK(cudaMemcpyAsync(h_cnt, d_cnt, W * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    for (int d = 0; d < W; d++) h_off[d + 1] = h_off[d] + h_cnt[d];
+    for (int d = 0; d < W; d++) { h_cnt[d] = M[(size_t)ctx->rank * W + d]; h_off[d + 1] = h_off[d] + h_cnt[d]; }
     if (h_off[W] != n) return ctx->fail(CDBG_ERR_INTERNAL, "route16: a record names a rank outside the world");
     if (n) {
         CK(cudaMemcpyAsync(d_off, h_off, (W + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(route_scatter, grid_for(ctx, n, 256, 4), 256, 0, d_recs, n, (uint32_t)W, d_off, d_cur, d_sorted);
     }
-    std::vector<uint64_t> M((size_t)W * W);
-    if ((rc = allgather_host_u64(ctx, h_cnt, W, M.data()))) return rc;
     uint64_t recv_cnt[MAX_WORLD];
     for (int s = 0; s < W; s++) recv_cnt[s] = M[(size_t)s * W + ctx->rank];
     void *recv = nullptr;
     if ((rc = exchange_with_counts(ctx, d_sorted, h_cnt, recv_cnt, 16, &recv, n_out))) return rc;
     *d_out = (ulonglong2 *)recv;
-    dfree(ctx, d_cnt); dfree(ctx, d_cur); dfree(ctx, d_off); dfree(ctx, d_sorted);
+    dfree(ctx, d_cnt); dfree(ctx, d_cur); dfree(ctx, d_off); dfree(ctx, d_all); dfree(ctx, d_sorted);
     return CDBG_OK;
 }
 
@@ -130,6 +131,8 @@ int shard_stage_count_sk(cdbg_ctx *ctx) {
     ulonglong2 *d_recs = nullptr;
     if ((rc = sk_run_k1(ctx, pl, Pc, wave, &d_recs, h_cnt, h_base))) return rc;
     TRACE("SK K1");
+    // (test hook: tests/test_gpu_sharded.py makes one rank fail here to check that the others do not wait for it for ever)
+    if (getenv("CDBG_FAULT_RANK") && atoi(getenv("CDBG_FAULT_RANK")) == me) return ctx->fail(CDBG_ERR_INTERNAL, "injected fault on rank %d (CDBG_FAULT_RANK)", me);
     // counts of every rank (+ its number of k-mer instances, which sizes the solid buffers)
     std::vector<uint64_t> mine(Pc + 1), all((size_t)W * (Pc + 1)), all_cnt((size_t)W * Pc);
     for (uint32_t b = 0; b < Pc; b++) mine[b] = h_cnt[b];
@@ -230,7 +233,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
         else LAUNCH(k1s_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 4), K1S_THREADS, k1s_smem_bytes(0, P), kp);
         tstop(ctx, T_K1H);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     }
     TRACE("k1 hist");
     uint64_t I_out = 0;
@@ -481,7 +484,7 @@ int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, ui
     if (S) {
         LAUNCH(k3s_ends<0>, g3, K3_THREADS, k3_smem_bytes(0, P), p3);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     }
     uint64_t acc = 0;
     for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; }
@@ -715,7 +718,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     uint64_t nt_range[2] = {0, 0};
     CK(cudaMemcpyAsync(&nt_range[0], d_unt_off + u_first, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&nt_range[1], d_unt_off + u_last, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    SYNC_STREAM(ctx);
     const uint64_t U_mine = u_last - u_first, nt_mine = nt_range[1] - nt_range[0];
     if ((rc = dalloc(ctx, &ctx->d_seq, nt_mine + 1))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_seq_off, U_mine + 1))) return rc;
@@ -729,7 +732,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     }
     CK(cudaMemcpyAsync(ctx->d_seq_off + U_mine, &nt_mine, 8, cudaMemcpyHostToDevice, ctx->stream));
     if (U_mine) CK(cudaMemcpyAsync(ctx->d_kc, d_kc_all + u_first, U_mine * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));   // nt_mine is a stack variable
+    SYNC_STREAM(ctx);   // nt_mine is a stack variable
 
     TRACE("assemble unitigs");
     // ---- collect every edge this GPU is responsible for as (from gid, to gid): join edges are already there;
@@ -779,7 +782,7 @@ int shard_stage_link(cdbg_ctx *ctx) {
     {
         int bad = 0;
         CK(cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
         if (bad) return ctx->fail(CDBG_ERR_INTERNAL, "an edge end is not a piece terminus");
     }
     const uint64_t U = ctx->U;

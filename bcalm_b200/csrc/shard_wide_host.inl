@@ -43,7 +43,7 @@ int shard_stage_count_wide(cdbg_ctx *ctx) {
         LAUNCH((kw1_extract<WW, 0>), g1, KW1_THREADS, kw1_smem_bytes(0, P), kp);
         tstop(ctx, T_K1H);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     }
     uint64_t I_out = 0;
     for (uint32_t b = 0; b < P; b++) { h_off[b] = I_out; I_out += h_cnt[b]; }
@@ -147,7 +147,7 @@ int shard_join_wide(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, uint
     if (S) {
         LAUNCH((kw3_ends<WW, 0>), g3, K3_THREADS, k3_smem_bytes(0, P), p3);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     }
     uint64_t acc = 0;
     for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; }

@@ -194,17 +194,32 @@ __global__ void __launch_bounds__(K1_THREADS, 2) sk1_extract(SK1Params p) {
         uint32_t a[64];
         {
             uint64_t hi = s_pk[t], lo = s_pk[t + 1];
-            uint64_t fm = hi >> (64 - 2 * m);
-            uint64_t rm = revcomp64(fm, m);
+            if (m == 16) {                                     // the usual case (inputs of 10 Mbases and more): the m-mer is the high word, 32-bit rolling
+                uint32_t fm = (uint32_t)(hi >> 32);
+                uint32_t rm = (uint32_t)revcomp64(fm, 16);
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                if (i > 0) {
-                    hi = (hi << 2) | (lo >> 62); lo <<= 2;
-                    fm = hi >> (64 - 2 * m);
-                    rm = (rm >> 2) | (((fm & 3) ^ 2) << (2 * (m - 1)));
+                for (int i = 0; i < 32; i++) {
+                    if (i > 0) {
+                        hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                        fm = (uint32_t)(hi >> 32);
+                        rm = (rm >> 2) | (((fm & 3u) ^ 2u) << 30);
+                    }
+                    a[i] = mmer_rank(fm < rm ? fm : rm);
+                    s_R[k1ts_pad((uint32_t)(t * 32 + i))] = a[i];
                 }
-                a[i] = mmer_rank((uint32_t)(fm < rm ? fm : rm));
-                s_R[k1ts_pad((uint32_t)(t * 32 + i))] = a[i];
+            } else {
+                uint64_t fm = hi >> (64 - 2 * m);
+                uint64_t rm = revcomp64(fm, m);
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if (i > 0) {
+                        hi = (hi << 2) | (lo >> 62); lo <<= 2;
+                        fm = hi >> (64 - 2 * m);
+                        rm = (rm >> 2) | (((fm & 3) ^ 2) << (2 * (m - 1)));
+                    }
+                    a[i] = mmer_rank((uint32_t)(fm < rm ? fm : rm));
+                    s_R[k1ts_pad((uint32_t)(t * 32 + i))] = a[i];
+                }
             }
             // the halo's m-mers (positions K1_TILE + j, j <= w - 2: all inside the halo word), one per thread
             if (t < w - 1) {

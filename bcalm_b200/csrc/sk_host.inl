@@ -33,7 +33,8 @@ bool sk_enabled(const cdbg_ctx *ctx) {
 #define SK_DEDUP_DEFAULT 0
 #endif
 #ifndef SK_TWO_PHASE_DEFAULT
-#define SK_TWO_PHASE_DEFAULT 0   // sk2c_count's two-phase insert (CDBG_SK_INSERT=two): opt-in until timed on a GPU
+#define SK_TWO_PHASE_DEFAULT 1   // sk2c_count's two-phase insert (C2 on a B200: table pass 1.246 -> 1.205 ms, 1.5 Gbases slice 13.65 -> 13.23 ms;
+                                 // profiles/r02_sk_ab4_*); CDBG_SK_INSERT=loop selects the plain probe loop
 #endif
 bool sk_dedup_enabled() {
     const char *s = getenv("CDBG_SK2C");
@@ -74,10 +75,9 @@ SKPlan sk_plan(const cdbg_ctx *ctx, uint64_t total_bytes, uint32_t world) {
     //   memory:   the records of one wave exist three times at the peak (K1 regions, send / receive or fine-partitioned copy).
     const double fine_cap = (double)(K1_MAX_BINS / world) * SK2P_MAX_F * world;
     uint64_t V = (uint64_t)ceil(n_fine / (fine_cap * 1.5));       // (a fine bin may hold 1.5x its nominal share before it splits often)
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) {
+    if (ctx->total_mem) {          // (the device's total memory, read once at cdbg_create: the same on every rank, no driver call per build)
         const double rec_bytes = (double)total_bytes / world * pl.rec_per_byte * 16.0 * 3.2;
-        const double budget = 0.55 * (double)total_b;
+        const double budget = 0.55 * (double)ctx->total_mem;
         V = std::max<uint64_t>(V, (uint64_t)ceil(rec_bytes / budget));
     }
     if (getenv("CDBG_SK_WAVES")) V = strtoull(getenv("CDBG_SK_WAVES"), nullptr, 10);

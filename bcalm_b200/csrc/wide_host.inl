@@ -29,7 +29,7 @@ int stage_count_wide(cdbg_ctx *ctx) {
         LAUNCH((kw1_extract<W, 0>), g1, KW1_THREADS, kw1_smem_bytes(0, P), kp);
         tstop(ctx, T_K1H);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
     }
     for (uint32_t b = 0; b < P; b++) { h_off[b] = I; I += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
     h_off[P] = I;
@@ -113,7 +113,7 @@ int stage_compact_wide(cdbg_ctx *ctx) {
         const int g3 = (int)std::max<uint64_t>(1, std::min<uint64_t>((S + K3_THREADS - 1) / K3_THREADS, (uint64_t)ctx->n_sm * 8));
         LAUNCH((kw3_ends<W, 0>), g3, K3_THREADS, k3_smem_bytes(0, P), p3);
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        SYNC_STREAM(ctx);
         uint64_t acc = 0;
         for (uint32_t b = 0; b < P; b++) { h_off[b] = acc; acc += h_cnt[b]; max_bin = std::max(max_bin, h_cnt[b]); }
         h_off[P] = acc;

@@ -18,10 +18,16 @@ K = 31
 n_reads = G * 30 // L
 T0 = time.time()
 BUDGET_S = float(os.environ.get("AB_BUDGET_S", "90"))
-TUN = ("CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_K2C_HASH", "CDBG_K1_THREADS", "CDBG_SK_DENSITY", "CDBG_K6", "CDBG_ZEROCOPY", "CDBG_SK_KC", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_MMER_RANK", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS")
+TUN = ("CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_K2C_HASH", "CDBG_K1_THREADS", "CDBG_SK_DENSITY", "CDBG_K6", "CDBG_ZEROCOPY", "CDBG_SK_KC", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_MMER_RANK", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_SK_INSERT", "CDBG_SK_THREADS")
 CONFIGS = [
     ("k-mer instances (round-1 default)", {"CDBG_S1": "kmer"}),
     ("super-k-mers default", {}),
+    ("sk two-phase insert", {"CDBG_SK_INSERT": "two"}),
+    ("sk two-phase insert mix64", {"CDBG_SK_INSERT": "two", "CDBG_K2C_HASH": "mix64"}),
+    ("sk two-phase insert fill 2.0", {"CDBG_SK_INSERT": "two", "CDBG_SK_FILL": "2.0"}),
+    ("sk two-phase insert fill 1.0", {"CDBG_SK_INSERT": "two", "CDBG_SK_FILL": "1.0"}),
+    ("sk two-phase 128 threads", {"CDBG_SK_INSERT": "two", "CDBG_SK_THREADS": "128"}),
+    ("sk K6 full (one level)", {"CDBG_K6": "full"}),
     ("super-k-mers direct count", {"CDBG_SK2C": "direct"}),
     ("super-k-mers dedup RS 1024", {"CDBG_SK2C": "dedup"}),
     ("super-k-mers dedup RS 2048", {"CDBG_SK2C": "dedup", "CDBG_SK_RS": "2048"}),

@@ -446,7 +446,7 @@ enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization 
 struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
 struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
 struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes = 0; cudaStream_t stream = nullptr; cudaLaunchAttribute *attrs = nullptr; unsigned numAttrs = 0; };
-struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
+struct cudaDeviceProp { int multiProcessorCount; char name[64]; size_t totalGlobalMem; };
 
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -456,6 +456,7 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
     const char *s = getenv("CDBG_EMU_SMS");
     p->multiProcessorCount = s ? atoi(s) : 2;
     snprintf(p->name, sizeof p->name, "CPU emulation (tests/emu)");
+    p->totalGlobalMem = (size_t)180 << 30;
     return cudaSuccess;
 }
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
@@ -499,6 +500,7 @@ static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { emu::stream_sync(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { emu::stream_sync(); return cudaSuccess; }
+static inline cudaError_t cudaStreamQuery(cudaStream_t) { emu::stream_sync(); return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b) { *free_b = *total_b = (size_t)180 << 30; return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {

@@ -74,3 +74,17 @@ def test_sharded_multi_word_kmers():
     if not w:
         pytest.skip("needs >= 2 GPUs")
     _run(w, [c["name"] for c in load_golden() if c["unitigs_fa"] is not None and c["k"] > 31], 29545, timeout=300)
+
+
+def test_sharded_failure_does_not_hang():
+    """a rank that fails before a collective must not leave the others blocked for ever.  Rank 1 fails inside stage 1
+    (CDBG_FAULT_RANK); every rank returns an error, the healthy ones after CDBG_SHARD_TIMEOUT_S."""
+    w = _world()
+    if not w:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29551", os.path.join(ROOT, "tests", "shard_fault_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=dict(os.environ, CDBG_FAULT_RANK="1", CDBG_SHARD_TIMEOUT_S="5"))
+    lines = [l for l in p.stdout.splitlines() if l.startswith("FAULT_RESULT")]
+    assert len(lines) == 2 and all("error after" in l for l in lines), (lines, p.stderr[-2000:])
+    assert any("injected fault" in l for l in lines) and any("did not reach the collective" in l for l in lines), lines
