@@ -49,6 +49,8 @@ struct cdbg_ctx {
     int n_sm = 148;
     uint64_t total_mem = 0;       // device memory (cudaDeviceProp::totalGlobalMem), for the wave planning of stage 1
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                 // sharded glue: the all-gather of the piece strings runs beside the piece-level ranking
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     Stage stage = ST_EMPTY;
     cdbg_stats st{};
@@ -1217,6 +1219,11 @@ int cdbg_create(cdbg_ctx **out, const cdbg_params *params) {
     ctx->n_sm = prop.multiProcessorCount;
     ctx->total_mem = (uint64_t)prop.totalGlobalMem;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    if (ctx->world > 1) {
+        CK(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
     CK(cudaMalloc(&ctx->d_ctr, 64 * sizeof(unsigned long long)));
     CK(cudaMalloc(&ctx->d_flag, 4 * sizeof(int)));
     CK(cudaHostAlloc(&ctx->h_ctr, 80 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -1243,6 +1250,9 @@ void cdbg_destroy(cdbg_ctx *ctx) {
         if (ctx->h_links) cudaFreeHost(ctx->h_links);
         if (ctx->h_link_off) cudaFreeHost(ctx->h_link_off);
         for (auto &t : ctx->tm) { if (t.a) cudaEventDestroy(t.a); if (t.b) cudaEventDestroy(t.b); }
+        if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+        if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+        if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -1458,7 +1468,8 @@ int cdbg_get_unitigs(cdbg_ctx *ctx, cdbg_unitig_view *view) {
 static bool try_zero_copy(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes) {
     const char *z = getenv("CDBG_ZEROCOPY"), *k1 = getenv("CDBG_K1"), *zmin = getenv("CDBG_ZEROCOPY_MIN");
     const uint64_t min_bytes = zmin ? strtoull(zmin, nullptr, 10) : (1u << 20);   // small inputs: a plain copy is as good
-    if (ctx->W != 1 || ctx->world != 1 || n_bytes < min_bytes || n_bytes == 0 || (reinterpret_cast<uintptr_t>(bytes) & 15)) return false;
+    if (ctx->W != 1 || n_bytes < min_bytes || n_bytes == 0 || (reinterpret_cast<uintptr_t>(bytes) & 15)) return false;
+    if (ctx->world != 1 && !sk_enabled(ctx)) return false;     // sharded: only the super-k-mer K1 reads its input once, through TMA
     if ((z && atoi(z) == 0) || (k1 && strcmp(k1, "single") != 0)) return false;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, bytes) != cudaSuccess) { cudaGetLastError(); return false; }

@@ -551,12 +551,26 @@ __global__ void __launch_bounds__(K5CS_THREADS) k5cs_join(K5CSParams p) {
 // ------------------------------------------------------------------------------------------------ generic routing of 16-byte records
 
 // destination = rank field of rec.x (bits 39..32)
+// (with 2..16 destinations a shared-memory atomic per record would serialise whole warps on one or two counters -- 24 ms for the 10 M
+//  link records of C3 on 2 GPUs -- so ranks and counts are taken per warp from one ballot per destination)
 __global__ void __launch_bounds__(256) route_hist(const ulonglong2 *__restrict__ recs, uint64_t n, uint32_t world, unsigned long long *count) {
     __shared__ uint32_t s_c[MAX_WORLD];
     if (threadIdx.x < MAX_WORLD) s_c[threadIdx.x] = 0;
     __syncthreads();
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&s_c[GID_RANK(recs[i].x)], 1u);
+    const uint32_t lane = lane_id();
+    uint32_t acc = 0;                                            // lane w counts destination w for its warp
+    const uint64_t per_iter = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t iters = (n + per_iter - 1) / per_iter;
+    for (uint64_t it = 0; it < iters; it++) {                    // warp-uniform trip count
+        const uint64_t i = it * per_iter + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+        const bool ok = i < n;
+        const uint32_t d = ok ? GID_RANK(recs[i].x) : 0xFFFFFFFFu;
+        for (uint32_t w = 0; w < world; w++) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, d == w);
+            if (lane == w) acc += __popc(m);
+        }
+    }
+    if (lane < world && acc) atomicAdd(&s_c[lane], acc);
     __syncthreads();
     if (threadIdx.x < world && s_c[threadIdx.x]) atomicAdd(&count[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
 }
@@ -565,14 +579,22 @@ __global__ void __launch_bounds__(256) route_scatter(const ulonglong2 *__restric
                                                      unsigned long long *cursor, ulonglong2 *out) {
     __shared__ uint32_t s_c[MAX_WORLD];
     __shared__ uint64_t s_base[MAX_WORLD];
+    const uint32_t lane = lane_id();
     const uint64_t per_iter = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t iters = (n + per_iter - 1) / per_iter;
     for (uint64_t it = 0; it < iters; it++) {
         uint64_t i = it * per_iter + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
         if (threadIdx.x < MAX_WORLD) s_c[threadIdx.x] = 0;
         __syncthreads();
-        ulonglong2 r = make_ulonglong2(0, 0); uint32_t d = 0, rk = 0; bool ok = i < n;
-        if (ok) { r = recs[i]; d = GID_RANK(r.x); rk = atomicAdd(&s_c[d], 1u); }
+        ulonglong2 r = make_ulonglong2(0, 0); uint32_t d = 0xFFFFFFFFu, rk = 0; const bool ok = i < n;
+        if (ok) { r = recs[i]; d = GID_RANK(r.x); }
+        for (uint32_t w = 0; w < world; w++) {                   // rank inside the block's share of destination w: one atomic per warp
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, d == w);
+            uint32_t b = 0;
+            if (lane == 0 && m) b = atomicAdd(&s_c[w], (uint32_t)__popc(m));
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            if (d == w) rk = b + __popc(m & ((1u << lane) - 1u));
+        }
         __syncthreads();
         if (threadIdx.x < world && s_c[threadIdx.x]) s_base[threadIdx.x] = off[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_c[threadIdx.x]);
         __syncthreads();

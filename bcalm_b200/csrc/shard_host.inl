@@ -23,6 +23,7 @@ int allgather_host_u64(cdbg_ctx *ctx, const uint64_t *h_in, size_t count, uint64
     if ((rc = dalloc(ctx, &d_out, count * ctx->world))) return rc;
     CK(cudaMemcpyAsync(d_in, h_in, count * 8, cudaMemcpyHostToDevice, ctx->stream));
     NK(ncclAllGather(d_in, d_out, count, ncclUint64, ctx->comm, ctx->stream));
+    SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
     CK(cudaMemcpyAsync(h_out, d_out, count * 8 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
     SYNC_STREAM(ctx);
     dfree(ctx, d_in); dfree(ctx, d_out);
@@ -37,11 +38,20 @@ int exchange_with_counts(cdbg_ctx *ctx, const void *d_send, const uint64_t *send
     for (int s = 0; s < ctx->world; s++) tot += recv_cnt[s];
     uint8_t *recv = nullptr;
     if ((rc = dalloc(ctx, &recv, tot * esz + 16))) return rc;
+    // this rank's own segment (with minimizer ownership: most of the end records) is a device copy, not a trip through NCCL
+    {
+        uint64_t so = 0, ro = 0;
+        for (int peer = 0; peer < ctx->rank; peer++) { so += send_cnt[peer]; ro += recv_cnt[peer]; }
+        if (send_cnt[ctx->rank])
+            CK(cudaMemcpyAsync(recv + ro * esz, (const uint8_t *)d_send + so * esz, send_cnt[ctx->rank] * esz, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     NK(ncclGroupStart());
     uint64_t so = 0, ro = 0;
     for (int peer = 0; peer < ctx->world; peer++) {
-        if (send_cnt[peer]) NK(ncclSend((const uint8_t *)d_send + so * esz, send_cnt[peer] * esz, ncclChar, peer, ctx->comm, ctx->stream));
-        if (recv_cnt[peer]) NK(ncclRecv(recv + ro * esz, recv_cnt[peer] * esz, ncclChar, peer, ctx->comm, ctx->stream));
+        if (peer != ctx->rank) {
+            if (send_cnt[peer]) NK(ncclSend((const uint8_t *)d_send + so * esz, send_cnt[peer] * esz, ncclChar, peer, ctx->comm, ctx->stream));
+            if (recv_cnt[peer]) NK(ncclRecv(recv + ro * esz, recv_cnt[peer] * esz, ncclChar, peer, ctx->comm, ctx->stream));
+        }
         so += send_cnt[peer]; ro += recv_cnt[peer];
     }
     NK(ncclGroupEnd());
@@ -66,6 +76,7 @@ int route16(cdbg_ctx *ctx, const ulonglong2 *d_recs, uint64_t n, ulonglong2 **d_
     if (n) LAUNCH(route_hist, grid_for(ctx, n, 256, 4), 256, 0, d_recs, n, (uint32_t)W, d_cnt);
     NK(ncclAllGather(d_cnt, d_all, W, ncclUint64, ctx->comm, ctx->stream));
     std::vector<uint64_t> M((size_t)W * W);
+    SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
     CK(cudaMemcpyAsync(M.data(), d_all, (size_t)W * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
     SYNC_STREAM(ctx);
     uint64_t h_cnt[MAX_WORLD] = {0}, h_off[MAX_WORLD + 1] = {0};
@@ -232,6 +243,7 @@ int shard_stage_count(cdbg_ctx *ctx) {
         if (k1_roll) LAUNCH(k1t_shard_hist, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 2), K1_THREADS, k1ts_smem_bytes(P), ks);
         else LAUNCH(k1s_extract<0>, (int)std::min<uint64_t>(n_tiles, (uint64_t)ctx->n_sm * 4), K1S_THREADS, k1s_smem_bytes(0, P), kp);
         tstop(ctx, T_K1H);
+        SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SYNC_STREAM(ctx);
     }
@@ -483,6 +495,7 @@ int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, ui
     const int g3 = (int)std::max<uint64_t>(1, std::min<uint64_t>((S + K3_TILE - 1) / K3_TILE, (uint64_t)ctx->n_sm * 4));
     if (S) {
         LAUNCH(k3s_ends<0>, g3, K3_THREADS, k3_smem_bytes(0, P), p3);
+        SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SYNC_STREAM(ctx);
     }
@@ -507,14 +520,22 @@ int shard_join_narrow(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, ui
         for (int sidx = 0; sidx < W; sidx++) T_in += recv_cnt[sidx];
         if ((rc = dalloc(ctx, &d_rec_key, T_in + 2))) return rc;
         if ((rc = dalloc(ctx, &d_rec_val, T_in + 2))) return rc;
+        {   // this rank's own records (~90 % with minimizer ownership) are a device copy
+            uint64_t so = 0, ro = 0;
+            for (int peer = 0; peer < me; peer++) { so += send_cnt[peer]; ro += recv_cnt[peer]; }
+            if (send_cnt[me]) {
+                CK(cudaMemcpyAsync(d_rec_key + ro, d_key_s + so, send_cnt[me] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(d_rec_val + ro, d_val_s + so, send_cnt[me] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
         NK(ncclGroupStart());
         uint64_t so = 0, ro = 0;
         for (int peer = 0; peer < W; peer++) {
-            if (send_cnt[peer]) {
+            if (peer != me && send_cnt[peer]) {
                 NK(ncclSend(d_key_s + so, send_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
                 NK(ncclSend(d_val_s + so, send_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
             }
-            if (recv_cnt[peer]) {
+            if (peer != me && recv_cnt[peer]) {
                 NK(ncclRecv(d_rec_key + ro, recv_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
                 NK(ncclRecv(d_rec_val + ro, recv_cnt[peer], ncclUint64, peer, ctx->comm, ctx->stream));
             }
@@ -658,12 +679,15 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     TRACE("glue describe + allgather desc");
     char *d_seq_all = nullptr;
     if ((rc = dalloc(ctx, &d_seq_all, max_nt * W))) return rc;
-    {   // pad my piece strings to max_nt for the all-gather
-        char *d_pad = nullptr;
-        if ((rc = dalloc(ctx, &d_pad, max_nt))) return rc;
-        if (piece_nt) CK(cudaMemcpyAsync(d_pad, d_pseq, piece_nt, cudaMemcpyDeviceToDevice, ctx->stream));
-        NK(ncclAllGather(d_pad, d_seq_all, max_nt, ncclChar, ctx->comm, ctx->stream));
-        dfree(ctx, d_pad);
+    char *d_pad_seq = nullptr;
+    {   // pad my piece strings to max_nt for the all-gather.  Only glue_assemble needs the strings: the all-gather runs on the second
+        // stream, beside the table build and the piece-level ranking (NCCL keeps the issue order of the collectives of a communicator)
+        if ((rc = dalloc(ctx, &d_pad_seq, max_nt))) return rc;
+        if (piece_nt) CK(cudaMemcpyAsync(d_pad_seq, d_pseq, piece_nt, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        NK(ncclAllGather(d_pad_seq, d_seq_all, max_nt, ncclChar, ctx->comm, ctx->stream2));
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
     }
     uint32_t *d_abund_all = nullptr;
     if (d_pabund) {   // the per-k-mer abundance lists travel like the piece strings
@@ -716,6 +740,7 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if (G) LAUNCH(glue_unitig_offsets, grid_for(ctx, G, 256, 8), 256, 0, ctx->d_pinfo, d_puid, d_pnt, G, d_unt_off);
     CK(cudaMemcpyAsync(d_unt_off + U_total, &nt_total, 8, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t nt_range[2] = {0, 0};
+    SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
     CK(cudaMemcpyAsync(&nt_range[0], d_unt_off + u_first, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&nt_range[1], d_unt_off + u_last, 8, cudaMemcpyDeviceToHost, ctx->stream));
     SYNC_STREAM(ctx);
@@ -723,6 +748,8 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     if ((rc = dalloc(ctx, &ctx->d_seq, nt_mine + 1))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_seq_off, U_mine + 1))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_kc, U_mine + 1))) return rc;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));      // the piece strings have arrived
+    dfree(ctx, d_pad_seq);
     if (G && U_mine) LAUNCH(glue_assemble, grid_for(ctx, G * 32, 256, 8), 256, 0, G, ctx->d_pinfo, ctx->d_unitig_of_piece, d_pnt, d_desc_all, max_p, (uint32_t)W,
                             d_piece_base, d_seq_all, max_nt, (uint32_t)u_first, (uint32_t)u_last, nt_range[0], k, ctx->d_seq, ctx->d_seq_off);
     if (d_abund_all) {
@@ -781,6 +808,7 @@ int shard_stage_link(cdbg_ctx *ctx) {
     tstop(ctx, T_XLINK);
     {
         int bad = 0;
+        SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
         CK(cudaMemcpyAsync(&bad, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SYNC_STREAM(ctx);
         if (bad) return ctx->fail(CDBG_ERR_INTERNAL, "an edge end is not a piece terminus");

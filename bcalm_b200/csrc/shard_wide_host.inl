@@ -42,6 +42,7 @@ int shard_stage_count_wide(cdbg_ctx *ctx) {
         tstart(ctx, T_K1H);
         LAUNCH((kw1_extract<WW, 0>), g1, KW1_THREADS, kw1_smem_bytes(0, P), kp);
         tstop(ctx, T_K1H);
+        SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SYNC_STREAM(ctx);
     }
@@ -146,6 +147,7 @@ int shard_join_wide(cdbg_ctx *ctx, uint64_t S_total, ulonglong2 **out_msgs, uint
     const int g3 = (int)std::max<uint64_t>(1, std::min<uint64_t>((S + K3_THREADS - 1) / K3_THREADS, (uint64_t)ctx->n_sm * 8));
     if (S) {
         LAUNCH((kw3_ends<WW, 0>), g3, K3_THREADS, k3_smem_bytes(0, P), p3);
+        SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
         CK(cudaMemcpyAsync(h_cnt.data(), d_bin_count, P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         SYNC_STREAM(ctx);
     }

@@ -141,6 +141,7 @@ int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, uint32_t wave, ulong
     tstart(ctx, T_K1S);
     LAUNCH(sk1_extract<1>, grid, K1_THREADS, sm, kp);
     tstop(ctx, T_K1S);
+    SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
     CK(cudaMemcpyAsync(h_cnt.data(), d_cursor, (size_t)Pc * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if ((rc = ctr_read(ctx))) return rc;
     if (((int *)(ctx->h_ctr + 64))[2]) {
@@ -168,6 +169,7 @@ int sk_run_k1(cdbg_ctx *ctx, const SKPlan &pl, uint32_t Pc, uint32_t wave, ulong
         LAUNCH(sk1_extract<1>, grid, K1_THREADS, sm, kp);
         tstop(ctx, T_K1H);
         std::vector<uint64_t> again(Pc);
+        SYNC_STREAM(ctx);   // (a copy to pageable memory blocks inside the call: wait by polling first, see stream_sync)
         CK(cudaMemcpyAsync(again.data(), d_cursor, (size_t)Pc * 8, cudaMemcpyDeviceToHost, ctx->stream));
         if ((rc = ctr_read(ctx))) return rc;
         if (((int *)(ctx->h_ctr + 64))[2] || again != h_cnt) return ctx->fail(CDBG_ERR_INTERNAL, "super-k-mer extraction is not reproducible (exact pass overflowed)");

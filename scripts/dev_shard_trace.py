@@ -8,8 +8,9 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 if rank != 0: os.environ.pop("CDBG_TRACE", None)
 c = Cdbg(k=31, abundance_min=2, device=local, rank=rank, world_size=world); c.shard_init_torch()
-G = 5_000_000 * world; n_reads = G * 30 // 100 // world
-ptr, n = c.synth_reads(G, 100, n_reads, 10000, 42, first_read=rank * n_reads)
+L = int(os.environ.get('DEV_L', '100'))
+G = int(os.environ.get('DEV_G', str(5_000_000 * world))); n_reads = G * 30 // L // world
+ptr, n = c.synth_reads(G, L, n_reads, 10000, 42, first_read=rank * n_reads)
 for it in range(4):
     dist.barrier(); torch.cuda.synchronize()
     if rank == 0: print(f"---- iter {it}", file=sys.stderr, flush=True)

@@ -501,8 +501,11 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; 
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { emu::stream_sync(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { emu::stream_sync(); return cudaSuccess; }
 static inline cudaError_t cudaStreamQuery(cudaStream_t) { emu::stream_sync(); return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }   // (the emulated streams run in issue order)
 static inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b) { *free_b = *total_b = (size_t)180 << 30; return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); return cudaSuccess; }
+#define cudaEventDisableTiming 2u
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = new emuEvent(); return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
     auto &v = emu::pending_events; v.erase(std::remove(v.begin(), v.end(), e), v.end());
     delete e; return cudaSuccess;

@@ -84,7 +84,7 @@ def test_sharded_failure_does_not_hang():
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29551", os.path.join(ROOT, "tests", "shard_fault_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=dict(os.environ, CDBG_FAULT_RANK="1", CDBG_SHARD_TIMEOUT_S="5"))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=90, env=dict(os.environ, CDBG_FAULT_RANK="1", CDBG_SHARD_TIMEOUT_S="5"))
     lines = [l for l in p.stdout.splitlines() if l.startswith("FAULT_RESULT")]
     assert len(lines) == 2 and all("error after" in l for l in lines), (lines, p.stderr[-2000:])
     assert any("injected fault" in l for l in lines) and any("did not reach the collective" in l for l in lines), lines
