@@ -19,6 +19,8 @@ built by all ranks together, sharded by minimizer).
           a single-GPU build of ALL reads on rank 0.  A mismatch prints "parity": "FAIL" and exits non-zero.
   extra.c3 : workload C3 (configs[2]: 250 Mbp genome, 150 bp reads, 30x = 7.5 Gbases) -- STRONG scaling: the same read set at
           every N, rank r taking an equal share; value, e2e, stage times and the same parity check (--no-c3 skips it).
+  extra.c4 / extra.c5 : at 8 GPUs (or with --c4 / --c5) also C4 at full size (configs[3]: 3 Gbp genome, 90 Gbases; properties parity) and a
+          scaled C5 (configs[4]: k=127, 250 bp reads, 3 Gbases; merged shards vs a single-GPU build).
   file_to_file : the same C2 workload through the CLI, FASTA file -> unitigs.fa (what the reference arm measures), N=1 only.
   cpu_baseline : the real reference binary (oracle/_ref/bcalm, kind "reference") -- or the C oracle (kind "port") when the
           binary is absent -- on the same C2 reads, all host cores (N=1, rank 0 only).
@@ -570,10 +572,12 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the extra C3 block")
     ap.add_argument("--c3-scale", type=float, default=1.0)
     ap.add_argument("--c3-steps", type=int, default=3)
-    ap.add_argument("--c4", action="store_true", help="also run C4 (3 Gbp genome, 90 Gbases; needs the HBM of 8 GPUs)")
+    ap.add_argument("--c4", action="store_true", help="also run C4 (3 Gbp genome, 90 Gbases; needs the HBM of 8 GPUs): on by default at --gpus 8")
+    ap.add_argument("--no-c4", action="store_true")
     ap.add_argument("--c4-scale", type=float, default=1.0)
     ap.add_argument("--c4-steps", type=int, default=1)
-    ap.add_argument("--c5", action="store_true", help="also run a scaled C5 (k=127, 250 bp reads)")
+    ap.add_argument("--c5", action="store_true", help="also run a scaled C5 (k=127, 250 bp reads): on by default at --gpus 8")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--c5-genome", type=float, default=50_000_000)
     ap.add_argument("--c5-steps", type=int, default=2)
     ap.add_argument("--c3-timeout", type=float, default=420.0, help="seconds after which a hung C3 block is abandoned (the main line is still printed)")
@@ -746,7 +750,11 @@ def main():
             out["extra"]["c3"] = c3
 
     # ---- extra (opt-in): C4 at full size and a scaled C5, each under its own watchdog
-    for name, flag, fn in (("c4", args.c4, run_c4), ("c5", args.c5, run_c5)):
+    want_c4 = (args.c4 or (world >= 8 and args.impl == "ours")) and not args.no_c4
+    want_c5 = (args.c5 or (world >= 8 and args.impl == "ours")) and not args.no_c5
+    if want_c5 and not args.c5:
+        args.c5_genome = 100_000_000
+    for name, flag, fn in (("c4", want_c4, run_c4), ("c5", want_c5, run_c5)):
         if not flag:
             continue
         def partial(name=name):
