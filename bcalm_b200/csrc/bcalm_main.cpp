@@ -114,7 +114,7 @@ Options parse(int argc, char **argv) {
         }
     }
     if (o.in.empty() && o.solid_in.empty()) { usage(); die("Option '-in' is mandatory"); }
-    if (o.nb_gpus < 1 || o.nb_gpus > 64) die("-nb-gpus must be between 1 and 64");
+    if (o.nb_gpus < 1 || o.nb_gpus > 16) die("-nb-gpus must be between 1 and 16 (the library shards one graph over at most 16 GPUs of one node)");
     if (o.nb_gpus > 1 && (!o.solid_in.empty() || !o.solid_out.empty() || o.gpu_parse == 1 || o.kff))
         die("-nb-gpus > 1 does not support -solid-kmers-in / -solid-kmers-out / -gpu-parse / -kff");
     return o;

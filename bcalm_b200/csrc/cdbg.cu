@@ -828,11 +828,16 @@ int rank_two_level(cdbg_ctx *ctx, const uint32_t *d_link, uint64_t *d_pair, uint
     return CDBG_OK;
 }
 
+// smallest edge-buffer size (CDBG_EDGE_MIN: tests shrink it to exercise the growth paths)
+uint64_t edge_min() { static const uint64_t v = getenv("CDBG_EDGE_MIN") ? strtoull(getenv("CDBG_EDGE_MIN"), nullptr, 10) : (1ULL << 16); return std::max<uint64_t>(v, 16); }
+
 // List ranking over `n_nodes` nodes with two ends each (link[2*n_nodes], NOLINK = chain end).  weight == nullptr: every node
 // counts 1 (k-mers); otherwise hop counts are weighted (pieces of several k-mers).  Cycles are cut at their smallest node;
 // the two edges of each cut junction are appended to edges[] (packed end ids) and *n_edges advanced.
-int run_ranking(cdbg_ctx *ctx, uint32_t *d_link, uint64_t n_nodes, const uint32_t *d_weight, uint64_t *d_edges, uint64_t edge_cap,
+int run_ranking(cdbg_ctx *ctx, uint32_t *d_link, uint64_t n_nodes, const uint32_t *d_weight, uint64_t **d_edges_io, uint64_t *edge_cap_io,
                 uint64_t *n_edges, uint64_t **d_pair_out) {
+    uint64_t *d_edges = *d_edges_io;
+    uint64_t edge_cap = *edge_cap_io;
     int rc;
     const uint64_t n2 = 2 * n_nodes;
     uint64_t *d_pair = nullptr;
@@ -857,6 +862,20 @@ int run_ranking(cdbg_ctx *ctx, uint32_t *d_link, uint64_t n_nodes, const uint32_
         int rounds = 2;
         for (uint64_t r = 1; r < remaining; r <<= 1) rounds++;
         for (int r = 0; r < rounds; r++) LAUNCH(k6_cycle_min, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2);
+        // room for the two edges of every cut: count the cycles first and grow the edge buffer if need be (inputs made of
+        // many small circular components used to end in "edge buffer overflow")
+        if ((rc = ctr_zero(ctx))) return rc;
+        LAUNCH(k6_cycle_count, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2, ctx->d_ctr + 1);
+        if ((rc = ctr_read(ctx))) return rc;
+        if (*n_edges + 2 * ctx->h_ctr[1] > edge_cap) {
+            const uint64_t new_cap = *n_edges + 2 * ctx->h_ctr[1] + 1024;
+            uint64_t *ne = nullptr;
+            if ((rc = dalloc(ctx, &ne, new_cap))) return rc;
+            if (*n_edges) CK(cudaMemcpyAsync(ne, d_edges, *n_edges * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            dfree(ctx, d_edges);
+            d_edges = ne; edge_cap = new_cap;
+            *d_edges_io = ne; *edge_cap_io = new_cap;
+        }
         if ((rc = ctr_zero(ctx))) return rc;
         CK(cudaMemcpyAsync(ctx->d_ctr + 0, n_edges, 8, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(k6_cycle_cut, grid_for(ctx, n2, 256, 8), 256, 0, d_cyc, d_lab, n2, d_link, d_edges, edge_cap, ctx->d_ctr + 0, ctx->d_ctr + 1);
@@ -977,7 +996,7 @@ int stage_compact_k5_smem(cdbg_ctx *ctx, uint32_t slots, double per_fine, const 
         CK(cudaMemsetAsync(d_fine_off, 0, (NF + 2) * 8, ctx->stream));
     }
 
-    ctx->edge_cap = std::max<uint64_t>(S / 2, 1 << 16);
+    ctx->edge_cap = std::max<uint64_t>(S / 2, edge_min());
     for (int attempt = 0; attempt < 2; attempt++) {
         if ((rc = dalloc(ctx, &ctx->d_edges, ctx->edge_cap))) return rc;
         CK(cudaMemsetAsync(ctx->d_link, 0xFF, (n2 + 1) * 4, ctx->stream));
@@ -1001,7 +1020,7 @@ int stage_compact_k5_smem(cdbg_ctx *ctx, uint32_t slots, double per_fine, const 
         ctx->n_edges = ctx->h_ctr[0];
         ctx->st.n_compactions = ctx->h_ctr[1];
         ctx->st.n_k5_splits = ctx->h_ctr[2];
-        if (ctx->n_edges + 2048 <= ctx->edge_cap) break;   // room for the two edges of every cut cycle
+        if (ctx->n_edges <= ctx->edge_cap) break;          // (the edges of cut cycles make their own room: run_ranking grows the buffer)
         if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow");
         dfree(ctx, ctx->d_edges);
         ctx->edge_cap = ctx->n_edges + std::max<uint64_t>(ctx->n_edges / 8, 1 << 16);
@@ -1112,7 +1131,7 @@ int stage_compact(cdbg_ctx *ctx) {
     // ---- K6: list ranking + unitig numbering
     uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;
     tstart(ctx, T_K6R);
-    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, ctx->d_edges, ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
+    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, &ctx->d_edges, &ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
     tstop(ctx, T_K6R);
     tstart(ctx, T_K6S);
     uint64_t U = 0, total_nt = 0;

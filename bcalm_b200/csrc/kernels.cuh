@@ -774,6 +774,14 @@ __global__ void __launch_bounds__(256) k6_cycle_min(const uint8_t *flag, uint64_
     }
 }
 
+// number of cycles about to be cut (= flagged minima): lets the host make room for their 2 edges each before k6_cycle_cut runs
+__global__ void __launch_bounds__(256) k6_cycle_count(const uint8_t *flag, const uint64_t *lab, uint64_t n2, unsigned long long *n_cycles) {
+    unsigned long long c = 0;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < n2; x += (uint64_t)gridDim.x * blockDim.x)
+        c += flag[x] && !(x & 1) && (uint32_t)lab[x] == (uint32_t)(x >> 1);
+    block_add(n_cycles, c);
+}
+
 __global__ void __launch_bounds__(256) k6_cycle_cut(const uint8_t *flag, const uint64_t *lab, uint64_t n2, uint32_t *link,
                                                     uint64_t *edges, uint64_t edge_cap, unsigned long long *n_edges,
                                                     unsigned long long *n_cycles) {

@@ -115,6 +115,19 @@ inline void plan_shard_exchange(uint32_t world, uint32_t me, uint32_t P_local, c
         }
 }
 
+// make room for `need` unitig-level edges in ctx->d_sedges (the edges of cut cycles are appended after the join has sized the buffer)
+int grow_sedges(cdbg_ctx *ctx, uint64_t need) {
+    if (need <= ctx->sedge_cap) return CDBG_OK;
+    int rc;
+    const uint64_t cap = need + need / 8 + 1024;
+    ulonglong2 *ne = nullptr;
+    if ((rc = dalloc(ctx, &ne, cap))) return rc;
+    if (ctx->n_sedges) CK(cudaMemcpyAsync(ne, ctx->d_sedges, ctx->n_sedges * sizeof(ulonglong2), cudaMemcpyDeviceToDevice, ctx->stream));
+    dfree(ctx, ctx->d_sedges);
+    ctx->d_sedges = ne; ctx->sedge_cap = cap;
+    return CDBG_OK;
+}
+
 inline uint32_t table_cap_for(uint64_t n) { return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1024, (n * 3 / 2 + 63) & ~63ULL), 0xFFFFFF00u); }
 
 // ------------------------------------------------------------------------------------------------ stage 1 (sharded)
@@ -423,7 +436,7 @@ int shard_join_smem(cdbg_ctx *ctx, const uint64_t *d_rec_key, const uint64_t *d_
     }
     ulonglong2 *d_link_msgs = nullptr;
     uint64_t link_cap = T_in / 4 + 4096;
-    ctx->sedge_cap = std::max<uint64_t>(T_in / 4, 1 << 16) + 4096;
+    ctx->sedge_cap = std::max<uint64_t>(T_in / 4, edge_min()) + 4096;
     if ((rc = dalloc(ctx, &ctx->d_link64, n2 + 1))) return rc;
     uint64_t n_link_msgs = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -453,7 +466,7 @@ int shard_join_smem(cdbg_ctx *ctx, const uint64_t *d_rec_key, const uint64_t *d_
         ctx->st.n_compactions = ctx->h_ctr[2];
         ctx->st.n_k5_splits = (uint32_t)ctx->h_ctr[3];
         // room is kept for the edges of locally cut cycles and of piece-level cycle cuts, which are appended later
-        if (n_link_msgs <= link_cap && ctx->n_sedges + 65536 + 4096 <= ctx->sedge_cap) break;
+        if (n_link_msgs <= link_cap && ctx->n_sedges <= ctx->sedge_cap) break;     // (edges of cut cycles are appended through grow_sedges)
         if (attempt == 1) return ctx->fail(CDBG_ERR_INTERNAL, "join output buffers overflow after resizing");
         dfree(ctx, d_link_msgs); dfree(ctx, ctx->d_sedges);
         link_cap = n_link_msgs + 4096;
@@ -635,11 +648,11 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     TRACE("X3 route link msgs + apply");
     // ---- stage 2 proper: local ranking -> pieces (the unitigs of this shard), spelled locally
     uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;
-    ctx->edge_cap = 1 << 16;
+    ctx->edge_cap = edge_min();
     if ((rc = dalloc(ctx, &ctx->d_edges, ctx->edge_cap))) return rc;
     ctx->n_edges = 0;
     tstart(ctx, T_K6R);
-    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, ctx->d_edges, ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
+    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, &ctx->d_edges, &ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
     if (n2) LAUNCH(shard_sync_cut, grid_for(ctx, n2, 256, 8), 256, 0, ctx->d_link, n2, (uint32_t)me, ctx->d_link64);
     tstop(ctx, T_K6R);
     tstart(ctx, T_K6S);
@@ -715,9 +728,9 @@ int shard_stage_compact(cdbg_ctx *ctx) {
         LAUNCH(glue_build, grid_for(ctx, G, 256, 8), 256, 0, d_desc_all, max_p, (uint32_t)W, d_piece_base, G, ctx->gid_table, d_plink, d_weight);
     }
     uint64_t *d_ppair = nullptr, *d_puid = nullptr, *d_pnt = nullptr, *d_pedges = nullptr; uint64_t n_pedges = 0;
-    const uint64_t pedge_cap = 1 << 16;
+    uint64_t pedge_cap = edge_min();
     if ((rc = dalloc(ctx, &d_pedges, pedge_cap))) return rc;
-    if ((rc = run_ranking(ctx, d_plink, G, d_weight, d_pedges, pedge_cap, &n_pedges, &d_ppair))) return rc;
+    if ((rc = run_ranking(ctx, d_plink, G, d_weight, &d_pedges, &pedge_cap, &n_pedges, &d_ppair))) return rc;
     uint64_t U_total = 0, nt_total = 0;
     if ((rc = number_units(ctx, d_ppair, G, d_weight, &ctx->d_pinfo, &d_puid, &d_pnt, &U_total, &nt_total))) return rc;
     dfree(ctx, d_ppair); dfree(ctx, d_plink);
@@ -765,11 +778,12 @@ int shard_stage_compact(cdbg_ctx *ctx) {
     // ---- collect every edge this GPU is responsible for as (from gid, to gid): join edges are already there;
     //      add the edges of locally cut cycles and of piece-level cut cycles
     if (ctx->n_edges) {
-        if (ctx->n_sedges + ctx->n_edges > ctx->sedge_cap) return ctx->fail(CDBG_ERR_INTERNAL, "edge buffer overflow");
+        if ((rc = grow_sedges(ctx, ctx->n_sedges + ctx->n_edges))) return rc;
         LAUNCH(shard_local_edges_to_gid, grid_for(ctx, ctx->n_edges, 256, 8), 256, 0, ctx->d_edges, ctx->n_edges, (uint32_t)me, ctx->d_sedges + ctx->n_sedges);
         ctx->n_sedges += ctx->n_edges;
     }
     if (n_pedges) {
+        if ((rc = grow_sedges(ctx, ctx->n_sedges + n_pedges))) return rc;
         if ((rc = ctr_zero(ctx))) return rc;
         CK(cudaMemcpyAsync(ctx->d_ctr + 0, &ctx->n_sedges, 8, cudaMemcpyHostToDevice, ctx->stream));
         LAUNCH(glue_cut_edges, grid_for(ctx, n_pedges, 256, 8), 256, 0, d_pedges, n_pedges, d_desc_all, max_p, (uint32_t)W, d_piece_base, (uint32_t)me,

@@ -160,7 +160,7 @@ int stage_compact_wide(cdbg_ctx *ctx) {
 
     uint64_t *d_pair = nullptr, *d_uid_scan = nullptr, *d_nt_scan = nullptr;
     tstart(ctx, T_K6R);
-    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, ctx->d_edges, ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
+    if ((rc = run_ranking(ctx, ctx->d_link, S, nullptr, &ctx->d_edges, &ctx->edge_cap, &ctx->n_edges, &d_pair))) return rc;
     tstop(ctx, T_K6R);
     tstart(ctx, T_K6S);
     uint64_t U = 0, total_nt = 0;

@@ -16,7 +16,7 @@ for line in txt.splitlines():
     m = re.match(r"\s*Function : (\S+)", line)
     if m:
         cur = m.group(1); body[cur] = []; continue
-    if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+    if cur and re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
         body[cur].append(line)
 dem = subprocess.run(["c++filt"], input="\n".join(body), capture_output=True, text=True).stdout.splitlines()
 names = dict(zip(body, dem))

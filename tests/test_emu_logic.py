@@ -397,3 +397,27 @@ def test_second_push_after_a_buffer_used_in_place_is_separated_by_a_break(emu_li
         g = c.unitigs()
     o = orc.run(np.concatenate([a, np.frombuffer(b"\n", np.uint8), b]), k, 1)
     assert parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k) == ""
+
+
+def _many_cycles(n_cycles, length, k, seed):
+    """Reads that each spell one isolated cycle of `length` k-mers (the circular string plus its first k-1 characters)."""
+    rng = np.random.default_rng(seed)
+    reads = []
+    for _ in range(n_cycles):
+        s = "".join("ACGT"[i] for i in rng.integers(0, 4, length))
+        reads.append(s + s[: k - 1])
+    return reads
+
+
+def test_many_small_cycles_grow_the_edge_buffers(emu_lib, knobs, monkeypatch):
+    """the edge buffer kept room for ~1000 cut cycles and failed beyond.  Hundreds of isolated cycles with the buffers
+    started at 16 entries (CDBG_EDGE_MIN): the join's retry and the cycle cutter's growth path must produce the oracle's graph."""
+    monkeypatch.setenv("CDBG_EDGE_MIN", "16")
+    k = 13
+    reads = _many_cycles(400, 17, k, 3)
+    with api.Cdbg(k=k, abundance_min=1, device=0) as c:
+        g = c.build(reads)
+    o = orc.run(reads, k, 1)
+    assert g.stats["n_cycles"] >= 300
+    d = parity.diff(parity.graph_to_records(g), parity.graph_to_records(o), k)
+    assert d == "", d

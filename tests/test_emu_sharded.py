@@ -172,3 +172,18 @@ def test_sharded_join_variants(emu_lib, monkeypatch, name, env):
     assert d == "", d
     if env.get("CDBG_K5S_FILL") == "8" and name == "reads_3_k31_a2":
         assert sum(g.stats["n_k5_splits"] for g in shards) > 0
+
+
+def test_sharded_many_small_cycles_grow_the_edge_buffers(emu_lib, monkeypatch):
+    """Cycles cut on a shard and cycles of pieces cut in the glue append their edges after the join has sized the buffers."""
+    monkeypatch.setenv("CDBG_EDGE_MIN", "16")
+    rng = np.random.default_rng(5)
+    k = 13
+    reads = []
+    for _ in range(300):
+        s = "".join("ACGT"[i] for i in rng.integers(0, 4, 19))
+        reads.append(s + s[: k - 1])
+    m, shards = sharded_build(reads, k, 1, 3)
+    o = orc.run(reads, k, 1)
+    d = parity.diff(parity.graph_to_records(m), parity.graph_to_records(o), k)
+    assert d == "", d
