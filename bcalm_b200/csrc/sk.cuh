@@ -537,8 +537,10 @@ struct SK2CParams {
     int *failed;
 };
 
-constexpr int SK2C_WCAP = 256;      // k-mers a warp expands per round into its private staging area (2 KB per warp)
-template <int SLOTS, int T> static inline size_t sk2c_smem_bytes() { return (size_t)SLOTS * 12 + (size_t)(T / 32) * SK2C_WCAP * 8 + 128; }
+// k-mers a warp expands per round into its private staging area: 256 (2 KB per warp); 128 for the 512-thread CTAs over a 4096-slot table,
+// so that three of them (48 warps) still fit one SM's shared memory
+template <int SLOTS, int T> constexpr int sk2c_wcap() { return (T >= 512 && SLOTS <= 4096) ? 128 : 256; }
+template <int SLOTS, int T> static inline size_t sk2c_smem_bytes() { return (size_t)SLOTS * 12 + (size_t)(T / 32) * sk2c_wcap<SLOTS, T>() * 8 + 128; }
 
 // One CTA per fine bin (grid-strided), the table of k2c_count (keys u64 + counts u32 in shared memory, linear probing, abandon at
 // 3/4 full and redo the bin as two halves selected by one more hash bit).  The difference is the input: every warp takes 32 records
@@ -553,7 +555,7 @@ template <int SLOTS, int T> static inline size_t sk2c_smem_bytes() { return (siz
 // area -- already consumed -- and finish in a second, short pass.
 template <int SLOTS, int T, bool MUL32, int KC, bool TWO = false>
 __global__ void __launch_bounds__(T) sk2c_count(SK2CParams p) {
-    constexpr int NW = T / 32, PER_WARP = SLOTS / NW;
+    constexpr int NW = T / 32, PER_WARP = SLOTS / NW, SK2C_WCAP = (T >= 512 && SLOTS <= 4096) ? 128 : 256;   // (= sk2c_wcap<SLOTS, T>())
     constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);

@@ -298,7 +298,7 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
                 if (pl.slots == 8192) { if (rs == 2048) SK2D_LAUNCH(8192, 2048, 256); else SK2D_LAUNCH(8192, 1024, 256); }
                 else { if (rs == 2048) SK2D_LAUNCH(4096, 2048, 256); else if (rs == 512) SK2D_LAUNCH(4096, 512, 256); else SK2D_LAUNCH(4096, 1024, 256); }
             } else if (pl.slots == 8192) { if (th == 512) SK2C_LAUNCH(8192, 512); else SK2C_LAUNCH(8192, 256); }
-            else { if (th == 128) SK2C_LAUNCH(4096, 128); else SK2C_LAUNCH(4096, 256); }
+            else { if (th == 128) SK2C_LAUNCH(4096, 128); else if (th == 512) SK2C_LAUNCH(4096, 512); else SK2C_LAUNCH(4096, 256); }
 #undef SK2C_LAUNCH
 #undef SK2C_LAUNCH1
 #undef SK2C_LAUNCH2

@@ -26,7 +26,9 @@ CONFIGS = [
     ("sk two-phase insert mix64", {"CDBG_SK_INSERT": "two", "CDBG_K2C_HASH": "mix64"}),
     ("sk two-phase insert fill 2.0", {"CDBG_SK_INSERT": "two", "CDBG_SK_FILL": "2.0"}),
     ("sk two-phase insert fill 1.0", {"CDBG_SK_INSERT": "two", "CDBG_SK_FILL": "1.0"}),
-    ("sk two-phase 128 threads", {"CDBG_SK_INSERT": "two", "CDBG_SK_THREADS": "128"}),
+    ("sk 512 threads per table", {"CDBG_SK_THREADS": "512"}),
+    ("sk 512 threads fill 2.0", {"CDBG_SK_THREADS": "512", "CDBG_SK_FILL": "2.0"}),
+    ("sk 512 threads loop insert", {"CDBG_SK_THREADS": "512", "CDBG_SK_INSERT": "loop"}),
     ("sk K6 full (one level)", {"CDBG_K6": "full"}),
     ("super-k-mers direct count", {"CDBG_SK2C": "direct"}),
     ("super-k-mers dedup RS 1024", {"CDBG_SK2C": "dedup"}),

@@ -32,7 +32,7 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
          "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
          "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH",
-         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_SK_KC", "CDBG_SK_WAVES", "CDBG_SK_INSERT")
+         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_SK_KC", "CDBG_SK_WAVES", "CDBG_SK_INSERT", "CDBG_SK_THREADS")
 
 
 @pytest.fixture(scope="module")
@@ -88,6 +88,8 @@ VARIANTS = {
     "sk_two_phase_insert": dict(CDBG_SK_INSERT="two"),
     "sk_two_phase_forced_splits": dict(CDBG_SK_INSERT="two", CDBG_SK_FILL=8),
     "sk_two_phase_8192_runtime_k": dict(CDBG_SK_INSERT="two", CDBG_SK_SLOTS=8192, CDBG_SK_KC=0, CDBG_K2C_HASH="mix64"),
+    "sk_512_threads_per_table": dict(CDBG_SK_THREADS=512),
+    "sk_512_threads_forced_splits_loop": dict(CDBG_SK_THREADS=512, CDBG_SK_FILL=8, CDBG_SK_INSERT="loop"),
     "sk_direct_count": dict(CDBG_SK2C="direct"),
     "sk_dedup_count": dict(CDBG_SK2C="dedup"),
     "sk_dedup_small_record_table": dict(CDBG_SK2C="dedup", CDBG_SK_RS=512, CDBG_SK_FILL=3),
@@ -168,7 +170,7 @@ def _synthetic_reads(genome_len, read_len, coverage, err, seed):
 
 
 @pytest.mark.parametrize("variant", ["default", "sk_forced_splits", "sk_exact_regions_after_overflow", "sk_m_16", "sk_direct_count", "sk_dedup_count",
-                                     "sk_dedup_small_record_table", "sk_dedup_forced_splits", "k6_two_level", "sk_two_phase_insert", "sk_two_phase_forced_splits", "sk_three_waves", "sk_waves_and_exact_regions", "k1_single_pass", "k1_512_threads", "k2_l2_tables",
+                                     "sk_dedup_small_record_table", "sk_dedup_forced_splits", "k6_two_level", "sk_512_threads_per_table", "sk_two_phase_insert", "sk_two_phase_forced_splits", "sk_three_waves", "sk_waves_and_exact_regions", "k1_single_pass", "k1_512_threads", "k2_l2_tables",
                                      "k5_l2_tables", "k1_twopass_tma", "k2_smem_forced_splits", "k5_smem_forced_splits"])
 def test_larger_synthetic_read_set_matches_oracle(emu_lib, knobs, variant):
     """40 kbp genome, 100 bp reads at 30x with 1 % errors (1.2 Mbases): several tiles, coarse and fine bins, real branching."""
