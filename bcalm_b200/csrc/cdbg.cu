@@ -802,25 +802,35 @@ int rank_two_level(cdbg_ctx *ctx, const uint32_t *d_link, uint64_t *d_pair, uint
     const uint64_t n_win = (n2 + 2 * K6L_NV - 1) / (2 * K6L_NV);
     LAUNCH(k6_local, (int)std::min<uint64_t>(n_win, (uint64_t)ctx->n_sm * 4), K6L_THREADS, 0, d_link, d_pair, n2, d_list[0], ctx->d_ctr + 4);
     if ((rc = ctr_read(ctx))) return rc;
-    uint64_t n_cur = ctx->h_ctr[4], prev = ~0ULL;
+    uint64_t n_cur = ctx->h_ctr[4];
     const uint32_t *in_list = d_list[0];
     int result = n_cur ? -1 : 0;
-    for (int round = 0, batch = 1; round < 96 && result < 0; round += 4, batch++) {
+    // Termination.  A round in which nothing moves means every path is ranked.  What still moves after log2(#representatives) + a few
+    // rounds is on a cycle: a representative's pointer at least doubles its reach per round once it points at another representative
+    // (one extra round to step over a parked element).  NOT "the number of moving elements stopped shrinking", the rule of the
+    // one-level ranking: there every chain has an element at every distance from its tail, here the representatives are sparse and
+    // two consecutive rounds can move the same number of them on plain paths (seen on a B200 with golden case wide_9_k127_a1, where
+    // the false alarm made the cycle cutter split a unitig).
+    int max_rounds = 6;
+    for (uint64_t r = 1; r < n_cur; r <<= 1) max_rounds++;
+    int rounds_done = 0;
+    for (int batch = 1; result < 0; batch++) {
         if ((rc = ctr_zero(ctx))) return rc;
         uint32_t *out_list = d_list[batch & 1];
         for (int j = 0; j < 4; j++)
             LAUNCH_PDL(k6_jump_list, grid_for(ctx, n_cur, 256, 8), 256, 0, d_pair, in_list, n_cur, j == 3 ? out_list : (uint32_t *)nullptr, ctx->d_ctr + 4,
                        ctx->d_ctr + j);
         ctx->st.rank_rounds += 4;
+        rounds_done += 4;
         if ((rc = ctr_read(ctx))) return rc;
-        for (int j = 0; j < 4 && result < 0; j++) {
-            const uint64_t c = ctx->h_ctr[j];
-            if (c == 0) { *remaining = 0; result = 0; }
-            else if (c == prev) { *remaining = std::min<uint64_t>(n2, c * 2 * K6L_NV); result = 0; }   // cycles: every moving representative stands for up to a window of elements
-            prev = c;
-        }
+        for (int j = 0; j < 4 && result < 0; j++)
+            if (ctx->h_ctr[j] == 0) { *remaining = 0; result = 0; }
         in_list = out_list; n_cur = ctx->h_ctr[4];
         if (result < 0 && n_cur == 0) { *remaining = 0; result = 0; }
+        if (result < 0 && rounds_done >= max_rounds) {          // cycles: every moving representative stands for up to a window of elements
+            *remaining = std::min<uint64_t>(n2, std::max<uint64_t>(ctx->h_ctr[3], 1) * 2 * K6L_NV);
+            result = 0;
+        }
     }
     dfree(ctx, d_list[0]); dfree(ctx, d_list[1]);
     if (result != 0) return ctx->fail(CDBG_ERR_INTERNAL, "list ranking did not converge");
