@@ -808,11 +808,12 @@ int rank_two_level(cdbg_ctx *ctx, const uint32_t *d_link, uint64_t *d_pair, uint
     // Termination.  A round in which nothing moves means every path is ranked.  What still moves after log2(#representatives) + a few
     // rounds is on a cycle: a representative's pointer at least doubles its reach per round once it points at another representative
     // (one extra round to step over a parked element).  NOT "the number of moving elements stopped shrinking", the rule of the
-    // one-level ranking: there every chain has an element at every distance from its tail, here the representatives are sparse and
+    // one-level ranking: there every chain has an element at every distance from its tail (its closest unfinished element finishes in
+    // the next round, so the count strictly shrinks while a path is unfinished), here the representatives are sparse and
     // two consecutive rounds can move the same number of them on plain paths (seen on a B200 with golden case wide_9_k127_a1, where
     // the false alarm made the cycle cutter split a unitig).
-    int max_rounds = 6;
-    for (uint64_t r = 1; r < n_cur; r <<= 1) max_rounds++;
+    int max_rounds = 8;                                          // 2 * ceil(log2(#representatives)) + 8: with asynchronous updates a pointer can
+    for (uint64_t r = 1; r < n_cur; r <<= 1) max_rounds += 2;    // land on a parked element every other round, which costs a round without doubling
     int rounds_done = 0;
     for (int batch = 1; result < 0; batch++) {
         if ((rc = ctr_zero(ctx))) return rc;
