@@ -58,7 +58,7 @@ class UnitigView(C.Structure):
 
 LINK_DTYPE = np.dtype([("from", "<u4"), ("to", "<u4"), ("from_sign", "u1"), ("to_sign", "u1"), ("pad", "u1", (2,))])
 
-EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_push_sequence_text", "cdbg_get_pushed_reads", "cdbg_count", "cdbg_compact",
+EXPORTS = ["cdbg_create", "cdbg_destroy", "cdbg_reset", "cdbg_last_error", "cdbg_push_reads", "cdbg_reserve_reads", "cdbg_push_sequence_text", "cdbg_get_pushed_reads", "cdbg_count", "cdbg_compact",
            "cdbg_link", "cdbg_get_unitigs", "cdbg_get_stats", "cdbg_build", "cdbg_get_solid_kmers", "cdbg_set_solid_kmers", "cdbg_synth_reads",
            "cdbg_copy_to_host", "cdbg_host_alloc", "cdbg_host_free", "cdbg_version", "cdbg_nccl_unique_id", "cdbg_shard_init", "cdbg_synth_reads_range", "cdbg_owner_of", "cdbg_plan_shard_exchange"]
 
@@ -81,6 +81,7 @@ def load_library():
     L.cdbg_last_error.argtypes = [C.c_void_p]
     L.cdbg_last_error.restype = C.c_char_p
     L.cdbg_push_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    L.cdbg_reserve_reads.argtypes = [C.c_void_p, C.c_uint64]
     L.cdbg_get_pushed_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, P(C.c_uint64)]
     L.cdbg_push_sequence_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, P(C.c_uint64)]
     for n in ("cdbg_count", "cdbg_compact", "cdbg_link", "cdbg_get_stats"):
@@ -219,6 +220,10 @@ class Cdbg:
         buf = np.empty(n.value, np.uint8)
         self._ck(self.lib.cdbg_get_pushed_reads(self.h, buf.ctypes.data, n.value, C.byref(n)))
         return buf.tobytes()
+
+    def reserve_reads(self, n_bytes: int):
+        """Make room on the device for n_bytes of reads before a series of pushes."""
+        self._ck(self.lib.cdbg_reserve_reads(self.h, int(n_bytes)))
 
     def push_device(self, dptr: int, n_bytes: int):
         self._ck(self.lib.cdbg_push_reads(self.h, C.c_void_p(dptr), n_bytes, MEM_DEVICE))

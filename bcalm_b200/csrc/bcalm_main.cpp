@@ -14,12 +14,18 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <chrono>
 #include <string>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -279,6 +285,79 @@ static int g_parse_threads = 1;
 static cdbg_ctx *g_gpu_parse_ctx = nullptr;   // -gpu-parse 1: files are pushed as text and parsed on the device
 static std::function<cdbg_ctx *()> g_gpu_parse_wait;   // the context is created on its own thread while the first file is read: join it here
 
+// A large plain-text FASTA file for the GPU parser: the file is mapped, cut at record starts into chunks of ~256 MB
+// (CDBG_CLI_CHUNK), and a reader thread copies chunk i + 1 from the page cache into one of two pinned buffers (all host threads
+// share the copy) while the GPU receives and parses chunk i -- instead of read() into a pageable buffer followed by one big
+// pageable H2D copy.  Returns false when nothing was pushed (the caller then reads the file the ordinary way).
+bool push_fasta_chunked(cdbg_ctx *ctx, const std::string &path, uint64_t &n_records) {
+    const size_t min_size = getenv("CDBG_CLI_CHUNK_MIN") ? strtoull(getenv("CDBG_CLI_CHUNK_MIN"), nullptr, 10) : (64u << 20);
+    const size_t CH = std::max<size_t>(getenv("CDBG_CLI_CHUNK") ? strtoull(getenv("CDBG_CLI_CHUNK"), nullptr, 10) : (256u << 20), 64);
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size < min_size) { close(fd); return false; }
+    const size_t n = (size_t)sb.st_size;
+    const char *map = (const char *)mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return false;
+    auto give_up = [&]() { munmap((void *)map, n); return false; };
+    if (map[0] != '>') return give_up();                           // gz, FASTQ, file of files, leading blank lines: the ordinary path
+    madvise((void *)map, n, MADV_SEQUENTIAL);
+    std::vector<size_t> cut{0};                                      // chunk i = [cut[i], cut[i + 1]), every cut at a record start
+    while (cut.back() < n) {
+        size_t e = std::min(n, cut.back() + CH);
+        if (e < n) {
+            size_t p = e;
+            while (p > cut.back() + 1 && !(map[p] == '>' && map[p - 1] == '\n')) p--;
+            if (p <= cut.back() + 1) { p = e; while (p < n && !(map[p] == '>' && map[p - 1] == '\n')) p++; }   // a record longer than a chunk
+            e = p;
+        }
+        cut.push_back(e);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    size_t maxc = 0;
+    for (size_t i = 0; i < n_chunks; i++) maxc = std::max(maxc, cut[i + 1] - cut[i]);
+    uint8_t *buf[2] = {(uint8_t *)cdbg_host_alloc(maxc), (uint8_t *)cdbg_host_alloc(maxc)};
+    if (!buf[0] || !buf[1]) { cdbg_host_free(buf[0]); cdbg_host_free(buf[1]); return give_up(); }
+    if (cdbg_reserve_reads(ctx, n + n_chunks + 64) != CDBG_OK) { cdbg_host_free(buf[0]); cdbg_host_free(buf[1]); return give_up(); }
+    std::mutex mu; std::condition_variable cv;
+    int filled[2] = {-1, -1};                                         // chunk held by each buffer, -1 = free
+    bool stop = false;
+    const int copy_threads = std::max(1, std::min(g_parse_threads, 16));
+    std::thread reader([&]() {
+        for (size_t i = 0; i < n_chunks; i++) {
+            const int b = (int)(i & 1);
+            { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[b] == -1 || stop; }); if (stop) return; }
+            const size_t len = cut[i + 1] - cut[i], per = (len + copy_threads - 1) / copy_threads;
+            std::vector<std::thread> pool;
+            for (int t = 1; t < copy_threads; t++) {
+                const size_t o0 = std::min(len, per * t), o1 = std::min(len, o0 + per);
+                if (o1 > o0) pool.emplace_back([=]() { memcpy(buf[b] + o0, map + cut[i] + o0, o1 - o0); });
+            }
+            memcpy(buf[b], map + cut[i], std::min(len, per));
+            for (auto &th : pool) th.join();
+            { std::lock_guard<std::mutex> lk(mu); filled[b] = (int)i; }
+            cv.notify_all();
+        }
+    });
+    bool ok = true, pushed_any = false;
+    std::string err;
+    for (size_t i = 0; i < n_chunks && ok; i++) {
+        const int b = (int)(i & 1);
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&]() { return filled[b] == (int)i; }); }
+        uint64_t nrec = 0;
+        if (cdbg_push_sequence_text(ctx, buf[b], cut[i + 1] - cut[i], CDBG_MEM_HOST, &nrec) != CDBG_OK) { ok = false; err = cdbg_last_error(ctx); }
+        else { n_records += nrec; pushed_any = true; }
+        { std::lock_guard<std::mutex> lk(mu); filled[b] = -1; if (!ok) stop = true; }
+        cv.notify_all();
+    }
+    reader.join();
+    cdbg_host_free(buf[0]); cdbg_host_free(buf[1]);
+    munmap((void *)map, n);
+    if (!ok && pushed_any) die("GPU parser failed in the middle of '" + path + "': " + err);
+    return ok;
+}
+
 void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, int depth = 0) {
     size_t start = 0;
     while (start <= spec.size()) {
@@ -286,6 +365,10 @@ void load_input(const std::string &spec, ByteBuf &stream, uint64_t &n_records, i
         std::string path = spec.substr(start, c == std::string::npos ? std::string::npos : c - start);
         start = c == std::string::npos ? spec.size() + 1 : c + 1;
         if (path.empty()) continue;
+        if (g_gpu_parse_wait || g_gpu_parse_ctx) {                  // large plain FASTA: streamed to the GPU parser in chunks
+            if (!g_gpu_parse_ctx) g_gpu_parse_ctx = g_gpu_parse_wait();
+            if (push_fasta_chunked(g_gpu_parse_ctx, path, n_records)) continue;
+        }
         FileBuf buf;
         if (!read_whole(path, buf)) die("Unable to open file '" + path + "'");
         size_t i = 0;
@@ -536,11 +619,9 @@ void write_outputs(const Options &o, const std::vector<const cdbg_unitig_view *>
     const int k = o.k;
     uint64_t total_nt = 0, n_unitigs = 0, n_links = 0;
     for (const cdbg_unitig_view *vp : views) { total_nt += vp->total_nt; n_unitigs += vp->n_unitigs; n_links += vp->n_links; }
-    std::string text;
-    text.reserve(total_nt + n_unitigs * 64 + n_links * 16 + 64);
-    for (const cdbg_unitig_view *vp : views) {
-        const cdbg_unitig_view &v = *vp;
-        for (uint64_t u = 0; u < v.n_unitigs; u++) {
+    // the records of unitigs [u0, u1) of one view, appended to `text`
+    auto format_range = [&](const cdbg_unitig_view &v, uint64_t u0, uint64_t u1, std::string &text) {
+        for (uint64_t u = u0; u < u1; u++) {
             const uint64_t b = v.seq_off[u], len = v.seq_off[u + 1] - b, nk = len - (uint64_t)(k - 1);
             const uint32_t *ab = v.abund ? v.abund + (b - u * (uint64_t)(k - 1)) : nullptr;
             text.push_back('>'); put_u64(text, v.first_unitig + u);
@@ -567,15 +648,46 @@ void write_outputs(const Options &o, const std::vector<const cdbg_unitig_view *>
             text.append(v.seq + b, len);
             text.push_back('\n');
         }
+    };
+    // formatted by all host threads (every piece a contiguous range of unitigs of about the same number of nucleotides), written in order
+    struct Piece { const cdbg_unitig_view *v; uint64_t u0, u1; std::string text; };
+    std::vector<Piece> pieces;
+    {
+        const uint64_t n_thr = (uint64_t)std::max(1, g_parse_threads);
+        const uint64_t target = std::max<uint64_t>((total_nt + n_unitigs * 48) / (n_thr * 4) + 1, 1u << 20);
+        for (const cdbg_unitig_view *vp : views) {
+            uint64_t u0 = 0;
+            while (u0 < vp->n_unitigs) {
+                uint64_t u1 = u0, acc = 0;
+                while (u1 < vp->n_unitigs && acc < target) { acc += vp->seq_off[u1 + 1] - vp->seq_off[u1] + 48; u1++; }
+                pieces.push_back(Piece{vp, u0, u1, std::string()});
+                u0 = u1;
+            }
+        }
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t i; (i = next.fetch_add(1)) < pieces.size();) {
+                Piece &pc = pieces[i];
+                pc.text.reserve((size_t)(pc.v->seq_off[pc.u1] - pc.v->seq_off[pc.u0]) + (size_t)(pc.u1 - pc.u0) * 72 +
+                                (size_t)(pc.v->link_off[pc.u1] - pc.v->link_off[pc.u0]) * 16 + 64);
+                format_range(*pc.v, pc.u0, pc.u1, pc.text);
+            }
+        };
+        std::vector<std::thread> pool;
+        const size_t nt_ = std::min<size_t>((size_t)n_thr, pieces.size());
+        for (size_t t = 1; t < nt_; t++) pool.emplace_back(work);
+        work();
+        for (auto &th : pool) th.join();
     }
     FILE *f = fopen(out_path.c_str(), "wb");
     if (!f) { if (ctx_for_cleanup) cdbg_destroy(ctx_for_cleanup); die("Unable to open output file '" + out_path + "'"); }
-    fwrite(text.data(), 1, text.size(), f);
+    size_t text_bytes = 0;
+    for (const Piece &pc : pieces) { fwrite(pc.text.data(), 1, pc.text.size(), f); text_bytes += pc.text.size(); }
     fclose(f);
 
     if (!o.out_gfa.empty()) {   // GFA1, same records as scripts/convertToGFA.py:74,97-114
         std::string g;
-        g.reserve(text.size() + n_links * 24);
+        g.reserve(text_bytes + n_links * 24);
         g += "H\tVN:Z:1.0\tks:i:"; put_u64(g, (uint64_t)k); g.push_back('\n');
         for (const cdbg_unitig_view *vp : views) {
             const cdbg_unitig_view &v = *vp;

@@ -1303,7 +1303,7 @@ int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int l
     CK(cudaSetDevice(ctx->prm.device));
     int rc;
     tstart(ctx, T_PUSH);
-    if (location == CDBG_MEM_DEVICE && ctx->stage == ST_EMPTY && (reinterpret_cast<uintptr_t>(bytes) & 15) == 0) {
+    if (location == CDBG_MEM_DEVICE && ctx->stage == ST_EMPTY && ctx->cap_bytes == 0 && (reinterpret_cast<uintptr_t>(bytes) & 15) == 0) {
         ctx->d_bytes = const_cast<uint8_t *>(bytes);   // used in place
         ctx->n_bytes = n_bytes; ctx->bytes_borrowed = true;
     } else {
@@ -1331,6 +1331,24 @@ int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int l
     }
     tstop(ctx, T_PUSH);
     ctx->stage = ST_PUSHED;
+    return CDBG_OK;
+}
+
+int cdbg_reserve_reads(cdbg_ctx *ctx, uint64_t n_bytes) {
+    if (!ctx || !ctx->stream) return CDBG_ERR_PARAM;
+    if (ctx->stage > ST_PUSHED) return ctx->fail(CDBG_ERR_STATE, "reserve after count: call cdbg_reset first");
+    CK(cudaSetDevice(ctx->prm.device));
+    if (n_bytes + 64 <= ctx->cap_bytes && !ctx->bytes_borrowed) return CDBG_OK;
+    int rc;
+    const uint64_t cap = std::max<uint64_t>(n_bytes, ctx->n_bytes + 2) + 64;
+    uint8_t *nb = nullptr;
+    if ((rc = dalloc(ctx, &nb, cap + 64))) return rc;
+    if (ctx->n_bytes) CK(cudaMemcpyAsync(nb, ctx->d_bytes, ctx->n_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->bytes_borrowed) {          // (a buffer used in place carries no break byte after its last read)
+        if (ctx->n_bytes) { CK(cudaMemsetAsync(nb + ctx->n_bytes, '\n', 1, ctx->stream)); ctx->n_bytes += 1; }
+    } else if (ctx->d_bytes) dfree(ctx, ctx->d_bytes);
+    ctx->d_bytes = nb; ctx->cap_bytes = cap; ctx->bytes_borrowed = false; ctx->bytes_hostmapped = false;
+    SYNC_STREAM(ctx);
     return CDBG_OK;
 }
 
@@ -1398,7 +1416,7 @@ int cdbg_push_sequence_text(cdbg_ctx *ctx, const uint8_t *text, uint64_t n_bytes
     if (bad) { dfree(ctx, d_out); return ctx->fail(CDBG_ERR_PARAM, "FASTQ text is not in strict 4-line records (multi-line FASTQ or stray lines): parse it on the host"); }
     if (n_records) *n_records = ctx->h_ctr[0];
     // hand the nucleotide stream to the normal path; as the first push it is used in place (the block stays allocated until reset)
-    const bool in_place = ctx->stage == ST_EMPTY;
+    const bool in_place = ctx->stage == ST_EMPTY && ctx->cap_bytes == 0;
     rc = cdbg_push_reads(ctx, d_out, total, CDBG_MEM_DEVICE);
     if (!in_place || rc != CDBG_OK) dfree(ctx, d_out);
     return rc;

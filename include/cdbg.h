@@ -142,6 +142,10 @@ const char *cdbg_last_error(const cdbg_ctx *ctx);
  * cdbg_count returns). */
 int cdbg_push_reads(cdbg_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, int location);
 
+/* Optional: make room on the device for `n_bytes` of reads before a series of pushes (a host that streams a large file in chunks
+ * knows the total; without it the read buffer grows by doubling).  Reads already pushed are kept. */
+int cdbg_reserve_reads(cdbg_ctx *ctx, uint64_t n_bytes);
+
 /* Append reads given as raw FASTA or FASTQ TEXT (the bytes of the file, after gunzip): headers, '+' and quality lines are
  * removed and multi-line records joined ON THE GPU (a parallel scan over the parser's state-transition functions, parse.cuh),
  * replacing the host-side Bank parser (G/bank/impl/BankFasta.cpp:390-560) for this path.  The text must start at a record

@@ -275,3 +275,29 @@ def test_kff_and_non_canonical_text_dumps_with_multi_word_kmers(cli, tmp_path, n
     run_cli(cli, tmp_path, "-solid-kmers-in", "dump.txt", "-kmer-size", str(k), "-abundance-min", str(c["abundance_min"]), "-out", "fromdump")
     d = parity.diff(parity.parse_unitigs_fa((tmp_path / "fromdump.unitigs.fa").read_text()), want, k)
     assert d == "", d
+
+
+@pytest.mark.parametrize("chunk", [64, 700, 5000])
+def test_large_fasta_is_streamed_to_the_gpu_parser_in_chunks(cli, tmp_path, monkeypatch, chunk):
+    """Plain FASTA files above a size threshold are mapped, cut at record starts and streamed through two pinned buffers
+    (push_fasta_chunked): with tiny chunks -- smaller than a record, about a record, many records -- the graph is the golden one and
+    the verbose line says the text was parsed on the GPU."""
+    monkeypatch.setenv("CDBG_CLI_CHUNK", str(chunk))
+    monkeypatch.setenv("CDBG_CLI_CHUNK_MIN", "0")
+    c = CASES["reads_3_k31_a2"]
+    fa = tmp_path / "in.fa"
+    write_fasta(fa, c["reads"], width=37)
+    out = run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(c["k"]), "-abundance-min", str(c["abundance_min"]))
+    assert "text parsed on the GPU" in out and f"sequences: {len(c['reads'])} " in out
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "in.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d == "", d
+    # two files in one run: the second is appended after the first
+    fb = tmp_path / "b.fa"
+    write_fasta(fb, c["reads"][::-1], width=50)
+    run_cli(cli, tmp_path, "-in", f"{fa},{fb}", "-kmer-size", str(c["k"]), "-abundance-min", str(2 * c["abundance_min"]), "-out", "twice")
+    d = parity.diff(parity.parse_unitigs_fa((tmp_path / "twice.unitigs.fa").read_text()), parity.parse_unitigs_fa(c["unitigs_fa"]), c["k"])
+    assert d.count("node multisets differ") <= 1      # same sequences, KC doubled: only the counts may differ
+    recs = parity.parse_unitigs_fa((tmp_path / "twice.unitigs.fa").read_text())
+    ref = parity.parse_unitigs_fa(c["unitigs_fa"])
+    assert sorted(min(r["seq"], parity.revcomp_str(r["seq"])) for r in recs) == sorted(min(r["seq"], parity.revcomp_str(r["seq"])) for r in ref)
+    assert sum(r["kc"] for r in recs) == 2 * sum(r["kc"] for r in ref)
