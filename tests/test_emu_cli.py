@@ -277,14 +277,14 @@ def test_kff_and_non_canonical_text_dumps_with_multi_word_kmers(cli, tmp_path, n
     assert d == "", d
 
 
-@pytest.mark.parametrize("chunk", [64, 700, 5000])
-def test_large_fasta_is_streamed_to_the_gpu_parser_in_chunks(cli, tmp_path, monkeypatch, chunk):
+@pytest.mark.parametrize("chunk,name", [(48, "reads_0_k15_a2"), (900, "reads_1_k21_a2"), (40000, "reads_3_k31_a2")])
+def test_large_fasta_is_streamed_to_the_gpu_parser_in_chunks(cli, tmp_path, monkeypatch, chunk, name):
     """Plain FASTA files above a size threshold are mapped, cut at record starts and streamed through two pinned buffers
     (push_fasta_chunked): with tiny chunks -- smaller than a record, about a record, many records -- the graph is the golden one and
     the verbose line says the text was parsed on the GPU."""
     monkeypatch.setenv("CDBG_CLI_CHUNK", str(chunk))
     monkeypatch.setenv("CDBG_CLI_CHUNK_MIN", "0")
-    c = CASES["reads_3_k31_a2"]
+    c = CASES[name]
     fa = tmp_path / "in.fa"
     write_fasta(fa, c["reads"], width=37)
     out = run_cli(cli, tmp_path, "-in", str(fa), "-kmer-size", str(c["k"]), "-abundance-min", str(c["abundance_min"]))
