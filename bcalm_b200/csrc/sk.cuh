@@ -539,8 +539,9 @@ struct SK2CParams {
 
 // k-mers a warp expands per round into its private staging area: 256 (2 KB per warp); 128 for the 512-thread CTAs over a 4096-slot table,
 // so that three of them (48 warps) still fit one SM's shared memory
-template <int SLOTS, int T> constexpr int sk2c_wcap() { return (T >= 512 && SLOTS <= 4096) ? 128 : 256; }
-template <int SLOTS, int T> static inline size_t sk2c_smem_bytes() { return (size_t)SLOTS * 12 + (size_t)(T / 32) * sk2c_wcap<SLOTS, T>() * 8 + 128; }
+// (SMALL: 128 also for 256-thread CTAs -- 56 KB per CTA, four CTAs per SM instead of three; CDBG_SK_WCAP=128)
+template <int SLOTS, int T, bool SMALL = false> constexpr int sk2c_wcap() { return (SMALL || (T >= 512 && SLOTS <= 4096)) ? 128 : 256; }
+template <int SLOTS, int T, bool SMALL = false> static inline size_t sk2c_smem_bytes() { return (size_t)SLOTS * 12 + (size_t)(T / 32) * sk2c_wcap<SLOTS, T, SMALL>() * 8 + 128; }
 
 // One CTA per fine bin (grid-strided), the table of k2c_count (keys u64 + counts u32 in shared memory, linear probing, abandon at
 // 3/4 full and redo the bin as two halves selected by one more hash bit).  The difference is the input: every warp takes 32 records
@@ -553,9 +554,9 @@ template <int SLOTS, int T> static inline size_t sk2c_smem_bytes() { return (siz
 // unluckiest lane (ncu: ~11 of 32 lanes active in the probe loop).  With TWO every staged k-mer gets exactly ONE probe with the whole
 // warp converged; the few keys that met a different key there (~the load factor) are written back to the front of the staging
 // area -- already consumed -- and finish in a second, short pass.
-template <int SLOTS, int T, bool MUL32, int KC, bool TWO = false>
+template <int SLOTS, int T, bool MUL32, int KC, bool TWO = false, bool SMALL = false>
 __global__ void __launch_bounds__(T) sk2c_count(SK2CParams p) {
-    constexpr int NW = T / 32, PER_WARP = SLOTS / NW, SK2C_WCAP = (T >= 512 && SLOTS <= 4096) ? 128 : 256;   // (= sk2c_wcap<SLOTS, T>())
+    constexpr int NW = T / 32, PER_WARP = SLOTS / NW, SK2C_WCAP = (SMALL || (T >= 512 && SLOTS <= 4096)) ? 128 : 256;   // (= sk2c_wcap<SLOTS, T, SMALL>())
     constexpr uint32_t MASK = SLOTS - 1, FILL_LIMIT = SLOTS / 4 * 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *s_keys = reinterpret_cast<uint64_t *>(smem_raw);

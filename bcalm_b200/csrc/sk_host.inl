@@ -293,7 +293,19 @@ int sk_partition_count(cdbg_ctx *ctx, const SKPlan &pl, const ulonglong2 *d_recs
             const int th = getenv("CDBG_SK_THREADS") ? atoi(getenv("CDBG_SK_THREADS")) : 256;
             const char *ins = getenv("CDBG_SK_INSERT");
             const bool two_phase = SK_TWO_PHASE_DEFAULT ? !(ins && strcmp(ins, "loop") == 0) : (ins && strcmp(ins, "two") == 0);
-            if (dedup) {
+            const bool small_stage = getenv("CDBG_SK_WCAP") && atoi(getenv("CDBG_SK_WCAP")) == 128 && pl.slots == 4096 && th == 256 && two_phase;
+            if (small_stage && !dedup) {
+#define SK2C_SMALL(MU, KC)                                                                                                                  \
+    do {                                                                                                                                    \
+        const size_t sm_ = sk2c_smem_bytes<4096, 256, true>();                                                                              \
+        CK(cudaFuncSetAttribute(sk2c_count<4096, 256, MU, KC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));          \
+        const uint64_t per_sm_ = std::max<uint64_t>(1, std::min<uint64_t>(2048 / 256, (227 * 1024) / (sm_ + 1024)));                        \
+        LAUNCH((sk2c_count<4096, 256, MU, KC, true, true>), (int)std::min<uint64_t>(NF, (uint64_t)ctx->n_sm * per_sm_), 256, sm_, cp);      \
+    } while (0)
+                if (k31) { if (mul32) SK2C_SMALL(true, 31); else SK2C_SMALL(false, 31); }
+                else { if (mul32) SK2C_SMALL(true, 0); else SK2C_SMALL(false, 0); }
+#undef SK2C_SMALL
+            } else if (dedup) {
                 const int rs = getenv("CDBG_SK_RS") ? atoi(getenv("CDBG_SK_RS")) : 1024;
                 if (pl.slots == 8192) { if (rs == 2048) SK2D_LAUNCH(8192, 2048, 256); else SK2D_LAUNCH(8192, 1024, 256); }
                 else { if (rs == 2048) SK2D_LAUNCH(4096, 2048, 256); else if (rs == 512) SK2D_LAUNCH(4096, 512, 256); else SK2D_LAUNCH(4096, 1024, 256); }

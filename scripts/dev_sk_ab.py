@@ -18,7 +18,7 @@ K = 31
 n_reads = G * 30 // L
 T0 = time.time()
 BUDGET_S = float(os.environ.get("AB_BUDGET_S", "90"))
-TUN = ("CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_K2C_HASH", "CDBG_K1_THREADS", "CDBG_SK_DENSITY", "CDBG_K6", "CDBG_ZEROCOPY", "CDBG_SK_KC", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_MMER_RANK", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_SK_INSERT", "CDBG_SK_THREADS")
+TUN = ("CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_K2C_HASH", "CDBG_K1_THREADS", "CDBG_SK_DENSITY", "CDBG_K6", "CDBG_ZEROCOPY", "CDBG_SK_KC", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_MMER_RANK", "CDBG_K5S_FILL", "CDBG_K5S_SLOTS", "CDBG_SK_INSERT", "CDBG_SK_THREADS", "CDBG_SK_WCAP")
 CONFIGS = [
     ("k-mer instances (round-1 default)", {"CDBG_S1": "kmer"}),
     ("super-k-mers default", {}),
@@ -26,6 +26,8 @@ CONFIGS = [
     ("sk two-phase insert mix64", {"CDBG_SK_INSERT": "two", "CDBG_K2C_HASH": "mix64"}),
     ("sk two-phase insert fill 2.0", {"CDBG_SK_INSERT": "two", "CDBG_SK_FILL": "2.0"}),
     ("sk two-phase insert fill 1.0", {"CDBG_SK_INSERT": "two", "CDBG_SK_FILL": "1.0"}),
+    ("sk small staging (4 CTAs/SM)", {"CDBG_SK_WCAP": "128"}),
+    ("sk small staging fill 1.25", {"CDBG_SK_WCAP": "128", "CDBG_SK_FILL": "1.25"}),
     ("sk 512 threads per table", {"CDBG_SK_THREADS": "512"}),
     ("sk 512 threads fill 2.0", {"CDBG_SK_THREADS": "512", "CDBG_SK_FILL": "2.0"}),
     ("sk 512 threads loop insert", {"CDBG_SK_THREADS": "512", "CDBG_SK_INSERT": "loop"}),

@@ -32,7 +32,7 @@ with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
 KNOBS = ("CDBG_K1", "CDBG_K2", "CDBG_K2S_SLOTS", "CDBG_K2S_FILL", "CDBG_K2S_P1", "CDBG_K1_SLACK", "CDBG_ZEROCOPY", "CDBG_ZEROCOPY_MIN",
          "CDBG_EMU_PINNED", "CDBG_BIN_TARGET", "CDBG_JOIN_TARGET", "CDBG_PDL", "CDBG_K5", "CDBG_K5S_SLOTS", "CDBG_K5S_FILL", "CDBG_K5S_P1",
          "CDBG_RANK", "CDBG_K6", "CDBG_K2C", "CDBG_K1_THREADS", "CDBG_K2P", "CDBG_K2C_HASH",
-         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_SK_KC", "CDBG_SK_WAVES", "CDBG_SK_INSERT", "CDBG_SK_THREADS")
+         "CDBG_S1", "CDBG_SK_M", "CDBG_SK_SLOTS", "CDBG_SK_FILL", "CDBG_SK_P1", "CDBG_SK_DENSITY", "CDBG_SK_SLACK", "CDBG_SK2C", "CDBG_SK_RS", "CDBG_SK_KC", "CDBG_SK_WAVES", "CDBG_SK_INSERT", "CDBG_SK_THREADS", "CDBG_SK_WCAP")
 
 
 @pytest.fixture(scope="module")
@@ -88,6 +88,7 @@ VARIANTS = {
     "sk_two_phase_insert": dict(CDBG_SK_INSERT="two"),
     "sk_two_phase_forced_splits": dict(CDBG_SK_INSERT="two", CDBG_SK_FILL=8),
     "sk_two_phase_8192_runtime_k": dict(CDBG_SK_INSERT="two", CDBG_SK_SLOTS=8192, CDBG_SK_KC=0, CDBG_K2C_HASH="mix64"),
+    "sk_small_staging_area": dict(CDBG_SK_WCAP=128),
     "sk_512_threads_per_table": dict(CDBG_SK_THREADS=512),
     "sk_512_threads_forced_splits_loop": dict(CDBG_SK_THREADS=512, CDBG_SK_FILL=8, CDBG_SK_INSERT="loop"),
     "sk_direct_count": dict(CDBG_SK2C="direct"),
